@@ -1,0 +1,62 @@
+// Host-side interface of the tcgen05 GEMM / implicit-GEMM conv3d kernel (gemm_tcgen05.cu).
+//
+// One kernel family serves every dense contraction on the LTX-Video hot path:
+//   * DiT projections (SURVEY §2b K1,K3,K6,K10,K11,K12,K14): C[M,N] = A[M,K] * W[N,K]^T, bf16 in, f32 accumulate
+//   * VAE CausalConv3d (V1, vae.rs:415-464) as an implicit GEMM over a zero/replicate-padded NDHWC volume:
+//     the 27 taps become 27 row-shifted views of the same [voxels, Cin] matrix (see DESIGN.md "conv3d").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ltxv {
+
+enum EpiMode : int {
+    EPI_STORE_BF16 = 0,       // out_bf16[row, col] = act(acc + bias)
+    EPI_STORE_F32 = 1,        // out_f32 [row, col] = acc + bias
+    EPI_RESIDUAL_F32 = 2,     // res_f32[row, col] += gate[col] * (acc + bias); optional bf16 copy of the new value
+    EPI_CONV_NDHWC = 3,       // out_bf16[voxel, col] = acc + bias (+ residual_bf16[voxel, col]); unpadded NDHWC
+    EPI_CONV_D2S = 4,         // upsampler: depth-to-space(2,2,2) + channel-tiled residual + drop frame 0
+    EPI_CONV_UNPATCHIFY = 5,  // conv_out: f32 NCDHW pixels through the p=4 unpatchify index map
+};
+
+enum ActMode : int { ACT_NONE = 0, ACT_GELU_TANH = 1 };
+
+struct GemmParams {
+    int M, N, K;       // logical problem; K is the full reduction length (27*Cin for conv)
+    int num_k_blocks;  // ceil(K / 64)
+    int epi;           // EpiMode
+    int act;           // ActMode (EPI_STORE_BF16 only)
+    int ldo;           // leading dimension (elements) of out / residual tensors
+
+    const float* bias;  // [N] f32 or null
+    const float* gate;  // [N] f32 or null (EPI_RESIDUAL_F32: null means gate = 1)
+    void* out;          // bf16 or f32 depending on epi; for EPI_RESIDUAL_F32 the optional bf16 copy (may be null)
+    float* res_f32;     // EPI_RESIDUAL_F32: read-modify-write residual stream
+    const void* res_bf16;  // EPI_CONV_NDHWC: optional residual (same layout as out)
+
+    // ---- implicit-GEMM conv3d ----
+    int conv;           // 0 = plain GEMM
+    int cin_blocks;     // Cin / 64 (k-blocks per tap)
+    int T, H, W;        // output volume (= input volume, stride 1), unpadded
+    int tap_off[27];    // A-row offset of tap (kt,kh,kw) relative to the output's padded-flat index
+    const void* a_ptr;  // base of the padded A volume (EPI_CONV_D2S reads its residual from here)
+    int cin;            // Cin
+    int post_u8_scale;  // EPI_CONV_UNPATCHIFY: 1 => also apply clamp(0.5x+0.5,0,1)*255 (t2v_pipeline.rs:147-155)
+};
+
+// A: [rows_a, K_a] bf16 row-major (K contiguous). B: [N, K] bf16 row-major (nn.Linear weight layout).
+// For conv, A is the padded volume viewed as [(T+2)*(H+2)*(W+2), Cin] and B is [Cout, 27*Cin] with k = tap*Cin + c.
+struct GemmOperands {
+    const void* a;
+    int64_t a_rows, a_cols;  // a_cols = row length in elements (row stride)
+    const void* b;
+    int64_t b_rows, b_cols;
+};
+
+// Returns cudaSuccess or the launch / tensor-map error. block_n: 0 = auto.
+cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int block_n, cudaStream_t stream);
+
+// Number of kernels launched by launch_gemm_bf16 since process start (bench.py's gpu_launches evidence).
+uint64_t gemm_launch_count();
+
+}  // namespace ltxv

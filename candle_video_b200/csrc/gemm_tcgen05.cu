@@ -1,0 +1,445 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA (128B swizzle) -> smem ring -> tcgen05.mma (UMMA,
+// accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue with the fused element-wise tails of the
+// LTX-Video DiT / VAE layers. Also runs CausalConv3d as an implicit GEMM (27 row-shifted A views).
+//
+// Warp roles (256 threads, 1 CTA / SM):
+//   warp 0   : TMA producer (one elected lane)
+//   warp 1   : UMMA issuer  (one elected lane)
+//   warp 2   : TMEM allocator / deallocator
+//   warp 3   : idle
+//   warps 4-7: epilogue; warp w owns TMEM lanes 32*(w%4) .. +31, one accumulator row per thread
+#include "common.cuh"
+#include "gemm.h"
+#include "tensormap.h"
+
+#include <atomic>
+
+namespace ltxv {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kABytes = kBlockM * kBlockK * 2;
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 192) ? 5 : (BLOCK_N >= 128) ? 6 : 8;
+    static constexpr int kTmemStride = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128) ? 128 : 256;
+    static constexpr int kTmemCols = 2 * kTmemStride;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
+    static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+};
+
+struct Tile {
+    int m0, n0;
+};
+
+__device__ __forceinline__ Tile tile_coords(int tile, int num_m) {
+    Tile t;
+    t.m0 = (tile % num_m) * kBlockM;
+    t.n0 = (tile / num_m);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue: one thread owns one accumulator row, 32 consecutive columns at a time.
+// ------------------------------------------------------------------------------------------------
+struct RowCtx {
+    bool valid;       // row participates in stores
+    int64_t out_row;  // row index in the output tensor (GEMM: m; conv: voxel index)
+    int t, h, w;      // conv only
+    int64_t a_row;    // conv only: row of the centre tap in the padded A volume
+};
+
+__device__ __forceinline__ RowCtx make_row_ctx(const GemmParams& p, int m) {
+    RowCtx c;
+    c.valid = m < p.M;
+    c.out_row = m;
+    c.t = c.h = c.w = 0;
+    c.a_row = 0;
+    if (p.conv) {
+        const int wp = p.W + 2, plane = (p.H + 2) * wp;
+        int t = m / plane;
+        int r = m - t * plane;
+        int hp = r / wp;
+        int wq = r - hp * wp;
+        c.t = t;
+        c.h = hp - 1;
+        c.w = wq - 1;
+        c.valid = c.valid && hp >= 1 && hp <= p.H && wq >= 1 && wq <= p.W;
+        c.out_row = (static_cast<int64_t>(t) * p.H + c.h) * p.W + c.w;
+        c.a_row = static_cast<int64_t>(m) + plane;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        d4[i] = u;
+    }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const RowCtx& rc, int col0, float (&v)[32]) {
+    // bias (same 32 values for every thread of the warp: broadcast loads)
+    if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 b = __ldg(b4 + i);
+            v[4 * i + 0] += b.x;
+            v[4 * i + 1] += b.y;
+            v[4 * i + 2] += b.z;
+            v[4 * i + 3] += b.w;
+        }
+    }
+    if (!rc.valid) return;
+
+    switch (p.epi) {
+        case EPI_STORE_BF16: {
+            if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_f32(v[i]);
+            }
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + rc.out_row * p.ldo + col0, v);
+            break;
+        }
+        case EPI_STORE_F32: {
+            float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + rc.out_row * p.ldo + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            break;
+        }
+        case EPI_RESIDUAL_F32: {
+            float4* r4 = reinterpret_cast<float4*>(p.res_f32 + rc.out_row * p.ldo + col0);
+            if (p.gate != nullptr) {
+                const float4* g4 = reinterpret_cast<const float4*>(p.gate + col0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 g = __ldg(g4 + i);
+                    v[4 * i + 0] *= g.x;
+                    v[4 * i + 1] *= g.y;
+                    v[4 * i + 2] *= g.z;
+                    v[4 * i + 3] *= g.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 r = r4[i];
+                v[4 * i + 0] += r.x;
+                v[4 * i + 1] += r.y;
+                v[4 * i + 2] += r.z;
+                v[4 * i + 3] += r.w;
+                r4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (p.out != nullptr)
+                store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + rc.out_row * p.ldo + col0, v);
+            break;
+        }
+        case EPI_CONV_NDHWC: {
+            if (p.res_bf16 != nullptr) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.res_bf16) + rc.out_row * p.ldo + col0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 u = __ldg(r4 + i);
+                    v[8 * i + 0] += bf16_lo(u.x);
+                    v[8 * i + 1] += bf16_hi(u.x);
+                    v[8 * i + 2] += bf16_lo(u.y);
+                    v[8 * i + 3] += bf16_hi(u.y);
+                    v[8 * i + 4] += bf16_lo(u.z);
+                    v[8 * i + 5] += bf16_hi(u.z);
+                    v[8 * i + 6] += bf16_lo(u.w);
+                    v[8 * i + 7] += bf16_hi(u.w);
+                }
+            }
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + rc.out_row * p.ldo + col0, v);
+            break;
+        }
+        case EPI_CONV_D2S: {
+            // Columns are stored sub-voxel major: col = sub * C' + c', sub = i*4 + j*2 + k (weights permuted at
+            // load time), so a 32-column chunk lands in one output voxel. vae.rs:1142-1161.
+            const int cprime = p.N >> 3;
+            const int sub = col0 / cprime;
+            const int c0 = col0 - sub * cprime;
+            const int i = sub >> 2, j = (sub >> 1) & 1, k = sub & 1;
+            const int to = 2 * rc.t + i - 1;  // drop frame 0 (vae.rs:1161)
+            if (to < 0) break;
+            // residual: x[(c' mod Cin/8) * 8 + sub] at the same voxel, channel-tiled (vae.rs:1101-1124)
+            const int cr0 = c0 % (p.cin >> 3);
+            const __nv_bfloat16* a =
+                reinterpret_cast<const __nv_bfloat16*>(p.a_ptr) + rc.a_row * p.cin + cr0 * 8 + sub;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] += __bfloat162float(a[q * 8]);
+            const int Ho = 2 * p.H, Wo = 2 * p.W;
+            const int64_t ov = (static_cast<int64_t>(to) * Ho + (2 * rc.h + j)) * Wo + (2 * rc.w + k);
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + ov * cprime + c0, v);
+            break;
+        }
+        case EPI_CONV_UNPATCHIFY: {
+            // out[c3, f, 4h+j, 4w+i] = x[c3*16 + i*4 + j] (vae.rs:1626-1654); N = 48 (3 colour planes)
+            float* out = reinterpret_cast<float*>(p.out);
+            const int Ho = 4 * p.H, Wo = 4 * p.W;
+#pragma unroll
+            for (int cl = 0; cl < 2; ++cl) {
+                const int c3 = (col0 >> 4) + cl;
+                if (c3 * 16 >= p.N) break;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 o = make_float4(v[cl * 16 + 0 + j], v[cl * 16 + 4 + j], v[cl * 16 + 8 + j],
+                                           v[cl * 16 + 12 + j]);
+                    if (p.post_u8_scale) {
+                        o.x = fminf(fmaxf(0.5f * o.x + 0.5f, 0.f), 1.f) * 255.f;
+                        o.y = fminf(fmaxf(0.5f * o.y + 0.5f, 0.f), 1.f) * 255.f;
+                        o.z = fminf(fmaxf(0.5f * o.z + 0.5f, 0.f), 1.f) * 255.f;
+                        o.w = fminf(fmaxf(0.5f * o.w + 0.5f, 0.f), 1.f) * 255.f;
+                    }
+                    const int64_t idx =
+                        ((static_cast<int64_t>(c3) * p.T + rc.t) * Ho + (4 * rc.h + j)) * Wo + 4 * rc.w;
+                    *reinterpret_cast<float4*>(out + idx) = o;
+                }
+            }
+            break;
+        }
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ GemmParams p) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzle atoms need 1024 B alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + C::kStages * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + C::kStages;
+    uint64_t* tmem_full_bar = bars + 2 * C::kStages;
+    uint64_t* tmem_empty_bar = bars + 2 * C::kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int num_m = (p.M + kBlockM - 1) / kBlockM;
+    const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = p.num_k_blocks;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        tmem_alloc<C::kTmemCols>(tmem_slot);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const Tile t = tile_coords(tile, num_m);
+                const int n0 = t.n0 * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    int a_row = t.m0, a_col = kb * kBlockK;
+                    if (p.conv) {
+                        const int tap = kb / p.cin_blocks;
+                        a_row += p.tap_off[tap];
+                        a_col = (kb - tap * p.cin_blocks) * kBlockK;
+                    }
+                    tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], a_col, a_row);
+                    tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== UMMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * C::kTmemStride;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * C::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(a_addr + k * kUmmaK * 2, 1024, 0);
+                        const uint64_t db = make_smem_desc_sw128(b_addr + k * kUmmaK * 2, 1024, 0);
+                        umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue =====================
+        const int quad = warp_idx & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const Tile t = tile_coords(tile, num_m);
+            const int n0 = t.n0 * BLOCK_N;
+            const int m = t.m0 + quad * 32 + lane;
+            const RowCtx rc = make_row_ctx(p, m);
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * C::kTmemStride;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (c == BLOCK_N / 32 - 1) {
+                    // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                const int col0 = n0 + c * 32;
+                if (col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    epilogue_chunk(p, rc, col0, v);
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+std::atomic<uint64_t> g_launches{0};
+
+template <int BLOCK_N>
+cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
+    using C = Cfg<BLOCK_N>;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    CUtensorMap ta, tb;
+    cudaError_t e = make_tensor_map_2d_bf16(&ta, ops.a, ops.a_rows, ops.a_cols, kBlockM, kBlockK);
+    if (e != cudaSuccess) return e;
+    e = make_tensor_map_2d_bf16(&tb, ops.b, ops.b_rows, ops.b_cols, BLOCK_N, kBlockK);
+    if (e != cudaSuccess) return e;
+    const int num_m = (p.M + kBlockM - 1) / kBlockM;
+    const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = num_m * num_n;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    gemm_bf16_tn_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+uint64_t gemm_launch_count() { return g_launches.load(); }
+
+cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int block_n, cudaStream_t stream) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
+    if (block_n == 0) {
+        // pick the tile width that minimises (rounds over 148 SMs) x (tile cost ~ BLOCK_N)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int cands[4] = {256, 192, 128, 64};
+        double best = 1e30;
+        const int num_m = (p.M + kBlockM - 1) / kBlockM;
+        for (int c : cands) {
+            if (c > 64 && p.N <= c / 2) continue;
+            const int tiles = num_m * ((p.N + c - 1) / c);
+            const int rounds = (tiles + sms - 1) / sms;
+            // narrower tiles re-read A more often and run the MMA at lower smem efficiency: small penalty
+            const double cost = rounds * (c + 24.0);
+            if (cost < best) {
+                best = cost;
+                block_n = c;
+            }
+        }
+    }
+    switch (block_n) {
+        case 256: return launch_impl<256>(ops, p, stream);
+        case 192: return launch_impl<192>(ops, p, stream);
+        case 128: return launch_impl<128>(ops, p, stream);
+        case 64: return launch_impl<64>(ops, p, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace ltxv
