@@ -1,0 +1,73 @@
+// Bandwidth-bound glue kernels of the DiT path and the pipeline (glue.cu): every kernel reads its input once
+// with 128-bit accesses and writes its output once.  SURVEY.md §2b rows K2,K4,K5,K7,K8,K14-K18.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ltxv {
+
+enum NormKind : int { NORM_RMS = 0, NORM_LAYER = 1 };
+
+// out_bf16[r, :] = norm(x[r, :]) * (1 + scale) + shift          (ltx_transformer.rs:99-119, :72-79, :874-889)
+// x f32 [rows, D]; scale / shift f32 [D] (null => no modulation).
+cudaError_t launch_norm_modulate(const float* x, void* out_bf16, const float* scale, const float* shift, int rows,
+                                 int D, float eps, int kind, cudaStream_t s);
+
+// In-place on a bf16 matrix [rows, ld]: for the D columns starting at col0:
+//   y = x * rsqrt(mean(x^2) + eps) * w ; if cos != null: interleaved-pair rotation with cos/sin [rows, D/2] f32
+// (RmsNorm across all heads :570-571,:671-672 + apply_rotary_emb :314-339).
+cudaError_t launch_qk_norm_rope(void* x_bf16, int64_t ld, int col0, int rows, int D, const float* w, float eps,
+                                const float* cos_t, const float* sin_t, cudaStream_t s);
+
+// cos/sin [S, D/2] f32 of the 3D video RoPE (LtxVideoRotaryPosEmbed::forward :436-524).
+// coords != null: coords [S,3] f32 (seconds, pixel-y, pixel-x), divided by base (20, 2048, 2048).
+// coords == null: token grid (f,h,w) from F,H,W, optionally multiplied by scale3 = (sf*pt/20, sh*p/2048, sw*p/2048).
+cudaError_t launch_rope_table(const float* coords, int F, int H, int W, const float* scale3_host, int S, int D,
+                              float theta, float* cos_t, float* sin_t, cudaStream_t s);
+
+// y[n] = act_out( sum_k act_in(x[k]) * W[n,k] + b[n] ),  W bf16 [N,K], x/y f32; batch rows handled by the caller.
+enum GemvAct : int { GEMV_NONE = 0, GEMV_SILU = 1 };
+cudaError_t launch_gemv(const float* x, const void* w_bf16, const float* bias, float* y, int N, int K, int act_in,
+                        int act_out, cudaStream_t s);
+
+// sinusoidal embedding [cos | sin], 256 wide.  style 0: DiT (ltx_transformer.rs:271-309, 1/10000^(i/128));
+// style 1: VAE (vae.rs:172-198, exp(-ln(1e4)/128*i)).  round_bf16: replay `timestep.to_dtype(bf16)` (:1051).
+// t is a device scalar; t_mul multiplies it first (VAE timestep_scale_multiplier).
+cudaError_t launch_sinusoid(const float* t_dev, const float* t_mul_dev, float* out256, int style, int round_bf16,
+                            cudaStream_t s);
+
+// dst[i] = a[i] + b[i]  (small f32 vectors: scale_shift_table + temb)
+cudaError_t launch_add_vec(const float* a, const float* b, float* dst, int n, cudaStream_t s);
+
+// f32 <-> bf16 converts
+cudaError_t launch_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
+cudaError_t launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s);
+
+// x = x*(1-m) + orig*m  (skip_layer_mask blend, ltx_transformer.rs:1112-1123)
+cudaError_t launch_blend(float* x, const float* orig, float m, int64_t n, cudaStream_t s);
+
+// ---- pipeline glue (t2v_pipeline.rs) ----
+// pack: [C,F,H,W] -> [S, C*pt*p*p];  unpack: inverse.  f32, bit-exact index maps (:474-550).
+cudaError_t launch_pack_latents(const float* in, float* out, int C, int F, int H, int W, int p, int pt, cudaStream_t s);
+cudaError_t launch_unpack_latents(const float* in, float* out, int C, int F, int H, int W, int p, int pt,
+                                  cudaStream_t s);
+// coords [S,3]: (clamp(8f-7,0,1000)*f32(1/fps), 32h, 32w)  (:798-847)
+cudaError_t launch_video_coords(float* out, int F, int H, int W, int ts_ratio, int sp_ratio, int fps, cudaStream_t s);
+
+// CFG / STG combine (+ optional std rescale) fused with the Euler update (:942-964, :227-243, scheduler.rs:576-582):
+//   comb = u + g (c - u);  if rescale > 0: comb = r comb std(c)/std(comb) + (1-r) comb;  comb += s_stg (c - p)
+//   latents += dt * comb ;  optional: noise_pred_out = comb
+// uncond / perturbed may be null.  n = elements of one batch entry.  scratch: >= 4 doubles (device).
+cudaError_t launch_guidance_euler(const float* cond, const float* uncond, const float* perturbed, float* latents,
+                                  float* noise_pred_out, int64_t n, float guidance_scale, float guidance_rescale,
+                                  float stg_scale, float dt, double* scratch, cudaStream_t s);
+
+// x*std_c*(1/sf)+mean_c on [C, N] (per-channel), f32  (:573-594)
+cudaError_t launch_denormalize(const float* in, float* out, const float* mean, const float* std, float inv_sf, int C,
+                               int64_t n_per_c, cudaStream_t s);
+// clamp(0.5x+0.5,0,1)*255  (:147-155)
+cudaError_t launch_postprocess(const float* in, float* out, int64_t n, cudaStream_t s);
+
+uint64_t glue_launch_count();
+
+}  // namespace ltxv

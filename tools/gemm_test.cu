@@ -55,8 +55,8 @@ __global__ void ref_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
 // ref conv: x padded [(T+2),(H+2),(W+2),Cin] bf16; w [Cout, 27*Cin]; out f32 [T,H,W,Cout]
 __global__ void ref_conv(const __nv_bfloat16* xp, const __nv_bfloat16* w, const float* bias, float* out, int T, int H,
                          int W, int Cin, int Cout) {
-    int co = blockIdx.x * blockDim.x + threadIdx.x;
-    int vox = blockIdx.y;
+    int co = blockIdx.y * blockDim.x + threadIdx.x;
+    int vox = blockIdx.x;
     if (co >= Cout) return;
     int t = vox / (H * W), r = vox % (H * W), h = r / W, x = r % W;
     int Hp = H + 2, Wp = W + 2;
@@ -193,7 +193,7 @@ static int test_conv(int T, int H, int W, int Cin, int Cout, bool timing) {
     fill_bf16<<<((size_t)Cout * 27 * Cin + 255) / 256, 256>>>(w, (size_t)Cout * 27 * Cin, 12, 1.0f / sqrtf(27.f * Cin));
     fill_bf16<<<((size_t)T * H * W * Cout + 255) / 256, 256>>>(resid, (size_t)T * H * W * Cout, 13, 1.0f);
     fill_f32<<<(Cout + 255) / 256, 256>>>(bias, Cout, 14, 0.5f);
-    ref_conv<<<dim3((Cout + 127) / 128, T * H * W), 128>>>(xp, w, bias, ref, T, H, W, Cin, Cout);
+    ref_conv<<<dim3(T * H * W, (Cout + 127) / 128), 128>>>(xp, w, bias, ref, T, H, W, Cin, Cout);
     CK(cudaDeviceSynchronize());
 
     GemmOperands ops{xp, (int64_t)rows, Cin, w, Cout, 27 * Cin};
