@@ -1,0 +1,564 @@
+"""candle_video_b200 -- host-side harness over libltxv_b200.so (the B200-native LTX-Video hot path).
+
+The product is the C-ABI shared library (`include/ltxv.h`, sources under `csrc/`): hand-written sm_100a CUDA
+(tcgen05/TMEM/TMA GEMM, implicit-GEMM conv3d and flash attention + 128-bit glue kernels) sequenced by C++ mirrors of
+the reference's `LtxVideoTransformer3DModel`, `AutoencoderKLLtxVideo` and the hot part of `LtxPipeline::call`.
+
+This Python module only binds that ABI with ctypes so that tests and `bench.py` can drive it exactly the way the
+reference's Rust traits would (`VideoTransformer3D::forward`, `VaeLtxVideo::decode`, t2v_pipeline.rs:63-103).  torch is
+used for device memory and streams only.  There is NO CPU fallback: if the library is missing or no B200 is present,
+every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Dict, Optional, Sequence, Tuple
+
+__all__ = [
+    "lib", "LtxvError", "DitConfig", "VaeConfig", "LtxVideoTransformer3DModel", "AutoencoderKLLtxVideo",
+    "pack_latents", "unpack_latents", "video_coords", "guidance_euler_step", "denormalize_latents",
+    "postprocess_video", "calculate_shift", "scheduler_set_timesteps", "PipelineParams", "pipeline_denoise",
+    "pipeline_decode", "launch_count", "EXPORTED_SYMBOLS", "library_path",
+]
+
+F32, BF16 = 0, 1
+
+EXPORTED_SYMBOLS = [
+    "ltxv_last_error", "ltxv_version", "ltxv_launch_count",
+    "ltxv_dit_config_preset", "ltxv_dit_create", "ltxv_dit_destroy", "ltxv_dit_load_tensor", "ltxv_dit_init_random",
+    "ltxv_dit_finalize", "ltxv_dit_set_skip_blocks", "ltxv_dit_get_config", "ltxv_dit_forward",
+    "ltxv_dit_forward_host", "ltxv_dit_prepare_context", "ltxv_dit_forward_ctx",
+    "ltxv_vae_config_default", "ltxv_vae_create", "ltxv_vae_destroy", "ltxv_vae_load_tensor", "ltxv_vae_init_random",
+    "ltxv_vae_finalize", "ltxv_vae_latents_mean", "ltxv_vae_latents_std", "ltxv_vae_spatial_compression_ratio",
+    "ltxv_vae_temporal_compression_ratio", "ltxv_vae_decode", "ltxv_vae_decode_host",
+    "ltxv_pack_latents", "ltxv_unpack_latents", "ltxv_video_coords", "ltxv_guidance_euler_step",
+    "ltxv_denormalize_latents", "ltxv_postprocess_video", "ltxv_calculate_shift", "ltxv_scheduler_set_timesteps",
+    "ltxv_pipeline_denoise", "ltxv_pipeline_decode",
+]
+
+
+class LtxvError(RuntimeError):
+    pass
+
+
+def library_path() -> Path:
+    return Path(os.environ.get("LTXV_B200_LIB", Path(__file__).resolve().parent / "lib" / "libltxv_b200.so"))
+
+
+class _DitConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_channels", "out_channels", "patch_size", "patch_size_t",
+                                         "num_attention_heads", "attention_head_dim", "cross_attention_dim",
+                                         "num_layers", "caption_channels")] + \
+               [("norm_eps", C.c_float), ("timestep_bf16_round", C.c_int32)]
+
+
+class _VaeConfigC(C.Structure):
+    _fields_ = [("latent_channels", C.c_int32), ("out_channels", C.c_int32),
+                ("decoder_block_out_channels", C.c_int32 * 3), ("decoder_layers_per_block", C.c_int32 * 4),
+                ("patch_size", C.c_int32), ("timestep_conditioning", C.c_int32), ("scaling_factor", C.c_float)]
+
+
+class _PipelineParamsC(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("num_frames", C.c_int32), ("frame_rate", C.c_int32),
+                ("num_inference_steps", C.c_int32), ("custom_sigmas", C.POINTER(C.c_float)),
+                ("guidance_scale", C.c_float), ("guidance_rescale", C.c_float), ("stg_scale", C.c_float),
+                ("skip_block_list", C.POINTER(C.c_int32)), ("num_skip_blocks", C.c_int32),
+                ("has_shift_terminal", C.c_int32), ("shift_terminal", C.c_float), ("decode_timestep", C.c_float)]
+
+
+def _load() -> C.CDLL:
+    path = library_path()
+    if not path.exists():
+        raise LtxvError(
+            f"{path} not found: build it with `python -m candle_video_b200.build` (nvcc, sm_100a). "
+            "There is no CPU/PyTorch fallback for this path.")
+    l = C.CDLL(str(path))
+    vp, i32, i64, f32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+    fp = C.POINTER(C.c_float)
+    l.ltxv_last_error.restype = C.c_char_p
+    l.ltxv_version.restype = C.c_char_p
+    l.ltxv_launch_count.restype = u64
+    l.ltxv_dit_config_preset.argtypes = [C.c_char_p, C.POINTER(_DitConfigC)]
+    l.ltxv_dit_create.argtypes = [C.POINTER(_DitConfigC), i32, C.POINTER(vp)]
+    l.ltxv_dit_destroy.argtypes = [vp]
+    l.ltxv_dit_destroy.restype = None
+    l.ltxv_dit_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
+    l.ltxv_dit_init_random.argtypes = [vp, u64]
+    l.ltxv_dit_finalize.argtypes = [vp]
+    l.ltxv_dit_set_skip_blocks.argtypes = [vp, C.POINTER(C.c_int32), i32]
+    l.ltxv_dit_get_config.argtypes = [vp, C.POINTER(_DitConfigC)]
+    l.ltxv_dit_forward.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, fp, vp, fp, vp, i32, vp]
+    l.ltxv_dit_forward_host.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, fp, vp, fp, vp, i32]
+    l.ltxv_dit_prepare_context.argtypes = [vp, i32, vp, i32, vp, i32, vp]
+    l.ltxv_dit_forward_ctx.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, fp, vp, fp, vp, i32, vp]
+    l.ltxv_vae_config_default.argtypes = [C.POINTER(_VaeConfigC)]
+    l.ltxv_vae_create.argtypes = [C.POINTER(_VaeConfigC), i32, C.POINTER(vp)]
+    l.ltxv_vae_destroy.argtypes = [vp]
+    l.ltxv_vae_destroy.restype = None
+    l.ltxv_vae_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
+    l.ltxv_vae_init_random.argtypes = [vp, u64]
+    l.ltxv_vae_finalize.argtypes = [vp]
+    l.ltxv_vae_latents_mean.argtypes = [vp]
+    l.ltxv_vae_latents_mean.restype = vp
+    l.ltxv_vae_latents_std.argtypes = [vp]
+    l.ltxv_vae_latents_std.restype = vp
+    l.ltxv_vae_spatial_compression_ratio.argtypes = [vp]
+    l.ltxv_vae_temporal_compression_ratio.argtypes = [vp]
+    l.ltxv_vae_decode.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp]
+    l.ltxv_vae_decode_host.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32]
+    l.ltxv_pack_latents.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    l.ltxv_unpack_latents.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    l.ltxv_video_coords.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    l.ltxv_guidance_euler_step.argtypes = [vp, vp, vp, vp, vp, i32, i64, f32, f32, f32, f32, f32, vp]
+    l.ltxv_denormalize_latents.argtypes = [vp, vp, vp, vp, f32, i32, i32, i64, vp]
+    l.ltxv_postprocess_video.argtypes = [vp, vp, i64, vp]
+    l.ltxv_calculate_shift.argtypes = [i32, fp]
+    l.ltxv_scheduler_set_timesteps.argtypes = [i32, fp, f32, i32, f32, fp, C.POINTER(i64)]
+    l.ltxv_pipeline_denoise.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32, vp]
+    l.ltxv_pipeline_decode.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp]
+    return l
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise LtxvError(lib().ltxv_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().ltxv_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# torch plumbing helpers
+# ------------------------------------------------------------------------------------------------------------
+def _torch():
+    import torch
+    return torch
+
+
+def _dtype_code(t) -> int:
+    torch = _torch()
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise LtxvError(f"unsupported tensor dtype {t.dtype}; expected float32 or bfloat16")
+
+
+def _dev(t, name: str):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise LtxvError(f"{name} must be a CUDA tensor (no CPU path exists)")
+    return t.contiguous()
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return _torch().cuda.current_stream().cuda_stream
+
+
+def _f3(v: Optional[Sequence[float]]):
+    if v is None:
+        return None
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# DiT
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class DitConfig:
+    """LtxVideoTransformer3DModelConfig (ltx_transformer.rs:22-59)."""
+    in_channels: int = 128
+    out_channels: int = 128
+    patch_size: int = 1
+    patch_size_t: int = 1
+    num_attention_heads: int = 32
+    attention_head_dim: int = 64
+    cross_attention_dim: int = 2048
+    num_layers: int = 28
+    caption_channels: int = 4096
+    norm_eps: float = 1e-6
+    timestep_bf16_round: bool = True
+
+    def to_c(self) -> _DitConfigC:
+        return _DitConfigC(self.in_channels, self.out_channels, self.patch_size, self.patch_size_t,
+                           self.num_attention_heads, self.attention_head_dim, self.cross_attention_dim,
+                           self.num_layers, self.caption_channels, self.norm_eps, int(self.timestep_bf16_round))
+
+    @staticmethod
+    def preset(name: str) -> "DitConfig":
+        c = _DitConfigC()
+        _check(lib().ltxv_dit_config_preset(name.encode(), C.byref(c)))
+        return DitConfig(c.in_channels, c.out_channels, c.patch_size, c.patch_size_t, c.num_attention_heads,
+                         c.attention_head_dim, c.cross_attention_dim, c.num_layers, c.caption_channels, c.norm_eps,
+                         bool(c.timestep_bf16_round))
+
+
+def _load_state_dict(load_fn, handle, sd: Dict[str, "object"]) -> None:
+    torch = _torch()
+    for key, t in sd.items():
+        t = t.detach()
+        if t.dtype not in (torch.float32, torch.bfloat16):
+            t = t.to(torch.float32)
+        t = t.contiguous()
+        shape = (C.c_int64 * max(t.dim(), 1))(*t.shape) if t.dim() else (C.c_int64 * 1)(0)
+        _check(load_fn(handle, key.encode(), t.data_ptr(), _dtype_code(t), shape, t.dim()))
+
+
+class LtxVideoTransformer3DModel:
+    """Binds `ltxv_dit_*`; mirrors LtxVideoTransformer3DModel + trait VideoTransformer3D (ltx_transformer.rs:1175-1215)."""
+
+    def __init__(self, config: DitConfig, device: int = 0):
+        self.config = config
+        self._h = C.c_void_p()
+        cc = config.to_c()
+        _check(lib().ltxv_dit_create(C.byref(cc), device, C.byref(self._h)))
+        self.device = device
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().ltxv_dit_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd) -> None:
+        """Tensors keyed by the reference's VarBuilder names (host or CUDA, f32 or bf16)."""
+        _load_state_dict(lib().ltxv_dit_load_tensor, self._h, sd)
+        _check(lib().ltxv_dit_finalize(self._h))
+
+    def init_random(self, seed: int = 0) -> None:
+        _check(lib().ltxv_dit_init_random(self._h, seed))
+
+    def set_skip_block_list(self, blocks: Sequence[int]) -> None:
+        arr = (C.c_int32 * max(len(blocks), 1))(*blocks)
+        _check(lib().ltxv_dit_set_skip_blocks(self._h, arr, len(blocks)))
+
+    def forward(self, hidden_states, encoder_hidden_states, timestep, encoder_attention_mask, num_frames: int,
+                height: int, width: int, rope_interpolation_scale: Optional[Tuple[float, float, float]] = None,
+                video_coords=None, skip_layer_mask=None, out_dtype=None):
+        """VideoTransformer3D::forward (t2v_pipeline.rs:63-83) on CUDA tensors; returns [B,S,out_channels]."""
+        torch = _torch()
+        hs = _dev(hidden_states, "hidden_states")
+        enc = _dev(encoder_hidden_states, "encoder_hidden_states")
+        B, S, _ = hs.shape
+        K = enc.shape[1]
+        ts = _dev(timestep, "timestep").to(torch.float32).reshape(-1).contiguous()
+        if ts.numel() != B:
+            raise LtxvError(f"timestep must have {B} entries")
+        mask = None if encoder_attention_mask is None else _dev(encoder_attention_mask, "mask").to(torch.float32).contiguous()
+        coords = None if video_coords is None else _dev(video_coords, "video_coords").to(torch.float32).contiguous()
+        slm = None
+        if skip_layer_mask is not None:
+            m = skip_layer_mask.detach().to("cpu", torch.float32).contiguous()
+            slm = (C.c_float * m.numel())(*m.flatten().tolist())
+        odt = hs.dtype if out_dtype is None else out_dtype
+        out = torch.empty((B, S, self.config.out_channels), dtype=odt, device=hs.device)
+        _check(lib().ltxv_dit_forward(self._h, _ptr(hs), _dtype_code(hs), _ptr(enc), _dtype_code(enc), _ptr(ts),
+                                      _ptr(mask), B, S, K, num_frames, height, width, _f3(rope_interpolation_scale),
+                                      _ptr(coords), slm, _ptr(out), _dtype_code(out), _stream()))
+        return out
+
+    def forward_host(self, hidden_states, encoder_hidden_states, timestep, encoder_attention_mask, num_frames: int,
+                     height: int, width: int, rope_interpolation_scale=None, video_coords=None, skip_layer_mask=None):
+        """Same call on HOST (CPU torch) tensors through ltxv_dit_forward_host: H2D + compute + D2H + sync."""
+        torch = _torch()
+        hs = hidden_states.contiguous()
+        enc = encoder_hidden_states.contiguous()
+        B, S, _ = hs.shape
+        K = enc.shape[1]
+        ts = timestep.to(torch.float32).reshape(-1).contiguous()
+        mask = None if encoder_attention_mask is None else encoder_attention_mask.to(torch.float32).contiguous()
+        coords = None if video_coords is None else video_coords.to(torch.float32).contiguous()
+        slm = None
+        if skip_layer_mask is not None:
+            m = skip_layer_mask.to(torch.float32).contiguous()
+            slm = (C.c_float * m.numel())(*m.flatten().tolist())
+        out = torch.empty((B, S, self.config.out_channels), dtype=hs.dtype)
+        _check(lib().ltxv_dit_forward_host(self._h, _ptr(hs), _dtype_code(hs), _ptr(enc), _dtype_code(enc), _ptr(ts),
+                                           _ptr(mask), B, S, K, num_frames, height, width,
+                                           _f3(rope_interpolation_scale), _ptr(coords), slm, _ptr(out),
+                                           _dtype_code(out)))
+        return out
+
+    def prepare_context(self, slot: int, encoder_hidden_states, encoder_attention_mask) -> None:
+        torch = _torch()
+        enc = _dev(encoder_hidden_states, "encoder_hidden_states")
+        if enc.dim() == 3:
+            enc = enc[0]
+        mask = None
+        if encoder_attention_mask is not None:
+            mask = _dev(encoder_attention_mask, "mask").to(torch.float32).reshape(-1).contiguous()
+        _check(lib().ltxv_dit_prepare_context(self._h, slot, _ptr(enc), _dtype_code(enc), _ptr(mask), enc.shape[0],
+                                              _stream()))
+
+    def forward_ctx(self, slot: int, hidden_states, timestep, num_frames: int, height: int, width: int,
+                    rope_interpolation_scale=None, video_coords=None, skip_layer_mask=None, out=None):
+        torch = _torch()
+        hs = _dev(hidden_states, "hidden_states")
+        if hs.dim() == 3:
+            hs = hs[0]
+        S = hs.shape[0]
+        ts = _dev(timestep, "timestep").to(torch.float32).reshape(-1).contiguous()
+        coords = None if video_coords is None else _dev(video_coords, "video_coords").to(torch.float32).reshape(-1, 3).contiguous()
+        slm = None
+        if skip_layer_mask is not None:
+            m = skip_layer_mask.detach().to("cpu", torch.float32).contiguous()
+            slm = (C.c_float * m.numel())(*m.flatten().tolist())
+        if out is None:
+            out = torch.empty((S, self.config.out_channels), dtype=torch.float32, device=hs.device)
+        _check(lib().ltxv_dit_forward_ctx(self._h, slot, _ptr(hs), _dtype_code(hs), _ptr(ts), S, num_frames, height,
+                                          width, _f3(rope_interpolation_scale), _ptr(coords), slm, _ptr(out),
+                                          _dtype_code(out), _stream()))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# VAE
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class VaeConfig:
+    """AutoencoderKLLtxVideoConfig, decoder fields (vae.rs:30-103)."""
+    latent_channels: int = 128
+    out_channels: int = 3
+    decoder_block_out_channels: Tuple[int, int, int] = (256, 512, 1024)
+    decoder_layers_per_block: Tuple[int, int, int, int] = (5, 5, 5, 5)
+    patch_size: int = 4
+    timestep_conditioning: bool = True
+    scaling_factor: float = 1.0
+
+    def to_c(self) -> _VaeConfigC:
+        return _VaeConfigC(self.latent_channels, self.out_channels, (C.c_int32 * 3)(*self.decoder_block_out_channels),
+                           (C.c_int32 * 4)(*self.decoder_layers_per_block), self.patch_size,
+                           int(self.timestep_conditioning), self.scaling_factor)
+
+
+class AutoencoderKLLtxVideo:
+    """Binds `ltxv_vae_*`; mirrors AutoencoderKLLtxVideo::decode + trait VaeLtxVideo (vae.rs:2101, :2437-2463)."""
+
+    def __init__(self, config: VaeConfig, device: int = 0):
+        self.config = config
+        self._h = C.c_void_p()
+        cc = config.to_c()
+        _check(lib().ltxv_vae_create(C.byref(cc), device, C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().ltxv_vae_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd) -> None:
+        _load_state_dict(lib().ltxv_vae_load_tensor, self._h, sd)
+        _check(lib().ltxv_vae_finalize(self._h))
+
+    def init_random(self, seed: int = 0) -> None:
+        _check(lib().ltxv_vae_init_random(self._h, seed))
+
+    @property
+    def spatial_compression_ratio(self) -> int:
+        return lib().ltxv_vae_spatial_compression_ratio(self._h)
+
+    @property
+    def temporal_compression_ratio(self) -> int:
+        return lib().ltxv_vae_temporal_compression_ratio(self._h)
+
+    def decode(self, latents, timestep=None, postprocess: bool = False, out_dtype=None):
+        """VaeLtxVideo::decode (t2v_pipeline.rs:102): [B,128,F,H,W] -> [B,3,8F-7,32H,32W] (CUDA tensors)."""
+        torch = _torch()
+        z = _dev(latents, "latents")
+        B, _, F, H, W = z.shape
+        ts = None if timestep is None else _dev(timestep, "timestep").to(torch.float32).reshape(-1).contiguous()
+        odt = torch.float32 if out_dtype is None else out_dtype
+        out = torch.empty((B, 3, 8 * F - 7, 32 * H, 32 * W), dtype=odt, device=z.device)
+        _check(lib().ltxv_vae_decode(self._h, _ptr(z), _dtype_code(z), _ptr(ts), B, F, H, W, _ptr(out),
+                                     _dtype_code(out), int(postprocess), _stream()))
+        return out
+
+    def decode_host(self, latents, timestep=None, postprocess: bool = False):
+        torch = _torch()
+        z = latents.contiguous()
+        B, _, F, H, W = z.shape
+        ts = None if timestep is None else timestep.to(torch.float32).reshape(-1).contiguous()
+        out = torch.empty((B, 3, 8 * F - 7, 32 * H, 32 * W), dtype=torch.float32)
+        _check(lib().ltxv_vae_decode_host(self._h, _ptr(z), _dtype_code(z), _ptr(ts), B, F, H, W, _ptr(out), F32,
+                                          int(postprocess)))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# pipeline glue (t2v_pipeline.rs)
+# ------------------------------------------------------------------------------------------------------------
+def pack_latents(latents, patch_size: int = 1, patch_size_t: int = 1):
+    """LtxPipeline::pack_latents (t2v_pipeline.rs:474-504), f32 CUDA tensor [B,C,F,H,W] -> [B,S,D]."""
+    torch = _torch()
+    x = _dev(latents, "latents").to(torch.float32).contiguous()
+    B, Cc, F, H, W = x.shape
+    p, pt = patch_size, patch_size_t
+    if p <= 0 or pt <= 0 or F % pt or H % p or W % p:
+        raise LtxvError("latents shape not divisible by patch sizes")
+    out = torch.empty((B, (F // pt) * (H // p) * (W // p), Cc * pt * p * p), dtype=torch.float32, device=x.device)
+    _check(lib().ltxv_pack_latents(_ptr(x), _ptr(out), B, Cc, F, H, W, p, pt, _stream()))
+    return out
+
+
+def unpack_latents(latents, num_frames: int, height: int, width: int, patch_size: int = 1, patch_size_t: int = 1):
+    """LtxPipeline::unpack_latents (t2v_pipeline.rs:506-550); num_frames/height/width are the patched grid dims."""
+    torch = _torch()
+    x = _dev(latents, "latents").to(torch.float32).contiguous()
+    B, S, D = x.shape
+    p, pt = patch_size, patch_size_t
+    if D % (pt * p * p):
+        raise LtxvError("D is not divisible by (pt*p*p)")
+    Cc = D // (pt * p * p)
+    F, H, W = num_frames * pt, height * p, width * p
+    out = torch.empty((B, Cc, F, H, W), dtype=torch.float32, device=x.device)
+    _check(lib().ltxv_unpack_latents(_ptr(x), _ptr(out), B, Cc, F, H, W, p, pt, _stream()))
+    return out
+
+
+def video_coords(batch: int, f: int, h: int, w: int, frame_rate: int, device="cuda", ts_ratio: int = 8,
+                 sp_ratio: int = 32):
+    torch = _torch()
+    out = torch.empty((batch, f * h * w, 3), dtype=torch.float32, device=device)
+    _check(lib().ltxv_video_coords(_ptr(out), batch, f, h, w, ts_ratio, sp_ratio, frame_rate, _stream()))
+    return out
+
+
+def guidance_euler_step(cond, uncond, perturbed, latents, guidance_scale: float, guidance_rescale: float,
+                        stg_scale: float, sigma: float, sigma_next: float, return_noise_pred: bool = False):
+    """CFG/STG combine + Euler update; `latents` (f32 CUDA, [B,S,C]) is updated in place."""
+    torch = _torch()
+    c = _dev(cond, "cond")
+    B = c.shape[0]
+    n = c[0].numel()
+    u = _dev(uncond, "uncond")
+    p = _dev(perturbed, "perturbed")
+    for t in (c, u, p, latents):
+        if t is not None and t.dtype != torch.float32:
+            raise LtxvError("guidance tensors must be float32")
+    noise = torch.empty_like(c) if return_noise_pred else None
+    _check(lib().ltxv_guidance_euler_step(_ptr(c), _ptr(u), _ptr(p), _ptr(latents), _ptr(noise), B, n,
+                                          guidance_scale, guidance_rescale, stg_scale, sigma, sigma_next, _stream()))
+    return noise
+
+
+def denormalize_latents(latents, mean, std, scaling_factor: float):
+    torch = _torch()
+    x = _dev(latents, "latents").to(torch.float32).contiguous()
+    B, Cc = x.shape[:2]
+    m = _dev(mean, "mean").to(torch.float32).contiguous()
+    s = _dev(std, "std").to(torch.float32).contiguous()
+    out = torch.empty_like(x)
+    _check(lib().ltxv_denormalize_latents(_ptr(x), _ptr(out), _ptr(m), _ptr(s), scaling_factor, B, Cc,
+                                          x[0, 0].numel(), _stream()))
+    return out
+
+
+def postprocess_video(video):
+    torch = _torch()
+    x = _dev(video, "video").to(torch.float32).contiguous()
+    out = torch.empty_like(x)
+    _check(lib().ltxv_postprocess_video(_ptr(x), _ptr(out), x.numel(), _stream()))
+    return out
+
+
+def calculate_shift(seq_len: int) -> float:
+    v = C.c_float()
+    _check(lib().ltxv_calculate_shift(seq_len, C.byref(v)))
+    return float(v.value)
+
+
+def scheduler_set_timesteps(num_steps: int, mu: float, sigmas: Optional[Sequence[float]] = None,
+                            shift_terminal: Optional[float] = 0.1):
+    cs = None if sigmas is None else (C.c_float * num_steps)(*sigmas)
+    so = (C.c_float * (num_steps + 1))()
+    to = (C.c_int64 * num_steps)()
+    _check(lib().ltxv_scheduler_set_timesteps(num_steps, cs, mu, int(shift_terminal is not None),
+                                              float(shift_terminal or 0.0), so, to))
+    return list(so), list(to)
+
+
+@dataclass
+class PipelineParams:
+    height: int = 512
+    width: int = 768
+    num_frames: int = 97
+    frame_rate: int = 25
+    num_inference_steps: int = 40
+    custom_sigmas: Optional[Sequence[float]] = None
+    guidance_scale: float = 3.0
+    guidance_rescale: float = 0.0
+    stg_scale: float = 0.0
+    skip_block_list: Optional[Sequence[int]] = None
+    shift_terminal: Optional[float] = 0.1
+    decode_timestep: float = 0.05
+
+    def to_c(self):
+        keep = []
+        cs = None
+        if self.custom_sigmas is not None:
+            cs = (C.c_float * len(self.custom_sigmas))(*self.custom_sigmas)
+            keep.append(cs)
+        sb = None
+        nsb = 0
+        if self.skip_block_list is not None:
+            nsb = len(self.skip_block_list)
+            sb = (C.c_int32 * max(nsb, 1))(*self.skip_block_list)
+            keep.append(sb)
+        p = _PipelineParamsC(self.height, self.width, self.num_frames, self.frame_rate, self.num_inference_steps,
+                             C.cast(cs, C.POINTER(C.c_float)) if cs is not None else None,
+                             self.guidance_scale, self.guidance_rescale, self.stg_scale,
+                             C.cast(sb, C.POINTER(C.c_int32)) if sb is not None else None, nsb,
+                             int(self.shift_terminal is not None), float(self.shift_terminal or 0.0),
+                             self.decode_timestep)
+        return p, keep
+
+
+def pipeline_denoise(dit: LtxVideoTransformer3DModel, params: PipelineParams, latents, prompt_embeds, prompt_mask,
+                     negative_embeds=None, negative_mask=None):
+    """Denoise loop of LtxPipeline::call (t2v_pipeline.rs:860-994); `latents` f32 CUDA [S,128], updated in place."""
+    torch = _torch()
+    p, keep = params.to_c()
+    pe = _dev(prompt_embeds, "prompt_embeds")
+    pe = pe[0] if pe.dim() == 3 else pe
+    ne = _dev(negative_embeds, "negative_embeds")
+    if ne is not None and ne.dim() == 3:
+        ne = ne[0]
+    pm = None if prompt_mask is None else _dev(prompt_mask, "prompt_mask").to(torch.float32).reshape(-1).contiguous()
+    nm = None if negative_mask is None else _dev(negative_mask, "negative_mask").to(torch.float32).reshape(-1).contiguous()
+    if latents.dtype != torch.float32 or not latents.is_cuda or not latents.is_contiguous():
+        raise LtxvError("latents must be a contiguous float32 CUDA tensor")
+    _check(lib().ltxv_pipeline_denoise(dit._h, C.byref(p), _ptr(latents), _ptr(pe), _ptr(pm), _ptr(ne), _ptr(nm),
+                                       _dtype_code(pe), pe.shape[0], _stream()))
+    return latents
+
+
+def pipeline_decode(vae: AutoencoderKLLtxVideo, params: PipelineParams, latents):
+    torch = _torch()
+    p, keep = params.to_c()
+    f = (params.num_frames - 1) // 8 + 1
+    out = torch.empty((3, 8 * f - 7, params.height, params.width), dtype=torch.float32, device=latents.device)
+    _check(lib().ltxv_pipeline_decode(vae._h, C.byref(p), _ptr(latents), _ptr(out), _stream()))
+    return out

@@ -35,6 +35,7 @@ LIB_SOURCES = [
     "vae.cu",
     "pipeline.cu",
     "ffi.cu",
+    "model_common.cu",
     "tensormap.cc",
 ]
 

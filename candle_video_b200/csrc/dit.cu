@@ -1,0 +1,414 @@
+// LtxVideoTransformer3DModel on B200: host-side sequencing of the sm_100a kernels (see dit.h).
+//
+// Data layout in HBM (one batch entry at a time; the reference's pipeline also runs B = 1 passes,
+// t2v_pipeline.rs:869-907):
+//   x      f32  [S, D]    residual stream (kept in f32: 28 layers of bf16 re-rounding would dominate the error)
+//   xb     bf16 [S, D]    bf16 copy of x written by the attn1 out-projection epilogue (A operand of attn2.to_q)
+//   h      bf16 [S, D]    AdaLN-modulated RMS-normed activations (A operand of QKV / FFN-in GEMMs)
+//   qkv    bf16 [S, 3D]   fused self-attention projections; q,k are normed + rotated in place
+//   attn   bf16 [S, D]    attention output (A operand of the out projections)
+//   ff     bf16 [S, 4D]   GELU(FFN-in) (A operand of FFN-out)
+//   ctx.kv bf16 [L][K,2D] per-layer cross-attention K (normed) | V of the text tokens (step-invariant, hoisted)
+#include "dit.h"
+
+#include <math.h>
+#include <string.h>
+
+#include "attention.h"
+#include "gemm.h"
+#include "glue.h"
+
+namespace ltxv {
+
+LtxVideoTransformer3DModel::LtxVideoTransformer3DModel(const ltxv_dit_config& cfg, int device)
+    : cfg_(cfg), device_(device) {
+    require_cuda_device(device);
+    const int D = inner_dim();
+    const int hd = cfg.attention_head_dim;
+    if (hd != 64 && hd != 128) fail("attention_head_dim must be 64 or 128 (got %d)", hd);
+    if (D % 64 != 0) fail("inner dim %d must be a multiple of 64", D);
+    if (cfg.in_channels % 8 != 0 || cfg.out_channels % 32 != 0 || cfg.caption_channels % 8 != 0 ||
+        cfg.cross_attention_dim % 8 != 0)
+        fail("channel counts must be multiples of 8 (out_channels of 32)");
+    if (cfg.num_layers <= 0) fail("num_layers must be positive");
+    const int X = cfg.cross_attention_dim;
+    if (X != D) fail("cross_attention_dim (%d) must equal the inner dim (%d): caption_projection feeds attn2", X, D);
+
+    auto vec = [&](int64_t n) {
+        storage_.emplace_back(new DevBuf());
+        storage_.back()->ensure(n * sizeof(float), true);
+        return storage_.back()->as<float>();
+    };
+    auto linear = [&](const std::string& key, LinearW& lin, int N, int K) {
+        lin = make_linear(N, K);
+        add_slot(key + ".weight", lin.w, true, {N, K});
+        add_slot(key + ".bias", lin.b, false, {N});
+    };
+    linear("proj_in", proj_in_, D, cfg.in_channels);
+    linear("time_embed.emb.timestep_embedder.linear_1", te1_, D, 256);
+    linear("time_embed.emb.timestep_embedder.linear_2", te2_, D, D);
+    linear("time_embed.linear", te_lin_, 6 * D, D);
+    linear("caption_projection.linear_1", cap1_, D, cfg.caption_channels);
+    linear("caption_projection.linear_2", cap2_, D, D);
+    linear("proj_out", proj_out_, cfg.out_channels, D);
+    sst_final_ = vec(2 * D);
+    add_slot("scale_shift_table", sst_final_, false, {2, D});
+    sst_blocks_ = vec(static_cast<int64_t>(cfg.num_layers) * 6 * D);
+
+    blocks_.resize(cfg.num_layers);
+    for (int i = 0; i < cfg.num_layers; ++i) {
+        DitBlockW& b = blocks_[i];
+        const std::string p = "transformer_blocks." + std::to_string(i) + ".";
+        add_slot(p + "scale_shift_table", sst_blocks_ + static_cast<int64_t>(i) * 6 * D, false, {6, D});
+        // fused QKV: rows [0,D) = to_q, [D,2D) = to_k, [2D,3D) = to_v
+        b.qkv1 = make_linear(3 * D, D);
+        const char* names[3] = {"to_q", "to_k", "to_v"};
+        for (int j = 0; j < 3; ++j) {
+            add_slot(p + "attn1." + names[j] + ".weight", b.qkv1.w + static_cast<int64_t>(j) * D * D, true, {D, D});
+            add_slot(p + "attn1." + names[j] + ".bias", b.qkv1.b + j * D, false, {D});
+        }
+        linear(p + "attn1.to_out.0", b.out1, D, D);
+        b.norm_q1 = vec(D);
+        b.norm_k1 = vec(D);
+        add_slot(p + "attn1.norm_q.weight", b.norm_q1, false, {D});
+        add_slot(p + "attn1.norm_k.weight", b.norm_k1, false, {D});
+        linear(p + "attn2.to_q", b.q2, D, D);
+        b.kv2 = make_linear(2 * D, X);
+        add_slot(p + "attn2.to_k.weight", b.kv2.w, true, {D, X});
+        add_slot(p + "attn2.to_k.bias", b.kv2.b, false, {D});
+        add_slot(p + "attn2.to_v.weight", b.kv2.w + static_cast<int64_t>(D) * X, true, {D, X});
+        add_slot(p + "attn2.to_v.bias", b.kv2.b + D, false, {D});
+        linear(p + "attn2.to_out.0", b.out2, D, D);
+        b.norm_q2 = vec(D);
+        b.norm_k2 = vec(D);
+        add_slot(p + "attn2.norm_q.weight", b.norm_q2, false, {D});
+        add_slot(p + "attn2.norm_k.weight", b.norm_k2, false, {D});
+        linear(p + "ff.net.0.proj", b.ff1, 4 * D, D);
+        linear(p + "ff.net.2", b.ff2, D, 4 * D);
+    }
+}
+
+LtxVideoTransformer3DModel::~LtxVideoTransformer3DModel() = default;
+
+LinearW LtxVideoTransformer3DModel::make_linear(int N, int K) {
+    LinearW l;
+    l.N = N;
+    l.K = K;
+    storage_.emplace_back(new DevBuf());
+    storage_.back()->ensure(static_cast<size_t>(N) * K * 2, true);
+    l.w = storage_.back()->as<__nv_bfloat16>();
+    storage_.emplace_back(new DevBuf());
+    // bias padded to a multiple of 256 so the GEMM epilogue's 32-wide bias loads never leave the allocation
+    storage_.back()->ensure(static_cast<size_t>((N + 255) / 256 * 256) * 4, true);
+    l.b = storage_.back()->as<float>();
+    return l;
+}
+
+void LtxVideoTransformer3DModel::add_slot(const std::string& key, void* dst, bool bf16, std::vector<int64_t> shape) {
+    ParamSlot s;
+    s.key = key;
+    s.dst = dst;
+    s.dst_bf16 = bf16;
+    s.shape = std::move(shape);
+    slots_[key] = std::move(s);
+}
+
+void LtxVideoTransformer3DModel::load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape,
+                                             int rank) {
+    auto it = slots_.find(key);
+    if (it == slots_.end()) fail("unknown transformer tensor key '%s'", key.c_str());
+    ParamSlot& s = it->second;
+    bool ok = rank == static_cast<int>(s.shape.size());
+    for (int i = 0; ok && i < rank; ++i) ok = shape[i] == s.shape[i];
+    if (!ok) {
+        std::string got = "[", want = "[";
+        for (int i = 0; i < rank; ++i) got += std::to_string(shape[i]) + (i + 1 < rank ? "," : "");
+        for (size_t i = 0; i < s.shape.size(); ++i) want += std::to_string(s.shape[i]) + (i + 1 < s.shape.size() ? "," : "");
+        fail("shape mismatch for '%s': got %s], expected %s]", key.c_str(), got.c_str(), want.c_str());
+    }
+    LTXV_CUDA(cudaSetDevice(device_));
+    ingest_tensor(s.dst, s.dst_bf16, data, dtype, s.numel());
+    s.loaded = true;
+    finalized_ = false;
+    for (auto& c : ctx_) c.valid = false;
+}
+
+void LtxVideoTransformer3DModel::init_random(uint64_t seed) {
+    LTXV_CUDA(cudaSetDevice(device_));
+    uint64_t n = 0;
+    for (auto& kv : slots_) {
+        ParamSlot& s = kv.second;
+        const uint64_t sd = seed * 1000003ull + (++n);
+        const std::string& k = s.key;
+        if (k.size() >= 17 && k.compare(k.size() - 17, 17, "scale_shift_table") == 0) {
+            fill_normal(s.dst, s.dst_bf16, s.numel(), 0.f, 1.0f / sqrtf(static_cast<float>(s.shape.back())), sd);
+        } else if (k.find("norm_q") != std::string::npos || k.find("norm_k") != std::string::npos) {
+            fill_normal(s.dst, s.dst_bf16, s.numel(), 1.0f, 0.1f, sd);
+        } else if (k.size() >= 5 && k.compare(k.size() - 5, 5, ".bias") == 0) {
+            fill_uniform(s.dst, s.dst_bf16, s.numel(), 0.05f, sd);
+        } else {
+            fill_uniform(s.dst, s.dst_bf16, s.numel(), 1.0f / sqrtf(static_cast<float>(s.shape.back())), sd);
+        }
+        s.loaded = true;
+    }
+    LTXV_CUDA(cudaDeviceSynchronize());
+    for (auto& c : ctx_) c.valid = false;
+    finalized_ = true;
+}
+
+void LtxVideoTransformer3DModel::finalize() {
+    std::string missing;
+    int n = 0;
+    for (auto& kv : slots_)
+        if (!kv.second.loaded) {
+            if (n < 8) missing += (n ? ", " : "") + kv.first;
+            ++n;
+        }
+    if (n) fail("%d transformer tensors were never loaded (first: %s)", n, missing.c_str());
+    finalized_ = true;
+}
+
+void LtxVideoTransformer3DModel::set_skip_block_list(const int32_t* idx, int n) {
+    skip_blocks_.assign(idx, idx + (n > 0 ? n : 0));
+}
+
+void LtxVideoTransformer3DModel::ensure_workspace(int S) {
+    const int D = inner_dim();
+    const int L = cfg_.num_layers;
+    const size_t sd = static_cast<size_t>(S) * D;
+    if (S > ws_S_) {
+        x_.ensure(sd * 4);
+        xb_.ensure(sd * 2);
+        h_.ensure(sd * 2);
+        qkv_.ensure(sd * 3 * 2);
+        attn_.ensure(sd * 2);
+        q2_.ensure(sd * 2);
+        ff_.ensure(sd * 4 * 2);
+        a_in_.ensure(static_cast<size_t>(S) * cfg_.in_channels * 2);
+        cos_.ensure(sd / 2 * 4);
+        sin_.ensure(sd / 2 * 4);
+        out_f32_.ensure(static_cast<size_t>(S) * cfg_.out_channels * 4);
+        ws_S_ = S;
+    }
+    small_.ensure((256 + 2 * static_cast<size_t>(D) + 6 * D + static_cast<size_t>(L) * 6 * D + 2 * D) * 4);
+}
+
+void LtxVideoTransformer3DModel::gemm(const void* a, int64_t a_rows, const LinearW& lin, int M, int epi, int act,
+                                      void* out, float* res, const float* gate, cudaStream_t s) {
+    GemmOperands ops{a, a_rows, lin.K, lin.w, lin.N, lin.K};
+    GemmParams p{};
+    p.M = M;
+    p.N = lin.N;
+    p.K = lin.K;
+    p.num_k_blocks = (lin.K + 63) / 64;
+    p.epi = epi;
+    p.act = act;
+    p.ldo = lin.N;
+    p.bias = lin.b;
+    p.gate = gate;
+    p.out = out;
+    p.res_f32 = res;
+    LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
+}
+
+// caption projection + per-layer cross K/V (ltx_transformer.rs:1056, :667-672 for attn2)
+void LtxVideoTransformer3DModel::prepare_context(int slot, const void* enc, int enc_dtype, const float* mask, int K,
+                                                 cudaStream_t s) {
+    if (!finalized_) finalize();
+    if (slot < 0 || slot > kNumSlots) fail("context slot %d out of range", slot);
+    if (K <= 0) fail("text length K must be positive");
+    LTXV_CUDA(cudaSetDevice(device_));
+    const int D = inner_dim();
+    const int L = cfg_.num_layers;
+    DitContext& c = ctx_[slot];
+    c.valid = false;
+    c.K = K;
+    const void* enc_b = enc;
+    if (enc_dtype == LTXV_F32) {
+        enc_bf16_.ensure(static_cast<size_t>(K) * cfg_.caption_channels * 2);
+        LTXV_CUDA(launch_f32_to_bf16(static_cast<const float*>(enc), enc_bf16_.p,
+                                     static_cast<int64_t>(K) * cfg_.caption_channels, s));
+        enc_b = enc_bf16_.p;
+    } else if (enc_dtype != LTXV_BF16) {
+        fail("unsupported encoder_hidden_states dtype %d", enc_dtype);
+    }
+    cap_mid_.ensure(static_cast<size_t>(K) * D * 2);
+    enc_proj_.ensure(static_cast<size_t>(K) * D * 2);
+    c.kv.ensure(static_cast<size_t>(L) * K * 2 * D * 2);
+    gemm(enc_b, K, cap1_, K, EPI_STORE_BF16, ACT_GELU_TANH, cap_mid_.p, nullptr, nullptr, s);
+    gemm(cap_mid_.p, K, cap2_, K, EPI_STORE_BF16, ACT_NONE, enc_proj_.p, nullptr, nullptr, s);
+    for (int l = 0; l < L; ++l) {
+        __nv_bfloat16* kv = c.kv.as<__nv_bfloat16>() + static_cast<size_t>(l) * K * 2 * D;
+        gemm(enc_proj_.p, K, blocks_[l].kv2, K, EPI_STORE_BF16, ACT_NONE, kv, nullptr, nullptr, s);
+        LTXV_CUDA(launch_qk_norm_rope(kv, 2 * D, 0, K, D, blocks_[l].norm_k2, 1e-5f, nullptr, nullptr, s));
+    }
+    c.has_mask = mask != nullptr;
+    if (mask != nullptr) {
+        // bias = (1 - mask) * -10000  (:1059-1064); computed with the affine kernel semantics
+        c.mask_bias.ensure(static_cast<size_t>(K) * 4);
+        LTXV_CUDA(launch_mask_bias(mask, c.mask_bias.as<float>(), K, s));
+    }
+    c.valid = true;
+}
+
+void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int hidden_dtype, const float* timestep_dev,
+                                             int S, int F, int H, int W, const float* rope_scale3_host,
+                                             const float* video_coords, const float* skip_mask, int skip_mask_stride,
+                                             void* out, int out_dtype, cudaStream_t s) {
+    if (!finalized_) finalize();
+    if (slot < 0 || slot > kNumSlots || !ctx_[slot].valid) fail("context slot %d has not been prepared", slot);
+    if (S <= 0) fail("sequence length must be positive");
+    if (video_coords == nullptr && static_cast<int64_t>(F) * H * W != S)
+        fail("num_frames*height*width (%d*%d*%d) must equal the sequence length %d when video_coords is not given", F, H,
+             W, S);
+    if (out_dtype != LTXV_F32 && out_dtype != LTXV_BF16) fail("unsupported output dtype %d", out_dtype);
+    LTXV_CUDA(cudaSetDevice(device_));
+    const DitContext& ctx = ctx_[slot];
+    const int D = inner_dim();
+    const int L = cfg_.num_layers;
+    const int heads = cfg_.num_attention_heads, hd = cfg_.attention_head_dim;
+    ensure_workspace(S);
+
+    float* sm = small_.as<float>();
+    float* tp = sm;                    // [256]
+    float* t1 = tp + 256;              // [D]
+    float* e = t1 + D;                 // [D]   embedded_timestep
+    float* temb = e + D;               // [6D]
+    float* ada = temb + 6 * D;         // [L, 6, D]
+    float* fin = ada + static_cast<size_t>(L) * 6 * D;  // [2, D]
+
+    // ---- timestep path: AdaLayerNormSingle (:262-267) ----
+    LTXV_CUDA(launch_sinusoid(timestep_dev, nullptr, tp, 0, cfg_.timestep_bf16_round, s));
+    LTXV_CUDA(launch_gemv(tp, te1_.w, te1_.b, t1, D, 256, GEMV_NONE, GEMV_SILU, s));
+    LTXV_CUDA(launch_gemv(t1, te2_.w, te2_.b, e, D, D, GEMV_NONE, GEMV_NONE, s));
+    LTXV_CUDA(launch_gemv(e, te_lin_.w, te_lin_.b, temb, 6 * D, D, GEMV_SILU, GEMV_NONE, s));
+    LTXV_CUDA(launch_add_vec(sst_blocks_, temb, ada, L * 6 * D, 6 * D, s));  // :847-854
+    LTXV_CUDA(launch_add_vec(sst_final_, e, fin, 2 * D, D, s));              // :1131-1147
+
+    // ---- RoPE table (:1073-1080) ----
+    float scale3[3];
+    const float* sc = nullptr;
+    if (video_coords == nullptr && rope_scale3_host != nullptr) {
+        // :410-412  (s * patch / base) as f32
+        scale3[0] = static_cast<float>(static_cast<double>(rope_scale3_host[0]) * cfg_.patch_size_t / 20.0);
+        scale3[1] = static_cast<float>(static_cast<double>(rope_scale3_host[1]) * cfg_.patch_size / 2048.0);
+        scale3[2] = static_cast<float>(static_cast<double>(rope_scale3_host[2]) * cfg_.patch_size / 2048.0);
+        sc = scale3;
+    }
+    LTXV_CUDA(launch_rope_table(video_coords, F, H, W, sc, S, D, 10000.0f, cos_.as<float>(), sin_.as<float>(), s));
+
+    // ---- proj_in (:1049) ----
+    const void* a_in = hidden;
+    if (hidden_dtype == LTXV_F32) {
+        LTXV_CUDA(launch_f32_to_bf16(static_cast<const float*>(hidden), a_in_.p,
+                                     static_cast<int64_t>(S) * cfg_.in_channels, s));
+        a_in = a_in_.p;
+    } else if (hidden_dtype != LTXV_BF16) {
+        fail("unsupported hidden_states dtype %d", hidden_dtype);
+    }
+    float* x = x_.as<float>();
+    gemm(a_in, S, proj_in_, S, EPI_STORE_F32, ACT_NONE, x, nullptr, nullptr, s);
+
+    const float attn_scale = 1.0f / sqrtf(static_cast<float>(hd));
+    for (int l = 0; l < L; ++l) {
+        bool skip = false;
+        for (int sidx : skip_blocks_) skip = skip || (sidx == l);  // :1094-1096
+        if (skip) continue;
+        float m = 0.f;
+        if (skip_mask != nullptr) m = skip_mask[static_cast<size_t>(l) * skip_mask_stride];
+        if (m == 1.0f) continue;  // x*(1-1) + orig*1 == orig  (:1112-1123)
+        const bool blend = (m != 0.0f);
+        if (blend) {
+            orig_.ensure(static_cast<size_t>(S) * D * 4);
+            LTXV_CUDA(cudaMemcpyAsync(orig_.p, x, static_cast<size_t>(S) * D * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        const DitBlockW& b = blocks_[l];
+        const float* a6 = ada + static_cast<size_t>(l) * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+
+        // --- self-attention ---
+        LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 1 * D, a6 + 0 * D, S, D, cfg_.norm_eps, NORM_RMS, s));
+        gemm(h_.p, S, b.qkv1, S, EPI_STORE_BF16, ACT_NONE, qkv_.p, nullptr, nullptr, s);
+        LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, 0, S, D, b.norm_q1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
+        LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, D, S, D, b.norm_k1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
+        {
+            AttnParams ap{};
+            ap.q = ap.k = ap.v = qkv_.p;
+            ap.ldq = ap.ldk = ap.ldv = 3 * D;
+            ap.q_col0 = 0;
+            ap.k_col0 = D;
+            ap.v_col0 = 2 * D;
+            ap.out = attn_.p;
+            ap.ldo = D;
+            ap.kv_bias = nullptr;
+            ap.B = 1;
+            ap.H = heads;
+            ap.Sq = S;
+            ap.Skv = S;
+            ap.D = hd;
+            ap.scale = attn_scale;
+            LTXV_CUDA(launch_attention(ap, s));
+        }
+        gemm(attn_.p, S, b.out1, S, EPI_RESIDUAL_F32, ACT_NONE, xb_.p, x, a6 + 2 * D, s);  // x += gate_msa * attn1
+
+        // --- cross-attention (no norm, no gate, no RoPE; :903-909) ---
+        gemm(xb_.p, S, b.q2, S, EPI_STORE_BF16, ACT_NONE, q2_.p, nullptr, nullptr, s);
+        LTXV_CUDA(launch_qk_norm_rope(q2_.p, D, 0, S, D, b.norm_q2, 1e-5f, nullptr, nullptr, s));
+        {
+            const __nv_bfloat16* kv = ctx.kv.as<__nv_bfloat16>() + static_cast<size_t>(l) * ctx.K * 2 * D;
+            AttnParams ap{};
+            ap.q = q2_.p;
+            ap.k = ap.v = kv;
+            ap.ldq = D;
+            ap.ldk = ap.ldv = 2 * D;
+            ap.q_col0 = 0;
+            ap.k_col0 = 0;
+            ap.v_col0 = D;
+            ap.out = attn_.p;
+            ap.ldo = D;
+            ap.kv_bias = ctx.has_mask ? ctx.mask_bias.as<float>() : nullptr;
+            ap.B = 1;
+            ap.H = heads;
+            ap.Sq = S;
+            ap.Skv = ctx.K;
+            ap.D = hd;
+            ap.scale = attn_scale;
+            LTXV_CUDA(launch_attention(ap, s));
+        }
+        gemm(attn_.p, S, b.out2, S, EPI_RESIDUAL_F32, ACT_NONE, nullptr, x, nullptr, s);  // x += attn2
+
+        // --- feed-forward ---
+        LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 4 * D, a6 + 3 * D, S, D, cfg_.norm_eps, NORM_RMS, s));
+        gemm(h_.p, S, b.ff1, S, EPI_STORE_BF16, ACT_GELU_TANH, ff_.p, nullptr, nullptr, s);
+        gemm(ff_.p, S, b.ff2, S, EPI_RESIDUAL_F32, ACT_NONE, nullptr, x, a6 + 5 * D, s);  // x += gate_mlp * ff
+
+        if (blend) LTXV_CUDA(launch_blend(x, orig_.as<float>(), m, static_cast<int64_t>(S) * D, s));
+    }
+
+    // ---- output head (:1126-1163): LayerNorm (no affine) -> (1+scale) x + shift -> proj_out ----
+    LTXV_CUDA(launch_norm_modulate(x, h_.p, fin + D, fin, S, D, 1e-6f, NORM_LAYER, s));
+    if (out_dtype == LTXV_F32) {
+        gemm(h_.p, S, proj_out_, S, EPI_STORE_F32, ACT_NONE, out, nullptr, nullptr, s);
+    } else {
+        gemm(h_.p, S, proj_out_, S, EPI_STORE_BF16, ACT_NONE, out, nullptr, nullptr, s);
+    }
+}
+
+void LtxVideoTransformer3DModel::forward(const void* hidden, int hidden_dtype, const void* enc, int enc_dtype,
+                                         const float* timestep, const float* mask, int B, int S, int K, int F, int H,
+                                         int W, const float* rope_scale3, const float* video_coords,
+                                         const float* skip_layer_mask, void* out, int out_dtype, cudaStream_t s) {
+    if (B <= 0) fail("batch must be positive");
+    const size_t hsz = hidden_dtype == LTXV_F32 ? 4 : 2, esz = enc_dtype == LTXV_F32 ? 4 : 2,
+                 osz = out_dtype == LTXV_F32 ? 4 : 2;
+    for (int b = 0; b < B; ++b) {
+        const char* hb = static_cast<const char*>(hidden) + static_cast<size_t>(b) * S * cfg_.in_channels * hsz;
+        const char* eb = static_cast<const char*>(enc) + static_cast<size_t>(b) * K * cfg_.caption_channels * esz;
+        char* ob = static_cast<char*>(out) + static_cast<size_t>(b) * S * cfg_.out_channels * osz;
+        prepare_context(kScratchSlot, eb, enc_dtype, mask ? mask + static_cast<size_t>(b) * K : nullptr, K, s);
+        forward_ctx(kScratchSlot, hb, hidden_dtype, timestep + b, S, F, H, W, rope_scale3,
+                    video_coords ? video_coords + static_cast<size_t>(b) * S * 3 : nullptr,
+                    skip_layer_mask ? skip_layer_mask + b : nullptr, B, ob, out_dtype, s);
+    }
+}
+
+}  // namespace ltxv

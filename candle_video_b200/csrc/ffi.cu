@@ -1,0 +1,342 @@
+// extern "C" boundary (include/ltxv.h): exceptions -> error codes, handles -> C++ model mirrors.
+#include <string.h>
+
+#include "attention.h"
+#include "dit.h"
+#include "gemm.h"
+#include "glue.h"
+#include "pipeline.h"
+#include "vae.h"
+#include "vae_glue.h"
+
+using namespace ltxv;
+
+struct ltxv_dit {
+    LtxVideoTransformer3DModel model;
+    DevBuf h_hidden, h_enc, h_t, h_mask, h_coords, h_out;  // device staging for the *_host entry points
+    ltxv_dit(const ltxv_dit_config& c, int dev) : model(c, dev) {}
+};
+struct ltxv_vae {
+    AutoencoderKLLtxVideo model;
+    DevBuf h_z, h_t, h_out;
+    ltxv_vae(const ltxv_vae_config& c, int dev) : model(c, dev) {}
+};
+
+#define LTXV_TRY try {
+#define LTXV_CATCH                                        \
+    }                                                     \
+    catch (const std::exception& e) {                     \
+        set_error("%s", e.what());                        \
+        return 1;                                         \
+    }                                                     \
+    catch (...) {                                         \
+        set_error("unknown C++ exception");               \
+        return 1;                                         \
+    }                                                     \
+    return 0;
+
+static size_t dsize(int dtype) {
+    if (dtype == LTXV_F32) return 4;
+    if (dtype == LTXV_BF16) return 2;
+    fail("unsupported dtype code %d", dtype);
+}
+
+extern "C" {
+
+const char* ltxv_last_error(void) { return last_error_ref().c_str(); }
+const char* ltxv_version(void) { return "ltxv_b200 0.1 (sm_100a: tcgen05 GEMM/conv3d/attention)"; }
+uint64_t ltxv_launch_count(void) {
+    return gemm_launch_count() + attention_launch_count() + glue_launch_count() + vae_glue_launch_count() +
+           common_launch_count();
+}
+
+int ltxv_dit_config_preset(const char* name, ltxv_dit_config* out) {
+    LTXV_TRY
+    if (out == nullptr || name == nullptr) fail("null argument");
+    ltxv_dit_config c{};
+    c.in_channels = 128; c.out_channels = 128; c.patch_size = 1; c.patch_size_t = 1;
+    c.num_attention_heads = 32; c.attention_head_dim = 64; c.cross_attention_dim = 2048; c.num_layers = 28;
+    c.caption_channels = 4096; c.norm_eps = 1e-6f; c.timestep_bf16_round = 1;
+    if (strcmp(name, "2b") == 0) {
+    } else if (strcmp(name, "13b") == 0) {  // configs.rs:151-160
+        c.attention_head_dim = 128; c.cross_attention_dim = 4096; c.num_layers = 48;
+    } else {
+        fail("unknown transformer preset '%s' (expected 2b or 13b)", name);
+    }
+    *out = c;
+    LTXV_CATCH
+}
+
+int ltxv_dit_create(const ltxv_dit_config* cfg, int device, ltxv_dit** out) {
+    LTXV_TRY
+    if (cfg == nullptr || out == nullptr) fail("null argument");
+    *out = new ltxv_dit(*cfg, device);
+    LTXV_CATCH
+}
+void ltxv_dit_destroy(ltxv_dit* m) { delete m; }
+
+int ltxv_dit_load_tensor(ltxv_dit* m, const char* key, const void* data, int dtype, const int64_t* shape, int rank) {
+    LTXV_TRY
+    if (m == nullptr || key == nullptr || data == nullptr) fail("null argument");
+    m->model.load_tensor(key, data, dtype, shape, rank);
+    LTXV_CATCH
+}
+int ltxv_dit_init_random(ltxv_dit* m, uint64_t seed) {
+    LTXV_TRY
+    if (m == nullptr) fail("null handle");
+    m->model.init_random(seed);
+    LTXV_CATCH
+}
+int ltxv_dit_finalize(ltxv_dit* m) {
+    LTXV_TRY
+    if (m == nullptr) fail("null handle");
+    m->model.finalize();
+    LTXV_CATCH
+}
+int ltxv_dit_set_skip_blocks(ltxv_dit* m, const int32_t* idx, int n) {
+    LTXV_TRY
+    if (m == nullptr) fail("null handle");
+    m->model.set_skip_block_list(idx, n);
+    LTXV_CATCH
+}
+int ltxv_dit_get_config(const ltxv_dit* m, ltxv_dit_config* out) {
+    LTXV_TRY
+    if (m == nullptr || out == nullptr) fail("null argument");
+    *out = m->model.config();
+    LTXV_CATCH
+}
+
+int ltxv_dit_forward(ltxv_dit* m, const void* hidden, int hidden_dtype, const void* enc, int enc_dtype,
+                     const float* timestep, const float* mask, int B, int S, int K, int F, int H, int W,
+                     const float* rope_scale3, const float* video_coords, const float* skip_layer_mask, void* out,
+                     int out_dtype, void* stream) {
+    LTXV_TRY
+    if (m == nullptr || hidden == nullptr || enc == nullptr || timestep == nullptr || out == nullptr)
+        fail("null argument");
+    m->model.forward(hidden, hidden_dtype, enc, enc_dtype, timestep, mask, B, S, K, F, H, W, rope_scale3, video_coords,
+                     skip_layer_mask, out, out_dtype, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+int ltxv_dit_forward_host(ltxv_dit* m, const void* hidden, int hidden_dtype, const void* enc, int enc_dtype,
+                          const float* timestep, const float* mask, int B, int S, int K, int F, int H, int W,
+                          const float* rope_scale3, const float* video_coords, const float* skip_layer_mask, void* out,
+                          int out_dtype) {
+    LTXV_TRY
+    if (m == nullptr || hidden == nullptr || enc == nullptr || timestep == nullptr || out == nullptr)
+        fail("null argument");
+    const ltxv_dit_config& c = m->model.config();
+    const size_t nh = static_cast<size_t>(B) * S * c.in_channels * dsize(hidden_dtype);
+    const size_t ne = static_cast<size_t>(B) * K * c.caption_channels * dsize(enc_dtype);
+    const size_t no = static_cast<size_t>(B) * S * c.out_channels * dsize(out_dtype);
+    cudaStream_t s = 0;
+    m->h_hidden.ensure(nh);
+    m->h_enc.ensure(ne);
+    m->h_t.ensure(B * 4);
+    m->h_out.ensure(no);
+    LTXV_CUDA(cudaMemcpyAsync(m->h_hidden.p, hidden, nh, cudaMemcpyHostToDevice, s));
+    LTXV_CUDA(cudaMemcpyAsync(m->h_enc.p, enc, ne, cudaMemcpyHostToDevice, s));
+    LTXV_CUDA(cudaMemcpyAsync(m->h_t.p, timestep, B * 4, cudaMemcpyHostToDevice, s));
+    const float* dmask = nullptr;
+    if (mask != nullptr) {
+        m->h_mask.ensure(static_cast<size_t>(B) * K * 4);
+        LTXV_CUDA(cudaMemcpyAsync(m->h_mask.p, mask, static_cast<size_t>(B) * K * 4, cudaMemcpyHostToDevice, s));
+        dmask = m->h_mask.as<float>();
+    }
+    const float* dcoords = nullptr;
+    if (video_coords != nullptr) {
+        m->h_coords.ensure(static_cast<size_t>(B) * S * 3 * 4);
+        LTXV_CUDA(cudaMemcpyAsync(m->h_coords.p, video_coords, static_cast<size_t>(B) * S * 3 * 4, cudaMemcpyHostToDevice, s));
+        dcoords = m->h_coords.as<float>();
+    }
+    m->model.forward(m->h_hidden.p, hidden_dtype, m->h_enc.p, enc_dtype, m->h_t.as<float>(), dmask, B, S, K, F, H, W,
+                     rope_scale3, dcoords, skip_layer_mask, m->h_out.p, out_dtype, s);
+    LTXV_CUDA(cudaMemcpyAsync(out, m->h_out.p, no, cudaMemcpyDeviceToHost, s));
+    LTXV_CUDA(cudaStreamSynchronize(s));
+    LTXV_CATCH
+}
+
+int ltxv_dit_prepare_context(ltxv_dit* m, int slot, const void* enc, int enc_dtype, const float* mask, int K,
+                             void* stream) {
+    LTXV_TRY
+    if (m == nullptr || enc == nullptr) fail("null argument");
+    if (slot < 0 || slot >= LtxVideoTransformer3DModel::kNumSlots) fail("context slot %d out of range", slot);
+    m->model.prepare_context(slot, enc, enc_dtype, mask, K, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+int ltxv_dit_forward_ctx(ltxv_dit* m, int slot, const void* hidden, int hidden_dtype, const float* timestep, int S,
+                         int F, int H, int W, const float* rope_scale3, const float* video_coords,
+                         const float* skip_layer_mask, void* out, int out_dtype, void* stream) {
+    LTXV_TRY
+    if (m == nullptr || hidden == nullptr || timestep == nullptr || out == nullptr) fail("null argument");
+    if (slot < 0 || slot >= LtxVideoTransformer3DModel::kNumSlots) fail("context slot %d out of range", slot);
+    m->model.forward_ctx(slot, hidden, hidden_dtype, timestep, S, F, H, W, rope_scale3, video_coords, skip_layer_mask,
+                         1, out, out_dtype, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+/* ---------------------------------------------------- VAE ---------------------------------------------------- */
+int ltxv_vae_config_default(ltxv_vae_config* out) {
+    LTXV_TRY
+    if (out == nullptr) fail("null argument");
+    ltxv_vae_config c{};
+    c.latent_channels = 128; c.out_channels = 3;
+    c.decoder_block_out_channels[0] = 256; c.decoder_block_out_channels[1] = 512; c.decoder_block_out_channels[2] = 1024;
+    for (int i = 0; i < 4; ++i) c.decoder_layers_per_block[i] = 5;
+    c.patch_size = 4; c.timestep_conditioning = 1; c.scaling_factor = 1.0f;
+    *out = c;
+    LTXV_CATCH
+}
+int ltxv_vae_create(const ltxv_vae_config* cfg, int device, ltxv_vae** out) {
+    LTXV_TRY
+    if (cfg == nullptr || out == nullptr) fail("null argument");
+    *out = new ltxv_vae(*cfg, device);
+    LTXV_CATCH
+}
+void ltxv_vae_destroy(ltxv_vae* m) { delete m; }
+int ltxv_vae_load_tensor(ltxv_vae* m, const char* key, const void* data, int dtype, const int64_t* shape, int rank) {
+    LTXV_TRY
+    if (m == nullptr || key == nullptr || data == nullptr) fail("null argument");
+    m->model.load_tensor(key, data, dtype, shape, rank);
+    LTXV_CATCH
+}
+int ltxv_vae_init_random(ltxv_vae* m, uint64_t seed) {
+    LTXV_TRY
+    if (m == nullptr) fail("null handle");
+    m->model.init_random(seed);
+    LTXV_CATCH
+}
+int ltxv_vae_finalize(ltxv_vae* m) {
+    LTXV_TRY
+    if (m == nullptr) fail("null handle");
+    m->model.finalize();
+    LTXV_CATCH
+}
+const float* ltxv_vae_latents_mean(const ltxv_vae* m) { return m ? m->model.latents_mean() : nullptr; }
+const float* ltxv_vae_latents_std(const ltxv_vae* m) { return m ? m->model.latents_std() : nullptr; }
+int ltxv_vae_spatial_compression_ratio(const ltxv_vae* m) { return m ? m->model.spatial_compression_ratio() : 0; }
+int ltxv_vae_temporal_compression_ratio(const ltxv_vae* m) { return m ? m->model.temporal_compression_ratio() : 0; }
+
+int ltxv_vae_decode(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
+                    void* out, int out_dtype, int postprocess, void* stream) {
+    LTXV_TRY
+    if (m == nullptr || z == nullptr || out == nullptr) fail("null argument");
+    m->model.decode(z, z_dtype, timestep, B, F, H, W, out, out_dtype, postprocess, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+int ltxv_vae_decode_host(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
+                         void* out, int out_dtype, int postprocess) {
+    LTXV_TRY
+    if (m == nullptr || z == nullptr || out == nullptr) fail("null argument");
+    const int C = m->model.config().latent_channels;
+    const size_t nz = static_cast<size_t>(B) * C * F * H * W * dsize(z_dtype);
+    const size_t no = static_cast<size_t>(B) * 3 * (8 * F - 7) * (32 * H) * (32 * W) * dsize(out_dtype);
+    cudaStream_t s = 0;
+    m->h_z.ensure(nz);
+    m->h_out.ensure(no);
+    LTXV_CUDA(cudaMemcpyAsync(m->h_z.p, z, nz, cudaMemcpyHostToDevice, s));
+    const float* dt = nullptr;
+    if (timestep != nullptr) {
+        m->h_t.ensure(B * 4);
+        LTXV_CUDA(cudaMemcpyAsync(m->h_t.p, timestep, B * 4, cudaMemcpyHostToDevice, s));
+        dt = m->h_t.as<float>();
+    }
+    m->model.decode(m->h_z.p, z_dtype, dt, B, F, H, W, m->h_out.p, out_dtype, postprocess, s);
+    LTXV_CUDA(cudaMemcpyAsync(out, m->h_out.p, no, cudaMemcpyDeviceToHost, s));
+    LTXV_CUDA(cudaStreamSynchronize(s));
+    LTXV_CATCH
+}
+
+/* ------------------------------------------------- pipeline glue ------------------------------------------------ */
+int ltxv_pack_latents(const float* in, float* out, int B, int C, int F, int H, int W, int p, int pt, void* stream) {
+    LTXV_TRY
+    if (in == nullptr || out == nullptr) fail("null argument");
+    if (p <= 0 || pt <= 0 || F % pt != 0 || H % p != 0 || W % p != 0)
+        fail("latents shape not divisible by patch sizes");  // t2v_pipeline.rs:486-488
+    const int64_t n = static_cast<int64_t>(C) * F * H * W;
+    for (int b = 0; b < B; ++b)
+        LTXV_CUDA(launch_pack_latents(in + b * n, out + b * n, C, F, H, W, p, pt, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_unpack_latents(const float* in, float* out, int B, int C, int F, int H, int W, int p, int pt, void* stream) {
+    LTXV_TRY
+    if (in == nullptr || out == nullptr) fail("null argument");
+    if (p <= 0 || pt <= 0 || F % pt != 0 || H % p != 0 || W % p != 0) fail("latents shape not divisible by patch sizes");
+    const int64_t n = static_cast<int64_t>(C) * F * H * W;
+    for (int b = 0; b < B; ++b)
+        LTXV_CUDA(launch_unpack_latents(in + b * n, out + b * n, C, F, H, W, p, pt, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_video_coords(float* out, int B, int F, int H, int W, int ts_ratio, int sp_ratio, int fps, void* stream) {
+    LTXV_TRY
+    if (out == nullptr) fail("null argument");
+    if (fps <= 0) fail("frame rate must be positive");
+    const int64_t n = static_cast<int64_t>(F) * H * W * 3;
+    for (int b = 0; b < B; ++b)
+        LTXV_CUDA(launch_video_coords(out + b * n, F, H, W, ts_ratio, sp_ratio, fps, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_guidance_euler_step(const float* cond, const float* uncond, const float* perturbed, float* latents,
+                             float* noise_pred_out, int B, int64_t n, float guidance_scale, float guidance_rescale,
+                             float stg_scale, float sigma, float sigma_next, void* stream) {
+    LTXV_TRY
+    if (cond == nullptr) fail("null argument");
+    static DevBuf scratch;
+    scratch.ensure(64);
+    const float dt = sigma_next - sigma;
+    for (int b = 0; b < B; ++b)
+        LTXV_CUDA(launch_guidance_euler(cond + b * n, uncond ? uncond + b * n : nullptr,
+                                        perturbed ? perturbed + b * n : nullptr, latents ? latents + b * n : nullptr,
+                                        noise_pred_out ? noise_pred_out + b * n : nullptr, n, guidance_scale,
+                                        guidance_rescale, stg_scale, dt, scratch.as<double>(),
+                                        static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_denormalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,
+                             int B, int C, int64_t n_per_channel, void* stream) {
+    LTXV_TRY
+    if (in == nullptr || out == nullptr || mean == nullptr || std == nullptr) fail("null argument");
+    const int64_t n = C * n_per_channel;
+    for (int b = 0; b < B; ++b)
+        LTXV_CUDA(launch_denormalize(in + b * n, out + b * n, mean, std, 1.0f / scaling_factor, C, n_per_channel,
+                                     static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_postprocess_video(const float* in, float* out, int64_t n, void* stream) {
+    LTXV_TRY
+    if (in == nullptr || out == nullptr) fail("null argument");
+    LTXV_CUDA(launch_postprocess(in, out, n, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_calculate_shift(int seq_len, float* mu_out) {
+    LTXV_TRY
+    if (mu_out == nullptr) fail("null argument");
+    *mu_out = calculate_shift(seq_len);
+    LTXV_CATCH
+}
+int ltxv_scheduler_set_timesteps(int num_steps, const float* custom_sigmas, float mu, int has_shift_terminal,
+                                 float shift_terminal, float* sigmas_out, int64_t* timesteps_out) {
+    LTXV_TRY
+    if (sigmas_out == nullptr || timesteps_out == nullptr) fail("null argument");
+    scheduler_set_timesteps(num_steps, custom_sigmas, mu, has_shift_terminal != 0, shift_terminal, sigmas_out,
+                            timesteps_out);
+    LTXV_CATCH
+}
+
+int ltxv_pipeline_denoise(ltxv_dit* dit, const ltxv_pipeline_params* p, float* latents, const void* prompt_embeds,
+                          const float* prompt_mask, const void* negative_embeds, const float* negative_mask,
+                          int embeds_dtype, int K, void* stream) {
+    LTXV_TRY
+    if (dit == nullptr || p == nullptr || latents == nullptr || prompt_embeds == nullptr) fail("null argument");
+    pipeline_denoise(dit->model, *p, latents, prompt_embeds, prompt_mask, negative_embeds, negative_mask, embeds_dtype,
+                     K, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out, void* stream) {
+    LTXV_TRY
+    if (vae == nullptr || p == nullptr || latents == nullptr || out == nullptr) fail("null argument");
+    pipeline_decode(vae->model, *p, latents, out, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+}  // extern "C"

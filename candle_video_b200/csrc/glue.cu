@@ -1,0 +1,502 @@
+// Bandwidth-bound glue kernels (see glue.h).  Rows are processed one warp per row with 128-bit accesses and
+// warp-shuffle reductions; nothing here is shaped into a GEMM.
+#include "common.cuh"
+#include "glue.h"
+
+#include <atomic>
+
+namespace ltxv {
+
+namespace {
+std::atomic<uint64_t> g_glue_launches{0};
+inline cudaError_t done() {
+    g_glue_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+constexpr int kWarpsPerBlock = 8;
+
+// ------------------------------------------------------------------------------------------------
+// norm + modulate: f32 row in, bf16 row out
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
+                     const float* __restrict__ shift, int rows, int D, float eps) {
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * D);
+    const int nv = D >> 2;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+        float4 v = xr[i];
+        s1 += v.x + v.y + v.z + v.w;
+        s2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    s2 = warp_sum(s2);
+    float mean = 0.f, rinv;
+    if (KIND == NORM_LAYER) {
+        s1 = warp_sum(s1);
+        mean = s1 / D;
+        // second pass for the centred variance (matches the reference's (x-mean)^2 form, :74-77)
+        float sv = 0.f;
+        for (int i = lane; i < nv; i += 32) {
+            float4 v = xr[i];
+            float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+            sv += a * a + b * b + c * c + d * d;
+        }
+        sv = warp_sum(sv);
+        rinv = rsqrtf(sv / D + eps);
+    } else {
+        rinv = rsqrtf(s2 * (1.0f / D) + eps);
+    }
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(row) * D);
+    const float4* sc4 = reinterpret_cast<const float4*>(scale);
+    const float4* sh4 = reinterpret_cast<const float4*>(shift);
+    for (int i = lane; i < nv; i += 32) {
+        float4 v = xr[i];
+        float a = (v.x - mean) * rinv, b = (v.y - mean) * rinv, c = (v.z - mean) * rinv, d = (v.w - mean) * rinv;
+        if (scale != nullptr) {
+            float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);
+            a = a * (1.0f + sc.x) + sh.x;
+            b = b * (1.0f + sc.y) + sh.y;
+            c = c * (1.0f + sc.z) + sh.z;
+            d = d * (1.0f + sc.w) + sh.w;
+        }
+        uint2 o;
+        o.x = pack_bf16x2(a, b);
+        o.y = pack_bf16x2(c, d);
+        orow[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// q/k RMS norm across heads (+ RoPE), in place on bf16
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+qk_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int rows, int D, const float* __restrict__ w,
+                    float eps, const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + col0);
+    const int nv = D >> 3;  // 8 bf16 per 16 B
+    float s2 = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+        uint4 u = xr[i];
+        float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                      bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2 += f[j] * f[j];
+    }
+    s2 = warp_sum(s2);
+    const float rinv = rsqrtf(s2 * (1.0f / D) + eps);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* c4 = cos_t ? reinterpret_cast<const float4*>(cos_t + static_cast<int64_t>(row) * (D >> 1)) : nullptr;
+    const float4* s4 = sin_t ? reinterpret_cast<const float4*>(sin_t + static_cast<int64_t>(row) * (D >> 1)) : nullptr;
+    for (int i = lane; i < nv; i += 32) {
+        uint4 u = xr[i];
+        float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                      bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+        float4 wa = __ldg(w4 + 2 * i), wb = __ldg(w4 + 2 * i + 1);
+        const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] * rinv * ww[j];
+        if (c4 != nullptr) {
+            float4 cc = __ldg(c4 + i), ss = __ldg(s4 + i);  // 4 pairs
+            const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float re = f[2 * j], im = f[2 * j + 1];
+                f[2 * j] = re * cv[j] - im * sv[j];      // x*cos + (-x_imag)*sin
+                f[2 * j + 1] = im * cv[j] + re * sv[j];  // x*cos + ( x_real)*sin
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        xr[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE table
+// ------------------------------------------------------------------------------------------------
+__global__ void rope_table_kernel(const float* __restrict__ coords, int F, int H, int W, float m0, float m1, float m2,
+                                  int S, int D, float theta_ln, float* __restrict__ cos_t, float* __restrict__ sin_t) {
+    const int half = D >> 1;
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<int64_t>(S) * half) return;
+    const int s = static_cast<int>(idx / half);
+    const int pi = static_cast<int>(idx - static_cast<int64_t>(s) * half);
+    const int steps = D / 6;
+    const int rem_pairs = (D % 6) >> 1;
+    float c = 1.0f, sn = 0.0f;
+    if (pi >= rem_pairs) {
+        const int q = pi - rem_pairs;  // = j*3 + a
+        const int j = q / 3, a = q - j * 3;
+        float g;
+        if (coords != nullptr) {
+            g = coords[static_cast<int64_t>(s) * 3 + a] * (a == 0 ? m0 : (a == 1 ? m1 : m2));
+        } else {
+            const int w = s % W, h = (s / W) % H, f = s / (W * H);
+            const float v = static_cast<float>(a == 0 ? f : (a == 1 ? h : w));
+            g = v * (a == 0 ? m0 : (a == 1 ? m1 : m2));
+        }
+        const float lin = (steps <= 1) ? 0.0f : __fmul_rn(static_cast<float>(j), 1.0f / static_cast<float>(steps - 1));
+        const float freq = __fmul_rn(expf(__fmul_rn(lin, theta_ln)), 1.5707963267948966f);
+        const float gs = __fadd_rn(__fmul_rn(g, 2.0f), -1.0f);
+        const float ang = __fmul_rn(gs, freq);
+        sincosf(ang, &sn, &c);
+    }
+    cos_t[idx] = c;
+    sin_t[idx] = sn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMV (weight-read bound): one warp per output row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gemv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+            float* __restrict__ y, int N, int K, int act_in, int act_out) {
+    const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<int64_t>(n) * K);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float acc = 0.f;
+    for (int i = lane; i < (K >> 3); i += 32) {
+        uint4 u = __ldg(wr + i);
+        float4 a = x4[2 * i], b = x4[2 * i + 1];
+        float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (act_in == GEMV_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = xv[j] / (1.0f + expf(-xv[j]));
+        }
+        acc += xv[0] * bf16_lo(u.x) + xv[1] * bf16_hi(u.x) + xv[2] * bf16_lo(u.y) + xv[3] * bf16_hi(u.y) +
+               xv[4] * bf16_lo(u.z) + xv[5] * bf16_hi(u.z) + xv[6] * bf16_lo(u.w) + xv[7] * bf16_hi(u.w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        float v = acc + (bias ? bias[n] : 0.f);
+        if (act_out == GEMV_SILU) v = v / (1.0f + expf(-v));
+        y[n] = v;
+    }
+}
+
+__global__ void sinusoid_kernel(const float* __restrict__ t_dev, const float* __restrict__ t_mul, float* __restrict__ out,
+                                int style, int round_bf16) {
+    const int i = threadIdx.x;  // 0..127
+    float t = t_dev[0];
+    if (t_mul != nullptr) t *= t_mul[0];
+    if (round_bf16) t = __bfloat162float(__float2bfloat16(t));
+    float fr;
+    if (style == 0) {
+        fr = 1.0f / powf(10000.0f, static_cast<float>(i) / 128.0f);
+    } else {
+        fr = expf(static_cast<float>(i) * (-9.210340371976184f / 128.0f));
+    }
+    const float a = t * fr;
+    out[i] = cosf(a);
+    out[128 + i] = sinf(a);
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* d, int n, int period) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = a[i] + b[i % period];
+}
+
+__global__ void mask_bias_kernel(const float* m, float* b, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = __fmul_rn(__fadd_rn(__fmul_rn(m[i], -1.0f), 1.0f), -10000.0f);
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+        for (; i < n; ++i) dst[i] = __float2bfloat16(src[i]);
+    }
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+__global__ void blend_kernel(float* __restrict__ x, const float* __restrict__ orig, float m, int64_t n) {
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) x[i] = x[i] * (1.0f - m) + orig[i] * m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack / unpack latents, coords
+// ------------------------------------------------------------------------------------------------
+// out[s, d], s = (f2*H2 + h2)*W2 + w2, d = ((c*pt + a)*p + i)*p + j  <-  in[c, f2*pt+a, h2*p+i, w2*p+j]
+template <bool PACK>
+__global__ void pack_unpack_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int F, int H, int W,
+                                   int p, int pt) {
+    const int F2 = F / pt, H2 = H / p, W2 = W / p;
+    const int Dd = C * pt * p * p;
+    const int64_t total = static_cast<int64_t>(F2) * H2 * W2 * Dd;
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    // idx enumerates the *packed* layout [S, Dd]
+    const int d = static_cast<int>(idx % Dd);
+    const int s = static_cast<int>(idx / Dd);
+    const int j = d % p, i = (d / p) % p, a = (d / (p * p)) % pt, c = d / (p * p * pt);
+    const int w2 = s % W2, h2 = (s / W2) % H2, f2 = s / (W2 * H2);
+    const int64_t src = ((static_cast<int64_t>(c) * F + (f2 * pt + a)) * H + (h2 * p + i)) * W + (w2 * p + j);
+    if (PACK) out[idx] = in[src];
+    else out[src] = in[idx];
+}
+
+// p = pt = 1 fast path: [C, N] <-> [N, C] tiled transpose through shared memory (coalesced both ways)
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+    for (int k = 0; k < 32; k += 8)
+        if (x < cols && y + k < rows) tile[threadIdx.y + k][threadIdx.x] = in[static_cast<int64_t>(y + k) * cols + x];
+    __syncthreads();
+    x = blockIdx.y * 32 + threadIdx.x;
+    y = blockIdx.x * 32 + threadIdx.y;
+    for (int k = 0; k < 32; k += 8)
+        if (x < rows && y + k < cols) out[static_cast<int64_t>(y + k) * rows + x] = tile[threadIdx.x][threadIdx.y + k];
+}
+
+__global__ void video_coords_kernel(float* __restrict__ out, int F, int H, int W, float ts_ratio, float sp_ratio,
+                                    float inv_fps) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= F * H * W) return;
+    const int w = s % W, h = (s / W) % H, f = s / (W * H);
+    // affine(ts, 1-ts) -> clamp(0,1000) -> affine(1/fps)   (each an individually rounded f32 op)
+    float vf = __fadd_rn(__fmul_rn(static_cast<float>(f), ts_ratio), 1.0f - ts_ratio);
+    vf = fminf(fmaxf(vf, 0.0f), 1000.0f);
+    vf = __fmul_rn(vf, inv_fps);
+    out[s * 3 + 0] = vf;
+    out[s * 3 + 1] = __fmul_rn(static_cast<float>(h), sp_ratio);
+    out[s * 3 + 2] = __fmul_rn(static_cast<float>(w), sp_ratio);
+}
+
+// ------------------------------------------------------------------------------------------------
+// guidance combine + Euler
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float combine_cfg(float c, float u, bool has_u, float g) {
+    // uncond + (cond - uncond).affine(g, 0): three individually rounded f32 ops (t2v_pipeline.rs:947-949)
+    return has_u ? __fadd_rn(u, __fmul_rn(__fsub_rn(c, u), g)) : c;
+}
+// pass 1 (only when guidance_rescale > 0): sums for the unbiased std of cond and of the CFG combination
+__global__ void guidance_stats_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, int64_t n,
+                                      float g, double* __restrict__ acc) {
+    double sc = 0, scc = 0, sm = 0, smm = 0;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float c = cond[i];
+        const float m = combine_cfg(c, uncond[i], true, g);
+        sc += c; scc += static_cast<double>(c) * c;
+        sm += m; smm += static_cast<double>(m) * m;
+    }
+    __shared__ double red[4][32];
+    double v[4] = {sc, scc, sm, smm};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int wi = 0; wi < (blockDim.x >> 5); ++wi) t += red[threadIdx.x][wi];
+        atomicAdd(&acc[threadIdx.x], t);
+    }
+}
+__global__ void guidance_euler_kernel(const float* __restrict__ cond, const float* __restrict__ uncond,
+                                      const float* __restrict__ pert, float* __restrict__ latents,
+                                      float* __restrict__ noise_out, int64_t n, float g, float r, float s_stg, float dt,
+                                      const double* __restrict__ acc) {
+    float ratio = 1.0f;
+    if (r > 0.0f && uncond != nullptr) {
+        const double nn = static_cast<double>(n);
+        const double var_c = (acc[1] - acc[0] * acc[0] / nn) / (nn - 1.0);
+        const double var_m = (acc[3] - acc[2] * acc[2] / nn) / (nn - 1.0);
+        ratio = static_cast<float>(sqrt(var_c) / sqrt(var_m));
+    }
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float c = cond[i];
+    float m = combine_cfg(c, uncond ? uncond[i] : 0.f, uncond != nullptr, g);
+    if (r > 0.0f && uncond != nullptr)
+        m = __fadd_rn(__fmul_rn(__fmul_rn(m, ratio), r), __fmul_rn(m, 1.0f - r));
+    if (pert != nullptr) m = __fadd_rn(m, __fmul_rn(__fsub_rn(c, pert[i]), s_stg));
+    if (noise_out != nullptr) noise_out[i] = m;
+    if (latents != nullptr) latents[i] = __fadd_rn(latents[i], __fmul_rn(m, dt));
+}
+
+__global__ void denorm_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ mean,
+                              const float* __restrict__ std, float inv_sf, int C, int64_t n_per_c) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= C * n_per_c) return;
+    const int c = static_cast<int>(i / n_per_c);
+    out[i] = __fadd_rn(__fmul_rn(__fmul_rn(in[i], std[c]), inv_sf), mean[c]);
+}
+__global__ void postprocess_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+    const int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(in + i);
+        v.x = fminf(fmaxf(__fmaf_rn(v.x, 0.5f, 0.5f), 0.f), 1.f) * 255.f;
+        v.y = fminf(fmaxf(__fmaf_rn(v.y, 0.5f, 0.5f), 0.f), 1.f) * 255.f;
+        v.z = fminf(fmaxf(__fmaf_rn(v.z, 0.5f, 0.5f), 0.f), 1.f) * 255.f;
+        v.w = fminf(fmaxf(__fmaf_rn(v.w, 0.5f, 0.5f), 0.f), 1.f) * 255.f;
+        *reinterpret_cast<float4*>(out + i) = v;
+    } else {
+        for (int64_t k = i; k < n; ++k) out[k] = fminf(fmaxf(__fmaf_rn(in[k], 0.5f, 0.5f), 0.f), 1.f) * 255.f;
+    }
+}
+
+inline int blocks_for(int64_t n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
+
+}  // namespace
+
+uint64_t glue_launch_count() { return g_glue_launches.load(); }
+
+cudaError_t launch_norm_modulate(const float* x, void* out, const float* scale, const float* shift, int rows, int D,
+                                 float eps, int kind, cudaStream_t s) {
+    if (D % 4 != 0 || (scale == nullptr) != (shift == nullptr)) return cudaErrorInvalidValue;
+    const int grid = blocks_for(rows, kWarpsPerBlock);
+    if (kind == NORM_LAYER)
+        norm_modulate_kernel<NORM_LAYER><<<grid, kWarpsPerBlock * 32, 0, s>>>(
+            x, reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, D, eps);
+    else
+        norm_modulate_kernel<NORM_RMS><<<grid, kWarpsPerBlock * 32, 0, s>>>(
+            x, reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, D, eps);
+    return done();
+}
+
+cudaError_t launch_qk_norm_rope(void* x, int64_t ld, int col0, int rows, int D, const float* w, float eps,
+                                const float* cos_t, const float* sin_t, cudaStream_t s) {
+    if (D % 8 != 0 || ld % 8 != 0 || col0 % 8 != 0) return cudaErrorInvalidValue;
+    qk_norm_rope_kernel<<<blocks_for(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+        reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, D, w, eps, cos_t, sin_t);
+    return done();
+}
+
+cudaError_t launch_rope_table(const float* coords, int F, int H, int W, const float* scale3, int S, int D, float theta,
+                              float* cos_t, float* sin_t, cudaStream_t s) {
+    float m0, m1, m2;
+    if (coords != nullptr) {  // :454-460, multiply by f32(1/base)
+        m0 = static_cast<float>(1.0 / static_cast<double>(20.0f));
+        m1 = static_cast<float>(1.0 / static_cast<double>(2048.0f));
+        m2 = m1;
+    } else if (scale3 != nullptr) {
+        m0 = scale3[0]; m1 = scale3[1]; m2 = scale3[2];
+    } else {
+        m0 = m1 = m2 = 1.0f;
+    }
+    const int64_t n = static_cast<int64_t>(S) * (D / 2);
+    rope_table_kernel<<<blocks_for(n, 256), 256, 0, s>>>(coords, F, H, W, m0, m1, m2, S, D,
+                                                        static_cast<float>(log(static_cast<double>(theta))), cos_t, sin_t);
+    return done();
+}
+
+cudaError_t launch_gemv(const float* x, const void* w, const float* bias, float* y, int N, int K, int act_in,
+                        int act_out, cudaStream_t s) {
+    if (K % 8 != 0) return cudaErrorInvalidValue;
+    gemv_kernel<<<blocks_for(N, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+        x, reinterpret_cast<const __nv_bfloat16*>(w), bias, y, N, K, act_in, act_out);
+    return done();
+}
+
+cudaError_t launch_sinusoid(const float* t_dev, const float* t_mul, float* out256, int style, int round_bf16,
+                            cudaStream_t s) {
+    sinusoid_kernel<<<1, 128, 0, s>>>(t_dev, t_mul, out256, style, round_bf16);
+    return done();
+}
+
+cudaError_t launch_add_vec(const float* a, const float* b, float* d, int n, int period, cudaStream_t s) {
+    add_vec_kernel<<<blocks_for(n, 256), 256, 0, s>>>(a, b, d, n, period);
+    return done();
+}
+
+cudaError_t launch_mask_bias(const float* mask, float* bias, int n, cudaStream_t s) {
+    mask_bias_kernel<<<blocks_for(n, 256), 256, 0, s>>>(mask, bias, n);
+    return done();
+}
+
+cudaError_t launch_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s) {
+    f32_to_bf16_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    return done();
+}
+cudaError_t launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s) {
+    bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+    return done();
+}
+cudaError_t launch_blend(float* x, const float* orig, float m, int64_t n, cudaStream_t s) {
+    blend_kernel<<<blocks_for(n, 256), 256, 0, s>>>(x, orig, m, n);
+    return done();
+}
+
+cudaError_t launch_pack_latents(const float* in, float* out, int C, int F, int H, int W, int p, int pt, cudaStream_t s) {
+    if (p <= 0 || pt <= 0 || F % pt || H % p || W % p) return cudaErrorInvalidValue;
+    if (p == 1 && pt == 1) {
+        const int rows = C, cols = F * H * W;  // [C, N] -> [N, C]
+        transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s>>>(in, out, rows, cols);
+    } else {
+        const int64_t n = static_cast<int64_t>(C) * F * H * W;
+        pack_unpack_kernel<true><<<blocks_for(n, 256), 256, 0, s>>>(in, out, C, F, H, W, p, pt);
+    }
+    return done();
+}
+cudaError_t launch_unpack_latents(const float* in, float* out, int C, int F, int H, int W, int p, int pt,
+                                  cudaStream_t s) {
+    // F,H,W here are the *unpacked* (output) dims
+    if (p <= 0 || pt <= 0 || F % pt || H % p || W % p) return cudaErrorInvalidValue;
+    if (p == 1 && pt == 1) {
+        const int rows = F * H * W, cols = C;  // [N, C] -> [C, N]
+        transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s>>>(in, out, rows, cols);
+    } else {
+        const int64_t n = static_cast<int64_t>(C) * F * H * W;
+        pack_unpack_kernel<false><<<blocks_for(n, 256), 256, 0, s>>>(in, out, C, F, H, W, p, pt);
+    }
+    return done();
+}
+cudaError_t launch_video_coords(float* out, int F, int H, int W, int ts_ratio, int sp_ratio, int fps, cudaStream_t s) {
+    video_coords_kernel<<<blocks_for(static_cast<int64_t>(F) * H * W, 256), 256, 0, s>>>(
+        out, F, H, W, static_cast<float>(ts_ratio), static_cast<float>(sp_ratio),
+        static_cast<float>(1.0 / static_cast<double>(fps)));
+    return done();
+}
+
+cudaError_t launch_guidance_euler(const float* cond, const float* uncond, const float* pert, float* latents,
+                                  float* noise_out, int64_t n, float g, float r, float s_stg, float dt, double* scratch,
+                                  cudaStream_t s) {
+    if (r > 0.0f && uncond != nullptr) {
+        if (scratch == nullptr) return cudaErrorInvalidValue;
+        cudaError_t e = cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s);
+        if (e != cudaSuccess) return e;
+        int grid = blocks_for(n, 256 * 8);
+        if (grid > 1184) grid = 1184;
+        guidance_stats_kernel<<<grid, 256, 0, s>>>(cond, uncond, n, g, scratch);
+        g_glue_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    guidance_euler_kernel<<<blocks_for(n, 256), 256, 0, s>>>(cond, uncond, pert, latents, noise_out, n, g, r, s_stg, dt,
+                                                            scratch);
+    return done();
+}
+
+cudaError_t launch_denormalize(const float* in, float* out, const float* mean, const float* std, float inv_sf, int C,
+                               int64_t n_per_c, cudaStream_t s) {
+    denorm_kernel<<<blocks_for(C * n_per_c, 256), 256, 0, s>>>(in, out, mean, std, inv_sf, C, n_per_c);
+    return done();
+}
+cudaError_t launch_postprocess(const float* in, float* out, int64_t n, cudaStream_t s) {
+    postprocess_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(in, out, n);
+    return done();
+}
+
+}  // namespace ltxv

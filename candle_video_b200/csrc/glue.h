@@ -36,8 +36,11 @@ cudaError_t launch_gemv(const float* x, const void* w_bf16, const float* bias, f
 cudaError_t launch_sinusoid(const float* t_dev, const float* t_mul_dev, float* out256, int style, int round_bf16,
                             cudaStream_t s);
 
-// dst[i] = a[i] + b[i]  (small f32 vectors: scale_shift_table + temb)
-cudaError_t launch_add_vec(const float* a, const float* b, float* dst, int n, cudaStream_t s);
+// dst[i] = a[i] + b[i % period]  (small f32 vectors: scale_shift_table[L,6,D] + temb[6D])
+cudaError_t launch_add_vec(const float* a, const float* b, float* dst, int n, int period, cudaStream_t s);
+
+// bias[i] = (1 - mask[i]) * -10000  (ltx_transformer.rs:1059-1064)
+cudaError_t launch_mask_bias(const float* mask, float* bias, int n, cudaStream_t s);
 
 // f32 <-> bf16 converts
 cudaError_t launch_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);

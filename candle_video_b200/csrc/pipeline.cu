@@ -1,0 +1,158 @@
+// Host-side mirror of the hot part of `LtxPipeline::call` (t2v_pipeline.rs:627-1073): schedule math (kept as in the
+// reference, host f32), the denoise loop with sequential CFG / STG passes, and the decode branch.
+#include "pipeline.h"
+
+#include <math.h>
+
+#include "glue.h"
+
+namespace ltxv {
+
+// t2v_pipeline.rs:159-169 with the scheduler's static SchedulerConfig {256, 4096, 0.5, 1.15} (scheduler.rs:615-640)
+float calculate_shift(int seq_len) {
+    const float base_shift = 0.5f, max_shift = 1.15f;
+    const float m = (max_shift - base_shift) / static_cast<float>(4096 - 256);
+    const float b = base_shift - m * static_cast<float>(256);
+    return static_cast<float>(seq_len) * m + b;
+}
+
+// FlowMatchEulerDiscreteScheduler::set_timesteps as driven by the pipeline (scheduler.rs:274-412, :646-660)
+void scheduler_set_timesteps(int n, const float* custom_sigmas, float mu, bool has_terminal, float terminal,
+                             float* sigmas_out, int64_t* timesteps_out) {
+    if (n <= 0) fail("num_inference_steps must be positive");
+    std::vector<float> s(n);
+    if (custom_sigmas != nullptr) {
+        for (int i = 0; i < n; ++i) s[i] = custom_sigmas[i];
+    } else {
+        // t2v_pipeline.rs:752-757, linspace(1, 1/n, n) (:171-182)
+        const float start = 1.0f, end = 1.0f / static_cast<float>(n);
+        if (n == 1) {
+            s[0] = start;
+        } else {
+            const float denom = static_cast<float>(n - 1);
+            for (int i = 0; i < n; ++i) s[i] = start + (end - start) * static_cast<float>(i) / denom;
+        }
+    }
+    // exponential time shift, sigma exponent 1.0 (scheduler.rs:172-179, :341-346)
+    const float emu = expf(mu);
+    for (int i = 0; i < n; ++i) {
+        const float base = powf(1.0f / s[i] - 1.0f, 1.0f);
+        s[i] = emu / (emu + base);
+    }
+    if (has_terminal) {  // stretch_shift_to_terminal_vec (scheduler.rs:188-207)
+        const float one_minus_last = 1.0f - s[n - 1];
+        const float denom = 1.0f - terminal;
+        if (fabsf(denom) < 1e-12f) fail("shift_terminal too close to 1.0");
+        const float scale = one_minus_last / denom;
+        for (int i = 0; i < n; ++i) s[i] = 1.0f - ((1.0f - s[i]) / scale);
+    }
+    for (int i = 0; i < n; ++i) {
+        sigmas_out[i] = s[i];
+        timesteps_out[i] = static_cast<int64_t>(s[i] * 1000.0f);  // `x as i64` truncation (scheduler.rs:658-659)
+    }
+    sigmas_out[n] = 0.0f;
+}
+
+namespace {
+struct PipeWs {
+    DevBuf cond, uncond, pert, coords, ts, scratch, unpacked, denorm, tdec;
+};
+PipeWs& ws() {
+    static PipeWs w;
+    return w;
+}
+}  // namespace
+
+void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_params& p, float* latents,
+                      const void* prompt, const float* prompt_mask, const void* negative, const float* negative_mask,
+                      int embeds_dtype, int K, cudaStream_t s) {
+    // check_inputs (t2v_pipeline.rs:323-327)
+    if (p.height % 32 != 0 || p.width % 32 != 0)
+        fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
+    if (p.num_frames < 1 || p.frame_rate < 1) fail("num_frames and frame_rate must be positive");
+    const int F = (p.num_frames - 1) / 8 + 1, H = p.height / 32, W = p.width / 32;  // :743-747
+    const int S = F * H * W;
+    const int C = dit.config().in_channels;
+    const bool do_cfg = p.guidance_scale > 1.0f;  // :308-310
+    const bool do_stg = p.stg_scale > 0.0f;       // :304-306
+    if (do_cfg && negative == nullptr) fail("negative prompt embeddings are required when guidance_scale > 1");
+
+    // skip-block policy (:691-697)
+    if (p.skip_block_list != nullptr) {
+        if (!do_stg) dit.set_skip_block_list(p.skip_block_list, p.num_skip_blocks);
+        else dit.set_skip_block_list(nullptr, 0);
+    }
+    const int n = p.num_inference_steps;
+    std::vector<float> sigmas(n + 1);
+    std::vector<int64_t> tsteps(n);
+    const float mu = p.custom_sigmas ? 0.0f : calculate_shift(S);  // :762-773
+    scheduler_set_timesteps(n, p.custom_sigmas, mu, p.has_shift_terminal != 0, p.shift_terminal, sigmas.data(),
+                            tsteps.data());
+
+    PipeWs& w = ws();
+    const size_t out_bytes = static_cast<size_t>(S) * C * 4;
+    w.cond.ensure(out_bytes);
+    if (do_cfg) w.uncond.ensure(out_bytes);
+    if (do_stg) w.pert.ensure(out_bytes);
+    w.coords.ensure(static_cast<size_t>(S) * 3 * 4);
+    w.ts.ensure(static_cast<size_t>(n) * 4);
+    w.scratch.ensure(64);
+    std::vector<float> ts_f(n);
+    for (int i = 0; i < n; ++i) ts_f[i] = static_cast<float>(tsteps[i]);  // Tensor::full(t as f32) (:874)
+    LTXV_CUDA(cudaMemcpyAsync(w.ts.p, ts_f.data(), n * 4, cudaMemcpyHostToDevice, s));
+    LTXV_CUDA(cudaStreamSynchronize(s));  // ts_f is a stack-lifetime host buffer
+    LTXV_CUDA(launch_video_coords(w.coords.as<float>(), F, H, W, 8, 32, p.frame_rate, s));  // :798-847
+
+    dit.prepare_context(0, prompt, embeds_dtype, prompt_mask, K, s);
+    if (do_cfg) dit.prepare_context(1, negative, embeds_dtype, negative_mask, K, s);
+
+    std::vector<float> stg_mask;
+    if (do_stg) {  // :911-923, mask [num_layers, b=1]: 1 = skip
+        stg_mask.assign(dit.config().num_layers, 0.0f);
+        for (int i = 0; i < p.num_skip_blocks; ++i)
+            if (p.skip_block_list[i] >= 0 && p.skip_block_list[i] < dit.config().num_layers)
+                stg_mask[p.skip_block_list[i]] = 1.0f;
+    }
+    const float* coords = w.coords.as<float>();
+    for (int i = 0; i < n; ++i) {
+        const float* t_dev = w.ts.as<float>() + i;
+        if (do_cfg)
+            dit.forward_ctx(1, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, nullptr, 1, w.uncond.p, LTXV_F32, s);
+        dit.forward_ctx(0, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, nullptr, 1, w.cond.p, LTXV_F32, s);
+        if (do_stg)
+            dit.forward_ctx(0, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, stg_mask.data(), 1, w.pert.p,
+                            LTXV_F32, s);
+        const float dt = sigmas[i + 1] - sigmas[i];  // scheduler.rs:544-549
+        LTXV_CUDA(launch_guidance_euler(w.cond.as<float>(), do_cfg ? w.uncond.as<float>() : nullptr,
+                                        do_stg ? w.pert.as<float>() : nullptr, latents, nullptr,
+                                        static_cast<int64_t>(S) * C, p.guidance_scale, p.guidance_rescale, p.stg_scale,
+                                        dt, w.scratch.as<double>(), s));
+    }
+}
+
+void pipeline_decode(AutoencoderKLLtxVideo& vae, const ltxv_pipeline_params& p, const float* latents, float* out,
+                     cudaStream_t s) {
+    if (p.height % 32 != 0 || p.width % 32 != 0)
+        fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
+    const int F = (p.num_frames - 1) / 8 + 1, H = p.height / 32, W = p.width / 32;
+    const int C = vae.config().latent_channels;
+    const int64_t n = static_cast<int64_t>(C) * F * H * W;
+    PipeWs& w = ws();
+    w.unpacked.ensure(n * 4);
+    w.denorm.ensure(n * 4);
+    w.tdec.ensure(4);
+    LTXV_CUDA(launch_unpack_latents(latents, w.unpacked.as<float>(), C, F, H, W, 1, 1, s));  // :1002-1009
+    const float inv_sf = 1.0f / vae.config().scaling_factor;
+    LTXV_CUDA(launch_denormalize(w.unpacked.as<float>(), w.denorm.as<float>(), vae.latents_mean(), vae.latents_std(),
+                                 inv_sf, C, static_cast<int64_t>(F) * H * W, s));  // :1011-1016
+    const float* t_dev = nullptr;
+    if (vae.config().timestep_conditioning) {
+        LTXV_CUDA(cudaMemcpyAsync(w.tdec.p, &p.decode_timestep, 4, cudaMemcpyHostToDevice, s));
+        LTXV_CUDA(cudaStreamSynchronize(s));
+        t_dev = w.tdec.as<float>();
+    }
+    // decode_noise_scale = 0 (the reference's device-RNG noise blend, :1055-1062, is not reproduced here)
+    vae.decode(w.denorm.p, LTXV_F32, t_dev, 1, F, H, W, out, LTXV_F32, /*postprocess=*/1, s);  // :1069-1070
+}
+
+}  // namespace ltxv

@@ -1,0 +1,359 @@
+// AutoencoderKLLtxVideo (decoder) on B200: host-side sequencing (see vae.h).
+//
+// Data layout in HBM: activations are channels-last bf16.  Level l of the decoder works on a volume
+// (T_l, H_l, W_l, C_l) with T_{l+1} = 2 T_l - 1, H/W doubling, C = 1024, 512, 256, 128 (vae.rs:1547-1567).
+//   x / x_alt : unpadded NDHWC [T,H,W,C]          residual stream of the resnets (ping-pong)
+//   hb        : unpadded NDHWC                      conv1 output of a resnet
+//   p_[l]     : padded [(T+2),(H+2),(W+2),C_l]      conv input: H/W border = 0 (zero padding, vae.rs:344),
+//                                                   frames 0 / T+1 = copies of frames 1 / T (replicate, vae.rs:388-411)
+// A conv is then one GEMM launch over the padded-flat row space with 27 row-shifted A views (gemm.h); its epilogue
+// writes bias (+ residual), the depth-to-space scatter of the upsamplers, or the unpatchified f32 pixels.
+#include "vae.h"
+
+#include <math.h>
+
+#include "gemm.h"
+#include "glue.h"
+#include "vae_glue.h"
+
+namespace ltxv {
+
+float* AutoencoderKLLtxVideo::vec(int64_t n) {
+    storage_.emplace_back(new DevBuf());
+    storage_.back()->ensure(static_cast<size_t>(n) * sizeof(float), true);
+    return storage_.back()->as<float>();
+}
+
+void AutoencoderKLLtxVideo::add_plain(const std::string& key, void* dst, bool bf16, std::vector<int64_t> shape) {
+    VSlot v;
+    v.ps.key = key;
+    v.ps.dst = dst;
+    v.ps.dst_bf16 = bf16;
+    v.ps.shape = std::move(shape);
+    slots_[key] = std::move(v);
+}
+
+void AutoencoderKLLtxVideo::add_conv(const std::string& prefix, ConvW& cw, int Cin, int Cout, bool d2s, int rows_out) {
+    cw.Cin = Cin;
+    cw.Cout = Cout;
+    cw.rows_out = rows_out;
+    cw.d2s = d2s;
+    storage_.emplace_back(new DevBuf());
+    storage_.back()->ensure(static_cast<size_t>(rows_out) * 27 * Cin * 2, true);
+    cw.w = storage_.back()->as<__nv_bfloat16>();
+    cw.b = vec((rows_out + 255) / 256 * 256);
+    VSlot w;
+    w.ps.key = prefix + ".conv.weight";
+    w.ps.dst = cw.w;
+    w.ps.shape = {Cout, Cin, 3, 3, 3};
+    w.kind = CONV_W;
+    w.conv = &cw;
+    slots_[w.ps.key] = w;
+    VSlot b;
+    b.ps.key = prefix + ".conv.bias";
+    b.ps.dst = cw.b;
+    b.ps.dst_bf16 = false;
+    b.ps.shape = {Cout};
+    b.kind = CONV_B;
+    b.conv = &cw;
+    slots_[b.ps.key] = b;
+}
+
+void AutoencoderKLLtxVideo::add_time_embedder(const std::string& prefix, TimeEmbW& te, int dim) {
+    te.dim = dim;
+    auto mk = [&](LinearW& l, int N, int K, const std::string& name) {
+        l.N = N;
+        l.K = K;
+        storage_.emplace_back(new DevBuf());
+        storage_.back()->ensure(static_cast<size_t>(N) * K * 2, true);
+        l.w = storage_.back()->as<__nv_bfloat16>();
+        l.b = vec(N);
+        add_plain(prefix + "timestep_embedder." + name + ".weight", l.w, true, {N, K});
+        add_plain(prefix + "timestep_embedder." + name + ".bias", l.b, false, {N});
+    };
+    mk(te.l1, dim, 256, "linear_1");
+    mk(te.l2, dim, dim, "linear_2");
+}
+
+AutoencoderKLLtxVideo::AutoencoderKLLtxVideo(const ltxv_vae_config& cfg, int device) : cfg_(cfg), device_(device) {
+    require_cuda_device(device);
+    // reversed lists, upsample_factor 2 everywhere (vae.rs:1507-1567)
+    ch_[0] = cfg.decoder_block_out_channels[2];
+    ch_[1] = cfg.decoder_block_out_channels[2] / 2;
+    ch_[2] = cfg.decoder_block_out_channels[1] / 2;
+    ch_[3] = cfg.decoder_block_out_channels[0] / 2;
+    for (int l = 0; l < 4; ++l)
+        if (ch_[l] != 128 && ch_[l] != 256 && ch_[l] != 512 && ch_[l] != 1024)
+            fail("decoder level %d has %d channels; supported widths are 128/256/512/1024", l, ch_[l]);
+    if (ch_[1] * 2 != ch_[0] || ch_[2] * 2 != ch_[1] || ch_[3] * 2 != ch_[2])
+        fail("decoder_block_out_channels must halve per level (got %d,%d,%d,%d)", ch_[0], ch_[1], ch_[2], ch_[3]);
+    if (cfg.latent_channels % 64 != 0) fail("latent_channels must be a multiple of 64");
+    if (cfg.patch_size != 4 || cfg.out_channels != 3) fail("only patch_size 4 / 3 output channels are supported");
+    const std::string P = "decoder.";
+    add_conv(P + "conv_in", conv_in_, cfg.latent_channels, ch_[0], false, ch_[0]);
+    const char* level_prefix[4] = {"mid_block.", "up_blocks.0.", "up_blocks.1.", "up_blocks.2."};
+    for (int l = 0; l < 4; ++l) {
+        const int C = ch_[l];
+        const int n = cfg.decoder_layers_per_block[l];
+        const std::string bp = P + level_prefix[l];
+        if (l > 0) add_conv(bp + "upsamplers.0.conv", ups_[l - 1], ch_[l - 1], C * 8, true, C * 8);
+        res_[l].resize(n);
+        sst_[l] = vec(static_cast<int64_t>(n) * 4 * C);
+        for (int i = 0; i < n; ++i) {
+            const std::string rp = bp + "resnets." + std::to_string(i) + ".";
+            add_conv(rp + "conv1", res_[l][i].conv1, C, C, false, C);
+            add_conv(rp + "conv2", res_[l][i].conv2, C, C, false, C);
+            add_plain(rp + "scale_shift_table", sst_[l] + static_cast<int64_t>(i) * 4 * C, false, {4, C});
+        }
+        add_time_embedder(bp + "time_embedder.", te_[l], 4 * C);
+    }
+    const int C3 = ch_[3];
+    add_conv(P + "conv_out", conv_out_, C3, cfg.out_channels * 16, false, 64);
+    add_time_embedder(P + "time_embedder.", te_final_, 2 * C3);
+    sst_final_ = vec(2 * C3);
+    add_plain(P + "scale_shift_table", sst_final_, false, {2, C3});
+    tsm_ = vec(1);
+    add_plain(P + "timestep_scale_multiplier", tsm_, false, {});
+    latents_mean_ = vec(cfg.latent_channels);
+    latents_std_ = vec(cfg.latent_channels);
+    fill_const(latents_std_, false, cfg.latent_channels, 1.0f);  // config default (vae.rs:91-92)
+    fill_const(tsm_, false, 1, 1.0f);
+    add_plain("latents_mean", latents_mean_, false, {cfg.latent_channels});
+    add_plain("latents_std", latents_std_, false, {cfg.latent_channels});
+    LTXV_CUDA(cudaDeviceSynchronize());
+}
+
+AutoencoderKLLtxVideo::~AutoencoderKLLtxVideo() = default;
+
+void AutoencoderKLLtxVideo::load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape,
+                                        int rank) {
+    auto it = slots_.find(key);
+    if (it == slots_.end()) {
+        // The reference also builds an encoder / quant convs the t2v path never runs (vae.rs:1772-1808): ignore.
+        if (key.rfind("encoder.", 0) == 0 || key.rfind("quant_conv", 0) == 0 || key.rfind("post_quant_conv", 0) == 0)
+            return;
+        fail("unknown VAE tensor key '%s'", key.c_str());
+    }
+    VSlot& v = it->second;
+    bool ok = rank == static_cast<int>(v.ps.shape.size());
+    for (int i = 0; ok && i < rank; ++i) ok = shape[i] == v.ps.shape[i];
+    if (!ok) fail("shape mismatch for VAE tensor '%s'", key.c_str());
+    LTXV_CUDA(cudaSetDevice(device_));
+    if (v.kind == PLAIN) {
+        ingest_tensor(v.ps.dst, v.ps.dst_bf16, data, dtype, v.ps.numel());
+    } else {
+        DevBuf tmp;
+        tmp.ensure(static_cast<size_t>(v.ps.numel()) * 4);
+        ingest_tensor(tmp.p, false, data, dtype, v.ps.numel());
+        const ConvW& cw = *v.conv;
+        if (v.kind == CONV_W)
+            LTXV_CUDA(launch_conv_weight_relayout(tmp.p, 0, cw.w, cw.Cout, cw.Cin, cw.rows_out, cw.d2s, 0));
+        else
+            LTXV_CUDA(launch_conv_bias_relayout(tmp.p, 0, cw.b, cw.Cout, cw.rows_out, cw.d2s, 0));
+        LTXV_CUDA(cudaDeviceSynchronize());
+    }
+    v.ps.loaded = true;
+    finalized_ = false;
+}
+
+void AutoencoderKLLtxVideo::init_random(uint64_t seed) {
+    LTXV_CUDA(cudaSetDevice(device_));
+    uint64_t n = 0;
+    for (auto& kv : slots_) {
+        VSlot& v = kv.second;
+        const std::string& k = v.ps.key;
+        const uint64_t sd = seed * 7919ull + (++n);
+        if (k == "latents_mean" || k == "latents_std") {
+            v.ps.loaded = true;
+            continue;
+        }
+        if (k.size() >= 25 && k.compare(k.size() - 25, 25, "timestep_scale_multiplier") == 0) {
+            fill_const(v.ps.dst, false, 1, 1000.0f);
+        } else if (v.kind == CONV_W) {
+            // generated directly in GEMM layout; the distribution is layout invariant. Padded rows stay zero.
+            fill_uniform(v.ps.dst, true, static_cast<int64_t>(v.conv->Cout) * 27 * v.conv->Cin,
+                         1.0f / sqrtf(27.0f * v.conv->Cin), sd);
+        } else if (v.kind == CONV_B) {
+            fill_uniform(v.ps.dst, false, v.conv->Cout, 0.05f, sd);
+        } else if (k.size() >= 17 && k.compare(k.size() - 17, 17, "scale_shift_table") == 0) {
+            fill_normal(v.ps.dst, false, v.ps.numel(), 0.f, 1.0f / sqrtf(static_cast<float>(v.ps.shape.back())), sd);
+        } else if (k.size() >= 5 && k.compare(k.size() - 5, 5, ".bias") == 0) {
+            fill_uniform(v.ps.dst, v.ps.dst_bf16, v.ps.numel(), 0.05f, sd);
+        } else {
+            fill_uniform(v.ps.dst, v.ps.dst_bf16, v.ps.numel(), 1.0f / sqrtf(static_cast<float>(v.ps.shape.back())), sd);
+        }
+        v.ps.loaded = true;
+    }
+    LTXV_CUDA(cudaDeviceSynchronize());
+    finalized_ = true;
+}
+
+void AutoencoderKLLtxVideo::finalize() {
+    std::string missing;
+    int n = 0;
+    for (auto& kv : slots_) {
+        const std::string& k = kv.first;
+        if (kv.second.ps.loaded) continue;
+        if (k == "latents_mean" || k == "latents_std") continue;  // optional (vae.rs:1827-1838)
+        if (!cfg_.timestep_conditioning &&
+            (k.find("time_embedder") != std::string::npos || k.find("scale_shift_table") != std::string::npos ||
+             k.find("timestep_scale_multiplier") != std::string::npos))
+            continue;
+        // The reference tolerates missing conditioning tensors with `.ok()` (vae.rs:692,:986,:1260,:1601-1604) and
+        // silently drops the conditioning; here they are required when timestep_conditioning is on.
+        if (n < 8) missing += (n ? ", " : "") + k;
+        ++n;
+    }
+    if (n) fail("%d VAE decoder tensors were never loaded (first: %s)", n, missing.c_str());
+    finalized_ = true;
+}
+
+void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
+    if (F == wsF_ && H == wsH_ && W == wsW_) return;
+    T_[0] = F;
+    H_[0] = H;
+    W_[0] = W;
+    for (int l = 1; l < 4; ++l) {
+        T_[l] = 2 * T_[l - 1] - 1;
+        H_[l] = 2 * H_[l - 1];
+        W_[l] = 2 * W_[l - 1];
+    }
+    size_t max_unpadded = 0;
+    for (int l = 0; l < 4; ++l) {
+        const size_t padded = static_cast<size_t>(T_[l] + 2) * (H_[l] + 2) * (W_[l] + 2) * ch_[l] * 2;
+        // geometry changed: the zero border must be re-established
+        p_[l].release();
+        p_[l].ensure(padded, true);
+        const size_t un = static_cast<size_t>(T_[l]) * H_[l] * W_[l] * ch_[l] * 2;
+        if (un > max_unpadded) max_unpadded = un;
+    }
+    a0_.release();
+    a0_.ensure(static_cast<size_t>(F + 2) * (H + 2) * (W + 2) * cfg_.latent_channels * 2, true);
+    xa_.ensure(max_unpadded);
+    xb_.ensure(max_unpadded);
+    hb_.ensure(max_unpadded);
+    size_t cond = 256 + 4096 + 4096;
+    for (int l = 0; l < 4; ++l) cond += static_cast<size_t>(cfg_.decoder_layers_per_block[l]) * 4 * ch_[l];
+    cond += 2 * ch_[3];
+    cond_.ensure(cond * 4);
+    wsF_ = F;
+    wsH_ = H;
+    wsW_ = W;
+}
+
+void AutoencoderKLLtxVideo::conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out,
+                                 const void* res, int post, cudaStream_t s) {
+    const int Wp = W + 2, plane = (H + 2) * Wp;
+    GemmOperands ops{a_padded, static_cast<int64_t>(T + 2) * plane, cw.Cin, cw.w, cw.rows_out, 27ll * cw.Cin};
+    GemmParams p{};
+    p.M = T * plane;
+    p.N = cw.Cout;
+    p.K = 27 * cw.Cin;
+    p.num_k_blocks = 27 * (cw.Cin / 64);
+    p.epi = epi;
+    p.ldo = cw.Cout;
+    p.bias = cw.b;
+    p.out = out;
+    p.res_bf16 = res;
+    p.conv = 1;
+    p.cin_blocks = cw.Cin / 64;
+    p.T = T;
+    p.H = H;
+    p.W = W;
+    p.cin = cw.Cin;
+    p.a_ptr = a_padded;
+    p.post_u8_scale = post;
+    for (int kt = 0; kt < 3; ++kt)
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) p.tap_off[(kt * 3 + kh) * 3 + kw] = kt * plane + (kh - 1) * Wp + (kw - 1);
+    LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
+}
+
+// LtxVideoResnetBlock3d::forward (vae.rs:755-821), in == out
+void AutoencoderKLLtxVideo::resnet(const ResnetW& rw, int l, const float* ss, __nv_bfloat16*& x, __nv_bfloat16*& x_alt,
+                                   cudaStream_t s) {
+    const int C = ch_[l], T = T_[l], H = H_[l], W = W_[l];
+    // ss = [shift1, scale1, shift2, scale2] (vae.rs:734-735)
+    LTXV_CUDA(launch_vae_prep(x, p_[l].p, ss ? ss + C : nullptr, ss ? ss : nullptr, 1, 1, T, H, W, C, s));
+    conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, 0, s);
+    LTXV_CUDA(launch_vae_prep(hb_.p, p_[l].p, ss ? ss + 3 * C : nullptr, ss ? ss + 2 * C : nullptr, 1, 1, T, H, W, C, s));
+    conv(rw.conv2, p_[l].p, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s);
+    std::swap(x, x_alt);
+}
+
+void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* timestep_dev, int B, int F, int H, int W,
+                                   void* out, int out_dtype, int postprocess, cudaStream_t s) {
+    if (!finalized_) finalize();
+    if (B <= 0 || F <= 0 || H <= 0 || W <= 0) fail("decode: invalid latent shape [%d,%d,%d,%d,%d]", B, cfg_.latent_channels, F, H, W);
+    if (z_dtype != LTXV_F32 && z_dtype != LTXV_BF16) fail("unsupported latent dtype %d", z_dtype);
+    if (out_dtype != LTXV_F32 && out_dtype != LTXV_BF16) fail("unsupported output dtype %d", out_dtype);
+    LTXV_CUDA(cudaSetDevice(device_));
+    ensure_workspace(F, H, W);
+    const bool cond = cfg_.timestep_conditioning && timestep_dev != nullptr;
+    const size_t zsz = z_dtype == LTXV_F32 ? 4 : 2;
+    const int64_t z_elems = static_cast<int64_t>(cfg_.latent_channels) * F * H * W;
+    const int To = T_[3], Ho = 4 * H_[3], Wo = 4 * W_[3];
+    const int64_t out_elems = 3ll * To * Ho * Wo;
+    if (out_dtype == LTXV_BF16) out_f32_.ensure(static_cast<size_t>(out_elems) * 4);
+
+    float* cb = cond_.as<float>();
+    float* sin256 = cb;
+    float* t1 = sin256 + 256;
+    float* tproj = t1 + 4096;
+    float* ss[4];
+    {
+        float* q = tproj + 4096;
+        for (int l = 0; l < 4; ++l) {
+            ss[l] = q;
+            q += static_cast<size_t>(cfg_.decoder_layers_per_block[l]) * 4 * ch_[l];
+        }
+    }
+    float* ssf = ss[3] + static_cast<size_t>(cfg_.decoder_layers_per_block[3]) * 4 * ch_[3];
+
+    for (int b = 0; b < B; ++b) {
+        const char* zb = static_cast<const char*>(z) + static_cast<size_t>(b) * z_elems * zsz;
+        if (cond) {
+            // temb * timestep_scale_multiplier (vae.rs:1669-1677) -> per-block embedders (vae.rs:998-1018, :1291-1298)
+            LTXV_CUDA(launch_sinusoid(timestep_dev + b, tsm_, sin256, 1, 0, s));
+            for (int l = 0; l < 4; ++l) {
+                const int dim = te_[l].dim;
+                LTXV_CUDA(launch_gemv(sin256, te_[l].l1.w, te_[l].l1.b, t1, dim, 256, GEMV_NONE, GEMV_SILU, s));
+                LTXV_CUDA(launch_gemv(t1, te_[l].l2.w, te_[l].l2.b, tproj, dim, dim, GEMV_NONE, GEMV_NONE, s));
+                LTXV_CUDA(launch_add_vec(sst_[l], tproj, ss[l], cfg_.decoder_layers_per_block[l] * dim, dim, s));
+            }
+            const int dim = te_final_.dim;  // 2 * C3: [shift | scale] (vae.rs:1702-1711)
+            LTXV_CUDA(launch_gemv(sin256, te_final_.l1.w, te_final_.l1.b, t1, dim, 256, GEMV_NONE, GEMV_SILU, s));
+            LTXV_CUDA(launch_gemv(t1, te_final_.l2.w, te_final_.l2.b, tproj, dim, dim, GEMV_NONE, GEMV_NONE, s));
+            LTXV_CUDA(launch_add_vec(sst_final_, tproj, ssf, dim, dim, s));
+        }
+        // conv_in (vae.rs:1664)
+        LTXV_CUDA(launch_vae_input(zb, z_dtype == LTXV_BF16, a0_.p, cfg_.latent_channels, F, H, W, s));
+        __nv_bfloat16* x = xa_.as<__nv_bfloat16>();
+        __nv_bfloat16* x_alt = xb_.as<__nv_bfloat16>();
+        conv(conv_in_, a0_.p, T_[0], H_[0], W_[0], EPI_CONV_NDHWC, x, nullptr, 0, s);
+        for (int l = 0; l < 4; ++l) {
+            if (l > 0) {
+                // LtxVideoUpsampler3d (vae.rs:1090-1169): conv on the raw x, depth-to-space + residual in the epilogue
+                const int lp = l - 1;
+                LTXV_CUDA(launch_vae_prep(x, p_[lp].p, nullptr, nullptr, 0, 0, T_[lp], H_[lp], W_[lp], ch_[lp], s));
+                conv(ups_[lp], p_[lp].p, T_[lp], H_[lp], W_[lp], EPI_CONV_D2S, x_alt, nullptr, 0, s);
+                std::swap(x, x_alt);
+            }
+            const int C = ch_[l];
+            for (size_t i = 0; i < res_[l].size(); ++i)
+                resnet(res_[l][i], l, cond ? ss[l] + i * 4 * C : nullptr, x, x_alt, s);
+        }
+        // norm_out -> scale/shift -> SiLU -> conv_out -> unpatchify (vae.rs:1686-1725)
+        const int C3 = ch_[3];
+        LTXV_CUDA(launch_vae_prep(x, p_[3].p, cond ? ssf + C3 : nullptr, cond ? ssf : nullptr, 1, 1, T_[3], H_[3], W_[3],
+                                  C3, s));
+        float* o32 = out_dtype == LTXV_F32 ? static_cast<float*>(out) + static_cast<size_t>(b) * out_elems
+                                           : out_f32_.as<float>();
+        conv(conv_out_, p_[3].p, T_[3], H_[3], W_[3], EPI_CONV_UNPATCHIFY, o32, nullptr, postprocess, s);
+        if (out_dtype == LTXV_BF16)
+            LTXV_CUDA(launch_f32_to_bf16(o32, static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(b) * out_elems,
+                                         out_elems, s));
+    }
+}
+
+}  // namespace ltxv

@@ -1,0 +1,84 @@
+// C++ host-side mirror of `AutoencoderKLLtxVideo` (decoder half; vae.rs:1472-1727, :2037-2136): owns the re-laid-out
+// bf16 conv weights and the NDHWC workspace, sequences the implicit-GEMM conv3d kernel and the glue kernels.
+// Bound to `Box<dyn VaeLtxVideo>` (t2v_pipeline.rs:91-103) through the C ABI in ffi.cu.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "dit.h"  // LinearW
+#include "model_common.h"
+
+namespace ltxv {
+
+struct ConvW {
+    __nv_bfloat16* w = nullptr;  // [rows_out, 27*Cin], k = tap*Cin + c
+    float* b = nullptr;          // [rows_out padded]
+    int Cin = 0, Cout = 0, rows_out = 0;
+    bool d2s = false;  // output channels stored sub-voxel major (upsampler)
+};
+struct ResnetW {
+    ConvW conv1, conv2;
+};
+struct TimeEmbW {
+    LinearW l1, l2;  // 256 -> dim -> dim
+    int dim = 0;
+};
+
+class AutoencoderKLLtxVideo {
+public:
+    AutoencoderKLLtxVideo(const ltxv_vae_config& cfg, int device);
+    ~AutoencoderKLLtxVideo();
+
+    const ltxv_vae_config& config() const { return cfg_; }
+    void load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape, int rank);
+    void init_random(uint64_t seed);
+    void finalize();
+    const float* latents_mean() const { return latents_mean_; }
+    const float* latents_std() const { return latents_std_; }
+    int spatial_compression_ratio() const { return 32; }   // vae.rs:85
+    int temporal_compression_ratio() const { return 8; }   // vae.rs:86
+
+    // z [B, C, F, H, W] -> out f32/bf16 [B, 3, 8F-7, 32H, 32W]
+    void decode(const void* z, int z_dtype, const float* timestep_dev, int B, int F, int H, int W, void* out,
+                int out_dtype, int postprocess, cudaStream_t s);
+
+private:
+    enum SlotKind { PLAIN = 0, CONV_W = 1, CONV_B = 2 };
+    struct VSlot {
+        ParamSlot ps;
+        int kind = PLAIN;
+        ConvW* conv = nullptr;
+    };
+    void add_plain(const std::string& key, void* dst, bool bf16, std::vector<int64_t> shape);
+    void add_conv(const std::string& prefix, ConvW& cw, int Cin, int Cout, bool d2s, int rows_out);
+    void add_time_embedder(const std::string& prefix, TimeEmbW& te, int dim);
+    float* vec(int64_t n);
+    void ensure_workspace(int F, int H, int W);
+    void conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out, const void* res, int post,
+              cudaStream_t s);
+    void resnet(const ResnetW& rw, int level, const float* ss, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s);
+
+    ltxv_vae_config cfg_;
+    int device_;
+    bool finalized_ = false;
+    std::vector<std::unique_ptr<DevBuf>> storage_;
+    std::map<std::string, VSlot> slots_;
+
+    int ch_[4];  // channel width per level: 1024, 512, 256, 128
+    ConvW conv_in_, conv_out_, ups_[3];
+    std::vector<ResnetW> res_[4];  // mid, up0, up1, up2
+    float* sst_[4] = {nullptr, nullptr, nullptr, nullptr};  // [n_res, 4, C] per level
+    TimeEmbW te_[4], te_final_;
+    float* sst_final_ = nullptr;  // [2, C3]
+    float* tsm_ = nullptr;        // timestep_scale_multiplier (device scalar)
+    float *latents_mean_ = nullptr, *latents_std_ = nullptr;
+
+    // workspace
+    int wsF_ = 0, wsH_ = 0, wsW_ = 0;
+    int T_[4], H_[4], W_[4];
+    DevBuf a0_, p_[4], xa_, xb_, hb_, cond_, out_f32_;
+};
+
+}  // namespace ltxv

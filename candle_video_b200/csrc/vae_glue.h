@@ -1,0 +1,31 @@
+// Bandwidth-bound kernels of the VAE decoder (vae_glue.cu).  Activations live in HBM as channels-last (NDHWC) bf16;
+// every conv input is a zero-bordered (H, W) / replicate-padded (T) copy so that CausalConv3d becomes 27 row-shifted
+// GEMM views (see gemm.h).  SURVEY.md §2b rows V2, V3, K18.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ltxv {
+
+// z [C, F, H, W] (NCDHW, f32 or bf16) -> padded NDHWC bf16 [(F+2), (H+2), (W+2), C]; frames 0 / F+1 replicate
+// frames 1 / F (non-causal decoder padding, vae.rs:388-411); the H/W border is left untouched (must be zero).
+cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out_padded, int C, int F, int H, int W, cudaStream_t s);
+
+// x bf16 [T,H,W,C] (unpadded NDHWC) -> padded bf16 [(T+2),(H+2),(W+2),C] with optional
+//   pixel norm (RMS over C, eps 1e-8, vae.rs:148-153), x*(1+scale)+shift (vae.rs:736-738), SiLU (vae.rs:161-163).
+// scale/shift: f32 [C] or null.
+cudaError_t launch_vae_prep(const void* x, void* out_padded, const float* scale, const float* shift, int do_norm,
+                            int do_silu, int T, int H, int W, int C, cudaStream_t s);
+
+// Conv3d weight [Cout, Cin, 3,3,3] (f32 or bf16, device) -> GEMM B matrix bf16 [rows_out, 27*Cin], k = tap*Cin + c.
+// d2s_perm: output channel co = c'*8 + sub is stored at row sub*(Cout/8) + c' (upsampler, see EPI_CONV_D2S).
+// rows_out >= Cout; extra rows are zero.
+cudaError_t launch_conv_weight_relayout(const void* w, int w_is_bf16, void* out, int Cout, int Cin, int rows_out,
+                                        int d2s_perm, cudaStream_t s);
+// bias [Cout] (f32 or bf16) -> f32 [rows_out] with the same row permutation / zero padding
+cudaError_t launch_conv_bias_relayout(const void* b, int b_is_bf16, float* out, int Cout, int rows_out, int d2s_perm,
+                                      cudaStream_t s);
+
+uint64_t vae_glue_launch_count();
+
+}  // namespace ltxv

@@ -1,0 +1,191 @@
+/* ltxv.h -- C ABI of libltxv_b200.so: the B200-native (sm_100a) drop-in for the LTX-Video hot path of
+ * FerrisMind/candle-video.
+ *
+ * Every entry point replaces one reference interface (Rust, cited as file:line under /root/reference):
+ *
+ *   ltxv_dit_*        <->  `trait VideoTransformer3D` (src/models/ltx_video/t2v_pipeline.rs:63-83) as implemented by
+ *                          `LtxVideoTransformer3DModel` (ltx_transformer.rs:1029-1215); construction through
+ *                          `VarBuilder` key names (ltx_transformer.rs:957-1022)
+ *   ltxv_vae_*        <->  `trait VaeLtxVideo` (t2v_pipeline.rs:91-103) as implemented by `AutoencoderKLLtxVideo`
+ *                          (vae.rs:2437-2463 -> :2101 decode -> :1656 LtxVideoDecoder3d::forward)
+ *   ltxv_pack_latents / ltxv_unpack_latents   <->  LtxPipeline::pack_latents / unpack_latents (t2v_pipeline.rs:474-550)
+ *   ltxv_video_coords                          <->  the coordinate grid built inline at t2v_pipeline.rs:798-847
+ *   ltxv_guidance_euler_step                   <->  CFG/STG combine (t2v_pipeline.rs:942-964), rescale_noise_cfg (:227-243)
+ *                                                   and FlowMatchEulerDiscreteScheduler::step (scheduler.rs:544-582)
+ *   ltxv_denormalize_latents / ltxv_postprocess_video <-> t2v_pipeline.rs:573-594 / :146-155
+ *   ltxv_scheduler_set_timesteps               <->  Scheduler::set_timesteps as driven by LtxPipeline::call
+ *                                                   (scheduler.rs:274-412, :646-660; t2v_pipeline.rs:752-792) -- host math
+ *   ltxv_pipeline_denoise / ltxv_pipeline_decode <-> LtxPipeline::call denoise loop (:860-994) and decode branch (:1000-1072)
+ *
+ * Conventions
+ *   - plain C types only; opaque handles; tensors are caller-owned, contiguous, row-major.
+ *   - `*_host` variants take HOST pointers and include the host<->device copies and a stream sync; all other tensor
+ *     arguments are DEVICE pointers and the call only enqueues work on `stream` (a cudaStream_t; NULL = default stream)
+ *     without synchronising, like a Candle CustomOp (cf. candle_flash_attn::flash_attn, ltx_transformer.rs:707).
+ *   - return value 0 = success, non-zero = error; ltxv_last_error() returns the message for the calling thread
+ *     (the reference returns candle_core::Error::Msg for the same conditions, e.g. ltx_transformer.rs:451-453,:834-844).
+ *   - dtype codes: LTXV_F32 = 0, LTXV_BF16 = 1.  The model computes in bf16 with f32 accumulation and f32
+ *     norm / softmax / GELU / RoPE math; there is no CPU fallback: without a CUDA device every
+ *     compute entry point fails with an error.
+ */
+#ifndef LTXV_H_
+#define LTXV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTXV_F32 0
+#define LTXV_BF16 1
+
+typedef struct ltxv_dit ltxv_dit;
+typedef struct ltxv_vae ltxv_vae;
+
+const char* ltxv_last_error(void);
+const char* ltxv_version(void);
+/* kernels launched by this library since process start (all streams); evidence for bench.py's gpu_launches */
+uint64_t ltxv_launch_count(void);
+
+/* ------------------------------------------------------------------ DiT ------------------------------------------ */
+/* LtxVideoTransformer3DModelConfig, ltx_transformer.rs:22-59 */
+typedef struct ltxv_dit_config {
+    int32_t in_channels;          /* 128 */
+    int32_t out_channels;         /* 128 */
+    int32_t patch_size;           /* 1 */
+    int32_t patch_size_t;         /* 1 */
+    int32_t num_attention_heads;  /* 32 */
+    int32_t attention_head_dim;   /* 64 (2B) | 128 (13B) */
+    int32_t cross_attention_dim;  /* 2048 | 4096 */
+    int32_t num_layers;           /* 28 | 48 */
+    int32_t caption_channels;     /* 4096 */
+    float norm_eps;               /* 1e-6 */
+    int32_t timestep_bf16_round;  /* 1: replay `timestep.to_dtype(bf16)` of a bf16 model (ltx_transformer.rs:1051) */
+} ltxv_dit_config;
+
+/* presets configs.rs:135-160: "2b", "13b" */
+int ltxv_dit_config_preset(const char* name, ltxv_dit_config* out);
+
+int ltxv_dit_create(const ltxv_dit_config* cfg, int device, ltxv_dit** out);
+void ltxv_dit_destroy(ltxv_dit* m);
+/* Copy one tensor into the model. `key` is the diffusers / VarBuilder name, `data` may be a
+ * host or a device pointer, dtype f32 or bf16; the shape must match the reference's. */
+int ltxv_dit_load_tensor(ltxv_dit* m, const char* key, const void* data, int dtype, const int64_t* shape, int rank);
+/* Synthetic random-init weights of the configured architecture, generated on the device (benchmarks). */
+int ltxv_dit_init_random(ltxv_dit* m, uint64_t seed);
+/* Fails (listing the missing keys) unless every tensor of the architecture has been loaded. */
+int ltxv_dit_finalize(ltxv_dit* m);
+/* VideoTransformer3D::set_skip_block_list, ltx_transformer.rs:1024-1026 */
+int ltxv_dit_set_skip_blocks(ltxv_dit* m, const int32_t* idx, int n);
+/* TransformerConfig accessors (t2v_pipeline.rs:55-61) */
+int ltxv_dit_get_config(const ltxv_dit* m, ltxv_dit_config* out);
+
+/* VideoTransformer3D::forward (t2v_pipeline.rs:63-83).  Device pointers:
+ *   hidden [B,S,in_channels] (hidden_dtype), enc [B,K,caption_channels] (enc_dtype), timestep f32 [B],
+ *   mask f32 [B,K] (1 keep / 0 pad; may be NULL = no mask), video_coords f32 [B,S,3] or NULL,
+ *   out [B,S,out_channels] (out_dtype).
+ * Host pointers (tiny control data): rope_scale3 (3 floats, or NULL), skip_layer_mask f32 [num_layers, B] or NULL. */
+int ltxv_dit_forward(ltxv_dit* m, const void* hidden, int hidden_dtype, const void* enc, int enc_dtype,
+                     const float* timestep, const float* mask, int B, int S, int K, int F, int H, int W,
+                     const float* rope_scale3, const float* video_coords, const float* skip_layer_mask, void* out,
+                     int out_dtype, void* stream);
+/* Same call on HOST buffers: copies inputs to the device, runs, copies the result back, synchronises. */
+int ltxv_dit_forward_host(ltxv_dit* m, const void* hidden, int hidden_dtype, const void* enc, int enc_dtype,
+                          const float* timestep, const float* mask, int B, int S, int K, int F, int H, int W,
+                          const float* rope_scale3, const float* video_coords, const float* skip_layer_mask, void* out,
+                          int out_dtype);
+
+/* Step-invariant text path, hoisted: caption projection (ltx_transformer.rs:186-190) and every block's cross-attention
+ * K/V projection + k-norm (:667-672) computed once into context slot `slot` (0..3) for a [K,caption_channels] prompt
+ * (one batch entry).  ltxv_dit_forward_ctx then runs VideoTransformer3D::forward for B = 1 against that slot. */
+int ltxv_dit_prepare_context(ltxv_dit* m, int slot, const void* enc, int enc_dtype, const float* mask, int K,
+                             void* stream);
+int ltxv_dit_forward_ctx(ltxv_dit* m, int slot, const void* hidden, int hidden_dtype, const float* timestep, int S,
+                         int F, int H, int W, const float* rope_scale3, const float* video_coords,
+                         const float* skip_layer_mask, void* out, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------ VAE ------------------------------------------ */
+/* AutoencoderKLLtxVideoConfig, decoder-relevant fields (vae.rs:30-103, configs.rs:84-93) */
+typedef struct ltxv_vae_config {
+    int32_t latent_channels;                /* 128 */
+    int32_t out_channels;                   /* 3 */
+    int32_t decoder_block_out_channels[3];  /* 256, 512, 1024 */
+    int32_t decoder_layers_per_block[4];    /* 5, 5, 5, 5 */
+    int32_t patch_size;                     /* 4 */
+    int32_t timestep_conditioning;          /* 1 */
+    float scaling_factor;                   /* 1.0 */
+} ltxv_vae_config;
+
+int ltxv_vae_config_default(ltxv_vae_config* out);
+int ltxv_vae_create(const ltxv_vae_config* cfg, int device, ltxv_vae** out);
+void ltxv_vae_destroy(ltxv_vae* m);
+/* keys carry the reference's `decoder.` prefix; `latents_mean` / `latents_std` (top level) are optional.
+ * `encoder.*` and other unknown keys are accepted and ignored (the reference builds an encoder the t2v path never runs). */
+int ltxv_vae_load_tensor(ltxv_vae* m, const char* key, const void* data, int dtype, const int64_t* shape, int rank);
+int ltxv_vae_init_random(ltxv_vae* m, uint64_t seed);
+int ltxv_vae_finalize(ltxv_vae* m);
+/* VaeLtxVideo accessors (t2v_pipeline.rs:91-99): 128-entry f32 device vectors, ratios 32 / 8 */
+const float* ltxv_vae_latents_mean(const ltxv_vae* m);
+const float* ltxv_vae_latents_std(const ltxv_vae* m);
+int ltxv_vae_spatial_compression_ratio(const ltxv_vae* m);
+int ltxv_vae_temporal_compression_ratio(const ltxv_vae* m);
+
+/* VaeLtxVideo::decode (t2v_pipeline.rs:102): z [B,128,F,H,W] NCDHW (z_dtype) -> out [B,3,8F-7,32H,32W] NCDHW.
+ * timestep: device f32 [B] or NULL.  postprocess != 0 additionally applies LtxVideoProcessor::postprocess_video
+ * (clamp(0.5x+0.5,0,1)*255, t2v_pipeline.rs:147-155) in the last kernel's epilogue. */
+int ltxv_vae_decode(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
+                    void* out, int out_dtype, int postprocess, void* stream);
+int ltxv_vae_decode_host(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
+                         void* out, int out_dtype, int postprocess);
+
+/* ------------------------------------------------------------- pipeline glue -------------------------------------- */
+/* f32 device tensors.  pack: [B,C,F,H,W] -> [B,S,C*pt*p*p]; unpack is the inverse (F,H,W = unpacked dims). */
+int ltxv_pack_latents(const float* in, float* out, int B, int C, int F, int H, int W, int p, int pt, void* stream);
+int ltxv_unpack_latents(const float* in, float* out, int B, int C, int F, int H, int W, int p, int pt, void* stream);
+/* out f32 [B,S,3]: (clamp(ts*f + 1 - ts, 0, 1000) * (float)(1/fps), sp*h, sp*w) in f,h,w token order */
+int ltxv_video_coords(float* out, int B, int F, int H, int W, int ts_ratio, int sp_ratio, int fps, void* stream);
+/* cond / uncond / perturbed / latents / noise_pred_out: f32 [B, n_per_batch] (uncond, perturbed, noise_pred_out,
+ * latents may be NULL).  comb = u + g(c-u) [rescaled] + s(c-p); latents += (sigma_next - sigma) * comb. */
+int ltxv_guidance_euler_step(const float* cond, const float* uncond, const float* perturbed, float* latents,
+                             float* noise_pred_out, int B, int64_t n_per_batch, float guidance_scale,
+                             float guidance_rescale, float stg_scale, float sigma, float sigma_next, void* stream);
+/* in/out f32 [B,C,n_per_channel]; mean/std device f32 [C] */
+int ltxv_denormalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,
+                             int B, int C, int64_t n_per_channel, void* stream);
+int ltxv_postprocess_video(const float* in, float* out, int64_t n, void* stream);
+
+/* Host-only schedule math (stays as in the reference): writes num_steps+1 sigmas (terminal 0 appended) and num_steps
+ * integer-truncated timesteps.  custom_sigmas may be NULL (then linspace(1, 1/n, n) with the SD3 shift mu). */
+int ltxv_calculate_shift(int seq_len, float* mu_out);
+int ltxv_scheduler_set_timesteps(int num_steps, const float* custom_sigmas, float mu, int has_shift_terminal,
+                                 float shift_terminal, float* sigmas_out, int64_t* timesteps_out);
+
+/* ------------------------------------------------------------- pipeline ------------------------------------------- */
+/* LtxPipeline::call with precomputed prompt embeddings (examples/ltx-video/main.rs:621-646). */
+typedef struct ltxv_pipeline_params {
+    int32_t height, width, num_frames, frame_rate;
+    int32_t num_inference_steps;
+    const float* custom_sigmas; /* host, num_inference_steps entries, or NULL */
+    float guidance_scale, guidance_rescale, stg_scale;
+    const int32_t* skip_block_list; /* host */
+    int32_t num_skip_blocks;
+    int32_t has_shift_terminal; /* preset configs.rs:113 */
+    float shift_terminal;
+    float decode_timestep;
+} ltxv_pipeline_params;
+
+/* Denoise loop (t2v_pipeline.rs:860-994), B = 1.  latents: device f32 [S,128] packed, updated in place.
+ * prompt/negative embeds: device [K, caption_channels] (dtype), masks device f32 [K]; negative_* may be NULL when
+ * guidance_scale <= 1.  Timesteps are trunc(sigma*1000) as in the reference. */
+int ltxv_pipeline_denoise(ltxv_dit* dit, const ltxv_pipeline_params* p, float* latents, const void* prompt_embeds,
+                          const float* prompt_mask, const void* negative_embeds, const float* negative_mask,
+                          int embeds_dtype, int K, void* stream);
+/* Decode branch (t2v_pipeline.rs:1000-1072) with decode_noise_scale = 0: unpack -> denormalize -> VAE decode ->
+ * postprocess.  latents: device f32 [S,128]; out: device f32 [3, num_frames, height, width] in 0..255. */
+int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTXV_H_ */

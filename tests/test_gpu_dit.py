@@ -1,0 +1,160 @@
+"""GPU parity: ltxv_dit_* (C ABI) vs the CPU f32 oracle on identical synthetic weights and inputs.
+
+Mirrors the reference's tests/verify_dit_parity.rs (tiny random-init DiT vs golden output) with the stated bf16
+tolerance: rel-L2 <= 2e-2 on the velocity; the reference's own f32 bar is max-abs < 2e-3 / MSE < 1e-4.
+"""
+import pytest
+import torch
+
+from oracle import ltx_oracle as O
+from tests.util import max_abs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 2e-2  # bf16 device model vs f32 oracle
+
+
+def small_cfg(layers=2, heads=4, head_dim=64, caption=256):
+    return O.DitConfig(num_attention_heads=heads, attention_head_dim=head_dim, cross_attention_dim=heads * head_dim,
+                       num_layers=layers, caption_channels=caption)
+
+
+def build(cfg, seed=42):
+    import candle_video_b200 as cv
+    w = O.init_dit_weights(cfg, seed)
+    m = cv.LtxVideoTransformer3DModel(cv.DitConfig(
+        in_channels=cfg.in_channels, out_channels=cfg.out_channels, patch_size=cfg.patch_size,
+        patch_size_t=cfg.patch_size_t, num_attention_heads=cfg.num_attention_heads,
+        attention_head_dim=cfg.attention_head_dim, cross_attention_dim=cfg.cross_attention_dim,
+        num_layers=cfg.num_layers, caption_channels=cfg.caption_channels, norm_eps=cfg.norm_eps,
+        timestep_bf16_round=True))
+    m.load_state_dict(w)
+    return m, w
+
+
+def inputs(cfg, B, F, H, W, K, seed=0, n_keep=None):
+    g = torch.Generator().manual_seed(seed)
+    S = F * H * W
+    hidden = torch.randn(B, S, cfg.in_channels, generator=g)
+    enc = torch.randn(B, K, cfg.caption_channels, generator=g)
+    mask = torch.ones(B, K)
+    if n_keep is not None:
+        mask[:, n_keep:] = 0
+    coords = O.video_coords(B, F, H, W, 25)
+    return hidden, enc, mask, coords
+
+
+@pytest.mark.parametrize("F,H,W,K,n_keep", [(2, 8, 8, 16, None), (3, 8, 12, 128, 48), (4, 7, 9, 77, 30)])
+def test_dit_forward_matches_oracle(cuda, F, H, W, K, n_keep):
+    cfg = small_cfg()
+    m, w = build(cfg)
+    hidden, enc, mask, coords = inputs(cfg, 1, F, H, W, K, n_keep=n_keep)
+    t = torch.tensor([993.0])
+    ref = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, None, coords, timestep_to_bf16=True)
+    out = m.forward(hidden.to(cuda), enc.to(cuda), t.to(cuda), mask.to(cuda), F, H, W, None, coords.to(cuda))
+    assert out.shape == ref.shape
+    assert torch.isfinite(out).all()
+    e = rel_l2(out, ref)
+    print(f"DiT rel_l2={e:.3e} max_abs={max_abs(out, ref):.3e} ref_rms={ref.pow(2).mean().sqrt():.3e}")
+    assert e <= REL_L2_TOL
+
+
+def test_dit_bf16_inputs_and_batch(cuda):
+    cfg = small_cfg()
+    m, w = build(cfg)
+    F, H, W, K = 2, 8, 8, 32
+    hidden, enc, mask, coords = inputs(cfg, 2, F, H, W, K, n_keep=20)
+    mask[1, 25:] = 0
+    mask[1, :25] = 1
+    t = torch.tensor([1000.0, 241.0])
+    hb, eb = hidden.bfloat16(), enc.bfloat16()
+    ref = O.dit_forward(w, cfg, hb.float(), eb.float(), t, mask, F, H, W, None, coords, timestep_to_bf16=True)
+    out = m.forward(hb.to(cuda), eb.to(cuda), t.to(cuda), mask.to(cuda), F, H, W, None, coords.to(cuda))
+    assert out.dtype == torch.bfloat16
+    assert rel_l2(out.float(), ref) <= REL_L2_TOL
+
+
+def test_dit_grid_rope_without_coords(cuda):
+    """video_coords = None path: prepare_video_coords + rope_interpolation_scale (ltx_transformer.rs:373-433)."""
+    cfg = small_cfg()
+    m, w = build(cfg)
+    F, H, W, K = 2, 8, 8, 16
+    hidden, enc, mask, _ = inputs(cfg, 1, F, H, W, K)
+    t = torch.tensor([500.0])
+    for scale in (None, (0.8, 32.0, 32.0)):
+        ref = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, scale, None, timestep_to_bf16=True)
+        out = m.forward(hidden.to(cuda), enc.to(cuda), t.to(cuda), mask.to(cuda), F, H, W, scale, None)
+        assert rel_l2(out, ref) <= REL_L2_TOL, scale
+
+
+def test_dit_skip_blocks_and_skip_layer_mask(cuda):
+    cfg = small_cfg(layers=3)
+    m, w = build(cfg)
+    F, H, W, K = 2, 8, 8, 16
+    hidden, enc, mask, coords = inputs(cfg, 2, F, H, W, K)
+    t = torch.tensor([700.0, 700.0])
+    dev = lambda x: x.to(cuda)  # noqa: E731
+    # permanent skip (distilled presets): set_skip_block_list (:1094-1096)
+    m.set_skip_block_list([1])
+    ref = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, None, coords, skip_block_list=[1], timestep_to_bf16=True)
+    out = m.forward(dev(hidden), dev(enc), dev(t), dev(mask), F, H, W, None, dev(coords))
+    assert rel_l2(out, ref) <= REL_L2_TOL
+    m.set_skip_block_list([])
+    # STG mask [num_layers, batch]: layer 0 skipped for batch 0, layer 2 for batch 1, and a fractional blend
+    slm = torch.tensor([[1.0, 0.0], [0.0, 0.0], [0.25, 1.0]])
+    ref = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, None, coords, skip_layer_mask=slm, timestep_to_bf16=True)
+    out = m.forward(dev(hidden), dev(enc), dev(t), dev(mask), F, H, W, None, dev(coords), skip_layer_mask=slm)
+    assert rel_l2(out, ref) <= REL_L2_TOL
+
+
+def test_dit_host_entry_point_matches_device(cuda):
+    cfg = small_cfg()
+    m, w = build(cfg)
+    F, H, W, K = 2, 8, 8, 16
+    hidden, enc, mask, coords = inputs(cfg, 1, F, H, W, K, n_keep=10)
+    t = torch.tensor([993.0])
+    out_d = m.forward(hidden.to(cuda), enc.to(cuda), t.to(cuda), mask.to(cuda), F, H, W, None, coords.to(cuda))
+    out_h = m.forward_host(hidden, enc, t, mask, F, H, W, None, coords)
+    assert torch.equal(out_d.cpu(), out_h)
+
+
+def test_dit_context_slots_match_plain_forward(cuda):
+    cfg = small_cfg()
+    m, w = build(cfg)
+    F, H, W, K = 2, 8, 8, 16
+    hidden, enc, mask, coords = inputs(cfg, 1, F, H, W, K, n_keep=10)
+    t = torch.tensor([993.0])
+    out = m.forward(hidden.to(cuda), enc.to(cuda), t.to(cuda), mask.to(cuda), F, H, W, None, coords.to(cuda))
+    m.prepare_context(0, enc.to(cuda), mask.to(cuda))
+    out2 = m.forward_ctx(0, hidden.to(cuda), t.to(cuda), F, H, W, None, coords.to(cuda))
+    assert torch.equal(out[0], out2)
+
+
+def test_dit_head_dim_128(cuda):
+    """13B head geometry (configs.rs:151-160) at reduced width."""
+    cfg = small_cfg(layers=1, heads=2, head_dim=128, caption=128)
+    m, w = build(cfg)
+    F, H, W, K = 2, 8, 10, 40
+    hidden, enc, mask, coords = inputs(cfg, 1, F, H, W, K, n_keep=33)
+    t = torch.tensor([800.0])
+    ref = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, None, coords, timestep_to_bf16=True)
+    out = m.forward(hidden.to(cuda), enc.to(cuda), t.to(cuda), mask.to(cuda), F, H, W, None, coords.to(cuda))
+    assert rel_l2(out, ref) <= REL_L2_TOL
+
+
+def test_dit_error_paths(cuda):
+    import candle_video_b200 as cv
+    cfg = small_cfg()
+    m = cv.LtxVideoTransformer3DModel(cv.DitConfig(num_attention_heads=4, attention_head_dim=64,
+                                                   cross_attention_dim=256, num_layers=2, caption_channels=256))
+    x = torch.zeros(1, 16, 128, device=cuda)
+    enc = torch.zeros(1, 4, 256, device=cuda)
+    with pytest.raises(cv.LtxvError, match="never loaded"):
+        m.forward(x, enc, torch.zeros(1, device=cuda), None, 1, 4, 4)
+    with pytest.raises(cv.LtxvError, match="unknown transformer tensor key"):
+        m.load_state_dict({"nope.weight": torch.zeros(1)})
+    with pytest.raises(cv.LtxvError, match="shape mismatch"):
+        m.load_state_dict({"proj_in.weight": torch.zeros(3, 3)})
+    with pytest.raises(cv.LtxvError, match="head_dim"):
+        cv.LtxVideoTransformer3DModel(cv.DitConfig(num_attention_heads=2, attention_head_dim=16,
+                                                   cross_attention_dim=32, num_layers=1, caption_channels=32))
