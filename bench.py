@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native LTX-Video hot path (BASELINE.json: DiT steps/s + VAE frames/s
+at 512x768x97, LTX-Video 2B bf16, CFG flow-matching denoise + 3D-VAE decode; `configs[1]`).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libltxv_b200.so through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one denoise step of LtxPipeline::call (t2v_pipeline.rs:860-994): 2 DiT forwards (uncond + cond, sequential
+CFG) + CFG combine + Euler update on a [4992,128] latent; the VAE decode (97 frames) is timed in the same run and
+reported beside it.  Synthetic latents/embeddings, random-init weights of the named architecture.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+HEIGHT, WIDTH, FRAMES, FPS, K_TEXT = 512, 768, 97, 25, 128
+GUIDANCE = 3.0  # preset 0.9.5 (configs.rs:165-171); stg_scale 0 here, the STG variant is reported separately
+
+
+def dit_flops(S, D=2048, L=28, K=128):
+    """SURVEY.md 8(d) / BASELINE.md 3: algorithmic FLOPs of one DiT forward."""
+    return (L * (28 * S * D * D + 4 * K * D * D + 4 * S * S * D + 4 * S * K * D) + 4 * S * 128 * D + 2 * K * 4096 * D
+            + 2 * K * D * D + 2 * (256 * D + 7 * D * D))
+
+
+def vae_flops(F, H, W):
+    """Sum over the decoder's 45 convs of 2*Cin*Cout*27*T*H*W."""
+    tot = 0
+    T, h, w = F, H, W
+    tot += 2 * 128 * 1024 * 27 * T * h * w
+    ch = [1024, 512, 256, 128]
+    for l in range(4):
+        if l > 0:
+            tot += 2 * ch[l - 1] * (8 * ch[l]) * 27 * T * h * w
+            T, h, w = 2 * T - 1, 2 * h, 2 * w
+        tot += 10 * 2 * ch[l] * ch[l] * 27 * T * h * w
+    tot += 2 * 128 * 48 * 27 * T * h * w
+    return tot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm_sorted = sorted(sm)
+        # median over the busier half of the samples = "under load"
+        load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path, restated (oracle/ltx_oracle.py), on a bounded sample of the same workload
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_block_sample(n_iter: int, warm: int):
+    """Time ONE transformer block of the 2B DiT at S=4992 (f32, all host threads) and scale to a CFG step
+    (28 blocks x 2 forwards).  Returns (steps_per_s, cores, seconds per block list)."""
+    import torch
+    from oracle import ltx_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.DitConfig(num_layers=1)
+    F, H, W = (FRAMES - 1) // 8 + 1, HEIGHT // 32, WIDTH // 32
+    S, D = F * H * W, cfg.inner_dim
+    g = torch.Generator().manual_seed(0)
+    shapes = {k: v for k, v in O.dit_weight_shapes(cfg).items() if k.startswith("transformer_blocks.0.")}
+    w = {k: O._init_tensor(k, s, g) for k, s in shapes.items()}
+    x = torch.randn(1, S, D, generator=g)
+    enc = torch.randn(1, K_TEXT, D, generator=g)
+    temb = torch.randn(1, 6 * D, generator=g) * 0.1
+    cos, sin = O.rope_cos_sin(O.video_coords(1, F, H, W, FPS), D)
+    mask_bias = torch.zeros(1, 1, K_TEXT)
+    times = []
+    with torch.no_grad():
+        for i in range(warm + n_iter):
+            t0 = time.perf_counter()
+            O.transformer_block(w, "transformer_blocks.0.", cfg, x, enc, temb, (cos, sin), mask_bias)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    t_blk = sum(times) / len(times)
+    return 1.0 / (t_blk * 28 * 2), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sps, cores, times = cpu_block_sample(args.steps, args.warmup)
+    sample = ("1 of 28 transformer blocks of the 2B DiT at S=4992 (f32 torch-CPU restatement of candle-video's CPU "
+              "path), per bench step; steps/s = 1 / (t_block * 28 blocks * 2 CFG forwards)")
+    line = {
+        "impl": "reference", "metric": "dit_denoise_steps_per_s", "value": sps, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference binary cannot be built here (no cargo/rustc; Candle not vendored): oracle port timed",
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    F, H, W = (FRAMES - 1) // 8 + 1, HEIGHT // 32, WIDTH // 32
+    return {"workload": "LTX-Video 2B 0.9.5 arch, CFG denoise step (2 DiT forwards + combine + Euler) + 3D-VAE decode "
+                        "at 512x768x97 (BASELINE configs[1])",
+            "height": HEIGHT, "width": WIDTH, "num_frames": FRAMES, "latent": [F, H, W], "tokens": F * H * W,
+            "text_tokens": K_TEXT, "guidance_scale": GUIDANCE, "forwards_per_step": 2,
+            "cache": "no explicit L2 flush: every step streams 3.8 GB of weights (>> 126 MB L2)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import candle_video_b200 as cv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    F, H, W = (FRAMES - 1) // 8 + 1, HEIGHT // 32, WIDTH // 32
+    S = F * H * W
+    dit = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset("2b"), device=local_rank)
+    dit.init_random(1234)
+    vae = cv.AutoencoderKLLtxVideo(cv.VaeConfig(), device=local_rank)
+    vae.init_random(4321)
+
+    g = torch.Generator().manual_seed(100 + rank)
+    lat_host = torch.randn(S, 128, generator=g).pin_memory()
+    pe_host = torch.randn(K_TEXT, 4096, generator=g).pin_memory()
+    ne_host = torch.randn(K_TEXT, 4096, generator=g).pin_memory()
+    pm_host = torch.cat([torch.ones(48), torch.zeros(K_TEXT - 48)]).pin_memory()
+    nm_host = torch.cat([torch.ones(8), torch.zeros(K_TEXT - 8)]).pin_memory()
+    latents = lat_host.to(dev)
+    pe, ne, pm, nm = pe_host.to(dev), ne_host.to(dev), pm_host.to(dev), nm_host.to(dev)
+
+    def params(n_steps):
+        return cv.PipelineParams(height=HEIGHT, width=WIDTH, num_frames=FRAMES, frame_rate=FPS,
+                                 num_inference_steps=n_steps, guidance_scale=GUIDANCE, guidance_rescale=0.0,
+                                 stg_scale=0.0, shift_terminal=0.1, decode_timestep=0.05)
+
+    # ---- warm-up ----
+    cv.pipeline_denoise(dit, params(max(args.warmup, 3)), latents, pe, pm, ne, nm)
+    torch.cuda.synchronize()
+
+    # ---- timed: exactly K denoise steps through the device-resident public API ----
+    latents.copy_(lat_host)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = cv.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cv.pipeline_denoise(dit, params(args.steps), latents, pe, pm, ne, nm)
+    e1.record()
+    barrier()
+    launches = cv.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    steps_per_s = world * 1000.0 / ms_per_step  # each rank denoises its own video (weak scaling)
+
+    # ---- timed: VAE decode (device resident) ----
+    n_dec = max(1, min(args.steps, 3))
+    out = cv.pipeline_decode(vae, params(1), latents)  # warm-up / workspace allocation
+    torch.cuda.synchronize()
+    barrier()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record()
+    for _ in range(n_dec):
+        cv.pipeline_decode(vae, params(1), latents)
+    v1.record()
+    barrier()
+    vae_ms = v0.elapsed_time(v1) / n_dec
+    if dist is not None:
+        t = torch.tensor([vae_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        vae_ms = float(t.item())
+    clocks = sampler.stop()
+    frames = 8 * F - 7
+    vae_fps = world * frames * 1000.0 / vae_ms
+    finite = bool(torch.isfinite(latents).all().item()) and bool(torch.isfinite(out).all().item())
+
+    line = {
+        "metric": "dit_denoise_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(),
+        "vae_frames_per_s": vae_fps, "vae_ms_per_decode": vae_ms, "vae_frames": frames,
+        "dit_forward_ms": ms_per_step / 2.0, "gpu_launches": int(launches), "outputs_finite": finite,
+        "clocks": clocks,
+    }
+    if world > 1:
+        line["config"]["parallelism"] = f"{world} independent replicas (one video per GPU), no data-path collective"
+
+    if rank == 0:
+        peaks = measured_peaks()
+        # ---- instrumented pass: per-kernel-class device time inside a real step (CUDA events on the stream) ----
+        cv.profile_begin()
+        cv.pipeline_denoise(dit, params(2), latents, pe, pm, ne, nm)
+        prof_dit = cv.profile_end()
+        cv.profile_begin()
+        cv.pipeline_decode(vae, params(1), latents)
+        prof_vae = cv.profile_end()
+
+        def tf(d):
+            return d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+
+        gm = prof_dit["gemm"]
+        line["roofline"] = {
+            "kernel": "gemm_bf16_tn_kernel (tcgen05 GEMM, DiT projections/FFN)", "bound": "tensor",
+            "achieved": tf(gm), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+            "frac": tf(gm) / peaks["tf_sustained"], "traffic": None,
+            "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+            "launches": gm["launches"], "avg_launch_ms": gm["ms"] / max(gm["launches"], 1),
+            "share_of_step": gm["ms"] / (2 * ms_per_step),
+        }
+        line["roofline_all"] = {
+            "dit_gemm": {"tflops": tf(gm), "ms_per_step": gm["ms"] / 2, "frac": tf(gm) / peaks["tf_sustained"]},
+            "dit_attn_self": {"tflops": tf(prof_dit["attn_self"]), "ms_per_step": prof_dit["attn_self"]["ms"] / 2,
+                              "frac": tf(prof_dit["attn_self"]) / peaks["tf_sustained"]},
+            "dit_attn_cross": {"tflops": tf(prof_dit["attn_cross"]), "ms_per_step": prof_dit["attn_cross"]["ms"] / 2},
+            "vae_conv3d": {"tflops": tf(prof_vae["conv3d"]), "ms_per_decode": prof_vae["conv3d"]["ms"],
+                           "frac": tf(prof_vae["conv3d"]) / peaks["tf_sustained"]},
+            "dit_step_algorithmic_tflops": 2 * dit_flops(S) / (ms_per_step * 1e-3) / 1e12,
+            "dit_step_frac_of_peak": 2 * dit_flops(S) / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"],
+            "vae_decode_algorithmic_tflops": vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12,
+            "vae_decode_frac_of_peak": vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12 / peaks["tf_sustained"],
+            "glue_ms_per_step": ms_per_step - (gm["ms"] + prof_dit["attn_self"]["ms"] + prof_dit["attn_cross"]["ms"]) / 2,
+        }
+
+        # ---- end to end through the host-buffer C ABI: per step H2D latents+embeddings, D2H latents ----
+        lat_e2e = lat_host.clone().pin_memory()
+        cv.pipeline_denoise_host(dit, params(1), lat_e2e, pe_host, pm_host, ne_host, nm_host)
+        n_e2e = max(1, min(args.steps, 5))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            cv.pipeline_denoise_host(dit, params(1), lat_e2e, pe_host, pm_host, ne_host, nm_host)
+        t_e2e = (time.perf_counter() - t0) / n_e2e
+        h2d = lat_host.numel() * 4 + 2 * pe_host.numel() * 4 + 2 * K_TEXT * 4
+        d2h = lat_host.numel() * 4
+        vid_host = torch.empty((3, frames, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
+        cv.pipeline_decode_host(vae, params(1), lat_e2e, vid_host)
+        t0 = time.perf_counter()
+        cv.pipeline_decode_host(vae, params(1), lat_e2e, vid_host)
+        t_vae_e2e = time.perf_counter() - t0
+        line["e2e"] = {"value": 1.0 / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h),
+                       "api": "ltxv_pipeline_denoise_host (1 step per call: context prep + 2 forwards + Euler)",
+                       "vae_frames_per_s": frames / t_vae_e2e, "vae_h2d_bytes": int(lat_host.numel() * 4),
+                       "vae_d2h_bytes": int(vid_host.numel() * 4), "vae_api": "ltxv_pipeline_decode_host"}
+
+        # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----
+        if world == 1 and not args.no_cpu_baseline:
+            sps, cores, times = cpu_block_sample(3, 1)
+            line["cpu_baseline"] = {
+                "value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                "sample": "1 of 28 transformer blocks of the 2B DiT at S=4992, f32 torch-CPU oracle restatement, "
+                          f"mean of 3 after 1 warm-up ({sum(times) / len(times):.2f} s/block), scaled x28 blocks x2 forwards"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,8 @@ EXPORTED_SYMBOLS = [
     "ltxv_vae_temporal_compression_ratio", "ltxv_vae_decode", "ltxv_vae_decode_host",
     "ltxv_pack_latents", "ltxv_unpack_latents", "ltxv_video_coords", "ltxv_guidance_euler_step",
     "ltxv_denormalize_latents", "ltxv_postprocess_video", "ltxv_calculate_shift", "ltxv_scheduler_set_timesteps",
-    "ltxv_pipeline_denoise", "ltxv_pipeline_decode",
+    "ltxv_pipeline_denoise", "ltxv_pipeline_decode", "ltxv_pipeline_denoise_host", "ltxv_pipeline_decode_host",
+    "ltxv_profile_begin", "ltxv_profile_end",
 ]
 
 
@@ -119,6 +120,10 @@ def _load() -> C.CDLL:
     l.ltxv_scheduler_set_timesteps.argtypes = [i32, fp, f32, i32, f32, fp, C.POINTER(i64)]
     l.ltxv_pipeline_denoise.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32, vp]
     l.ltxv_pipeline_decode.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp]
+    l.ltxv_pipeline_denoise_host.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32]
+    l.ltxv_pipeline_decode_host.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp]
+    l.ltxv_profile_begin.argtypes = []
+    l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return l
 
 
@@ -562,3 +567,47 @@ def pipeline_decode(vae: AutoencoderKLLtxVideo, params: PipelineParams, latents)
     out = torch.empty((3, 8 * f - 7, params.height, params.width), dtype=torch.float32, device=latents.device)
     _check(lib().ltxv_pipeline_decode(vae._h, C.byref(p), _ptr(latents), _ptr(out), _stream()))
     return out
+
+
+def pipeline_denoise_host(dit: LtxVideoTransformer3DModel, params: PipelineParams, latents, prompt_embeds, prompt_mask,
+                          negative_embeds=None, negative_mask=None):
+    """ltxv_pipeline_denoise_host: all tensors are HOST (CPU torch) tensors; latents f32 [S,128] updated in place."""
+    torch = _torch()
+    p, keep = params.to_c()
+    pe = prompt_embeds[0] if prompt_embeds.dim() == 3 else prompt_embeds
+    pe = pe.contiguous()
+    ne = None
+    if negative_embeds is not None:
+        ne = (negative_embeds[0] if negative_embeds.dim() == 3 else negative_embeds).contiguous()
+    pm = None if prompt_mask is None else prompt_mask.to(torch.float32).reshape(-1).contiguous()
+    nm = None if negative_mask is None else negative_mask.to(torch.float32).reshape(-1).contiguous()
+    if latents.is_cuda or latents.dtype != torch.float32 or not latents.is_contiguous():
+        raise LtxvError("latents must be a contiguous float32 CPU tensor")
+    _check(lib().ltxv_pipeline_denoise_host(dit._h, C.byref(p), _ptr(latents), _ptr(pe), _ptr(pm), _ptr(ne), _ptr(nm),
+                                            _dtype_code(pe), pe.shape[0]))
+    return latents
+
+
+def pipeline_decode_host(vae: AutoencoderKLLtxVideo, params: PipelineParams, latents, out=None):
+    torch = _torch()
+    p, keep = params.to_c()
+    f = (params.num_frames - 1) // 8 + 1
+    if out is None:
+        out = torch.empty((3, 8 * f - 7, params.height, params.width), dtype=torch.float32)
+    _check(lib().ltxv_pipeline_decode_host(vae._h, C.byref(p), _ptr(latents.contiguous()), _ptr(out)))
+    return out
+
+
+PROFILE_CLASSES = ("gemm", "conv3d", "attn_self", "attn_cross")
+
+
+def profile_begin() -> None:
+    _check(lib().ltxv_profile_begin())
+
+
+def profile_end() -> Dict[str, Dict[str, float]]:
+    n = (C.c_uint64 * 4)()
+    ms = (C.c_double * 4)()
+    fl = (C.c_double * 4)()
+    _check(lib().ltxv_profile_end(n, ms, fl))
+    return {PROFILE_CLASSES[i]: {"launches": int(n[i]), "ms": float(ms[i]), "flops": float(fl[i])} for i in range(4)}

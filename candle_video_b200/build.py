@@ -37,11 +37,12 @@ LIB_SOURCES = [
     "ffi.cu",
     "model_common.cu",
     "tensormap.cc",
+    "profile.cc",
 ]
 
 TOOLS = {
-    "gemm_test": (["tools/gemm_test.cu"], ["gemm_tcgen05.cu", "tensormap.cc"]),
-    "attn_test": (["tools/attn_test.cu"], ["attention_tcgen05.cu", "tensormap.cc"]),
+    "gemm_test": (["tools/gemm_test.cu"], ["gemm_tcgen05.cu", "tensormap.cc", "profile.cc"]),
+    "attn_test": (["tools/attn_test.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc"]),
 }
 
 

@@ -12,6 +12,7 @@
 #include "attention.h"
 #include "common.cuh"
 #include "tensormap.h"
+#include "profile.h"
 
 #include <atomic>
 
@@ -346,7 +347,11 @@ cudaError_t launch_attn_impl(const AttnParams& p, cudaStream_t stream) {
     e = make_tensor_map_3d_bf16(&tv, p.v, p.B, p.Skv, p.ldv, kTileKV, 64, p.ldv, p.ldv * (int64_t)p.Skv);
     if (e != cudaSuccess) return e;
     dim3 grid((p.Sq + kTileQ - 1) / kTileQ, p.H, p.B);
-    flash_attn_kernel<D><<<grid, kAttnThreads, C::kSmemBytes, stream>>>(tq, tk, tv, p);
+    {
+        ProfScope prof(p.kv_bias != nullptr || p.Skv != p.Sq ? PROF_ATTN_CROSS : PROF_ATTN_SELF,
+                       4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * D, stream);
+        flash_attn_kernel<D><<<grid, kAttnThreads, C::kSmemBytes, stream>>>(tq, tk, tv, p);
+    }
     g_attn_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

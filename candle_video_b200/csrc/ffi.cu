@@ -6,6 +6,7 @@
 #include "gemm.h"
 #include "glue.h"
 #include "pipeline.h"
+#include "profile.h"
 #include "vae.h"
 #include "vae_glue.h"
 
@@ -48,6 +49,17 @@ const char* ltxv_version(void) { return "ltxv_b200 0.1 (sm_100a: tcgen05 GEMM/co
 uint64_t ltxv_launch_count(void) {
     return gemm_launch_count() + attention_launch_count() + glue_launch_count() + vae_glue_launch_count() +
            common_launch_count();
+}
+
+int ltxv_profile_begin(void) {
+    profiling_begin();
+    return 0;
+}
+int ltxv_profile_end(uint64_t* launches4, double* ms4, double* flops4) {
+    LTXV_TRY
+    if (launches4 == nullptr || ms4 == nullptr || flops4 == nullptr) fail("null argument");
+    profiling_end(launches4, ms4, flops4);
+    LTXV_CATCH
 }
 
 int ltxv_dit_config_preset(const char* name, ltxv_dit_config* out) {
@@ -336,6 +348,61 @@ int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const flo
     LTXV_TRY
     if (vae == nullptr || p == nullptr || latents == nullptr || out == nullptr) fail("null argument");
     pipeline_decode(vae->model, *p, latents, out, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+int ltxv_pipeline_denoise_host(ltxv_dit* dit, const ltxv_pipeline_params* p, float* latents, const void* prompt_embeds,
+                               const float* prompt_mask, const void* negative_embeds, const float* negative_mask,
+                               int embeds_dtype, int K) {
+    LTXV_TRY
+    if (dit == nullptr || p == nullptr || latents == nullptr || prompt_embeds == nullptr) fail("null argument");
+    const ltxv_dit_config& c = dit->model.config();
+    const int F = (p->num_frames - 1) / 8 + 1, H = p->height / 32, W = p->width / 32;
+    const size_t nl = static_cast<size_t>(F) * H * W * c.in_channels * 4;
+    const size_t ne = static_cast<size_t>(K) * c.caption_channels * dsize(embeds_dtype);
+    cudaStream_t s = 0;
+    static DevBuf d_lat, d_pe, d_ne, d_pm, d_nm;
+    d_lat.ensure(nl);
+    d_pe.ensure(ne);
+    LTXV_CUDA(cudaMemcpyAsync(d_lat.p, latents, nl, cudaMemcpyHostToDevice, s));
+    LTXV_CUDA(cudaMemcpyAsync(d_pe.p, prompt_embeds, ne, cudaMemcpyHostToDevice, s));
+    const float *pm = nullptr, *nm = nullptr;
+    const void* nep = nullptr;
+    if (prompt_mask != nullptr) {
+        d_pm.ensure(K * 4);
+        LTXV_CUDA(cudaMemcpyAsync(d_pm.p, prompt_mask, K * 4, cudaMemcpyHostToDevice, s));
+        pm = d_pm.as<float>();
+    }
+    if (negative_embeds != nullptr) {
+        d_ne.ensure(ne);
+        LTXV_CUDA(cudaMemcpyAsync(d_ne.p, negative_embeds, ne, cudaMemcpyHostToDevice, s));
+        nep = d_ne.p;
+    }
+    if (negative_mask != nullptr) {
+        d_nm.ensure(K * 4);
+        LTXV_CUDA(cudaMemcpyAsync(d_nm.p, negative_mask, K * 4, cudaMemcpyHostToDevice, s));
+        nm = d_nm.as<float>();
+    }
+    pipeline_denoise(dit->model, *p, d_lat.as<float>(), d_pe.p, pm, nep, nm, embeds_dtype, K, s);
+    LTXV_CUDA(cudaMemcpyAsync(latents, d_lat.p, nl, cudaMemcpyDeviceToHost, s));
+    LTXV_CUDA(cudaStreamSynchronize(s));
+    LTXV_CATCH
+}
+int ltxv_pipeline_decode_host(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out) {
+    LTXV_TRY
+    if (vae == nullptr || p == nullptr || latents == nullptr || out == nullptr) fail("null argument");
+    const int C = vae->model.config().latent_channels;
+    const int F = (p->num_frames - 1) / 8 + 1, H = p->height / 32, W = p->width / 32;
+    const size_t nl = static_cast<size_t>(F) * H * W * C * 4;
+    const size_t no = 3ull * (8 * F - 7) * (32 * H) * (32 * W) * 4;
+    cudaStream_t s = 0;
+    static DevBuf d_lat, d_out;
+    d_lat.ensure(nl);
+    d_out.ensure(no);
+    LTXV_CUDA(cudaMemcpyAsync(d_lat.p, latents, nl, cudaMemcpyHostToDevice, s));
+    pipeline_decode(vae->model, *p, d_lat.as<float>(), d_out.as<float>(), s);
+    LTXV_CUDA(cudaMemcpyAsync(out, d_out.p, no, cudaMemcpyDeviceToHost, s));
+    LTXV_CUDA(cudaStreamSynchronize(s));
     LTXV_CATCH
 }
 

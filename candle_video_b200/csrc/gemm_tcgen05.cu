@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "tensormap.h"
+#include "profile.h"
 
 #include <atomic>
 
@@ -402,7 +403,12 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = num_m * num_n;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_bf16_tn_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, p);
+    {
+        double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
+        if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;  // unpadded voxels
+        ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
+        gemm_bf16_tn_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, p);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -1,0 +1,26 @@
+// Optional per-kernel-class device timing (CUDA events on the launching stream) used by bench.py to compute the
+// roofline of the dominant kernels inside a real step.  Off by default: zero overhead on the product path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ltxv {
+
+enum ProfClass : int { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN_SELF = 2, PROF_ATTN_CROSS = 3, PROF_NUM = 4 };
+
+bool profiling_enabled();
+void profiling_begin();
+// returns, per class: launches, total milliseconds, total algorithmic FLOPs
+void profiling_end(uint64_t* launches, double* ms, double* flops);
+
+struct ProfScope {
+    bool on;
+    int cls;
+    double flops;
+    cudaStream_t s;
+    cudaEvent_t e0, e1;
+    ProfScope(int cls, double flops, cudaStream_t s);
+    ~ProfScope();
+};
+
+}  // namespace ltxv

@@ -48,6 +48,12 @@ const char* ltxv_version(void);
 /* kernels launched by this library since process start (all streams); evidence for bench.py's gpu_launches */
 uint64_t ltxv_launch_count(void);
 
+/* Measurement hook (bench.py): between begin/end every GEMM / conv3d / attention launch is bracketed by CUDA events
+ * on its stream.  end() synchronises and returns per class {0 GEMM, 1 conv3d, 2 self-attention, 3 cross-attention}:
+ * launches, summed device milliseconds, summed algorithmic FLOPs.  Not part of the reference interface. */
+int ltxv_profile_begin(void);
+int ltxv_profile_end(uint64_t* launches4, double* ms4, double* flops4);
+
 /* ------------------------------------------------------------------ DiT ------------------------------------------ */
 /* LtxVideoTransformer3DModelConfig, ltx_transformer.rs:22-59 */
 typedef struct ltxv_dit_config {
@@ -184,6 +190,13 @@ int ltxv_pipeline_denoise(ltxv_dit* dit, const ltxv_pipeline_params* p, float* l
 /* Decode branch (t2v_pipeline.rs:1000-1072) with decode_noise_scale = 0: unpack -> denormalize -> VAE decode ->
  * postprocess.  latents: device f32 [S,128]; out: device f32 [3, num_frames, height, width] in 0..255. */
 int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out, void* stream);
+
+/* HOST-buffer variants of the two calls above (what a caller holding CPU tensors uses): inputs are copied to the
+ * device, the loop / decode runs, the result is copied back and the stream is synchronised. */
+int ltxv_pipeline_denoise_host(ltxv_dit* dit, const ltxv_pipeline_params* p, float* latents, const void* prompt_embeds,
+                               const float* prompt_mask, const void* negative_embeds, const float* negative_mask,
+                               int embeds_dtype, int K);
+int ltxv_pipeline_decode_host(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out);
 
 #ifdef __cplusplus
 }
