@@ -217,6 +217,12 @@ def run_ours(args):
     pe, ne, pm, nm = pe_host.to(dev), ne_host.to(dev), pm_host.to(dev), nm_host.to(dev)
 
     def params(n_steps):
+        if n_steps == 1:
+            # single-step calls (e2e leg): an explicit sigma, because linspace(1, 1, 1) stretched to the 0.1 terminal
+            # is 0/0 in the reference's schedule as well
+            return cv.PipelineParams(height=HEIGHT, width=WIDTH, num_frames=FRAMES, frame_rate=FPS,
+                                     num_inference_steps=1, custom_sigmas=[0.9], guidance_scale=GUIDANCE,
+                                     guidance_rescale=0.0, stg_scale=0.0, shift_terminal=None, decode_timestep=0.05)
         return cv.PipelineParams(height=HEIGHT, width=WIDTH, num_frames=FRAMES, frame_rate=FPS,
                                  num_inference_steps=n_steps, guidance_scale=GUIDANCE, guidance_rescale=0.0,
                                  stg_scale=0.0, shift_terminal=0.1, decode_timestep=0.05)
@@ -329,6 +335,8 @@ def run_ours(args):
         t0 = time.perf_counter()
         cv.pipeline_decode_host(vae, params(1), lat_e2e, vid_host)
         t_vae_e2e = time.perf_counter() - t0
+        finite = finite and bool(torch.isfinite(lat_e2e).all().item()) and bool(torch.isfinite(vid_host).all().item())
+        line["outputs_finite"] = finite
         line["e2e"] = {"value": 1.0 / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h),
                        "api": "ltxv_pipeline_denoise_host (1 step per call: context prep + 2 forwards + Euler)",

@@ -48,7 +48,9 @@ void scheduler_set_timesteps(int n, const float* custom_sigmas, float mu, bool h
     }
     for (int i = 0; i < n; ++i) {
         sigmas_out[i] = s[i];
-        timesteps_out[i] = static_cast<int64_t>(s[i] * 1000.0f);  // `x as i64` truncation (scheduler.rs:658-659)
+        // `x as i64` (scheduler.rs:658-659): truncation; Rust maps NaN to 0 (n = 1 with a terminal stretch is 0/0)
+        const float tv = s[i] * 1000.0f;
+        timesteps_out[i] = isnan(tv) ? 0 : static_cast<int64_t>(tv);
     }
     sigmas_out[n] = 0.0f;
 }

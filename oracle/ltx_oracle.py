@@ -589,7 +589,8 @@ def euler_step(sample: Tensor, model_output: Tensor, sigma: float, sigma_next: f
 def denormalize_latents(latents: Tensor, mean: Tensor, std: Tensor, scaling_factor: float) -> Tensor:
     """t2v_pipeline.rs:573-594."""
     c = latents.shape[1]
-    return latents * std.reshape(1, c, 1, 1, 1) * torch.tensor(1.0 / scaling_factor, dtype=F32) + mean.reshape(1, c, 1, 1, 1)
+    inv_sf = torch.tensor(1.0, dtype=F32) / torch.tensor(scaling_factor, dtype=F32)  # (1.0 / scaling_factor: f32) as f64
+    return latents * std.reshape(1, c, 1, 1, 1) * inv_sf + mean.reshape(1, c, 1, 1, 1)
 
 
 def postprocess_video(video: Tensor) -> Tensor:
@@ -629,6 +630,8 @@ def scheduler_set_timesteps(num_steps: int, mu: float, sigmas: Optional[Sequence
     if shift_terminal is not None and len(s) > 0:
         one_minus_last = f(1.0) - s[-1]
         scale = one_minus_last / (f(1.0) - f(shift_terminal))
-        s = (f(1.0) - (f(1.0) - s) / scale).astype(f)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = (f(1.0) - (f(1.0) - s) / scale).astype(f)
     ts = (s * f(1000.0)).astype(f)
-    return [float(v) for v in s] + [0.0], [int(v) for v in ts]
+    # Rust `f32 as i64` saturates and maps NaN to 0 (n = 1 with a terminal stretch divides 0/0 in the reference too)
+    return [float(v) for v in s] + [0.0], [0 if np.isnan(v) else int(v) for v in ts]

@@ -1,0 +1,222 @@
+"""Pin the CPU oracle against the reference's self-contained known-answer tests.
+
+The reference's numeric fixtures (gen_*.safetensors) are git-ignored and absent, so these closed-form KATs are the
+only in-tree pins: AdaLN value, attention scale, pack/unpack identity, video-coordinate closed form, CFG formula,
+unbiased std, sinusoid layout, RoPE padding channels, depth-to-space / unpatchify index maps, preset constants,
+Euler formula, scheduler closed forms.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ltx_oracle as O
+
+
+def test_adaln_known_answer():
+    # tests/verify_rope_parity.rs:646-733: x[i] = 0.1 i, scale[i] = 0.01 i, shift[i] = 0.001 i; result[1] = 0.1*1.01+0.001
+    x = torch.arange(8, dtype=torch.float32) * 0.1
+    scale = torch.arange(8, dtype=torch.float32) * 0.01
+    shift = torch.arange(8, dtype=torch.float32) * 0.001
+    r = x * (1.0 + scale) + shift
+    assert abs(float(r[1]) - (0.1 * 1.01 + 0.001)) < 1e-6
+
+
+def test_attention_scale_known_answer():
+    # tests/verify_rope_parity.rs:472-511: head_dim 64 -> scale 0.125
+    cfg = O.dit_config_2b()
+    assert cfg.attention_head_dim == 64
+    assert abs(1.0 / math.sqrt(cfg.attention_head_dim) - 0.125) < 1e-7
+
+
+def test_attention_uniform_scores_average_values():
+    # with q = 0 every key gets the same weight: output = mean(v) (softmax semantic of :735)
+    d, heads, S, K = 16, 2, 5, 7
+    w = {}
+    D = d * heads
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        w[f"a.{n}.weight"] = torch.eye(D)
+        w[f"a.{n}.bias"] = torch.zeros(D)
+    w["a.to_q.weight"] = torch.zeros(D, D)
+    w["a.norm_q.weight"] = torch.ones(D)
+    w["a.norm_k.weight"] = torch.ones(D)
+    x = torch.randn(1, S, D)
+    enc = torch.randn(1, K, D)
+    out = O.attention(w, "a.", heads, x, enc, None, None)
+    assert torch.allclose(out, enc.mean(1, keepdim=True).expand(1, S, D), atol=1e-5)
+
+
+def test_mask_bias_removes_padded_keys():
+    d, heads, S, K = 16, 2, 3, 6
+    D = d * heads
+    g = torch.Generator().manual_seed(0)
+    w = {}
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        w[f"a.{n}.weight"] = torch.randn(D, D, generator=g) / math.sqrt(D)
+        w[f"a.{n}.bias"] = torch.zeros(D)
+    w["a.norm_q.weight"] = torch.ones(D)
+    w["a.norm_k.weight"] = torch.ones(D)
+    x = torch.randn(1, S, D, generator=g)
+    enc = torch.randn(1, K, D, generator=g)
+    mask = torch.tensor([[1., 1., 1., 1., 0., 0.]])
+    bias = ((1 - mask) * -10000.0).unsqueeze(1)
+    a = O.attention(w, "a.", heads, x, enc, bias, None)
+    b = O.attention(w, "a.", heads, x, enc[:, :4], None, None)
+    assert torch.allclose(a, b, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,p,pt", [((2, 128, 3, 4, 6), 1, 1), ((1, 8, 4, 4, 6), 2, 2), ((1, 16, 2, 6, 9), 3, 1)])
+def test_pack_unpack_round_trip_identity(shape, p, pt):
+    # tests/verify_pipeline_parity.rs:742-771
+    x = torch.randn(*shape)
+    b, c, f, h, w = shape
+    packed = O.pack_latents(x, p, pt)
+    assert packed.shape == (b, (f // pt) * (h // p) * (w // p), c * pt * p * p)
+    back = O.unpack_latents(packed, f // pt, h // p, w // p, p, pt)
+    assert torch.equal(back, x)
+
+
+def test_pack_index_map_p1():
+    # p = pt = 1: out[b, (f*H+h)*W+w, c] = in[b,c,f,h,w]  
+    x = torch.arange(2 * 3 * 2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 2, 3, 4)
+    p = O.pack_latents(x)
+    for (b, c, f, h, w) in [(0, 0, 0, 0, 0), (1, 2, 1, 2, 3), (0, 1, 1, 0, 2)]:
+        assert p[b, (f * 3 + h) * 4 + w, c] == x[b, c, f, h, w]
+
+
+@pytest.mark.parametrize("nf,hh,ww,fps", [(9, 256, 256, 25), (25, 512, 768, 25), (97, 512, 768, 25),
+                                          (161, 512, 768, 25), (9, 512, 768, 30), (25, 768, 512, 24)])
+def test_video_coords_closed_form(nf, hh, ww, fps):
+    # the configurations of tests/verify_video_coords_parity.rs:109-116 against the closed form (f32 arithmetic)
+    F, H, W = (nf - 1) // 8 + 1, hh // 32, ww // 32
+    c = O.video_coords(1, F, H, W, fps)
+    assert c.shape == (1, F * H * W, 3)
+    inv = np.float32(1.0 / fps)
+    for (f, h, w) in [(0, 0, 0), (F - 1, H - 1, W - 1), (F // 2, H // 3, W // 2)]:
+        s = (f * H + h) * W + w
+        exp_f = np.float32(min(max(np.float32(f) * np.float32(8) + np.float32(-7), 0), 1000)) * inv
+        assert c[0, s, 0].item() == float(exp_f)
+        assert c[0, s, 1].item() == 32.0 * h
+        assert c[0, s, 2].item() == 32.0 * w
+    assert c[0, 0, 0].item() == 0.0  # causal fix: first latent frame clamps to t = 0
+
+
+def test_cfg_formula_and_rescale():
+    g = torch.Generator().manual_seed(1)
+    u, c = torch.randn(2, 6, 8, generator=g), torch.randn(2, 6, 8, generator=g)
+    out = O.guidance_combine(c, u, None, 3.0, 0.0, 0.0)
+    assert torch.allclose(out, u + 3.0 * (c - u), atol=1e-6)
+    # guidance_scale 1 -> cond  (tests/verify_cfg_parity.rs scale variations)
+    assert torch.allclose(O.guidance_combine(c, u, None, 1.0, 0.0, 0.0), c, atol=1e-6)
+    # rescale = 1 forces std(comb) == std(cond) per batch entry (unbiased std over all non-batch elements)
+    r = O.guidance_combine(c, u, None, 3.0, 1.0, 0.0)
+    assert torch.allclose(O.std_over_dims_except0(r), O.std_over_dims_except0(c), rtol=1e-4)
+    # rescale = 0 is the identity (test_rescale_noise_cfg_zero)
+    assert torch.equal(O.rescale_noise_cfg(out, c, 0.0), out * 0.0 + out)
+    # STG term
+    p = torch.randn(2, 6, 8, generator=g)
+    assert torch.allclose(O.guidance_combine(c, None, p, 1.0, 0.0, 1.5), c + 1.5 * (c - p), atol=1e-6)
+
+
+def test_std_is_unbiased():
+    x = torch.tensor([[1.0, 2.0, 3.0, 4.0]])
+    assert abs(float(O.std_over_dims_except0(x)) - math.sqrt(5.0 / 3.0)) < 1e-6
+
+
+def test_sinusoid_layouts():
+    # tests/verify_timestep_embedding.rs:55-61 values of t; layout [cos | sin], dim 256
+    for t in (0.0, 0.05, 0.1, 0.5, 1.0):
+        e = O.vae_timestep_embedding(torch.tensor([t * 1000.0]))
+        d = O.dit_timestep_embedding(torch.tensor([t * 1000.0]))
+        assert e.shape == d.shape == (1, 256)
+        # frequency 0 is 1: first cos = cos(t), first sin = sin(t)
+        assert abs(float(e[0, 0]) - math.cos(t * 1000.0)) < 1e-4
+        assert abs(float(e[0, 128]) - math.sin(t * 1000.0)) < 1e-4
+        # the two formulations (powf vs exp) agree
+        assert torch.allclose(e, d, atol=2e-3)
+    z = O.dit_timestep_embedding(torch.tensor([0.0]))
+    assert torch.equal(z[0, :128], torch.ones(128)) and torch.equal(z[0, 128:], torch.zeros(128))
+
+
+def test_rope_padding_channels_and_layout():
+    # D = 2048: n = 341 frequencies, first D mod 6 = 2 channels are identity (ltx_transformer.rs:514-521)
+    coords = O.video_coords(1, 2, 2, 3, 25)
+    cos, sin = O.rope_cos_sin(coords, 2048)
+    assert cos.shape == sin.shape == (1, 12, 2048)
+    assert torch.equal(cos[..., :2], torch.ones(1, 12, 2)) and torch.equal(sin[..., :2], torch.zeros(1, 12, 2))
+    # repeat_interleave(2): channel pairs share the angle
+    assert torch.equal(cos[..., 2::2], cos[..., 3::2]) and torch.equal(sin[..., 2::2], sin[..., 3::2])
+    # token 0: frame coord 0 -> g = 0 -> angle = freq_j * (2*0 - 1) = -freq_j; lowest frequency is pi/2 -> cos = 0, sin = -1
+    assert abs(float(cos[0, 0, 2])) < 1e-6 and abs(float(sin[0, 0, 2]) + 1.0) < 1e-6
+    # D = 4096 -> rem 4
+    c2, s2 = O.rope_cos_sin(coords, 4096)
+    assert torch.equal(c2[..., :4], torch.ones(1, 12, 4))
+
+
+def test_apply_rotary_is_pairwise_rotation():
+    x = torch.randn(1, 3, 8)
+    ang = torch.randn(1, 3, 4)
+    cos, sin = ang.cos().repeat_interleave(2, -1), ang.sin().repeat_interleave(2, -1)
+    y = O.apply_rotary_emb(x, cos, sin)
+    xr, xi = x[..., 0::2], x[..., 1::2]
+    assert torch.allclose(y[..., 0::2], xr * ang.cos() - xi * ang.sin(), atol=1e-6)
+    assert torch.allclose(y[..., 1::2], xi * ang.cos() + xr * ang.sin(), atol=1e-6)
+    assert torch.allclose(y.norm(dim=-1), x.norm(dim=-1), atol=1e-5)  # rotations preserve the norm
+
+
+def test_depth_to_space_and_unpatchify_index_maps():
+    # R22: out[b,c,2t+i,2h+j,2w+k] = y[b, c*8+i*4+j*2+k, t,h,w]
+    y = torch.arange(1 * 16 * 2 * 3 * 2, dtype=torch.float32).reshape(1, 16, 2, 3, 2)
+    o = O.depth_to_space(y, 2, 2, 2)
+    assert o.shape == (1, 2, 4, 6, 4)
+    for (c, t, h, w, i, j, k) in [(0, 0, 0, 0, 0, 0, 0), (1, 1, 2, 1, 1, 0, 1), (1, 0, 1, 1, 0, 1, 1)]:
+        assert o[0, c, 2 * t + i, 2 * h + j, 2 * w + k] == y[0, c * 8 + i * 4 + j * 2 + k, t, h, w]
+    # R23: out[b,c,f,4h+j,4w+i] = x[b, c*16+i*4+j, f,h,w]  (W sub-pixel is the slower channel index)
+    x = torch.arange(1 * 48 * 2 * 2 * 3, dtype=torch.float32).reshape(1, 48, 2, 2, 3)
+    u = O.unpatchify(x, 4, 1)
+    assert u.shape == (1, 3, 2, 8, 12)
+    for (c, f, h, w, i, j) in [(0, 0, 0, 0, 0, 0), (2, 1, 1, 2, 3, 1), (1, 0, 1, 0, 2, 3)]:
+        assert u[0, c, f, 4 * h + j, 4 * w + i] == x[0, c * 16 + i * 4 + j, f, h, w]
+
+
+def test_causal_conv3d_padding_rules():
+    # kt=3 non-causal: replicate 1 frame each side; causal: 2 copies of frame 0 on the left; H/W zero pad
+    w = torch.zeros(1, 1, 3, 3, 3)
+    w[0, 0, 0, 1, 1] = 1.0  # picks input frame t-1 (non-causal) / t-2 (causal)
+    b = torch.zeros(1)
+    x = torch.arange(4, dtype=torch.float32).reshape(1, 1, 4, 1, 1).expand(1, 1, 4, 2, 2).contiguous()
+    y = O.causal_conv3d(x, w, b, is_causal=False)
+    assert y[0, 0, :, 0, 0].tolist() == [0.0, 0.0, 1.0, 2.0]
+    yc = O.causal_conv3d(x, w, b, is_causal=True)
+    assert yc[0, 0, :, 0, 0].tolist() == [0.0, 0.0, 0.0, 1.0]
+    w2 = torch.zeros(1, 1, 3, 3, 3)
+    w2[0, 0, 1, 1, 0] = 1.0  # left neighbour in W: zero padded at w = 0
+    y2 = O.causal_conv3d(x + 1, w2, b)
+    assert (y2[0, 0, :, :, 0] == 0).all() and (y2[0, 0, :, :, 1] == x[0, 0, :, :, 0] + 1).all()
+
+
+def test_preset_constants():
+    # configs.rs:289-324 / :135-160
+    c2, c13 = O.dit_config_2b(), O.dit_config_13b()
+    assert (c2.num_layers, c2.num_attention_heads, c2.attention_head_dim, c2.cross_attention_dim) == (28, 32, 64, 2048)
+    assert (c13.num_layers, c13.attention_head_dim, c13.cross_attention_dim) == (48, 128, 4096)
+    v = O.VaeConfig()
+    assert v.stage_channels() == [1024, 512, 256, 128]
+    assert len(O.vae_weight_shapes(v)) == 2 + 4 * 4 + 3 * 2 + 20 * 5 + 2 + 4 + 2
+
+
+def test_euler_and_schedule_closed_forms():
+    x, v = torch.randn(1, 4, 8), torch.randn(1, 4, 8)
+    assert torch.allclose(O.euler_step(x, v, 1.0, 0.75), x - 0.25 * v, atol=1e-6)
+    # calculate_shift: linear through (256, 0.5) and (4096, 1.15)
+    assert abs(O.calculate_shift(256) - 0.5) < 1e-6 and abs(O.calculate_shift(4096) - 1.15) < 1e-6
+    assert abs(O.calculate_shift(4992) - 1.3017) < 1e-3
+    sig, ts = O.scheduler_set_timesteps(40, O.calculate_shift(4992))
+    assert len(sig) == 41 and len(ts) == 40 and sig[-1] == 0.0
+    assert ts[:6] == [1000, 993, 986, 978, 971, 963]  # SURVEY.md Appendix C replay
+    assert abs(sig[39] - 0.1) < 1e-6 and all(a > b for a, b in zip(sig, sig[1:]))
+    # distilled sigmas: mu = 0 leaves them unchanged up to the terminal stretch
+    s8 = [1.0, 0.9937, 0.9875, 0.9812, 0.975, 0.9094, 0.725, 0.4219]
+    sig2, ts2 = O.scheduler_set_timesteps(8, 0.0, sigmas=s8, shift_terminal=None)
+    assert np.allclose(sig2[:-1], s8, atol=1e-6) and ts2[0] == 1000
