@@ -43,6 +43,7 @@ LIB_SOURCES = [
 TOOLS = {
     "gemm_test": (["tools/gemm_test.cu"], ["gemm_tcgen05.cu", "tensormap.cc", "profile.cc"]),
     "attn_test": (["tools/attn_test.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc"]),
+    "attn_prof": (["tools/attn_prof.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc"]),
 }
 
 

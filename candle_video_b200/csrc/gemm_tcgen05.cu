@@ -271,7 +271,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp_idx == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {  // one elected lane: ptxas keeps the tcgen05/TMA operands on the uniform datapath
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -297,7 +297,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp_idx == 1) {
         // ===================== UMMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {  // one elected lane: ptxas keeps the tcgen05/TMA operands on the uniform datapath
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, false, false);
             int stage = 0;
             uint32_t phase = 0;
@@ -425,14 +425,17 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int cands[4] = {256, 192, 128, 64};
+        // relative cost of one tile per k-block, from the measured tensor-pipe activity of each width
+        // (profiles/r01_ncu_full_*.csv: 63 % at 256, 57 % at 192, 43 % at 128: narrow tiles are smem-bandwidth bound)
+        const double tile_cost[4] = {1.00, 0.83, 0.73, 0.50};
         double best = 1e30;
         const int num_m = (p.M + kBlockM - 1) / kBlockM;
-        for (int c : cands) {
+        for (int i = 0; i < 4; ++i) {
+            const int c = cands[i];
             if (c > 64 && p.N <= c / 2) continue;
             const int tiles = num_m * ((p.N + c - 1) / c);
             const int rounds = (tiles + sms - 1) / sms;
-            // narrower tiles re-read A more often and run the MMA at lower smem efficiency: small penalty
-            const double cost = rounds * (c + 24.0);
+            const double cost = rounds * tile_cost[i];
             if (cost < best) {
                 best = cost;
                 block_n = c;

@@ -29,66 +29,92 @@ __global__ void vae_input_kernel(const TIn* __restrict__ z, __nv_bfloat16* __res
     if (f == F - 1) out[at(F + 1)] = b;
 }
 
-// one warp per voxel; each lane owns C/32 contiguous channels
+// Channels are split into 16-byte chunks of 8; chunk j of a voxel is owned by lane (j % 32) so that every warp-wide
+// access is a contiguous 256/512-byte run.  C = 128 uses half a warp per voxel (2 voxels per warp), C >= 256 a full warp
+// with C/256 chunks per lane.  Warps stride over the voxels (persistent grid) with scale/shift held in registers.
 template <int C>
 __global__ void __launch_bounds__(256)
 vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
                 const float* __restrict__ shift, int do_norm, int do_silu, int T, int H, int W) {
-    constexpr int VPL = C / 32;  // values per lane: 4, 8, 16, 32
-    const int64_t vox = blockIdx.x * 8ll + (threadIdx.x >> 5);
+    constexpr int LPV = (C / 8 < 32) ? C / 8 : 32;  // lanes per voxel
+    constexpr int VPW = 32 / LPV;                    // voxels per warp
+    constexpr int CPL = (C / 8) / LPV;               // chunks per lane
     const int lane = threadIdx.x & 31;
+    const int sub = lane / LPV, l = lane % LPV;
     const int64_t nvox = static_cast<int64_t>(T) * H * W;
-    if (vox >= nvox) return;
-    const __nv_bfloat16* src = x + vox * C + lane * VPL;
-    float v[VPL];
-    if constexpr (VPL == 4) {
-        uint2 u = *reinterpret_cast<const uint2*>(src);
-        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-    } else {
-#pragma unroll
-        for (int q = 0; q < VPL / 8; ++q) {
-            uint4 u = reinterpret_cast<const uint4*>(src)[q];
-            v[8 * q + 0] = bf16_lo(u.x); v[8 * q + 1] = bf16_hi(u.x);
-            v[8 * q + 2] = bf16_lo(u.y); v[8 * q + 3] = bf16_hi(u.y);
-            v[8 * q + 4] = bf16_lo(u.z); v[8 * q + 5] = bf16_hi(u.z);
-            v[8 * q + 6] = bf16_lo(u.w); v[8 * q + 7] = bf16_hi(u.w);
-        }
-    }
-    if (do_norm) {
-        float s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) s2 += v[i] * v[i];
-        s2 = warp_sum(s2);
-        const float rinv = rsqrtf(s2 * (1.0f / C) + 1e-8f);
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) v[i] *= rinv;
-    }
+    const int64_t warp0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * VPW;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * 8 * VPW;
+    const int Hp = H + 2, Wp = W + 2;
+
+    float sc[CPL][8], sh[CPL][8];
     if (scale != nullptr) {
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) v[i] = v[i] * (1.0f + __ldg(scale + lane * VPL + i)) + __ldg(shift + lane * VPL + i);
-    }
-    if (do_silu) {
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) v[i] = silu_f32(v[i]);
-    }
-    const int w = static_cast<int>(vox % W), h = static_cast<int>((vox / W) % H), t = static_cast<int>(vox / (W * H));
-    const int Hp = H + 2, Wp = W + 2;
-    uint32_t pk[VPL / 2];
-#pragma unroll
-    for (int i = 0; i < VPL / 2; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-    auto store = [&](int tp) {
-        __nv_bfloat16* dst = out + ((static_cast<int64_t>(tp) * Hp + (h + 1)) * Wp + (w + 1)) * C + lane * VPL;
-        if constexpr (VPL == 4) {
-            *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < VPL / 8; ++q)
-                reinterpret_cast<uint4*>(dst)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int k = 0; k < CPL; ++k) {
+            const int c0 = (k * LPV + l) * 8;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(shift + c0));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+            sc[k][0] = 1.f + a.x; sc[k][1] = 1.f + a.y; sc[k][2] = 1.f + a.z; sc[k][3] = 1.f + a.w;
+            sc[k][4] = 1.f + b.x; sc[k][5] = 1.f + b.y; sc[k][6] = 1.f + b.z; sc[k][7] = 1.f + b.w;
+            sh[k][0] = c.x; sh[k][1] = c.y; sh[k][2] = c.z; sh[k][3] = c.w;
+            sh[k][4] = d.x; sh[k][5] = d.y; sh[k][6] = d.z; sh[k][7] = d.w;
         }
-    };
-    store(t + 1);
-    if (t == 0) store(0);
-    if (t == T - 1) store(T + 1);
+    }
+    for (int64_t base = warp0; base < nvox; base += stride) {
+        const int64_t vox_raw = base + sub;
+        const bool valid = vox_raw < nvox;
+        const int64_t vox = valid ? vox_raw : nvox - 1;
+        float v[CPL][8];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + vox * C + (k * LPV + l) * 8);
+            v[k][0] = bf16_lo(u.x); v[k][1] = bf16_hi(u.x); v[k][2] = bf16_lo(u.y); v[k][3] = bf16_hi(u.y);
+            v[k][4] = bf16_lo(u.z); v[k][5] = bf16_hi(u.z); v[k][6] = bf16_lo(u.w); v[k][7] = bf16_hi(u.w);
+        }
+        if (do_norm) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s2 += v[k][i] * v[k][i];
+#pragma unroll
+            for (int o = LPV / 2; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            const float rinv = rsqrtf(s2 * (1.0f / C) + 1e-8f);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[k][i] *= rinv;
+        }
+        if (scale != nullptr) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[k][i] = v[k][i] * sc[k][i] + sh[k][i];
+        }
+        if (do_silu) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[k][i] = silu_f32(v[k][i]);
+        }
+        if (!valid) continue;
+        const int w = static_cast<int>(vox % W), h = static_cast<int>((vox / W) % H), t = static_cast<int>(vox / (W * H));
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            uint4 o;
+            o.x = pack_bf16x2(v[k][0], v[k][1]);
+            o.y = pack_bf16x2(v[k][2], v[k][3]);
+            o.z = pack_bf16x2(v[k][4], v[k][5]);
+            o.w = pack_bf16x2(v[k][6], v[k][7]);
+            const int c0 = (k * LPV + l) * 8;
+            const int64_t row = (static_cast<int64_t>(t + 1) * Hp + (h + 1)) * Wp + (w + 1);
+            const int64_t plane = static_cast<int64_t>(Hp) * Wp;
+            *reinterpret_cast<uint4*>(out + row * C + c0) = o;
+            if (t == 0) *reinterpret_cast<uint4*>(out + (row - plane) * C + c0) = o;          // replicate frame 0
+            if (t == T - 1) *reinterpret_cast<uint4*>(out + (row + plane) * C + c0) = o;      // replicate frame T-1
+        }
+    }
 }
 
 template <typename TIn>
@@ -144,7 +170,9 @@ cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out, int C, int
 cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const float* shift, int do_norm, int do_silu,
                             int T, int H, int W, int C, cudaStream_t s) {
     const int64_t nvox = static_cast<int64_t>(T) * H * W;
-    const int grid = static_cast<int>((nvox + 7) / 8);
+    const int vpb = 8 * (C == 128 ? 2 : 1);  // voxels per block pass
+    int64_t want = (nvox + vpb - 1) / vpb;
+    const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
     switch (C) {

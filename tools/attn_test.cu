@@ -143,6 +143,8 @@ int main(int argc, char** argv) {
     fails += run(2, 4, 384, 384, 64, true, false, false, 2.0f);   // several kv tiles, batch
     fails += run(1, 3, 200, 200, 64, true, false, false, 4.0f);   // ragged q and kv tails, peaky softmax (rescale path)
     fails += run(1, 2, 1000, 1000, 64, true, false, false, 6.0f);
+    fails += run(1, 2, 300, 700, 64, false, false, false, 3.0f);  // v2 kernel: odd query tile count, ragged kv tail
+    fails += run(2, 3, 640, 1300, 64, false, false, false, 5.0f);  // v2: batch, peaky softmax (rescale path)
     fails += run(2, 4, 384, 128, 64, false, true, false, 1.0f);   // cross-attention with key-padding bias
     fails += run(1, 4, 300, 77, 64, false, true, false, 1.0f);    // ragged text length
     fails += run(1, 2, 256, 256, 128, true, false, false, 1.0f);  // 13B head_dim
