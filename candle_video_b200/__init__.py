@@ -38,6 +38,8 @@ EXPORTED_SYMBOLS = [
     "ltxv_denormalize_latents", "ltxv_postprocess_video", "ltxv_calculate_shift", "ltxv_scheduler_set_timesteps",
     "ltxv_pipeline_denoise", "ltxv_pipeline_decode", "ltxv_pipeline_denoise_host", "ltxv_pipeline_decode_host",
     "ltxv_profile_begin", "ltxv_profile_end",
+    "ltxv_comm_create", "ltxv_comm_destroy", "ltxv_comm_get_handle", "ltxv_comm_open", "ltxv_comm_barrier",
+    "ltxv_parallel_plan", "ltxv_pipeline_denoise_parallel", "ltxv_vae_set_comm",
 ]
 
 
@@ -122,6 +124,15 @@ def _load() -> C.CDLL:
     l.ltxv_pipeline_decode.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp]
     l.ltxv_pipeline_denoise_host.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32]
     l.ltxv_pipeline_decode_host.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp]
+    l.ltxv_comm_create.argtypes = [i32, i32, i32, u64, C.POINTER(vp)]
+    l.ltxv_comm_destroy.argtypes = [vp]
+    l.ltxv_comm_destroy.restype = None
+    l.ltxv_comm_get_handle.argtypes = [vp, vp]
+    l.ltxv_comm_open.argtypes = [vp, vp]
+    l.ltxv_comm_barrier.argtypes = [vp, vp]
+    l.ltxv_parallel_plan.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int32)]
+    l.ltxv_pipeline_denoise_parallel.argtypes = [vp, vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32, vp]
+    l.ltxv_vae_set_comm.argtypes = [vp, vp]
     l.ltxv_profile_begin.argtypes = []
     l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return l
@@ -611,3 +622,74 @@ def profile_end() -> Dict[str, Dict[str, float]]:
     fl = (C.c_double * 4)()
     _check(lib().ltxv_profile_end(n, ms, fl))
     return {PROFILE_CLASSES[i]: {"launches": int(n[i]), "ms": float(ms[i]), "flops": float(fl[i])} for i in range(4)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# multi-GPU (one process per GPU): peer-memory communicator bootstrapped over torch.distributed
+# ------------------------------------------------------------------------------------------------------------
+def parallel_plan(nranks: int, rank: int, seq_len: int, do_cfg: bool) -> Dict[str, int]:
+    """Host-only sharding plan of pipeline_denoise_parallel (CFG branch groups x Ulysses token shards)."""
+    out = (C.c_int32 * 6)()
+    _check(lib().ltxv_parallel_plan(nranks, rank, seq_len, int(do_cfg), out))
+    keys = ("cfg_groups", "sp_size", "branch", "sp_rank", "local_tokens", "token0")
+    return dict(zip(keys, [int(v) for v in out]))
+
+
+def exchange_handles(handle: bytes, group=None):
+    """All-gather the 64-byte CUDA IPC handles over torch.distributed (gloo or nccl); returns nranks*64 bytes."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    return b"".join(bytes(t.cpu().tolist()) for t in allh)
+
+
+class PeerComm:
+    """ltxv_comm: symmetric heap + flag barrier over NVLink peer memory (see include/ltxv.h, csrc/comm.h)."""
+
+    def __init__(self, nranks: int, rank: int, device: int, heap_bytes: int = 3 << 30, group=None):
+        self.nranks, self.rank = nranks, rank
+        self._h = C.c_void_p()
+        _check(lib().ltxv_comm_create(nranks, rank, device, heap_bytes, C.byref(self._h)))
+        if nranks > 1:
+            buf = (C.c_uint8 * 64)()
+            _check(lib().ltxv_comm_get_handle(self._h, buf))
+            allh = exchange_handles(bytes(buf), group)
+            _check(lib().ltxv_comm_open(self._h, allh))
+
+    def barrier(self) -> None:
+        _check(lib().ltxv_comm_barrier(self._h, _stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().ltxv_comm_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pipeline_denoise_parallel(dit: LtxVideoTransformer3DModel, comm: PeerComm, params: PipelineParams, latents,
+                              prompt_embeds, prompt_mask, negative_embeds=None, negative_mask=None):
+    """Denoise loop sharded over all ranks of `comm`: CFG branch split x Ulysses sequence parallelism."""
+    torch = _torch()
+    p, keep = params.to_c()
+    pe = _dev(prompt_embeds, "prompt_embeds")
+    pe = pe[0] if pe.dim() == 3 else pe
+    ne = _dev(negative_embeds, "negative_embeds")
+    if ne is not None and ne.dim() == 3:
+        ne = ne[0]
+    pm = None if prompt_mask is None else _dev(prompt_mask, "prompt_mask").to(torch.float32).reshape(-1).contiguous()
+    nm = None if negative_mask is None else _dev(negative_mask, "negative_mask").to(torch.float32).reshape(-1).contiguous()
+    if latents.dtype != torch.float32 or not latents.is_cuda or not latents.is_contiguous():
+        raise LtxvError("latents must be a contiguous float32 CUDA tensor")
+    _check(lib().ltxv_pipeline_denoise_parallel(dit._h, comm._h, C.byref(p), _ptr(latents), _ptr(pe), _ptr(pm),
+                                                _ptr(ne), _ptr(nm), _dtype_code(pe), pe.shape[0], _stream()))
+    return latents
+
+
+def vae_set_comm(vae: AutoencoderKLLtxVideo, comm: Optional[PeerComm]) -> None:
+    _check(lib().ltxv_vae_set_comm(vae._h, comm._h if comm is not None else None))

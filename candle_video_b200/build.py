@@ -34,6 +34,7 @@ LIB_SOURCES = [
     "dit.cu",
     "vae.cu",
     "pipeline.cu",
+    "comm.cu",
     "ffi.cu",
     "model_common.cu",
     "tensormap.cc",

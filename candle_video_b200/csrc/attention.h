@@ -20,6 +20,12 @@ struct AttnParams {
     const float* kv_bias;         // optional [B, Skv] additive bias on the scaled scores (e.g. (1-mask)*-10000)
     int B, H, Sq, Skv, D;         // D in {64, 128}
     float scale;                  // 1/sqrt(D)  (ltx_transformer.rs:686)
+    // Sequence-parallel epilogue (Ulysses gather fused into the attention kernel): when out_rows_per_peer > 0, query
+    // row q belongs to rank q / out_rows_per_peer and is stored at out_peer[that rank] row (q % out_rows_per_peer),
+    // column out_col0 + head*D of an [out_rows_per_peer, ldo] matrix (NVLink peer store).
+    void* out_peer[8];
+    int out_rows_per_peer;
+    int out_col0;
 };
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);

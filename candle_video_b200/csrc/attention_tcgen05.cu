@@ -41,6 +41,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #endif
 }
 
+
+__device__ __forceinline__ __nv_bfloat16* attn_out_row(const AttnParams& p, int batch, int qrow, int head, int D) {
+    if (p.out_rows_per_peer > 0) {
+        const int owner = qrow / p.out_rows_per_peer;
+        const int lr = qrow - owner * p.out_rows_per_peer;
+        return reinterpret_cast<__nv_bfloat16*>(p.out_peer[owner]) + static_cast<int64_t>(lr) * p.ldo + p.out_col0 + head * D;
+    }
+    return reinterpret_cast<__nv_bfloat16*>(p.out) + (static_cast<int64_t>(batch) * p.Sq + qrow) * p.ldo + head * D;
+}
+
 template <int D>
 struct ACfg {
     static constexpr int kQBytes = kTileQ * D * 2;
@@ -303,8 +313,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         tcgen05_fence_after();
         const float inv_l = 1.0f / l;
         const int qrow = q0 + row;
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                              (static_cast<int64_t>(batch) * p.Sq + qrow) * p.ldo + head * D;
+        __nv_bfloat16* orow = attn_out_row(p, batch, qrow < p.Sq ? qrow : 0, head, D);
 #pragma unroll 1
         for (int dc = 0; dc < D / 32; ++dc) {
             uint32_t r[32];
@@ -662,8 +671,7 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tcgen05_fence_after();
             const float inv_l = 1.0f / (l0 + l1);
             const int qrow = q0 + t * kTileQ + row;
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                  (static_cast<int64_t>(batch) * p.Sq + qrow) * p.ldo + head * D;
+            __nv_bfloat16* orow = attn_out_row(p, batch, qrow < p.Sq ? qrow : 0, head, D);
 #pragma unroll 1
             for (int dc = 0; dc < D / 32; ++dc) {
                 uint32_t r[32];

@@ -172,6 +172,25 @@ void LtxVideoTransformer3DModel::set_skip_block_list(const int32_t* idx, int n) 
     skip_blocks_.assign(idx, idx + (n > 0 ? n : 0));
 }
 
+void LtxVideoTransformer3DModel::set_comm(PeerComm* comm, int first, int count) {
+    if (comm == nullptr || count <= 1) {
+        comm_ = nullptr;
+        sp_first_ = 0;
+        sp_count_ = 1;
+        return;
+    }
+    if (first < 0 || first + count > comm->nranks() || comm->rank() < first || comm->rank() >= first + count)
+        fail("sequence-parallel group [%d,%d) does not contain rank %d", first, first + count, comm->rank());
+    if (cfg_.num_attention_heads % count != 0)
+        fail("num_attention_heads (%d) must be divisible by the sequence-parallel size %d", cfg_.num_attention_heads, count);
+    comm_ = comm;
+    sp_first_ = first;
+    sp_count_ = count;
+    if (comm->id() != sp_alloc_comm_ || count != sp_alloc_count_) sp_S_ = 0;  // otherwise keep the heap buffers
+    sp_alloc_comm_ = comm->id();
+    sp_alloc_count_ = count;
+}
+
 void LtxVideoTransformer3DModel::ensure_workspace(int S) {
     const int D = inner_dim();
     const int L = cfg_.num_layers;
@@ -191,6 +210,14 @@ void LtxVideoTransformer3DModel::ensure_workspace(int S) {
         ws_S_ = S;
     }
     small_.ensure((256 + 2 * static_cast<size_t>(D) + 6 * D + static_cast<size_t>(L) * 6 * D + 2 * D) * 4);
+    if (comm_ != nullptr && S != sp_S_) {
+        // a new shard size carves fresh buffers (the symmetric heap is a bump allocator; all ranks of the group take
+        // this branch in the same call, so offsets stay identical across ranks)
+        const size_t Dg = static_cast<size_t>(D) / sp_count_;
+        sp_qkv_off_ = comm_->alloc(static_cast<size_t>(S) * sp_count_ * 3 * Dg * 2);
+        sp_attn_off_ = comm_->alloc(static_cast<size_t>(S) * D * 2);
+        sp_S_ = S;
+    }
 }
 
 void LtxVideoTransformer3DModel::gemm(const void* a, int64_t a_rows, const LinearW& lin, int M, int epi, int act,
@@ -258,9 +285,9 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
     if (!finalized_) finalize();
     if (slot < 0 || slot > kNumSlots || !ctx_[slot].valid) fail("context slot %d has not been prepared", slot);
     if (S <= 0) fail("sequence length must be positive");
-    if (video_coords == nullptr && static_cast<int64_t>(F) * H * W != S)
+    if (video_coords == nullptr && static_cast<int64_t>(F) * H * W != static_cast<int64_t>(S) * sp_count_)
         fail("num_frames*height*width (%d*%d*%d) must equal the sequence length %d when video_coords is not given", F, H,
-             W, S);
+             W, S * sp_count_);
     if (out_dtype != LTXV_F32 && out_dtype != LTXV_BF16) fail("unsupported output dtype %d", out_dtype);
     LTXV_CUDA(cudaSetDevice(device_));
     const DitContext& ctx = ctx_[slot];
@@ -295,7 +322,10 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
         scale3[2] = static_cast<float>(static_cast<double>(rope_scale3_host[2]) * cfg_.patch_size / 2048.0);
         sc = scale3;
     }
-    LTXV_CUDA(launch_rope_table(video_coords, F, H, W, sc, S, D, 10000.0f, cos_.as<float>(), sin_.as<float>(), s));
+    const bool sp = comm_ != nullptr;
+    const int spn = sp_count_, spr = sp_rank();
+    LTXV_CUDA(launch_rope_table(video_coords, F, H, W, sc, S, D, 10000.0f, cos_.as<float>(), sin_.as<float>(), s,
+                                sp ? spr * S : 0));
 
     // ---- proj_in (:1049) ----
     const void* a_in = hidden;
@@ -328,9 +358,10 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
         // --- self-attention ---
         LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 1 * D, a6 + 0 * D, S, D, cfg_.norm_eps, NORM_RMS, s));
         gemm(h_.p, S, b.qkv1, S, EPI_STORE_BF16, ACT_NONE, qkv_.p, nullptr, nullptr, s);
-        LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, 0, S, D, b.norm_q1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
-        LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, D, S, D, b.norm_k1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
-        {
+        const void* attn1_out = attn_.p;
+        if (!sp) {
+            LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, 0, S, D, b.norm_q1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
+            LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, D, S, D, b.norm_k1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
             AttnParams ap{};
             ap.q = ap.k = ap.v = qkv_.p;
             ap.ldq = ap.ldk = ap.ldv = 3 * D;
@@ -347,8 +378,38 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
             ap.D = hd;
             ap.scale = attn_scale;
             LTXV_CUDA(launch_attention(ap, s));
+        } else {
+            // Ulysses: tokens -> heads.  The norm+RoPE kernel stores each head group straight into the rank that owns
+            // those heads; the attention epilogue stores each query block straight into the rank that owns those tokens.
+            const int Dg = D / spn;
+            ScatterDst dst{};
+            for (int g = 0; g < spn; ++g) dst.p[g] = comm_->peer(sp_first_ + g, sp_qkv_off_);
+            LTXV_CUDA(launch_qkv_norm_rope_scatter(qkv_.p, S, D, spn, spr * S, b.norm_q1, b.norm_k1, 1e-5f,
+                                                   cos_.as<float>(), sin_.as<float>(), dst, s));
+            comm_->barrier(s, 1, sp_first_, spn);
+            AttnParams ap{};
+            ap.q = ap.k = ap.v = comm_->local(sp_qkv_off_);
+            ap.ldq = ap.ldk = ap.ldv = 3 * Dg;
+            ap.q_col0 = 0;
+            ap.k_col0 = Dg;
+            ap.v_col0 = 2 * Dg;
+            ap.out = nullptr;
+            ap.ldo = D;
+            ap.kv_bias = nullptr;
+            ap.B = 1;
+            ap.H = heads / spn;
+            ap.Sq = S * spn;
+            ap.Skv = S * spn;
+            ap.D = hd;
+            ap.scale = attn_scale;
+            for (int g = 0; g < spn; ++g) ap.out_peer[g] = comm_->peer(sp_first_ + g, sp_attn_off_);
+            ap.out_rows_per_peer = S;
+            ap.out_col0 = spr * Dg;
+            LTXV_CUDA(launch_attention(ap, s));
+            comm_->barrier(s, 1, sp_first_, spn);
+            attn1_out = comm_->local(sp_attn_off_);
         }
-        gemm(attn_.p, S, b.out1, S, EPI_RESIDUAL_F32, ACT_NONE, xb_.p, x, a6 + 2 * D, s);  // x += gate_msa * attn1
+        gemm(attn1_out, S, b.out1, S, EPI_RESIDUAL_F32, ACT_NONE, xb_.p, x, a6 + 2 * D, s);  // x += gate_msa * attn1
 
         // --- cross-attention (no norm, no gate, no RoPE; :903-909) ---
         gemm(xb_.p, S, b.q2, S, EPI_STORE_BF16, ACT_NONE, q2_.p, nullptr, nullptr, s);

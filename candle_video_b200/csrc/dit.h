@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.h"
 #include "model_common.h"
 
 namespace ltxv {
@@ -49,6 +50,11 @@ public:
     void init_random(uint64_t seed);
     void finalize();
     void set_skip_block_list(const int32_t* idx, int n);  // ltx_transformer.rs:1024
+    // Ulysses sequence parallelism over ranks [first, first+count) of `comm`: forward_ctx then takes this rank's
+    // contiguous token shard (S = local tokens) and exchanges heads <-> tokens around self-attention through peer memory
+    void set_comm(PeerComm* comm, int first, int count);
+    int sp_size() const { return sp_count_; }
+    int sp_rank() const { return comm_ ? comm_->rank() - sp_first_ : 0; }
 
     // hoisted text path (one batch entry)
     void prepare_context(int slot, const void* enc, int enc_dtype, const float* mask, int K, cudaStream_t s);
@@ -90,6 +96,14 @@ private:
     DevBuf x_, xb_, h_, qkv_, attn_, q2_, ff_, a_in_, cos_, sin_, out_f32_, orig_;
     DevBuf small_;  // tp[256] | t1[D] | e[D] | temb[6D] | ada[L*6D] | fin[2D]
     DevBuf enc_bf16_, cap_mid_, enc_proj_;
+
+    // sequence parallel state
+    PeerComm* comm_ = nullptr;
+    int sp_first_ = 0, sp_count_ = 1;
+    int sp_S_ = 0;                       // local token capacity of the symmetric buffers
+    uint64_t sp_alloc_comm_ = 0;         // communicator id / group size the symmetric buffers were carved for
+    int sp_alloc_count_ = 0;
+    size_t sp_qkv_off_ = 0, sp_attn_off_ = 0;  // heap offsets: qkv_full [S_total, 3*D/N], attn_in [S_local, D]
 };
 
 }  // namespace ltxv

@@ -2,6 +2,7 @@
 #include <string.h>
 
 #include "attention.h"
+#include "comm.h"
 #include "dit.h"
 #include "gemm.h"
 #include "glue.h"
@@ -16,6 +17,10 @@ struct ltxv_dit {
     LtxVideoTransformer3DModel model;
     DevBuf h_hidden, h_enc, h_t, h_mask, h_coords, h_out;  // device staging for the *_host entry points
     ltxv_dit(const ltxv_dit_config& c, int dev) : model(c, dev) {}
+};
+struct ltxv_comm {
+    PeerComm comm;
+    ltxv_comm(int n, int r, int dev, size_t heap) : comm(n, r, dev, heap) {}
 };
 struct ltxv_vae {
     AutoencoderKLLtxVideo model;
@@ -48,7 +53,7 @@ const char* ltxv_last_error(void) { return last_error_ref().c_str(); }
 const char* ltxv_version(void) { return "ltxv_b200 0.1 (sm_100a: tcgen05 GEMM/conv3d/attention)"; }
 uint64_t ltxv_launch_count(void) {
     return gemm_launch_count() + attention_launch_count() + glue_launch_count() + vae_glue_launch_count() +
-           common_launch_count();
+           common_launch_count() + comm_launch_count();
 }
 
 int ltxv_profile_begin(void) {
@@ -348,6 +353,57 @@ int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const flo
     LTXV_TRY
     if (vae == nullptr || p == nullptr || latents == nullptr || out == nullptr) fail("null argument");
     pipeline_decode(vae->model, *p, latents, out, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+int ltxv_comm_create(int nranks, int rank, int device, uint64_t heap_bytes, ltxv_comm** out) {
+    LTXV_TRY
+    if (out == nullptr) fail("null argument");
+    *out = new ltxv_comm(nranks, rank, device, static_cast<size_t>(heap_bytes));
+    LTXV_CATCH
+}
+void ltxv_comm_destroy(ltxv_comm* c) { delete c; }
+int ltxv_comm_get_handle(ltxv_comm* c, void* handle64) {
+    LTXV_TRY
+    if (c == nullptr || handle64 == nullptr) fail("null argument");
+    c->comm.get_handle(handle64);
+    LTXV_CATCH
+}
+int ltxv_comm_open(ltxv_comm* c, const void* all_handles) {
+    LTXV_TRY
+    if (c == nullptr || all_handles == nullptr) fail("null argument");
+    c->comm.open_peers(all_handles);
+    LTXV_CATCH
+}
+int ltxv_comm_barrier(ltxv_comm* c, void* stream) {
+    LTXV_TRY
+    if (c == nullptr) fail("null argument");
+    c->comm.barrier(static_cast<cudaStream_t>(stream), 0);
+    LTXV_CATCH
+}
+int ltxv_parallel_plan(int nranks, int rank, int S, int do_cfg, int32_t* out6) {
+    LTXV_TRY
+    if (out6 == nullptr) fail("null argument");
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) fail("invalid rank %d of %d", rank, nranks);
+    const ParallelPlan pl = make_parallel_plan(nranks, rank, S, do_cfg != 0);
+    out6[0] = pl.cfg_groups; out6[1] = pl.sp; out6[2] = pl.branch; out6[3] = pl.sp_rank; out6[4] = pl.s_local;
+    out6[5] = pl.token0;
+    LTXV_CATCH
+}
+int ltxv_pipeline_denoise_parallel(ltxv_dit* dit, ltxv_comm* c, const ltxv_pipeline_params* p, float* latents,
+                                   const void* prompt_embeds, const float* prompt_mask, const void* negative_embeds,
+                                   const float* negative_mask, int embeds_dtype, int K, void* stream) {
+    LTXV_TRY
+    if (dit == nullptr || c == nullptr || p == nullptr || latents == nullptr || prompt_embeds == nullptr)
+        fail("null argument");
+    pipeline_denoise_parallel(dit->model, c->comm, *p, latents, prompt_embeds, prompt_mask, negative_embeds,
+                              negative_mask, embeds_dtype, K, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+int ltxv_vae_set_comm(ltxv_vae* vae, ltxv_comm* c) {
+    LTXV_TRY
+    if (vae == nullptr) fail("null argument");
+    vae->model.set_comm(c ? &c->comm : nullptr);
     LTXV_CATCH
 }
 

@@ -42,6 +42,8 @@ struct GemmParams {
     const void* a_ptr;  // base of the padded A volume (EPI_CONV_D2S reads its residual from here)
     int cin;            // Cin
     int post_u8_scale;  // EPI_CONV_UNPATCHIFY: 1 => also apply clamp(0.5x+0.5,0,1)*255 (t2v_pipeline.rs:147-155)
+    int out_h0;         // EPI_CONV_UNPATCHIFY, H-slab decode: first pixel row of this slab in the full frame
+    int out_h_full;     // ... and the full frame height in pixels (0 = 4*H, single slab)
 };
 
 // A: [rows_a, K_a] bf16 row-major (K contiguous). B: [N, K] bf16 row-major (nn.Linear weight layout).

@@ -192,7 +192,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const RowCtx
         case EPI_CONV_UNPATCHIFY: {
             // out[c3, f, 4h+j, 4w+i] = x[c3*16 + i*4 + j] (vae.rs:1626-1654); N = 48 (3 colour planes)
             float* out = reinterpret_cast<float*>(p.out);
-            const int Ho = 4 * p.H, Wo = 4 * p.W;
+            const int Ho = p.out_h_full > 0 ? p.out_h_full : 4 * p.H, Wo = 4 * p.W;
 #pragma unroll
             for (int cl = 0; cl < 2; ++cl) {
                 const int c3 = (col0 >> 4) + cl;
@@ -208,7 +208,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const RowCtx
                         o.w = fminf(fmaxf(0.5f * o.w + 0.5f, 0.f), 1.f) * 255.f;
                     }
                     const int64_t idx =
-                        ((static_cast<int64_t>(c3) * p.T + rc.t) * Ho + (4 * rc.h + j)) * Wo + 4 * rc.w;
+                        ((static_cast<int64_t>(c3) * p.T + rc.t) * Ho + (p.out_h0 + 4 * rc.h + j)) * Wo + 4 * rc.w;
                     *reinterpret_cast<float4*>(out + idx) = o;
                 }
             }

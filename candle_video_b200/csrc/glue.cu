@@ -121,11 +121,73 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int row
     }
 }
 
+// Ulysses scatter fused with the q/k norm + RoPE (see glue.h)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+qkv_norm_rope_scatter_kernel(const __nv_bfloat16* __restrict__ x, int rows, int D, int nranks, int row0,
+                             const float* __restrict__ wq, const float* __restrict__ wk, float eps,
+                             const float* __restrict__ cos_t, const float* __restrict__ sin_t, ScatterDst dst) {
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = D >> 3;
+    const int Dg = D / nranks;
+    const int64_t drow = static_cast<int64_t>(row0 + row) * 3 * Dg;
+    const float4* c4 = reinterpret_cast<const float4*>(cos_t + static_cast<int64_t>(row) * (D >> 1));
+    const float4* s4 = reinterpret_cast<const float4*>(sin_t + static_cast<int64_t>(row) * (D >> 1));
+#pragma unroll 1
+    for (int which = 0; which < 3; ++which) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * 3 * D + which * D);
+        float rinv = 1.0f;
+        const float* w = which == 0 ? wq : wk;
+        if (which < 2) {
+            float s2 = 0.f;
+            for (int i = lane; i < nv; i += 32) {
+                uint4 u = xr[i];
+                float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                              bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s2 += f[j] * f[j];
+            }
+            s2 = warp_sum(s2);
+            rinv = rsqrtf(s2 * (1.0f / D) + eps);
+        }
+        for (int i = lane; i < nv; i += 32) {
+            uint4 u = xr[i];
+            if (which < 2) {
+                float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                              bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * i);
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+                const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = f[j] * rinv * ww[j];
+                const float4 cc = __ldg(c4 + i), ss = __ldg(s4 + i);
+                const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float re = f[2 * j], im = f[2 * j + 1];
+                    f[2 * j] = re * cv[j] - im * sv[j];
+                    f[2 * j + 1] = im * cv[j] + re * sv[j];
+                }
+                u.x = pack_bf16x2(f[0], f[1]);
+                u.y = pack_bf16x2(f[2], f[3]);
+                u.z = pack_bf16x2(f[4], f[5]);
+                u.w = pack_bf16x2(f[6], f[7]);
+            }
+            const int col = i * 8;
+            const int g = col / Dg;
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst.p[g]) + drow + which * Dg + (col - g * Dg);
+            *reinterpret_cast<uint4*>(d) = u;  // NVLink peer store (or local when g == rank)
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // RoPE table
 // ------------------------------------------------------------------------------------------------
 __global__ void rope_table_kernel(const float* __restrict__ coords, int F, int H, int W, float m0, float m1, float m2,
-                                  int S, int D, float theta_ln, float* __restrict__ cos_t, float* __restrict__ sin_t) {
+                                  int S, int D, float theta_ln, float* __restrict__ cos_t, float* __restrict__ sin_t,
+                                  int token0) {
     const int half = D >> 1;
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<int64_t>(S) * half) return;
@@ -141,7 +203,8 @@ __global__ void rope_table_kernel(const float* __restrict__ coords, int F, int H
         if (coords != nullptr) {
             g = coords[static_cast<int64_t>(s) * 3 + a] * (a == 0 ? m0 : (a == 1 ? m1 : m2));
         } else {
-            const int w = s % W, h = (s / W) % H, f = s / (W * H);
+            const int sg = s + token0;  // global token index (sequence-parallel shards start at token0)
+            const int w = sg % W, h = (sg / W) % H, f = sg / (W * H);
             const float v = static_cast<float>(a == 0 ? f : (a == 1 ? h : w));
             g = v * (a == 0 ? m0 : (a == 1 ? m1 : m2));
         }
@@ -319,12 +382,18 @@ __global__ void guidance_stats_kernel(const float* __restrict__ cond, const floa
 __global__ void guidance_euler_kernel(const float* __restrict__ cond, const float* __restrict__ uncond,
                                       const float* __restrict__ pert, float* __restrict__ latents,
                                       float* __restrict__ noise_out, int64_t n, float g, float r, float s_stg, float dt,
-                                      const double* __restrict__ acc) {
+                                      StatParts parts) {
     float ratio = 1.0f;
     if (r > 0.0f && uncond != nullptr) {
-        const double nn = static_cast<double>(n);
-        const double var_c = (acc[1] - acc[0] * acc[0] / nn) / (nn - 1.0);
-        const double var_m = (acc[3] - acc[2] * acc[2] / nn) / (nn - 1.0);
+        // the std runs over ALL non-batch elements (t2v_pipeline.rs:209-224): with token shards the per-rank partial
+        // sums are added here in rank order, so every rank of the group derives the same ratio
+        double a[4] = {0, 0, 0, 0};
+        for (int k = 0; k < parts.n; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] += parts.p[k][j];
+        const double nn = static_cast<double>(parts.n_total);
+        const double var_c = (a[1] - a[0] * a[0] / nn) / (nn - 1.0);
+        const double var_m = (a[3] - a[2] * a[2] / nn) / (nn - 1.0);
         ratio = static_cast<float>(sqrt(var_c) / sqrt(var_m));
     }
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -386,8 +455,17 @@ cudaError_t launch_qk_norm_rope(void* x, int64_t ld, int col0, int rows, int D, 
     return done();
 }
 
+cudaError_t launch_qkv_norm_rope_scatter(const void* x, int rows, int D, int nranks, int row0, const float* wq,
+                                         const float* wk, float eps, const float* cos_t, const float* sin_t,
+                                         const ScatterDst& dst, cudaStream_t s) {
+    if (D % (8 * nranks) != 0 || cos_t == nullptr || sin_t == nullptr) return cudaErrorInvalidValue;
+    qkv_norm_rope_scatter_kernel<<<blocks_for(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), rows, D, nranks, row0, wq, wk, eps, cos_t, sin_t, dst);
+    return done();
+}
+
 cudaError_t launch_rope_table(const float* coords, int F, int H, int W, const float* scale3, int S, int D, float theta,
-                              float* cos_t, float* sin_t, cudaStream_t s) {
+                              float* cos_t, float* sin_t, cudaStream_t s, int token0) {
     float m0, m1, m2;
     if (coords != nullptr) {  // :454-460, multiply by f32(1/base)
         m0 = static_cast<float>(1.0 / static_cast<double>(20.0f));
@@ -400,7 +478,7 @@ cudaError_t launch_rope_table(const float* coords, int F, int H, int W, const fl
     }
     const int64_t n = static_cast<int64_t>(S) * (D / 2);
     rope_table_kernel<<<blocks_for(n, 256), 256, 0, s>>>(coords, F, H, W, m0, m1, m2, S, D,
-                                                        static_cast<float>(log(static_cast<double>(theta))), cos_t, sin_t);
+                                                        static_cast<float>(log(static_cast<double>(theta))), cos_t, sin_t, token0);
     return done();
 }
 
@@ -472,21 +550,38 @@ cudaError_t launch_video_coords(float* out, int F, int H, int W, int ts_ratio, i
     return done();
 }
 
+cudaError_t launch_guidance_stats(const float* cond, const float* uncond, int64_t n, float g, double* acc4,
+                                  cudaStream_t s) {
+    if (acc4 == nullptr || uncond == nullptr) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(acc4, 0, 4 * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    int grid = blocks_for(n, 256 * 8);
+    if (grid > 1184) grid = 1184;
+    guidance_stats_kernel<<<grid, 256, 0, s>>>(cond, uncond, n, g, acc4);
+    return done();
+}
+
+cudaError_t launch_guidance_euler_parts(const float* cond, const float* uncond, const float* pert, float* latents,
+                                        float* noise_out, int64_t n, float g, float r, float s_stg, float dt,
+                                        const StatParts& parts, cudaStream_t s) {
+    if (r > 0.0f && uncond != nullptr && (parts.n < 1 || parts.n > 8 || parts.n_total < 2)) return cudaErrorInvalidValue;
+    guidance_euler_kernel<<<blocks_for(n, 256), 256, 0, s>>>(cond, uncond, pert, latents, noise_out, n, g, r, s_stg, dt,
+                                                            parts);
+    return done();
+}
+
 cudaError_t launch_guidance_euler(const float* cond, const float* uncond, const float* pert, float* latents,
                                   float* noise_out, int64_t n, float g, float r, float s_stg, float dt, double* scratch,
                                   cudaStream_t s) {
+    StatParts parts{};
     if (r > 0.0f && uncond != nullptr) {
-        if (scratch == nullptr) return cudaErrorInvalidValue;
-        cudaError_t e = cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s);
+        cudaError_t e = launch_guidance_stats(cond, uncond, n, g, scratch, s);
         if (e != cudaSuccess) return e;
-        int grid = blocks_for(n, 256 * 8);
-        if (grid > 1184) grid = 1184;
-        guidance_stats_kernel<<<grid, 256, 0, s>>>(cond, uncond, n, g, scratch);
-        g_glue_launches.fetch_add(1, std::memory_order_relaxed);
+        parts.p[0] = scratch;
+        parts.n = 1;
+        parts.n_total = n;
     }
-    guidance_euler_kernel<<<blocks_for(n, 256), 256, 0, s>>>(cond, uncond, pert, latents, noise_out, n, g, r, s_stg, dt,
-                                                            scratch);
-    return done();
+    return launch_guidance_euler_parts(cond, uncond, pert, latents, noise_out, n, g, r, s_stg, dt, parts, s);
 }
 
 cudaError_t launch_denormalize(const float* in, float* out, const float* mean, const float* std, float inv_sf, int C,

@@ -23,7 +23,17 @@ cudaError_t launch_qk_norm_rope(void* x_bf16, int64_t ld, int col0, int rows, in
 // coords != null: coords [S,3] f32 (seconds, pixel-y, pixel-x), divided by base (20, 2048, 2048).
 // coords == null: token grid (f,h,w) from F,H,W, optionally multiplied by scale3 = (sf*pt/20, sh*p/2048, sw*p/2048).
 cudaError_t launch_rope_table(const float* coords, int F, int H, int W, const float* scale3_host, int S, int D,
-                              float theta, float* cos_t, float* sin_t, cudaStream_t s);
+                              float theta, float* cos_t, float* sin_t, cudaStream_t s, int token0 = 0);
+
+// Ulysses scatter fused with q/k RMS-norm + RoPE: local fused projections x [rows, 3D] (q | k | v) are normed /
+// rotated (q, k) or copied (v) and written head-group-wise into the peers' [S_total, 3*D/nranks] buffers:
+// columns of head group g go to dst[g] at row (row0 + r), column (which * D/nranks + col % (D/nranks)).
+struct ScatterDst {
+    void* p[8];
+};
+cudaError_t launch_qkv_norm_rope_scatter(const void* x_bf16, int rows, int D, int nranks, int row0, const float* wq,
+                                         const float* wk, float eps, const float* cos_t, const float* sin_t,
+                                         const ScatterDst& dst, cudaStream_t s);
 
 // y[n] = act_out( sum_k act_in(x[k]) * W[n,k] + b[n] ),  W bf16 [N,K], x/y f32; batch rows handled by the caller.
 enum GemvAct : int { GEMV_NONE = 0, GEMV_SILU = 1 };
@@ -64,6 +74,20 @@ cudaError_t launch_video_coords(float* out, int F, int H, int W, int ts_ratio, i
 cudaError_t launch_guidance_euler(const float* cond, const float* uncond, const float* perturbed, float* latents,
                                   float* noise_pred_out, int64_t n, float guidance_scale, float guidance_rescale,
                                   float stg_scale, float dt, double* scratch, cudaStream_t s);
+
+// Token-sharded form of the same update (multi-GPU): every rank first accumulates the partial sums of ITS shard
+// (launch_guidance_stats -> acc4 = {sum c, sum c^2, sum comb, sum comb^2}, f64), then -- after a barrier -- the update
+// kernel adds the partials of all ranks of the group (peer pointers) so the std is the one over the whole tensor.
+struct StatParts {
+    const double* p[8];
+    int n;            // number of partial-sum blocks
+    int64_t n_total;  // elements of the whole (unsharded) batch entry
+};
+cudaError_t launch_guidance_stats(const float* cond, const float* uncond, int64_t n, float guidance_scale, double* acc4,
+                                  cudaStream_t s);
+cudaError_t launch_guidance_euler_parts(const float* cond, const float* uncond, const float* perturbed, float* latents,
+                                        float* noise_pred_out, int64_t n, float guidance_scale, float guidance_rescale,
+                                        float stg_scale, float dt, const StatParts& parts, cudaStream_t s);
 
 // x*std_c*(1/sf)+mean_c on [C, N] (per-channel), f32  (:573-594)
 cudaError_t launch_denormalize(const float* in, float* out, const float* mean, const float* std, float inv_sf, int C,

@@ -132,6 +132,144 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
     }
 }
 
+ParallelPlan make_parallel_plan(int nranks, int rank, int S, bool do_cfg) {
+    ParallelPlan pl{};
+    pl.cfg_groups = (do_cfg && nranks % 2 == 0) ? 2 : 1;
+    pl.sp = nranks / pl.cfg_groups;
+    if (S % pl.sp != 0) fail("sequence length %d is not divisible by the sequence-parallel size %d", S, pl.sp);
+    pl.branch = rank / pl.sp;   // 0 = unconditional (or the only branch), 1 = conditional
+    pl.sp_rank = rank % pl.sp;
+    pl.s_local = S / pl.sp;
+    pl.token0 = pl.sp_rank * pl.s_local;
+    return pl;
+}
+
+void pipeline_denoise_parallel(LtxVideoTransformer3DModel& dit, PeerComm& comm, const ltxv_pipeline_params& p,
+                               float* latents, const void* prompt, const float* prompt_mask, const void* negative,
+                               const float* negative_mask, int embeds_dtype, int K, cudaStream_t s) {
+    if (p.height % 32 != 0 || p.width % 32 != 0)
+        fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
+    const int F = (p.num_frames - 1) / 8 + 1, H = p.height / 32, W = p.width / 32;
+    const int S = F * H * W;
+    const int C = dit.config().in_channels;
+    const bool do_cfg = p.guidance_scale > 1.0f;
+    const bool do_stg = p.stg_scale > 0.0f;
+    if (do_cfg && negative == nullptr) fail("negative prompt embeddings are required when guidance_scale > 1");
+    const int N = comm.nranks(), rank = comm.rank();
+    const ParallelPlan pl = make_parallel_plan(N, rank, S, do_cfg);
+    const bool split = pl.cfg_groups == 2;
+    if (p.skip_block_list != nullptr) {
+        if (!do_stg) dit.set_skip_block_list(p.skip_block_list, p.num_skip_blocks);
+        else dit.set_skip_block_list(nullptr, 0);
+    }
+    dit.set_comm(&comm, pl.branch * pl.sp, pl.sp);
+
+    const int n = p.num_inference_steps;
+    std::vector<float> sigmas(n + 1);
+    std::vector<int64_t> tsteps(n);
+    const float mu = p.custom_sigmas ? 0.0f : calculate_shift(S);
+    scheduler_set_timesteps(n, p.custom_sigmas, mu, p.has_shift_terminal != 0, p.shift_terminal, sigmas.data(),
+                            tsteps.data());
+    PipeWs& w = ws();
+    const size_t loc_elems = static_cast<size_t>(pl.s_local) * C;
+    w.coords.ensure(static_cast<size_t>(S) * 3 * 4);
+    w.ts.ensure(static_cast<size_t>(n) * 4);
+    w.scratch.ensure(64);
+    // symmetric buffers: branch outputs [3][s_local, C] f32 (uncond, cond, perturbed) and the gathered latents [S, C]
+    static size_t xchg_off = 0, lat_off = 0, stat_off = 0;
+    static uint64_t xchg_comm = 0;
+    static size_t xchg_elems = 0;
+    if (xchg_comm != comm.id() || xchg_elems != loc_elems) {
+        xchg_off = comm.alloc(3 * loc_elems * 4);
+        lat_off = comm.alloc(static_cast<size_t>(S) * C * 4);
+        stat_off = comm.alloc(4 * sizeof(double));
+        xchg_comm = comm.id();
+        xchg_elems = loc_elems;
+    }
+    float* x_unc = static_cast<float*>(comm.local(xchg_off));
+    float* x_cond = x_unc + loc_elems;
+    float* x_pert = x_cond + loc_elems;
+    float* lat_loc = latents + static_cast<size_t>(pl.token0) * C;  // this rank updates only its token shard
+
+    std::vector<float> ts_f(n);
+    for (int i = 0; i < n; ++i) ts_f[i] = static_cast<float>(tsteps[i]);
+    LTXV_CUDA(cudaMemcpyAsync(w.ts.p, ts_f.data(), n * 4, cudaMemcpyHostToDevice, s));
+    LTXV_CUDA(cudaStreamSynchronize(s));
+    LTXV_CUDA(launch_video_coords(w.coords.as<float>(), F, H, W, 8, 32, p.frame_rate, s));
+    const float* coords_loc = w.coords.as<float>() + static_cast<size_t>(pl.token0) * 3;
+
+    // text contexts: only the branches this rank runs
+    const bool run_uncond = do_cfg && (!split || pl.branch == 0);
+    const bool run_cond = !split || pl.branch == 1 || !do_cfg;
+    if (run_cond) dit.prepare_context(0, prompt, embeds_dtype, prompt_mask, K, s);
+    if (run_uncond) dit.prepare_context(1, negative, embeds_dtype, negative_mask, K, s);
+    std::vector<float> stg_mask;
+    if (do_stg) {
+        stg_mask.assign(dit.config().num_layers, 0.0f);
+        for (int i = 0; i < p.num_skip_blocks; ++i)
+            if (p.skip_block_list[i] >= 0 && p.skip_block_list[i] < dit.config().num_layers)
+                stg_mask[p.skip_block_list[i]] = 1.0f;
+    }
+    const int partner = split ? (rank + pl.sp) % N : rank;
+    const bool rescale = do_cfg && p.guidance_rescale > 0.0f;
+    for (int i = 0; i < n; ++i) {
+        const float* t_dev = w.ts.as<float>() + i;
+        if (run_uncond)
+            dit.forward_ctx(1, lat_loc, LTXV_F32, t_dev, pl.s_local, F, H, W, nullptr, coords_loc, nullptr, 1, x_unc,
+                            LTXV_F32, s);
+        if (run_cond) {
+            dit.forward_ctx(0, lat_loc, LTXV_F32, t_dev, pl.s_local, F, H, W, nullptr, coords_loc, nullptr, 1, x_cond,
+                            LTXV_F32, s);
+            if (do_stg)
+                dit.forward_ctx(0, lat_loc, LTXV_F32, t_dev, pl.s_local, F, H, W, nullptr, coords_loc, stg_mask.data(),
+                                1, x_pert, LTXV_F32, s);
+        }
+        if (split) {
+            // hand this branch's velocity shard to the partner rank of the other CFG group (same token shard)
+            float* px = static_cast<float*>(comm.peer(partner, xchg_off));
+            if (pl.branch == 0) {
+                LTXV_CUDA(cudaMemcpyAsync(px, x_unc, loc_elems * 4, cudaMemcpyDeviceToDevice, s));
+            } else {
+                LTXV_CUDA(cudaMemcpyAsync(px + loc_elems, x_cond, loc_elems * 4, cudaMemcpyDeviceToDevice, s));
+                if (do_stg)
+                    LTXV_CUDA(cudaMemcpyAsync(px + 2 * loc_elems, x_pert, loc_elems * 4, cudaMemcpyDeviceToDevice, s));
+            }
+            comm.barrier(s, 0);
+        }
+        const float dt = sigmas[i + 1] - sigmas[i];
+        StatParts parts{};
+        if (rescale) {
+            // unbiased std over the WHOLE tensor (t2v_pipeline.rs:209-224): partial sums per token shard, summed by
+            // every rank of the sequence-parallel group after a group barrier
+            double* acc = static_cast<double*>(comm.local(stat_off));
+            LTXV_CUDA(launch_guidance_stats(x_cond, x_unc, static_cast<int64_t>(loc_elems), p.guidance_scale, acc, s));
+            if (pl.sp > 1) comm.barrier(s, 1, pl.branch * pl.sp, pl.sp);
+            for (int k = 0; k < pl.sp; ++k)
+                parts.p[k] = static_cast<const double*>(comm.peer(pl.branch * pl.sp + k, stat_off));
+            parts.n = pl.sp;
+            parts.n_total = static_cast<int64_t>(S) * C;
+        }
+        LTXV_CUDA(launch_guidance_euler_parts(x_cond, do_cfg ? x_unc : nullptr, do_stg ? x_pert : nullptr, lat_loc,
+                                              nullptr, static_cast<int64_t>(loc_elems), p.guidance_scale,
+                                              p.guidance_rescale, p.stg_scale, dt, parts, s));
+        // partners must not overwrite the exchange buffers / partial sums before they are consumed
+        if (split) comm.barrier(s, 0);
+        else if (rescale && pl.sp > 1) comm.barrier(s, 1, pl.branch * pl.sp, pl.sp);
+    }
+    // all-gather the latent shards: every rank stores its shard into every rank's gathered buffer
+    if (N > 1) {
+        for (int r = 0; r < N; ++r) {
+            float* dst = static_cast<float*>(comm.peer(r, lat_off)) + static_cast<size_t>(pl.token0) * C;
+            if (pl.branch == 0 || !split)
+                LTXV_CUDA(cudaMemcpyAsync(dst, lat_loc, loc_elems * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        comm.barrier(s, 0);
+        LTXV_CUDA(cudaMemcpyAsync(latents, comm.local(lat_off), static_cast<size_t>(S) * C * 4, cudaMemcpyDeviceToDevice, s));
+        comm.barrier(s, 0);
+    }
+    dit.set_comm(nullptr, 0, 1);
+}
+
 void pipeline_decode(AutoencoderKLLtxVideo& vae, const ltxv_pipeline_params& p, const float* latents, float* out,
                      cudaStream_t s) {
     if (p.height % 32 != 0 || p.width % 32 != 0)

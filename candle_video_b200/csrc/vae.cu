@@ -208,27 +208,54 @@ void AutoencoderKLLtxVideo::finalize() {
     finalized_ = true;
 }
 
+void AutoencoderKLLtxVideo::set_comm(PeerComm* comm) {
+    comm_ = (comm != nullptr && comm->nranks() > 1) ? comm : nullptr;
+    wsF_ = wsH_ = wsW_ = 0;  // force a workspace rebuild for the new partitioning
+}
+
 void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
     if (F == wsF_ && H == wsH_ && W == wsW_) return;
+    const int N = comm_ ? comm_->nranks() : 1;
+    if (H % N != 0) fail("latent height %d is not divisible by the number of decode ranks %d", H, N);
     T_[0] = F;
-    H_[0] = H;
+    Hfull_[0] = H;
+    H_[0] = H / N;  // local slab rows
     W_[0] = W;
     for (int l = 1; l < 4; ++l) {
         T_[l] = 2 * T_[l - 1] - 1;
+        Hfull_[l] = 2 * Hfull_[l - 1];
         H_[l] = 2 * H_[l - 1];
         W_[l] = 2 * W_[l - 1];
     }
     size_t max_unpadded = 0;
     for (int l = 0; l < 4; ++l) {
         const size_t padded = static_cast<size_t>(T_[l] + 2) * (H_[l] + 2) * (W_[l] + 2) * ch_[l] * 2;
-        // geometry changed: the zero border must be re-established
-        p_[l].release();
-        p_[l].ensure(padded, true);
+        if (comm_ == nullptr) {
+            // geometry changed: the zero border must be re-established
+            p_[l].release();
+            p_[l].ensure(padded, true);
+        } else {
+            for (int k = 0; k < 2; ++k) {
+                p_off_[l][k] = comm_->alloc(padded);
+                LTXV_CUDA(cudaMemset(comm_->local(p_off_[l][k]), 0, padded));
+            }
+            pp_[l] = 0;
+        }
         const size_t un = static_cast<size_t>(T_[l]) * H_[l] * W_[l] * ch_[l] * 2;
         if (un > max_unpadded) max_unpadded = un;
     }
-    a0_.release();
-    a0_.ensure(static_cast<size_t>(F + 2) * (H + 2) * (W + 2) * cfg_.latent_channels * 2, true);
+    const size_t a0_bytes = static_cast<size_t>(F + 2) * (H_[0] + 2) * (W + 2) * cfg_.latent_channels * 2;
+    if (comm_ == nullptr) {
+        a0_.release();
+        a0_.ensure(a0_bytes, true);
+    } else {
+        a0_off_ = comm_->alloc(a0_bytes);
+        LTXV_CUDA(cudaMemset(comm_->local(a0_off_), 0, a0_bytes));
+        video_off_ = comm_->alloc(3ull * T_[3] * (4 * Hfull_[3]) * (4 * W_[3]) * 4);
+        LTXV_CUDA(cudaDeviceSynchronize());
+        comm_->barrier(0, 0);  // every rank's halo rows are zeroed before any neighbour may write them
+        LTXV_CUDA(cudaDeviceSynchronize());
+    }
     xa_.ensure(max_unpadded);
     xb_.ensure(max_unpadded);
     hb_.ensure(max_unpadded);
@@ -239,6 +266,22 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
     wsF_ = F;
     wsH_ = H;
     wsW_ = W;
+}
+
+void* AutoencoderKLLtxVideo::prep(const void* x, int l, const float* scale, const float* shift, int do_norm,
+                                  int do_silu, cudaStream_t s) {
+    if (comm_ == nullptr) {
+        LTXV_CUDA(launch_vae_prep(x, p_[l].p, scale, shift, do_norm, do_silu, T_[l], H_[l], W_[l], ch_[l], s));
+        return p_[l].p;
+    }
+    pp_[l] ^= 1;
+    const size_t off = p_off_[l][pp_[l]];
+    const int r = comm_->rank(), N = comm_->nranks();
+    void* up = r > 0 ? comm_->peer(r - 1, off) : nullptr;
+    void* dn = r < N - 1 ? comm_->peer(r + 1, off) : nullptr;
+    LTXV_CUDA(launch_vae_prep(x, comm_->local(off), scale, shift, do_norm, do_silu, T_[l], H_[l], W_[l], ch_[l], s, up, dn));
+    comm_->barrier(s, 0);  // halo rows from both neighbours have landed
+    return comm_->local(off);
 }
 
 void AutoencoderKLLtxVideo::conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out,
@@ -263,6 +306,8 @@ void AutoencoderKLLtxVideo::conv(const ConvW& cw, const void* a_padded, int T, i
     p.cin = cw.Cin;
     p.a_ptr = a_padded;
     p.post_u8_scale = post;
+    p.out_h0 = slab_h0_;
+    p.out_h_full = slab_hfull_;
     for (int kt = 0; kt < 3; ++kt)
         for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) p.tap_off[(kt * 3 + kh) * 3 + kw] = kt * plane + (kh - 1) * Wp + (kw - 1);
@@ -274,10 +319,10 @@ void AutoencoderKLLtxVideo::resnet(const ResnetW& rw, int l, const float* ss, __
                                    cudaStream_t s) {
     const int C = ch_[l], T = T_[l], H = H_[l], W = W_[l];
     // ss = [shift1, scale1, shift2, scale2] (vae.rs:734-735)
-    LTXV_CUDA(launch_vae_prep(x, p_[l].p, ss ? ss + C : nullptr, ss ? ss : nullptr, 1, 1, T, H, W, C, s));
-    conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, 0, s);
-    LTXV_CUDA(launch_vae_prep(hb_.p, p_[l].p, ss ? ss + 3 * C : nullptr, ss ? ss + 2 * C : nullptr, 1, 1, T, H, W, C, s));
-    conv(rw.conv2, p_[l].p, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s);
+    void* a1 = prep(x, l, ss ? ss + C : nullptr, ss ? ss : nullptr, 1, 1, s);
+    conv(rw.conv1, a1, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, 0, s);
+    void* a2 = prep(hb_.p, l, ss ? ss + 3 * C : nullptr, ss ? ss + 2 * C : nullptr, 1, 1, s);
+    conv(rw.conv2, a2, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s);
     std::swap(x, x_alt);
 }
 
@@ -292,7 +337,8 @@ void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* time
     const bool cond = cfg_.timestep_conditioning && timestep_dev != nullptr;
     const size_t zsz = z_dtype == LTXV_F32 ? 4 : 2;
     const int64_t z_elems = static_cast<int64_t>(cfg_.latent_channels) * F * H * W;
-    const int To = T_[3], Ho = 4 * H_[3], Wo = 4 * W_[3];
+    const int To = T_[3], Ho = 4 * Hfull_[3], Wo = 4 * W_[3];
+    const int prank = comm_ ? comm_->rank() : 0;
     const int64_t out_elems = 3ll * To * Ho * Wo;
     if (out_dtype == LTXV_BF16) out_f32_.ensure(static_cast<size_t>(out_elems) * 4);
 
@@ -327,16 +373,17 @@ void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* time
             LTXV_CUDA(launch_add_vec(sst_final_, tproj, ssf, dim, dim, s));
         }
         // conv_in (vae.rs:1664)
-        LTXV_CUDA(launch_vae_input(zb, z_dtype == LTXV_BF16, a0_.p, cfg_.latent_channels, F, H, W, s));
+        void* a0 = comm_ ? comm_->local(a0_off_) : a0_.p;
+        LTXV_CUDA(launch_vae_input(zb, z_dtype == LTXV_BF16, a0, cfg_.latent_channels, F, H, W, prank * H_[0], H_[0], s));
         __nv_bfloat16* x = xa_.as<__nv_bfloat16>();
         __nv_bfloat16* x_alt = xb_.as<__nv_bfloat16>();
-        conv(conv_in_, a0_.p, T_[0], H_[0], W_[0], EPI_CONV_NDHWC, x, nullptr, 0, s);
+        conv(conv_in_, a0, T_[0], H_[0], W_[0], EPI_CONV_NDHWC, x, nullptr, 0, s);
         for (int l = 0; l < 4; ++l) {
             if (l > 0) {
                 // LtxVideoUpsampler3d (vae.rs:1090-1169): conv on the raw x, depth-to-space + residual in the epilogue
                 const int lp = l - 1;
-                LTXV_CUDA(launch_vae_prep(x, p_[lp].p, nullptr, nullptr, 0, 0, T_[lp], H_[lp], W_[lp], ch_[lp], s));
-                conv(ups_[lp], p_[lp].p, T_[lp], H_[lp], W_[lp], EPI_CONV_D2S, x_alt, nullptr, 0, s);
+                void* au = prep(x, lp, nullptr, nullptr, 0, 0, s);
+                conv(ups_[lp], au, T_[lp], H_[lp], W_[lp], EPI_CONV_D2S, x_alt, nullptr, 0, s);
                 std::swap(x, x_alt);
             }
             const int C = ch_[l];
@@ -345,11 +392,24 @@ void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* time
         }
         // norm_out -> scale/shift -> SiLU -> conv_out -> unpatchify (vae.rs:1686-1725)
         const int C3 = ch_[3];
-        LTXV_CUDA(launch_vae_prep(x, p_[3].p, cond ? ssf + C3 : nullptr, cond ? ssf : nullptr, 1, 1, T_[3], H_[3], W_[3],
-                                  C3, s));
+        void* af = prep(x, 3, cond ? ssf + C3 : nullptr, cond ? ssf : nullptr, 1, 1, s);
         float* o32 = out_dtype == LTXV_F32 ? static_cast<float*>(out) + static_cast<size_t>(b) * out_elems
                                            : out_f32_.as<float>();
-        conv(conv_out_, p_[3].p, T_[3], H_[3], W_[3], EPI_CONV_UNPATCHIFY, o32, nullptr, postprocess, s);
+        if (comm_ == nullptr) {
+            conv(conv_out_, af, T_[3], H_[3], W_[3], EPI_CONV_UNPATCHIFY, o32, nullptr, postprocess, s);
+        } else {
+            // every rank stores its pixel rows into rank 0's frame buffer; rank 0 hands the assembled video out
+            slab_h0_ = prank * 4 * H_[3];
+            slab_hfull_ = Ho;
+            conv(conv_out_, af, T_[3], H_[3], W_[3], EPI_CONV_UNPATCHIFY, comm_->peer(0, video_off_), nullptr, postprocess, s);
+            slab_h0_ = slab_hfull_ = 0;
+            comm_->barrier(s, 0);
+            if (prank == 0)
+                LTXV_CUDA(cudaMemcpyAsync(o32, comm_->local(video_off_), static_cast<size_t>(out_elems) * 4,
+                                          cudaMemcpyDeviceToDevice, s));
+            comm_->barrier(s, 0);  // the frame buffer may be overwritten by the next decode only after the copy
+            if (prank != 0) continue;
+        }
         if (out_dtype == LTXV_BF16)
             LTXV_CUDA(launch_f32_to_bf16(o32, static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(b) * out_elems,
                                          out_elems, s));

@@ -40,6 +40,12 @@ public:
     int spatial_compression_ratio() const { return 32; }   // vae.rs:85
     int temporal_compression_ratio() const { return 8; }   // vae.rs:86
 
+    // Multi-GPU decode: the volume is cut into H-slabs, one per rank of `comm`; every conv input's halo rows are
+    // written by the neighbouring rank's pixel-norm kernel straight into this rank's padded buffer (peer memory), and
+    // every rank's conv_out epilogue stores its pixel rows into rank 0's frame buffer.  decode() then takes the full
+    // (replicated) latent on every rank and delivers the video on rank 0.
+    void set_comm(PeerComm* comm);
+
     // z [B, C, F, H, W] -> out f32/bf16 [B, 3, 8F-7, 32H, 32W]
     void decode(const void* z, int z_dtype, const float* timestep_dev, int B, int F, int H, int W, void* out,
                 int out_dtype, int postprocess, cudaStream_t s);
@@ -59,6 +65,8 @@ private:
     void conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out, const void* res, int post,
               cudaStream_t s);
     void resnet(const ResnetW& rw, int level, const float* ss, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s);
+    // pixel-norm / modulate / SiLU into the level's padded conv input (+ halo exchange and barrier when sharded)
+    void* prep(const void* x, int level, const float* scale, const float* shift, int do_norm, int do_silu, cudaStream_t s);
 
     ltxv_vae_config cfg_;
     int device_;
@@ -79,6 +87,13 @@ private:
     int wsF_ = 0, wsH_ = 0, wsW_ = 0;
     int T_[4], H_[4], W_[4];
     DevBuf a0_, p_[4], xa_, xb_, hb_, cond_, out_f32_;
+    // sharded decode
+    PeerComm* comm_ = nullptr;
+    int Hfull_[4] = {0, 0, 0, 0};
+    size_t p_off_[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // double-buffered padded inputs in the symmetric heap
+    int pp_[4] = {0, 0, 0, 0};
+    size_t a0_off_ = 0, video_off_ = 0;
+    int slab_h0_ = 0, slab_hfull_ = 0;  // unpatchify row offset / full height of the conv_out being launched
 };
 
 }  // namespace ltxv

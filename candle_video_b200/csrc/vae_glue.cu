@@ -13,17 +13,22 @@ inline cudaError_t done() {
 }
 
 template <typename TIn>
-__global__ void vae_input_kernel(const TIn* __restrict__ z, __nv_bfloat16* __restrict__ out, int C, int F, int H, int W) {
+__global__ void vae_input_kernel(const TIn* __restrict__ z, __nv_bfloat16* __restrict__ out, int C, int F, int Hfull, int W,
+                                 int h0, int Hs) {
+    // enumerates the local padded rows hp in [0, Hs+2) that exist in the latent (global row h0 + hp - 1)
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t n = static_cast<int64_t>(F) * H * W * C;
+    const int64_t n = static_cast<int64_t>(F) * (Hs + 2) * W * C;
     if (idx >= n) return;
     const int c = static_cast<int>(idx % C);
     const int64_t vox = idx / C;
-    const int w = static_cast<int>(vox % W), h = static_cast<int>((vox / W) % H), f = static_cast<int>(vox / (W * H));
-    const float v = static_cast<float>(z[((static_cast<int64_t>(c) * F + f) * H + h) * W + w]);
+    const int w = static_cast<int>(vox % W), hp = static_cast<int>((vox / W) % (Hs + 2)),
+              f = static_cast<int>(vox / (static_cast<int64_t>(W) * (Hs + 2)));
+    const int h = h0 + hp - 1;
+    if (h < 0 || h >= Hfull) return;  // true volume border: stays zero (vae.rs:344)
+    const float v = static_cast<float>(z[((static_cast<int64_t>(c) * F + f) * Hfull + h) * W + w]);
     const __nv_bfloat16 b = __float2bfloat16(v);
-    const int Hp = H + 2, Wp = W + 2;
-    auto at = [&](int tp) { return ((static_cast<int64_t>(tp) * Hp + (h + 1)) * Wp + (w + 1)) * C + c; };
+    const int Hp = Hs + 2, Wp = W + 2;
+    auto at = [&](int tp) { return ((static_cast<int64_t>(tp) * Hp + hp) * Wp + (w + 1)) * C + c; };
     out[at(f + 1)] = b;
     if (f == 0) out[at(0)] = b;
     if (f == F - 1) out[at(F + 1)] = b;
@@ -35,7 +40,8 @@ __global__ void vae_input_kernel(const TIn* __restrict__ z, __nv_bfloat16* __res
 template <int C>
 __global__ void __launch_bounds__(256)
 vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
-                const float* __restrict__ shift, int do_norm, int do_silu, int T, int H, int W) {
+                const float* __restrict__ shift, int do_norm, int do_silu, int T, int H, int W,
+                __nv_bfloat16* __restrict__ halo_up, __nv_bfloat16* __restrict__ halo_dn) {
     constexpr int LPV = (C / 8 < 32) ? C / 8 : 32;  // lanes per voxel
     constexpr int VPW = 32 / LPV;                    // voxels per warp
     constexpr int CPL = (C / 8) / LPV;               // chunks per lane
@@ -108,11 +114,16 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             o.z = pack_bf16x2(v[k][4], v[k][5]);
             o.w = pack_bf16x2(v[k][6], v[k][7]);
             const int c0 = (k * LPV + l) * 8;
-            const int64_t row = (static_cast<int64_t>(t + 1) * Hp + (h + 1)) * Wp + (w + 1);
             const int64_t plane = static_cast<int64_t>(Hp) * Wp;
-            *reinterpret_cast<uint4*>(out + row * C + c0) = o;
-            if (t == 0) *reinterpret_cast<uint4*>(out + (row - plane) * C + c0) = o;          // replicate frame 0
-            if (t == T - 1) *reinterpret_cast<uint4*>(out + (row + plane) * C + c0) = o;      // replicate frame T-1
+            auto put = [&](__nv_bfloat16* base, int hp) {
+                const int64_t row = (static_cast<int64_t>(t + 1) * Hp + hp) * Wp + (w + 1);
+                *reinterpret_cast<uint4*>(base + row * C + c0) = o;
+                if (t == 0) *reinterpret_cast<uint4*>(base + (row - plane) * C + c0) = o;      // replicate frame 0
+                if (t == T - 1) *reinterpret_cast<uint4*>(base + (row + plane) * C + c0) = o;  // replicate frame T-1
+            };
+            put(out, h + 1);
+            if (halo_up != nullptr && h == 0) put(halo_up, H + 1);   // my first row = bottom halo of the slab above
+            if (halo_dn != nullptr && h == H - 1) put(halo_dn, 0);   // my last row  = top halo of the slab below
         }
     }
 }
@@ -156,19 +167,26 @@ __global__ void conv_bias_relayout_kernel(const TIn* __restrict__ b, float* __re
 uint64_t vae_glue_launch_count() { return g_vae_glue_launches.load(); }
 
 cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out, int C, int F, int H, int W, cudaStream_t s) {
-    const int64_t n = static_cast<int64_t>(F) * H * W * C;
+    return launch_vae_input(z, z_is_bf16, out, C, F, H, W, 0, H, s);
+}
+
+cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out, int C, int F, int H, int W, int h0, int Hs,
+                             cudaStream_t s) {
+    const int64_t n = static_cast<int64_t>(F) * (Hs + 2) * W * C;
     const int grid = static_cast<int>((n + 255) / 256);
     if (z_is_bf16)
         vae_input_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z),
-                                                             reinterpret_cast<__nv_bfloat16*>(out), C, F, H, W);
+                                                             reinterpret_cast<__nv_bfloat16*>(out), C, F, H, W, h0, Hs);
     else
         vae_input_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(z),
-                                                     reinterpret_cast<__nv_bfloat16*>(out), C, F, H, W);
+                                                     reinterpret_cast<__nv_bfloat16*>(out), C, F, H, W, h0, Hs);
     return done();
 }
 
 cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const float* shift, int do_norm, int do_silu,
-                            int T, int H, int W, int C, cudaStream_t s) {
+                            int T, int H, int W, int C, cudaStream_t s, void* halo_up, void* halo_dn) {
+    __nv_bfloat16* hu = reinterpret_cast<__nv_bfloat16*>(halo_up);
+    __nv_bfloat16* hd = reinterpret_cast<__nv_bfloat16*>(halo_dn);
     const int64_t nvox = static_cast<int64_t>(T) * H * W;
     const int vpb = 8 * (C == 128 ? 2 : 1);  // voxels per block pass
     int64_t want = (nvox + vpb - 1) / vpb;
@@ -176,10 +194,10 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
     switch (C) {
-        case 128: vae_prep_kernel<128><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W); break;
-        case 256: vae_prep_kernel<256><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W); break;
-        case 512: vae_prep_kernel<512><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W); break;
-        case 1024: vae_prep_kernel<1024><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W); break;
+        case 128: vae_prep_kernel<128><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 256: vae_prep_kernel<256><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 512: vae_prep_kernel<512><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 1024: vae_prep_kernel<1024><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
         default: return cudaErrorInvalidValue;
     }
     return done();

@@ -10,12 +10,19 @@ namespace ltxv {
 // z [C, F, H, W] (NCDHW, f32 or bf16) -> padded NDHWC bf16 [(F+2), (H+2), (W+2), C]; frames 0 / F+1 replicate
 // frames 1 / F (non-causal decoder padding, vae.rs:388-411); the H/W border is left untouched (must be zero).
 cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out_padded, int C, int F, int H, int W, cudaStream_t s);
+// Slab variant (multi-GPU decode, H split across ranks): the local padded buffer covers global rows h0-1 .. h0+Hs of
+// the H_full-row latent; halo rows that exist in the (replicated) latent are filled from it, rows outside stay zero.
+cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out_padded, int C, int F, int H_full, int W, int h0,
+                             int Hs, cudaStream_t s);
 
 // x bf16 [T,H,W,C] (unpadded NDHWC) -> padded bf16 [(T+2),(H+2),(W+2),C] with optional
 //   pixel norm (RMS over C, eps 1e-8, vae.rs:148-153), x*(1+scale)+shift (vae.rs:736-738), SiLU (vae.rs:161-163).
 // scale/shift: f32 [C] or null.
+// halo_up / halo_dn: the padded buffers of the ranks owning the slab above / below (peer memory) or null: the first /
+// last local row is also stored into their bottom / top halo row (conv halo exchange fused into the producer).
 cudaError_t launch_vae_prep(const void* x, void* out_padded, const float* scale, const float* shift, int do_norm,
-                            int do_silu, int T, int H, int W, int C, cudaStream_t s);
+                            int do_silu, int T, int H, int W, int C, cudaStream_t s, void* halo_up = nullptr,
+                            void* halo_dn = nullptr);
 
 // Conv3d weight [Cout, Cin, 3,3,3] (f32 or bf16, device) -> GEMM B matrix bf16 [rows_out, 27*Cin], k = tap*Cin + c.
 // d2s_perm: output channel co = c'*8 + sub is stored at row sub*(Cout/8) + c' (upsampler, see EPI_CONV_D2S).

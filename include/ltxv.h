@@ -191,6 +191,31 @@ int ltxv_pipeline_denoise(ltxv_dit* dit, const ltxv_pipeline_params* p, float* l
  * postprocess.  latents: device f32 [S,128]; out: device f32 [3, num_frames, height, width] in 0..255. */
 int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out, void* stream);
 
+/* ------------------------------------------------------------- multi-GPU ------------------------------------------ */
+/* One process per GPU.  The reference has no distributed code at all; these entry
+ * points add the sharding BASELINE.json's north_star names: CFG cond/uncond split across two rank groups, Ulysses
+ * sequence parallelism (head <-> token exchange around self-attention) inside a group, and H-slab VAE decode with
+ * conv halo exchange.  All data-path traffic is NVLink peer stores issued by the producing kernels into a symmetric
+ * heap (one cudaMalloc per rank whose 64-byte CUDA IPC handle the host harness exchanges once with any
+ * all-gather it has); ordering is a system-scope flag barrier kernel.  No NCCL on the data path. */
+typedef struct ltxv_comm ltxv_comm;
+int ltxv_comm_create(int nranks, int rank, int device, uint64_t heap_bytes, ltxv_comm** out);
+void ltxv_comm_destroy(ltxv_comm* c);
+int ltxv_comm_get_handle(ltxv_comm* c, void* handle64);             /* out: 64 bytes */
+int ltxv_comm_open(ltxv_comm* c, const void* all_handles);          /* in: nranks * 64 bytes, indexed by rank */
+int ltxv_comm_barrier(ltxv_comm* c, void* stream);
+/* host-only: the sharding plan of ltxv_pipeline_denoise_parallel for (nranks, rank, S tokens, CFG on/off):
+ * out6 = {cfg_groups, sp_size, branch (0 uncond / 1 cond), sp_rank, local tokens, first token} */
+int ltxv_parallel_plan(int nranks, int rank, int S, int do_cfg, int32_t* out6);
+/* ltxv_pipeline_denoise over all ranks of `c`: `latents` is the full [S,128] f32 tensor on every rank (identical on
+ * entry, identical on exit); each rank runs one CFG branch on its token shard. */
+int ltxv_pipeline_denoise_parallel(ltxv_dit* dit, ltxv_comm* c, const ltxv_pipeline_params* p, float* latents,
+                                   const void* prompt_embeds, const float* prompt_mask, const void* negative_embeds,
+                                   const float* negative_mask, int embeds_dtype, int K, void* stream);
+/* H-slab decode over all ranks of `c` (NULL restores single-GPU decode): ltxv_vae_decode / ltxv_pipeline_decode then
+ * take the full latent on every rank and deliver the video on rank 0 (other ranks' `out` is left untouched). */
+int ltxv_vae_set_comm(ltxv_vae* vae, ltxv_comm* c);
+
 /* HOST-buffer variants of the two calls above (what a caller holding CPU tensors uses): inputs are copied to the
  * device, the loop / decode runs, the result is copied back and the stream is synchronised. */
 int ltxv_pipeline_denoise_host(ltxv_dit* dit, const ltxv_pipeline_params* p, float* latents, const void* prompt_embeds,
