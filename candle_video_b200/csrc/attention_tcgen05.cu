@@ -343,17 +343,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 }
 
 
-// ================================================================================================
-// v2 (head_dim 64, long key sequences): one CTA per (batch, head, 256 queries) = two 128-row query tiles that share
-// every K/V tile.  384 threads, 1 CTA / SM:
-//   warp 0     : TMA producer (Q0,Q1 once; K_j / V_j through 3-stage rings)
-//   warp 1     : TMEM allocator + UMMA issuer: S_t = Q_t K_j^T -> TMEM cols [128t, 128t+128),
-//                O_t += P_t V_j -> TMEM cols [256+64t, +64)
-//   warps 4-7  : softmax of query tile 0      warps 8-11: softmax of query tile 1
-// Each softmax thread pulls its whole 128-wide score row into registers with four back-to-back tcgen05.ld and
-// immediately hands the S buffer back (s_free), so the tensor pipe computes S(j+1) while the exponentials of tile j
-// run; the only steady-state limiter left is the MUFU pipe (128 exp2 per row per key tile, 16 exp2/clk/SM).
-// ================================================================================================
 #ifdef LTXV_ATTN_TIMING
 __device__ long long g_attn_timing[32];
 #define TMARK(idx)                                                           \
@@ -367,269 +356,482 @@ __device__ long long g_attn_timing[32];
 #else
 #define TMARK(idx) do { } while (0)
 #endif
-constexpr int kV2Threads = 384;  // warpgroup 0: control (TMA, MMA), warpgroups 1,2: softmax of query tile 0 / 1
-constexpr int kV2Stages = 3;
-constexpr int kV2QBytes = kTileQ * 64 * 2;   // 16 KB per query tile
+constexpr int kV2QBytes = kTileQ * 64 * 2;    // 16 KB per query tile
 constexpr int kV2KVBytes = kTileKV * 64 * 2;  // 16 KB per K or V tile
-constexpr int kV2SmemBytes = 2 * kV2QBytes + 2 * kV2Stages * kV2KVBytes + 2 * kPBytes + 256;
 
-// exp2 of 32 scores (scaled, shifted), row-sum, bf16 pack into the swizzled P tile
+// ================================================================================================
+// v3 (head_dim 64, long key sequences): same CTA shape as v2 (256 queries = two 128-row tiles sharing every K/V tile,
+// 384 threads, 1 CTA / SM) with the per-element instruction count and the synchronisation chain cut down:
+//   * P never touches shared memory: each softmax thread packs its row of probabilities to bf16x2 and stores it with
+//     tcgen05.st into TMEM (cols 384+64t), and O_t += P_t V_j runs as a TMEM-A ("TS") tcgen05.mma -- no STS, no swizzle
+//     address math, no proxy fence, half the smem operand traffic of the PV MMA;
+//   * packed f32x2 arithmetic (FFMA2 for s*c-m, FADD2 for the row sum) and 3-input max (FMNMX3): 3.1 issue slots per
+//     score instead of 4.6, so a single warp per scheduler keeps the MUFU pipe (16 exp2/clk/SM) fed;
+//   * setmaxnreg: the control warpgroup drops to 48 registers, the two softmax warpgroups rise to 224 -- the 128
+//     register-resident scores + 32 in-flight exponentials no longer spill;
+//   * one UMMA issuer warp PER query tile (warps 1, 2): tile 0's QK^T / PV never queue behind tile 1's barriers;
+//   * 4-stage K/V rings (the 64 KB that held P).
+// TMEM map (512 columns): S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512).
+// ================================================================================================
+#ifdef LTXV_ATTN_TRACE
+// absolute clock64 timestamps of the hand-off events of one CTA: [role][kv tile][event]
+//   roles 0,1: softmax warp 0 of tile 0/1; 2,3: UMMA issuer of tile 0/1; 4: TMA producer
+__device__ long long g_attn_trace[11][40][8];
+#define TRACE(role, j, ev)                                                                     \
+    do {                                                                                       \
+        if (tr_on && (j) < 40) g_attn_trace[role][j][ev] = clock64();                          \
+    } while (0)
+#else
+#define TRACE(role, j, ev) do { } while (0)
+#endif
+constexpr int kV3Threads = 384;
+constexpr int kV3Stages = 6;
+constexpr int kV3L2Ahead = 4;  // K/V tiles prefetched into L2 beyond the smem ring
+constexpr int kV3SmemBytes = 2 * kV2QBytes + 2 * kV3Stages * kV2KVBytes + 512;
+#ifndef LTXV_ATTN_PINGPONG
+#define LTXV_ATTN_PINGPONG 0
+#endif
+
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: A = 128 lanes x K bf16 packed two per 32-bit column (K-major)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Warp-level mbarrier hand-offs: ONE lane polls / arrives and the warp is released / gathered with __syncwarp.
+// 128 threads polling the same mbarrier word serialise in the SYNCS unit (measured: ~200 clk for an already
+// satisfied wait, >1000 clk wake-up for the UMMA issuer queued behind them).
+__device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait_sleep(bar, parity);
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_mbar_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 template <bool TAIL>
-__device__ __forceinline__ void softmax_chunk(uint32_t (&r)[32], float c, float neg_m, int kv_col0, int skv,
-                                              float& l0, float& l1, uint8_t* pbase, int chunk0, int sw) {
-    float pv[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c, neg_m));
+__device__ __forceinline__ float max32_v3(uint32_t (&r)[32], int kv_col0, int skv) {
     if (TAIL) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (kv_col0 + i >= skv) pv[i] = 0.f;
+            if (kv_col0 + i >= skv) r[i] = 0xff800000u;  // -inf: ignored by the max, exp2 -> 0
     }
+    float a = __uint_as_float(r[0]), b = __uint_as_float(r[1]);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        l0 += pv[i];
-        l1 += pv[i + 1];
+    for (int i = 2; i < 32; i += 4) {
+        a = max3(a, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        if (i + 3 < 32) b = max3(b, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
     }
+    return fmaxf(a, b);
+}
+// 2^x for a pair on the FMA/ALU pipes (no MUFU): x = n + r with n = rint(x) by the 1.5*2^23 magic-number add,
+// r in [-0.5, 0.5]; 2^r by a degree-3 minimax polynomial (max rel. error 7.5e-5, far below the bf16 rounding of P);
+// 2^n by adding n to the exponent field.  x is clamped at -126 so the exponent arithmetic cannot wrap.
+__device__ __forceinline__ void ex2_poly_pair(float x0, float x1, float& e0, float& e1) {
+    const uint64_t magic2 = pack_f32x2(12582912.0f, 12582912.0f);
+    const uint64_t nmagic2 = pack_f32x2(-12582912.0f, -12582912.0f);
+    const uint64_t m1 = pack_f32x2(-1.0f, -1.0f);
+    const uint64_t x2 = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t fi2 = add_f32x2(x2, magic2);
+    const uint64_t nf2 = add_f32x2(fi2, nmagic2);
+    const uint64_t r2 = fma_f32x2(nf2, m1, x2);
+    uint64_t p2 = fma_f32x2(r2, pack_f32x2(0.0551716649f, 0.0551716649f), pack_f32x2(0.2426111219f, 0.2426111219f));
+    p2 = fma_f32x2(p2, r2, pack_f32x2(0.6932609862f, 0.6932609862f));
+    p2 = fma_f32x2(p2, r2, pack_f32x2(0.9999280736f, 0.9999280736f));
+    float p0, p1, f0, f1;
+    unpack_f32x2(p2, p0, p1);
+    unpack_f32x2(fi2, f0, f1);
+    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(f0) << 23));
+    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(f1) << 23));
+}
+#ifndef LTXV_ATTN_POLY
+#define LTXV_ATTN_POLY 2  // pairs out of every 8 (16 scores) whose exp2 runs on the FMA pipe instead of MUFU: 0..8
+#endif
+// 32 scores -> exp2(s*c - m) -> row-sum (packed) -> 16 bf16x2 words
+__device__ __forceinline__ void exp_chunk_v3(const uint32_t (&r)[32], uint64_t c2, uint64_t negm2, uint64_t& l2a,
+                                             uint64_t& l2b, uint32_t* out16) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        float x0, x1, x2, x3;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, negm2), x0, x1);
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, negm2), x2, x3);
+        float e0, e1, e2, e3;
+        // the MUFU pipe (16 exp2/clk/SM) is the attention bottleneck at head_dim 64: a fixed share of the
+        // exponentials is computed on the otherwise idle FMA pipe
+        // pair index within a group of 8 pairs: a = (i/2)&7, b = a+1; emulated pairs are spread evenly: 7,3,5,1,6,2,4,0
+        constexpr int kOrder[8] = {7, 3, 5, 1, 6, 2, 4, 0};
+        bool poly_a = false, poly_b = false;
+#pragma unroll
+        for (int q = 0; q < LTXV_ATTN_POLY; ++q) {
+            poly_a = poly_a || (kOrder[q] == ((i >> 1) & 7));
+            poly_b = poly_b || (kOrder[q] == (((i >> 1) + 1) & 7));
+        }
+        if (poly_a) {
+            ex2_poly_pair(x0, x1, e0, e1);
+        } else {
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+        }
+        if (poly_b) {
+            ex2_poly_pair(x2, x3, e2, e3);
+        } else {
+            e2 = ex2_approx(x2);
+            e3 = ex2_approx(x3);
+        }
+        l2a = add_f32x2(l2a, pack_f32x2(e0, e1));
+        l2b = add_f32x2(l2b, pack_f32x2(e2, e3));
+        out16[i / 2] = pack_bf16x2(e0, e1);
+        out16[i / 2 + 1] = pack_bf16x2(e2, e3);
+    }
+}
+
+// Tail splitting.  The grid is one CTA per (batch, head, 256-query block) unit; with U units on 148 SMs the last wave
+// holds only U mod 148 CTAs (c2: 640 units = 4.32 waves -> the 5th wave runs 48 CTAs on 148 SMs).  Those last units are
+// cut along the key axis into nsplit = 148 / (U mod 148) ranges each, so the tail wave fills the machine and lasts
+// 1/nsplit as long; each range CTA publishes its unnormalised (O, m, l) rows to a scratch buffer and the last CTA of a
+// unit to finish (ticket counter) merges them:  O = sum_i 2^(m_i - M) O_i,  l = sum_i 2^(m_i - M) l_i,  M = max_i m_i.
+struct SplitPlan {
+    int n_qb;           // 256-query blocks per (batch, head)
+    int n_units;        // B * H * n_qb
+    int n_split_units;  // trailing units that are split (0 = none)
+    int nsplit;         // key ranges per split unit (>= 1)
+    float* scratch;     // [n_split_units][nsplit][kSplitCols4 float4 columns][256 rows]
+    int* counters;      // [n_split_units] tickets, zero between launches
+};
+constexpr int kSplitCols4 = 17;  // float4 columns per row: 16 x 4 O columns + (m, l, -, -)
+constexpr int kMaxSplit = 8;
+
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32], float inv_l) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint4 u;
-        u.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
-        u.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
-        u.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
-        u.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
-        *reinterpret_cast<uint4*>(pbase + (((chunk0 + q) ^ sw) << 4)) = u;
+        u.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) * inv_l, __uint_as_float(r[8 * q + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv_l, __uint_as_float(r[8 * q + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv_l, __uint_as_float(r[8 * q + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv_l, __uint_as_float(r[8 * q + 7]) * inv_l);
+        d4[q] = u;
     }
-}
-template <bool TAIL>
-__device__ __forceinline__ float max32(const uint32_t (&r)[32], int kv_col0, int skv) {
-    float a = -INFINITY, b = -INFINITY, c = -INFINITY, d = -INFINITY;
-    if (!TAIL) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            a = fmaxf(a, __uint_as_float(r[i]));
-            b = fmaxf(b, __uint_as_float(r[i + 1]));
-            c = fmaxf(c, __uint_as_float(r[i + 2]));
-            d = fmaxf(d, __uint_as_float(r[i + 3]));
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (kv_col0 + i < skv) a = fmaxf(a, __uint_as_float(r[i]));
-    }
-    return fmaxf(fmaxf(a, b), fmaxf(c, d));
 }
 
-__global__ void __launch_bounds__(kV2Threads, 1)
-flash_attn2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kV3Threads, 1)
+flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ AttnParams p,
+                   const SplitPlan sp) {
     constexpr int D = 64;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sq = smem;
     uint8_t* sk = sq + 2 * kV2QBytes;
-    uint8_t* sv = sk + kV2Stages * kV2KVBytes;
-    uint8_t* sp = sv + kV2Stages * kV2KVBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sp + 2 * kPBytes);
+    uint8_t* sv = sk + kV3Stages * kV2KVBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sv + kV3Stages * kV2KVBytes);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;                   // [3]
-    uint64_t* k_empty = bars + 1 + kV2Stages;      // [3]
-    uint64_t* v_full = bars + 1 + 2 * kV2Stages;   // [3]
-    uint64_t* v_empty = bars + 1 + 3 * kV2Stages;  // [3]
-    uint64_t* s_full = bars + 1 + 4 * kV2Stages;   // [2]  S_t landed in TMEM
+    uint64_t* k_full = bars + 1;                   // [St]
+    uint64_t* k_empty = bars + 1 + kV3Stages;      // [St]  one arrival per active query tile
+    uint64_t* v_full = bars + 1 + 2 * kV3Stages;   // [St]
+    uint64_t* v_empty = bars + 1 + 3 * kV3Stages;  // [St]  one arrival per active query tile
+    uint64_t* s_full = bars + 1 + 4 * kV3Stages;   // [2]  S_t landed in TMEM
     uint64_t* s_free = s_full + 2;                 // [2]  S_t copied to registers (128 arrivals)
-    uint64_t* p_full = s_free + 2;                 // [2]  P_t written to smem (128 arrivals)
+    uint64_t* p_full = s_free + 2;                 // [2]  P_t stored to TMEM (128 arrivals)
     uint64_t* pv_done = p_full + 2;                // [2]  O_t += P_t V retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    volatile uint32_t* split_flag = tmem_slot + 1;  // 1 = this CTA drew the last ticket of its split unit
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * (2 * kTileQ);
-    const int head = blockIdx.y;
-    const int batch = blockIdx.z;
-    const int n_tiles = (p.Skv + kTileKV - 1) / kTileKV;
+#ifdef LTXV_ATTN_TRACE
+    const long long t_entry = clock64();
+    const long long t_entry_ns = static_cast<long long>(globaltimer_ns());
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_attn_trace[9][19][4] = t_entry_ns;
+    if (threadIdx.x == 0 && blockIdx.x >= gridDim.x - 8) g_attn_trace[9][10 + (gridDim.x - 1 - blockIdx.x)][0] = t_entry_ns;
+#endif
+    // work item -> (unit = (batch, head, 256-query block), key-tile range).  The last `sp.n_split_units` units (the
+    // partial last wave of CTAs) are cut into sp.nsplit key ranges each, see SplitPlan.
+    const int item = blockIdx.x;
+    const int first_split = sp.n_units - sp.n_split_units;
+    int unit = item, split = 0;
+    const bool is_split = item >= first_split;
+    if (is_split) {
+        unit = first_split + (item - first_split) / sp.nsplit;
+        split = (item - first_split) % sp.nsplit;
+    }
+    const int qb = unit % sp.n_qb;
+    const int head = (unit / sp.n_qb) % p.H;
+    const int batch = unit / (sp.n_qb * p.H);
+    const int q0 = qb * (2 * kTileQ);
+    const int n_tiles_all = (p.Skv + kTileKV - 1) / kTileKV;
+    const int jt0 = is_split ? (split * n_tiles_all) / sp.nsplit : 0;
+    const int jt1 = is_split ? ((split + 1) * n_tiles_all) / sp.nsplit : n_tiles_all;
+    const int n_tiles = jt1 - jt0;  // key tiles of THIS work item; j below is the local tile index
     const bool two = (q0 + kTileQ) < p.Sq;  // second query tile has rows
+    const int nt = two ? 2 : 1;
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) {
-            printf("ltxv attention v2: dynamic smem base not 1024B aligned\n");
+            printf("ltxv attention v3: dynamic smem base not 1024B aligned\n");
             __trap();
         }
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v);
         mbar_init(q_full, 1);
-        for (int i = 0; i < kV2Stages; ++i) {
+        for (int i = 0; i < kV3Stages; ++i) {
             mbar_init(&k_full[i], 1);
-            mbar_init(&k_empty[i], 1);
+            mbar_init(&k_empty[i], nt);
             mbar_init(&v_full[i], 1);
-            mbar_init(&v_empty[i], 1);
+            mbar_init(&v_empty[i], nt);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&s_full[t], 1);
-            mbar_init(&s_free[t], 128);
-            mbar_init(&p_full[t], 128);
+            mbar_init(&s_free[t], 4);  // one arrival per softmax warp
+            mbar_init(&p_full[t], 4);
             mbar_init(&pv_done[t], 1);
         }
         fence_barrier_init();
     }
-    if (warp_idx == 1) tmem_alloc<512>(tmem_slot);
+    if (warp_idx == 11) tmem_alloc<512>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
-    if (warp_idx == 0) {
-        if (elect_one()) {  // one elected lane: ptxas keeps the tcgen05/TMA operands on the uniform datapath
-            mbar_arrive_expect_tx(q_full, (two ? 2 : 1) * kV2QBytes);
-            tma_load_3d(sq, &tm_q, q_full, p.q_col0 + head * D, q0, batch);
-            if (two) tma_load_3d(sq + kV2QBytes, &tm_q, q_full, p.q_col0 + head * D, q0 + kTileQ, batch);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_tiles; ++j) {
-                const int kv0 = j * kTileKV;
-                mbar_wait(&k_empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&k_full[stage], kV2KVBytes);
-                tma_load_3d(sk + stage * kV2KVBytes, &tm_k, &k_full[stage], p.k_col0 + head * D, kv0, batch);
-                mbar_wait(&v_empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&v_full[stage], kV2KVBytes);
-                tma_load_3d(sv + stage * kV2KVBytes, &tm_v, &v_full[stage], p.v_col0 + head * D, kv0, batch);
-                if (++stage == kV2Stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-        }
-    } else if (warp_idx == 1) {
-        if (elect_one()) {  // one elected lane: ptxas keeps the tcgen05/TMA operands on the uniform datapath
-            constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, false, false);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, D, false, true);
-            const uint32_t q_addr = smem_u32(sq);
-            const uint32_t p_addr = smem_u32(sp);
-            const int nt = two ? 2 : 1;
-
-            auto issue_s = [&](int t, int stage) {
-                const uint32_t k_addr = smem_u32(sk + stage * kV2KVBytes);
-                const uint32_t qa = q_addr + t * kV2QBytes;
-#pragma unroll
-                for (int ks = 0; ks < D / 16; ++ks)
-                    umma_bf16_ss(tmem_base + t * 128, make_smem_desc_sw128(qa + ks * 32, 1024, 0),
-                                 make_smem_desc_sw128(k_addr + ks * 32, 1024, 0), idesc_s, ks != 0 ? 1u : 0u);
-            };
-            auto issue_pv = [&](int t, int stage, bool first) {
-                const uint32_t v_addr = smem_u32(sv + stage * kV2KVBytes);
-                const uint32_t pa = p_addr + t * kPBytes;
-#pragma unroll
-                for (int ks = 0; ks < kTileKV / 16; ++ks) {
-                    const uint64_t da = make_smem_desc_sw128(pa + (ks >> 2) * (kTileQ * 128) + (ks & 3) * 32, 1024, 0);
-                    const uint64_t db = make_smem_desc_sw128(v_addr + ks * (16 * 128), 1024, kTileKV * 128);
-                    umma_bf16_ss(tmem_base + 256 + t * 64, da, db, idesc_pv, (!first || ks != 0) ? 1u : 0u);
-                }
-            };
-
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[0], 0);
-            tcgen05_fence_after();
-            for (int t = 0; t < nt; ++t) {
-                issue_s(t, 0);
-                umma_commit(&s_full[t]);
-            }
-            umma_commit(&k_empty[0]);
-#ifdef LTXV_ATTN_TIMING
-            const bool tm_on = (blockIdx.x == 3 && blockIdx.y == 5);
-            long long tm_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            long long tm_last = clock64();
+#ifdef LTXV_ATTN_TRACE
+    if (threadIdx.x == 0 && qb == 3 && head == 5 && split == 0) {
+        g_attn_trace[10][39][0] = t_entry;
+        g_attn_trace[10][39][1] = clock64();
+    }
 #endif
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_tiles; ++j) {
-                int nstage = stage + 1;
-                uint32_t nphase = phase;
-                if (nstage == kV2Stages) {
-                    nstage = 0;
-                    nphase ^= 1;
-                }
-                if (j + 1 < n_tiles) {
-                    // S_t(j+1) as soon as the softmax group holds S_t(j) in registers: overlaps with its exponentials
-                    mbar_wait(&k_full[nstage], nphase);
-                    TMARK(0);
-                    for (int t = 0; t < nt; ++t) {
-                        mbar_wait(&s_free[t], j & 1);
-                        TMARK(1 + t);
-                        tcgen05_fence_after();
-                        issue_s(t, nstage);
-                        umma_commit(&s_full[t]);
-                        TMARK(3);
+
+    // warps 0-7: softmax (tile 0: 0-3, tile 1: 4-7); warps 8-11: control (TMA, UMMA issuer of tile 0, of tile 1, TMEM
+    // owner).  The control warps sit at the HIGH warp ids on purpose: their few instructions win the issue
+    // arbitration against the always-ready softmax warps that share their scheduler.
+    if (warp_idx >= 8) {
+        setmaxnreg_dec<48>();
+        if (warp_idx == 8) {
+            // ===================== TMA producer =====================
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, nt * kV2QBytes);
+                tma_load_3d(sq, &tm_q, q_full, p.q_col0 + head * D, q0, batch);
+                if (two) tma_load_3d(sq + kV2QBytes, &tm_q, q_full, p.q_col0 + head * D, q0 + kTileQ, batch);
+                int stage = 0;
+                uint32_t phase = 0;
+#ifdef LTXV_ATTN_TRACE
+                const bool tr_on = (qb == 3 && head == 5 && split == 0);
+#endif
+                for (int j = 0; j < n_tiles; ++j) {
+                    const int kv0 = (jt0 + j) * kTileKV;
+                    if (j + kV3Stages + kV3L2Ahead - 1 < n_tiles) {
+                        // the ring only looks kV3Stages tiles ahead and its slots free up late (after the PV MMAs
+                        // retire); an L2 prefetch further out turns the ring's loads into L2 hits
+                        const int kvp = kv0 + (kV3Stages + kV3L2Ahead - 1) * kTileKV;
+                        tma_prefetch_3d(&tm_k, p.k_col0 + head * D, kvp, batch);
+                        tma_prefetch_3d(&tm_v, p.v_col0 + head * D, kvp, batch);
                     }
-                    umma_commit(&k_empty[nstage]);
+                    mbar_wait_sleep(&k_empty[stage], phase ^ 1);
+                    TRACE(10, j, 0);
+                    mbar_arrive_expect_tx(&k_full[stage], kV2KVBytes);
+                    tma_load_3d(sk + stage * kV2KVBytes, &tm_k, &k_full[stage], p.k_col0 + head * D, kv0, batch);
+                    mbar_wait_sleep(&v_empty[stage], phase ^ 1);
+                    TRACE(10, j, 1);
+                    mbar_arrive_expect_tx(&v_full[stage], kV2KVBytes);
+                    tma_load_3d(sv + stage * kV2KVBytes, &tm_v, &v_full[stage], p.v_col0 + head * D, kv0, batch);
+                    if (++stage == kV3Stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
-                mbar_wait(&v_full[stage], phase);
-                TMARK(4);
-                for (int t = 0; t < nt; ++t) {
-                    mbar_wait(&p_full[t], j & 1);
-                    TMARK(5 + t);
-                    tcgen05_fence_after();
-                    issue_pv(t, stage, j == 0);
-                    umma_commit(&pv_done[t]);
-                    TMARK(7);
-                }
-                umma_commit(&v_empty[stage]);
-                stage = nstage;
-                phase = nphase;
             }
+        } else if (warp_idx == 9 || (warp_idx == 10 && two)) {
+            // ===================== UMMA issuer of query tile t =====================
+            const int t = warp_idx - 9;
+            if (elect_one()) {
+                constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, false, false);
+                constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, D, false, true);  // B = V is MN-major
+                const uint32_t qa = smem_u32(sq) + t * kV2QBytes;
+                const uint32_t tmem_s = tmem_base + t * 128;
+                const uint32_t tmem_o = tmem_base + 256 + t * 64;
+                const uint32_t tmem_p = tmem_base + 384 + t * 64;
+                auto issue_s = [&](int stage) {
+                    const uint32_t k_addr = smem_u32(sk + stage * kV2KVBytes);
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_bf16_ss(tmem_s, make_smem_desc_sw128(qa + ks * 32, 1024, 0),
+                                     make_smem_desc_sw128(k_addr + ks * 32, 1024, 0), idesc_s, ks != 0 ? 1u : 0u);
+                };
+                mbar_wait_sleep(q_full, 0);
+                mbar_wait_sleep(&k_full[0], 0);
+                tcgen05_fence_after();
+                issue_s(0);
+                umma_commit(&s_full[t]);
+                umma_commit(&k_empty[0]);
 #ifdef LTXV_ATTN_TIMING
-            if (tm_on)
-                for (int i = 0; i < 8; ++i) g_attn_timing[16 + i] = tm_acc[i];
+                const bool tm_on = (qb == 3 && head == 5 && split == 0);
+                long long tm_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                long long tm_last = clock64();
 #endif
+#ifdef LTXV_ATTN_TRACE
+                const bool tr_on = (qb == 3 && head == 5 && split == 0);
+#endif
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_tiles; ++j) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == kV3Stages) {
+                        nstage = 0;
+                        nphase ^= 1;
+                    }
+                    if (j + 1 < n_tiles) {
+#ifdef LTXV_ATTN_TIMING
+                        TMARK(7);
+                        mbar_wait_sleep(q_full, 0);  // completed long ago: measures the fixed cost of a satisfied wait
+                        TMARK(6);
+#endif
+                        // S_t(j+1) as soon as the softmax group holds S_t(j) in registers
+                        mbar_wait_sleep(&k_full[nstage], nphase);
+                        TMARK(0);
+                        TRACE(8 + t, j, 0);
+                        mbar_wait_sleep(&s_free[t], j & 1);
+                        TMARK(1);
+                        TRACE(8 + t, j, 1);
+                        tcgen05_fence_after();
+                        issue_s(nstage);
+                        umma_commit(&s_full[t]);
+                        umma_commit(&k_empty[nstage]);
+                        TMARK(2);
+                        TRACE(8 + t, j, 2);
+                    }
+                    mbar_wait_sleep(&v_full[stage], phase);
+                    TMARK(3);
+                    TRACE(8 + t, j, 3);
+                    mbar_wait_sleep(&p_full[t], j & 1);
+                    TMARK(4);
+                    TRACE(8 + t, j, 4);
+                    tcgen05_fence_after();
+                    const uint32_t v_addr = smem_u32(sv + stage * kV2KVBytes);
+#pragma unroll
+                    for (int ks = 0; ks < kTileKV / 16; ++ks)
+                        umma_bf16_ts(tmem_o, tmem_p + ks * 8,
+                                     make_smem_desc_sw128(v_addr + ks * (16 * 128), 1024, kTileKV * 128), idesc_pv,
+                                     (j | ks) != 0 ? 1u : 0u);
+                    umma_commit(&pv_done[t]);
+                    umma_commit(&v_empty[stage]);
+                    TMARK(5);
+                    TRACE(8 + t, j, 5);
+                    stage = nstage;
+                    phase = nphase;
+                }
+#ifdef LTXV_ATTN_TIMING
+                if (tm_on)
+                    for (int i = 0; i < 8; ++i) g_attn_timing[16 + 8 * t + i] = tm_acc[i];
+#endif
+            }
         }
-    } else if (warp_idx >= 4) {
-        const int t = (warp_idx - 4) >> 2;  // query tile of this softmax group
+    } else {
+        setmaxnreg_inc<224>();
+        const int t = warp_idx >> 2;  // query tile of this softmax group
         if (t == 0 || two) {
             const int quad = warp_idx & 3;
             const int row = quad * 32 + lane;
             const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
             const uint32_t tmem_s = lane_base + t * 128;
             const uint32_t tmem_o = lane_base + 256 + t * 64;
+            const uint32_t tmem_p = lane_base + 384 + t * 64;
             const float c = p.scale * kLog2e;
-            uint8_t* prow = sp + t * kPBytes + row * 128;
-            const int sw = row & 7;
+            const uint64_t c2 = pack_f32x2(c, c);
             float m_used = -INFINITY;
-            float l0 = 0.f, l1 = 0.f;
+            uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+#if LTXV_ATTN_PINGPONG
+            // ping-pong between the two softmax groups (named barriers 1 + t): the MUFU-heavy exponential phases of
+            // the two query tiles alternate, so each runs at the full 16 exp2/clk/SM while the other group does its
+            // TMEM load / max / waits.
+            if (two && t == 1) named_bar_arrive(1, 256);  // tile 0 goes first
+#endif
 #ifdef LTXV_ATTN_TIMING
-            const bool tm_on = (blockIdx.x == 3 && blockIdx.y == 5 && lane == 0 && (warp_idx == 4 || warp_idx == 8));
+            const bool tm_on = (qb == 3 && head == 5 && split == 0 && lane == 0 && (warp_idx == 0 || warp_idx == 4));
             long long tm_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long tm_last = clock64();
 #endif
-            // ping-pong between the two softmax groups (named barriers 1 + t): the MUFU-heavy exponential phases of
-            // the two query tiles alternate instead of colliding, so each runs at the full 16 exp2/clk/SM while the
-            // other group does its TMEM load / max / waits.
-            if (two && t == 1) named_bar_arrive(1, 256);  // tile 0 goes first
+#ifdef LTXV_ATTN_TRACE
+            const bool tr_on = (qb == 3 && head == 5 && split == 0 && lane == 0);
+#endif
             auto tile = [&](int j, auto tail_tag) {
                 constexpr bool TAIL = decltype(tail_tag)::value;
-                const int kv0 = j * kTileKV;
+                const int kv0 = (jt0 + j) * kTileKV;
                 uint32_t s0[32], s1[32], s2[32], s3[32];
-                mbar_wait(&s_full[t], j & 1);
+                TRACE(warp_idx, j, 0);
+                warp_mbar_wait(&s_full[t], j & 1, lane);
+                TRACE(warp_idx, j, 1);
                 TMARK(0);
                 tcgen05_fence_after();
+#ifdef LTXV_ATTN_EXPERIMENT_MMA_ONLY
+                // timing experiment: no softmax work at all, only the barrier handshakes -> tensor-side floor
+                tcgen05_fence_before();
+                warp_mbar_arrive(&s_free[t], lane);
+                if (j > 0) warp_mbar_wait(&pv_done[t], (j - 1) & 1, lane);
+                tcgen05_fence_before();
+                warp_mbar_arrive(&p_full[t], lane);
+                return;
+#endif
                 tmem_ld_32x32b_x32(tmem_s + 0, s0);
                 tmem_ld_32x32b_x32(tmem_s + 32, s1);
                 tmem_ld_32x32b_x32(tmem_s + 64, s2);
                 tmem_ld_32x32b_x32(tmem_s + 96, s3);
                 tmem_ld_wait();
                 tcgen05_fence_before();
-                mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next QK^T
+                warp_mbar_arrive(&s_free[t], lane);  // S_t may be overwritten by the next QK^T
+                TRACE(warp_idx, j, 2);
                 TMARK(1);
-                float mx = fmaxf(fmaxf(max32<TAIL>(s0, kv0, p.Skv), max32<TAIL>(s1, kv0 + 32, p.Skv)),
-                                 fmaxf(max32<TAIL>(s2, kv0 + 64, p.Skv), max32<TAIL>(s3, kv0 + 96, p.Skv)));
+                float mx = fmaxf(fmaxf(max32_v3<TAIL>(s0, kv0, p.Skv), max32_v3<TAIL>(s1, kv0 + 32, p.Skv)),
+                                 fmaxf(max32_v3<TAIL>(s2, kv0 + 64, p.Skv), max32_v3<TAIL>(s3, kv0 + 96, p.Skv)));
                 mx *= c;
                 TMARK(2);
+                bool pv_waited = (j == 0);
                 if (j == 0) {
                     m_used = mx;
                 } else {
-                    // previous P_t V must have retired before O_t is rescaled or P_t is overwritten
-                    mbar_wait(&pv_done[t], (j - 1) & 1);
-                    TMARK(3);
-                    tcgen05_fence_after();
                     const float m_new = fmaxf(m_used, mx);
                     if (__any_sync(0xffffffffu, (m_new - m_used) > kRescaleThreshold)) {
+                        // rare (first few key tiles): O_t is rescaled in TMEM, which needs the previous P_t V retired
+                        warp_mbar_wait(&pv_done[t], (j - 1) & 1, lane);
+                        pv_waited = true;
+                        tcgen05_fence_after();
                         const float alpha = ex2_approx(m_used - m_new);
 #pragma unroll 1
                         for (int dc = 0; dc < D / 32; ++dc) {
@@ -641,52 +843,167 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                             tmem_st_32x32b_x32(tmem_o + dc * 32, r);
                         }
                         tmem_st_wait();
-                        l0 *= alpha;
-                        l1 *= alpha;
+                        const uint64_t a2 = pack_f32x2(alpha, alpha), z2 = pack_f32x2(0.f, 0.f);
+                        l2a = fma_f32x2(l2a, a2, z2);
+                        l2b = fma_f32x2(l2b, a2, z2);
                         m_used = m_new;
                     }
-                    TMARK(4);
                 }
-                const float neg_m = -m_used;
+                TMARK(3);
+                const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
+#if LTXV_ATTN_PINGPONG
                 if (two) named_bar_sync(1 + t, 256);  // my turn on the MUFU pipe
-                softmax_chunk<TAIL>(s0, c, neg_m, kv0, p.Skv, l0, l1, prow, 0, sw);
-                softmax_chunk<TAIL>(s1, c, neg_m, kv0 + 32, p.Skv, l0, l1, prow, 4, sw);
-                softmax_chunk<TAIL>(s2, c, neg_m, kv0 + 64, p.Skv, l0, l1, prow + kTileQ * 128, 0, sw);
-                softmax_chunk<TAIL>(s3, c, neg_m, kv0 + 96, p.Skv, l0, l1, prow + kTileQ * 128, 4, sw);
-                if (two) named_bar_arrive(1 + (t ^ 1), 256);  // hand the MUFU pipe to the other tile
+#endif
+                uint32_t pk[32];
+                exp_chunk_v3(s0, c2, negm2, l2a, l2b, pk);
+                exp_chunk_v3(s1, c2, negm2, l2a, l2b, pk + 16);
+                TMARK(4);
+                TRACE(warp_idx, j, 3);
+                if (!pv_waited) {
+                    // P_t is single-buffered: the previous P_t V must have read it before it is overwritten.  The wait
+                    // sits here, after half of the exponentials, so the PV MMA latency hides behind them.
+                    warp_mbar_wait(&pv_done[t], (j - 1) & 1, lane);
+                    tcgen05_fence_after();
+                }
                 TMARK(5);
-                tcgen05_fence_before();
-                fence_proxy_async_smem();
-                mbar_arrive(&p_full[t]);
+                TRACE(warp_idx, j, 4);
+                tmem_st_32x32b_x32(tmem_p, pk);          // keys  0..63  -> P columns  0..31
+                exp_chunk_v3(s2, c2, negm2, l2a, l2b, pk);
+                exp_chunk_v3(s3, c2, negm2, l2a, l2b, pk + 16);
+                tmem_st_32x32b_x32(tmem_p + 32, pk);     // keys 64..127 -> P columns 32..63
+#if LTXV_ATTN_PINGPONG
+                if (two) named_bar_arrive(1 + (t ^ 1), 256);  // hand the MUFU pipe to the other tile
+#endif
                 TMARK(6);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                warp_mbar_arrive(&p_full[t], lane);
+                TRACE(warp_idx, j, 5);
+                TMARK(7);
             };
-            const int n_full = p.Skv / kTileKV;  // tiles without a ragged tail
+#ifdef LTXV_ATTN_TRACE
+            if (tr_on && warp_idx == 0) g_attn_trace[10][39][2] = clock64();
+#endif
+            const bool ragged = (jt1 == n_tiles_all) && (p.Skv % kTileKV != 0);  // last key tile has a tail
+            const int n_full = n_tiles - (ragged ? 1 : 0);
             for (int j = 0; j < n_full; ++j) tile(j, std::false_type{});
-            if (n_full < n_tiles) tile(n_full, std::true_type{});
+            if (ragged) tile(n_full, std::true_type{});
 #ifdef LTXV_ATTN_TIMING
             if (tm_on)
-                for (int i = 0; i < 8; ++i) g_attn_timing[(warp_idx == 4 ? 0 : 8) + i] = tm_acc[i];
+                for (int i = 0; i < 8; ++i) g_attn_timing[(warp_idx == 0 ? 0 : 8) + i] = tm_acc[i];
 #endif
-            mbar_wait(&pv_done[t], (n_tiles - 1) & 1);
+            warp_mbar_wait(&pv_done[t], (n_tiles - 1) & 1, lane);
             tcgen05_fence_after();
-            const float inv_l = 1.0f / (l0 + l1);
+#ifdef LTXV_ATTN_TRACE
+            if (tr_on && warp_idx == 0) g_attn_trace[10][39][3] = clock64();
+#endif
+            float la, lb, lc, ld;
+            unpack_f32x2(l2a, la, lb);
+            unpack_f32x2(l2b, lc, ld);
+            float l_row = (la + lb) + (lc + ld);
             const int qrow = q0 + t * kTileQ + row;
             __nv_bfloat16* orow = attn_out_row(p, batch, qrow < p.Sq ? qrow : 0, head, D);
+            if (!is_split) {
+                const float inv_l = 1.0f / l_row;
 #pragma unroll 1
-            for (int dc = 0; dc < D / 32; ++dc) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_o + dc * 32, r);
-                tmem_ld_wait();
-                if (qrow < p.Sq) {
-                    uint4* d4 = reinterpret_cast<uint4*>(orow + dc * 32);
+                for (int dc = 0; dc < D / 32; ++dc) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tmem_o + dc * 32, r);
+                    tmem_ld_wait();
+                    if (qrow < p.Sq) store_row_bf16(orow + dc * 32, r, inv_l);
+                }
+            } else {
+#ifdef LTXV_ATTN_TRACE
+                const bool ts_on = (unit == first_split && threadIdx.x == 0);
+                if (ts_on) {
+                    g_attn_trace[9][20 + split][0] = t_entry;
+                    g_attn_trace[9][20 + split][1] = clock64();
+                }
+#endif
+                // ---- split unit: publish (O unnormalised, m, l) of this key range; the LAST of the nsplit CTAs of the
+                // unit (ticket counter) merges all partials and writes the output rows ----
+                const int su = unit - first_split;
+                const int r256 = t * kTileQ + row;
+                // scratch is column-major per work item ([17 float4 columns][256 rows]): the 32 rows of a warp are
+                // contiguous, so every store / load below is a fully coalesced 512-byte access
+                float4* mine = reinterpret_cast<float4*>(sp.scratch) +
+                               static_cast<int64_t>(su * sp.nsplit + split) * (kSplitCols4 * 256) + r256;
+#pragma unroll 1
+                for (int dc = 0; dc < D / 32; ++dc) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tmem_o + dc * 32, r);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        u.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) * inv_l, __uint_as_float(r[8 * q + 1]) * inv_l);
-                        u.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv_l, __uint_as_float(r[8 * q + 3]) * inv_l);
-                        u.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv_l, __uint_as_float(r[8 * q + 5]) * inv_l);
-                        u.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv_l, __uint_as_float(r[8 * q + 7]) * inv_l);
-                        d4[q] = u;
+                    for (int q = 0; q < 8; ++q)
+                        mine[(dc * 8 + q) * 256] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                }
+                mine[16 * 256] = make_float4(m_used, l_row, 0.f, 0.f);
+                __threadfence();
+                named_bar_sync(1, 128 * nt);  // all softmax threads of the CTA have published
+#ifdef LTXV_ATTN_TRACE
+                if (ts_on) g_attn_trace[9][20 + split][2] = clock64();
+#endif
+                if (threadIdx.x == 0) {
+                    const int ticket = atomicAdd(sp.counters + su, 1);
+                    *split_flag = (ticket == sp.nsplit - 1) ? 1 : 0;
+                    if (ticket == sp.nsplit - 1) sp.counters[su] = 0;  // re-arm for the next launch on this stream
+                    __threadfence();
+                }
+                named_bar_sync(1, 128 * nt);
+#ifdef LTXV_ATTN_TRACE
+                if (ts_on) g_attn_trace[9][20 + split][3] = clock64();
+#endif
+                if (*split_flag != 0) {
+                    const float4* base = reinterpret_cast<const float4*>(sp.scratch) +
+                                         static_cast<int64_t>(su * sp.nsplit) * (kSplitCols4 * 256) + r256;
+                    constexpr int64_t stride = kSplitCols4 * 256;  // float4s per work item
+                    // all (m, l) pairs in flight at once (one L2 round trip), then the weights 2^(m_i - M)
+                    float4 ml[kMaxSplit];
+#pragma unroll
+                    for (int i = 0; i < kMaxSplit; ++i)
+                        ml[i] = i < sp.nsplit ? __ldcg(base + i * stride + 16 * 256) : make_float4(-INFINITY, 0.f, 0.f, 0.f);
+                    float m_all = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < kMaxSplit; ++i) m_all = fmaxf(m_all, ml[i].x);
+                    float wgt[kMaxSplit];
+                    float l_all = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kMaxSplit; ++i) {
+                        wgt[i] = i < sp.nsplit ? ex2_approx(ml[i].x - m_all) : 0.f;
+                        l_all = fmaf(ml[i].y, wgt[i], l_all);
+                    }
+                    const float inv_l = 1.0f / l_all;
+#pragma unroll 1
+                    for (int dc = 0; dc < D / 16; ++dc) {  // 16 output columns at a time: 4 x float4 per partial in flight
+                        float acc[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < kMaxSplit; ++i) {
+                            if (i < sp.nsplit) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 v = __ldcg(base + i * stride + (dc * 4 + q) * 256);
+                                    acc[4 * q + 0] = fmaf(v.x, wgt[i], acc[4 * q + 0]);
+                                    acc[4 * q + 1] = fmaf(v.y, wgt[i], acc[4 * q + 1]);
+                                    acc[4 * q + 2] = fmaf(v.z, wgt[i], acc[4 * q + 2]);
+                                    acc[4 * q + 3] = fmaf(v.w, wgt[i], acc[4 * q + 3]);
+                                }
+                            }
+                        }
+                        if (qrow < p.Sq) {
+                            uint4* d4 = reinterpret_cast<uint4*>(orow + dc * 16);
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                uint4 u;
+                                u.x = pack_bf16x2(acc[8 * q + 0] * inv_l, acc[8 * q + 1] * inv_l);
+                                u.y = pack_bf16x2(acc[8 * q + 2] * inv_l, acc[8 * q + 3] * inv_l);
+                                u.z = pack_bf16x2(acc[8 * q + 4] * inv_l, acc[8 * q + 5] * inv_l);
+                                u.w = pack_bf16x2(acc[8 * q + 6] * inv_l, acc[8 * q + 7] * inv_l);
+                                d4[q] = u;
+                            }
+                        }
                     }
                 }
             }
@@ -695,19 +1012,56 @@ flash_attn2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp_idx == 1) {
+#ifdef LTXV_ATTN_TRACE
+    if (threadIdx.x == 0 && qb == 3 && head == 5 && split == 0) g_attn_trace[10][39][4] = clock64();
+    if (threadIdx.x == 0 && is_split && unit == first_split) {
+        g_attn_trace[9][20 + split][4] = clock64();
+        g_attn_trace[9][20 + split][5] = static_cast<long long>(globaltimer_ns());
+        g_attn_trace[9][20 + split][6] = *split_flag;
+    }
+    if (threadIdx.x == 0 && item == 0) g_attn_trace[9][19][5] = static_cast<long long>(globaltimer_ns());
+#endif
+    if (warp_idx == 11) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
 }
 
+
 std::atomic<uint64_t> g_attn_launches{0};
 
-cudaError_t launch_attn2_impl(const AttnParams& p, cudaStream_t stream) {
+// per-device scratch for the tail split (148 work items x 256 rows x 17 float4 = 10.3 MB) + ticket counters
+struct SplitScratch {
+    float* scratch = nullptr;
+    int* counters = nullptr;
+    int n_sm = 0;
+};
+cudaError_t split_scratch(SplitScratch** out) {
+    static SplitScratch per_dev[16];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
+    SplitScratch& s = per_dev[dev];
+    if (s.scratch == nullptr) {
+        e = cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&s.scratch, static_cast<size_t>(s.n_sm) * 256 * kSplitCols4 * sizeof(float4));
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&s.counters, static_cast<size_t>(s.n_sm) * sizeof(int));
+        if (e != cudaSuccess) return e;
+        e = cudaMemset(s.counters, 0, static_cast<size_t>(s.n_sm) * sizeof(int));
+        if (e != cudaSuccess) return e;
+    }
+    *out = &s;
+    return cudaSuccess;
+}
+
+cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e =
-            cudaFuncSetAttribute(flash_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes);
+            cudaFuncSetAttribute(flash_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV3SmemBytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -718,10 +1072,32 @@ cudaError_t launch_attn2_impl(const AttnParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     e = make_tensor_map_3d_bf16(&tv, p.v, p.B, p.Skv, p.ldv, kTileKV, 64, p.ldv, p.ldv * (int64_t)p.Skv);
     if (e != cudaSuccess) return e;
-    dim3 grid((p.Sq + 2 * kTileQ - 1) / (2 * kTileQ), p.H, p.B);
+    SplitScratch* ss = nullptr;
+    e = split_scratch(&ss);
+    if (e != cudaSuccess) return e;
+    SplitPlan sp{};
+    sp.n_qb = (p.Sq + 2 * kTileQ - 1) / (2 * kTileQ);
+    sp.n_units = p.B * p.H * sp.n_qb;
+    sp.nsplit = 1;
+    sp.n_split_units = 0;
+    sp.scratch = ss->scratch;
+    sp.counters = ss->counters;
+    const int n_tiles = (p.Skv + kTileKV - 1) / kTileKV;
+    const int rem = sp.n_units % ss->n_sm;
+    if (rem != 0 && getenv("LTXV_ATTN_NOSPLIT") == nullptr) {
+        int ns = ss->n_sm / rem;                // key ranges per tail unit so that the tail wave fills the SMs
+        if (ns > n_tiles / 4) ns = n_tiles / 4;  // keep >= 4 key tiles per range (pipeline fill / drain)
+        if (ns > kMaxSplit) ns = kMaxSplit;
+        if (const char* ev = getenv("LTXV_ATTN_NSPLIT")) ns = atoi(ev) < ns ? atoi(ev) : ns;  // experiment knob
+        if (ns >= 2) {
+            sp.nsplit = ns;
+            sp.n_split_units = rem;
+        }
+    }
+    const int n_items = sp.n_units - sp.n_split_units + sp.n_split_units * sp.nsplit;
     {
         ProfScope prof(PROF_ATTN_SELF, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 64, stream);
-        flash_attn2_kernel<<<grid, kV2Threads, kV2SmemBytes, stream>>>(tq, tk, tv, p);
+        flash_attn3_kernel<<<n_items, kV3Threads, kV3SmemBytes, stream>>>(tq, tk, tv, p, sp);
     }
     g_attn_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
@@ -757,6 +1133,9 @@ cudaError_t launch_attn_impl(const AttnParams& p, cudaStream_t stream) {
 }  // namespace
 
 uint64_t attention_launch_count() { return g_attn_launches.load(); }
+#ifdef LTXV_ATTN_TRACE
+void attention_debug_trace(long long* out) { cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(long long) * 11 * 40 * 8); }
+#endif
 #ifdef LTXV_ATTN_TIMING
 void attention_debug_timing(long long* out32) { cudaMemcpyFromSymbol(out32, g_attn_timing, sizeof(long long) * 32); }
 #endif
@@ -764,7 +1143,7 @@ void attention_debug_timing(long long* out32) { cudaMemcpyFromSymbol(out32, g_at
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Skv <= 0) return cudaErrorInvalidValue;
     if (p.D == 64 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && getenv("LTXV_ATTN_V1") == nullptr)
-        return launch_attn2_impl(p, stream);
+        return launch_attn3_impl(p, stream);
     if (p.D == 64) return launch_attn_impl<64>(p, stream);
     if (p.D == 128) return launch_attn_impl<128>(p, stream);
     return cudaErrorInvalidValue;

@@ -17,16 +17,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns_host_safe() {
 
 struct PeerFlags {
     uint32_t* p[kMaxRanks];
+    uint32_t epoch[kMaxRanks];  // per-partner epoch: ranks a and b count only the barriers that include both of them
 };
 
 // One block, one thread per peer.  Thread r publishes `epoch` into rank r's flag slot for this rank, then waits
 // until rank r has published `epoch` (or later) into ours.  System-scope release/acquire orders the peer stores
 // issued by earlier kernels of this stream before the flag, and the flag before later kernels' loads.
-__global__ void barrier_kernel(PeerFlags flags, uint32_t* local_flags, int first, int count, int rank, uint32_t epoch) {
+__global__ void barrier_kernel(PeerFlags flags, uint32_t* local_flags, int first, int count, int rank) {
     const int r = first + threadIdx.x;
     if (static_cast<int>(threadIdx.x) >= count) return;
     __threadfence_system();
     if (r != rank) {
+        const uint32_t epoch = flags.epoch[r];
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[r] + rank), "r"(epoch) : "memory");
         const unsigned long long t0 = globaltimer_ns_host_safe();
         uint32_t v;
@@ -95,13 +97,18 @@ void PeerComm::barrier(cudaStream_t s, int domain, int first, int count) {
     if (domain < 0 || domain > 1 || first < 0 || first + count > nranks_ || rank_ < first || rank_ >= first + count)
         fail("invalid barrier group [%d,%d) / domain %d for rank %d", first, first + count, domain, rank_);
     if (!opened_) fail("communicator peers have not been opened");
-    ++epoch_[domain];
     PeerFlags f;
-    // flag word for (domain, source rank) lives at heap offset (domain * kMaxRanks + src) * 4 on every rank
-    for (int r = 0; r < kMaxRanks; ++r)
+    // flag word for (domain, source rank) lives at heap offset (domain * kMaxRanks + src) * 4 on every rank.  The
+    // epoch is kept per partner: two ranks may have taken part in different numbers of sub-group barriers with
+    // third parties (e.g. the CFG branch groups run different numbers of forwards), but the sequence of barriers that
+    // contain BOTH of them is the same on both sides.
+    for (int r = 0; r < kMaxRanks; ++r) {
         f.p[r] = r < nranks_ ? static_cast<uint32_t*>(peer_base_[r]) + domain * kMaxRanks : nullptr;
-    barrier_kernel<<<1, 32, 0, s>>>(f, static_cast<uint32_t*>(heap_) + domain * kMaxRanks, first, count, rank_,
-                                    epoch_[domain]);
+        f.epoch[r] = 0;
+    }
+    for (int r = first; r < first + count; ++r)
+        if (r != rank_) f.epoch[r] = ++epoch_[domain][r];
+    barrier_kernel<<<1, 32, 0, s>>>(f, static_cast<uint32_t*>(heap_) + domain * kMaxRanks, first, count, rank_);
     ++launches_;
     g_comm_launches.fetch_add(1, std::memory_order_relaxed);
     LTXV_CUDA(cudaGetLastError());

@@ -49,7 +49,7 @@ private:
     size_t heap_bytes_ = 0, top_ = kReserved;
     void* peer_base_[kMaxRanks] = {nullptr};
     bool opened_ = false;
-    uint32_t epoch_[2] = {0, 0};
+    uint32_t epoch_[2][kMaxRanks] = {{0}, {0}};  // [domain][partner]
     uint64_t launches_ = 0;
     uint64_t id_ = 0;
 };

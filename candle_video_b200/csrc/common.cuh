@@ -66,6 +66,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with an explicit suspend-time hint (ns): the thread sleeps IN HARDWARE until the phase completes or the hint
+// expires, instead of returning after the (very short) default slice.  A control warp that spins on plain try_wait
+// issues TRYWAIT+BRA back to back and steals issue slots from the compute warps on its scheduler.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+#ifndef LTXV_MBAR_HINT_NS
+#define LTXV_MBAR_HINT_NS 20000u
+#endif
+// same contract as mbar_wait (trap on a protocol bug), sleeping between polls
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, LTXV_MBAR_HINT_NS)) {
+        if (++spins > 400000u) __trap();  // >= several seconds with a 20 us slice
+    }
+}
+
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging the GPU box.
 #ifndef LTXV_MBAR_TIMEOUT_NS
 #define LTXV_MBAR_TIMEOUT_NS 4000000000ull
@@ -119,6 +146,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
         "r"(c2)
         : "memory");
+}
+
+// pull a box into L2 ahead of the smem load (no completion tracking)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------

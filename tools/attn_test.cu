@@ -138,13 +138,21 @@ static int run(int B, int H, int Sq, int Skv, int D, bool packed, bool use_bias,
 int main(int argc, char** argv) {
     bool big = argc > 1 && atoi(argv[1]) > 0;
     int fails = 0;
+    if (argc > 1 && atoi(argv[1]) == 2) {  // timing of the Ulysses shard shapes only
+        run(1, 8, 4992, 4992, 64, true, false, true, 1.0f);
+        run(1, 16, 4992, 4992, 64, true, false, true, 1.0f);
+        run(1, 32, 4992, 4992, 64, true, false, true, 1.0f);
+        return 0;
+    }
     fails += run(1, 2, 128, 128, 64, true, false, false, 1.0f);
     fails += run(1, 2, 256, 256, 64, true, false, false, 1.0f);
     fails += run(2, 4, 384, 384, 64, true, false, false, 2.0f);   // several kv tiles, batch
     fails += run(1, 3, 200, 200, 64, true, false, false, 4.0f);   // ragged q and kv tails, peaky softmax (rescale path)
     fails += run(1, 2, 1000, 1000, 64, true, false, false, 6.0f);
-    fails += run(1, 2, 300, 700, 64, false, false, false, 3.0f);  // v2 kernel: odd query tile count, ragged kv tail
-    fails += run(2, 3, 640, 1300, 64, false, false, false, 5.0f);  // v2: batch, peaky softmax (rescale path)
+    fails += run(1, 2, 300, 700, 64, false, false, false, 3.0f);  // 2-tile kernel: odd query tile count, ragged kv tail
+    fails += run(2, 3, 640, 1300, 64, false, false, false, 5.0f);  // 2-tile kernel: batch, peaky softmax (rescale path)
+    fails += run(1, 2, 300, 2000, 64, false, false, false, 4.0f);  // tail split x4, odd query tile count, ragged kv tail
+    fails += run(1, 4, 1280, 4096, 64, false, false, false, 2.0f);  // tail split: 20 units -> 7 key ranges each
     fails += run(2, 4, 384, 128, 64, false, true, false, 1.0f);   // cross-attention with key-padding bias
     fails += run(1, 4, 300, 77, 64, false, true, false, 1.0f);    // ragged text length
     fails += run(1, 2, 256, 256, 128, true, false, false, 1.0f);  // 13B head_dim
@@ -152,6 +160,8 @@ int main(int argc, char** argv) {
     if (big) {
         fails += run(1, 32, 4992, 4992, 64, true, false, true, 1.0f);
         fails += run(1, 32, 4992, 128, 64, false, true, true, 1.0f);
+        fails += run(1, 8, 4992, 4992, 64, true, false, true, 1.0f);   // Ulysses shard at 8 GPUs: 160 units on 148 SMs
+        fails += run(1, 16, 4992, 4992, 64, true, false, true, 1.0f);  // Ulysses shard at 4 GPUs
         fails += run(1, 32, 13376, 13376, 64, true, false, true, 1.0f);
         fails += run(1, 32, 4992, 4992, 128, true, false, true, 1.0f);
     }
