@@ -1028,6 +1028,227 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 
+
+// ================================================================================================
+// Cross-attention (head_dim 64, <= 128 keys: the T5 text tokens).  The whole key axis is ONE tile, so there is no online
+// softmax and no key loop to pipeline; what has to be amortised is the per-CTA fixed cost.  The general kernel above
+// spends one CTA per (head, 128 queries): 1248 CTAs of ~15 us each at c2, 62 us per launch for 5 GFLOP.  Here a CTA
+// owns one (batch, head) and a contiguous range of query tiles: K and V are loaded once, Q tiles stream through a
+// 2-deep TMA ring per softmax group, and the two groups (two query tiles in flight, as in v3) overlap one tile's
+// exponentials with the other's TMEM load / PV MMA / output stores.  P stays in TMEM (TS-form MMA).
+// TMEM map: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512).
+// ================================================================================================
+constexpr int kXThreads = 384;
+constexpr int kXQStages = 2;
+constexpr int kXSmemBytes = 2 * kV2KVBytes + 2 * kXQStages * kV2QBytes + 1024;
+
+__global__ void __launch_bounds__(kXThreads, 1)
+cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ AttnParams p, const int ctas_per_head) {
+    constexpr int D = 64;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sk = smem;
+    uint8_t* sv = sk + kV2KVBytes;
+    uint8_t* sq = sv + kV2KVBytes;  // [group][stage] 16 KB each
+    float* sbias = reinterpret_cast<float*>(sq + 2 * kXQStages * kV2QBytes);  // [128] bias * log2e, -inf beyond Skv
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 128);
+    uint64_t* kv_full = bars + 0;
+    uint64_t* q_full = bars + 1;                    // [2][stages]
+    uint64_t* q_empty = q_full + 2 * kXQStages;     // [2][stages]
+    uint64_t* s_full = q_empty + 2 * kXQStages;     // [2]
+    uint64_t* s_free = s_full + 2;                  // [2] 4 warp arrivals
+    uint64_t* p_full = s_free + 2;                  // [2] 4 warp arrivals
+    uint64_t* pv_done = p_full + 2;                 // [2]
+    uint64_t* o_free = pv_done + 2;                 // [2] 4 warp arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int bh = blockIdx.x / ctas_per_head;
+    const int part = blockIdx.x % ctas_per_head;
+    const int head = bh % p.H;
+    const int batch = bh / p.H;
+    const int nq = (p.Sq + kTileQ - 1) / kTileQ;
+    const int qt0 = (part * nq) / ctas_per_head;  // this CTA's query tiles [qt0, qt1)
+    const int qt1 = ((part + 1) * nq) / ctas_per_head;
+    // group g handles tiles qt0 + g, qt0 + g + 2, ...
+    auto n_of = [&](int g) { return (qt1 - qt0 - g + 1) / 2; };
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2 * kXQStages; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1);
+            mbar_init(&s_free[g], 4);
+            mbar_init(&p_full[g], 4);
+            mbar_init(&pv_done[g], 1);
+            mbar_init(&o_free[g], 4);
+        }
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 128) {
+        const int k = threadIdx.x;
+        float b = (k < p.Skv) ? 0.f : -INFINITY;
+        if (p.kv_bias != nullptr && k < p.Skv) b = __ldg(p.kv_bias + static_cast<int64_t>(batch) * p.Skv + k) * kLog2e;
+        sbias[k] = b;
+    }
+    if (warp_idx == 11) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp_idx >= 8) {
+        setmaxnreg_dec<48>();
+        if (warp_idx == 8) {
+            // ===================== TMA producer: K, V once; Q tiles of both groups =====================
+            if (elect_one()) {
+                mbar_arrive_expect_tx(kv_full, 2 * kV2KVBytes);
+                tma_load_3d(sk, &tm_k, kv_full, p.k_col0 + head * D, 0, batch);
+                tma_load_3d(sv, &tm_v, kv_full, p.v_col0 + head * D, 0, batch);
+                const int n0 = n_of(0), n1 = n_of(1);
+                for (int j = 0; j < n0; ++j) {
+                    for (int g = 0; g < 2; ++g) {
+                        if (j >= (g == 0 ? n0 : n1)) continue;
+                        const int stage = j % kXQStages;
+                        const uint32_t phase = (j / kXQStages) & 1;
+                        uint64_t* full = &q_full[g * kXQStages + stage];
+                        mbar_wait_sleep(&q_empty[g * kXQStages + stage], phase ^ 1);
+                        mbar_arrive_expect_tx(full, kV2QBytes);
+                        tma_load_3d(sq + (g * kXQStages + stage) * kV2QBytes, &tm_q, full, p.q_col0 + head * D,
+                                    (qt0 + 2 * j + g) * kTileQ, batch);
+                    }
+                }
+            }
+        } else if (warp_idx == 9 || warp_idx == 10) {
+            // ===================== UMMA issuer of group g =====================
+            const int g = warp_idx - 9;
+            const int n = n_of(g);
+            if (n > 0 && elect_one()) {
+                constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, false, false);
+                constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, D, false, true);
+                const uint32_t k_addr = smem_u32(sk), v_addr = smem_u32(sv);
+                const uint32_t tmem_s = tmem_base + g * 128;
+                const uint32_t tmem_o = tmem_base + 256 + g * 64;
+                const uint32_t tmem_p = tmem_base + 384 + g * 64;
+                mbar_wait_sleep(kv_full, 0);
+                for (int j = 0; j < n; ++j) {
+                    const int stage = j % kXQStages;
+                    const uint32_t phase = (j / kXQStages) & 1;
+                    mbar_wait_sleep(&q_full[g * kXQStages + stage], phase);
+                    if (j > 0) mbar_wait_sleep(&s_free[g], (j - 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t qa = smem_u32(sq + (g * kXQStages + stage) * kV2QBytes);
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_bf16_ss(tmem_s, make_smem_desc_sw128(qa + ks * 32, 1024, 0),
+                                     make_smem_desc_sw128(k_addr + ks * 32, 1024, 0), idesc_s, ks != 0 ? 1u : 0u);
+                    umma_commit(&s_full[g]);
+                    umma_commit(&q_empty[g * kXQStages + stage]);
+                    mbar_wait_sleep(&p_full[g], j & 1);
+                    if (j > 0) mbar_wait_sleep(&o_free[g], (j - 1) & 1);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < kTileKV / 16; ++ks)
+                        umma_bf16_ts(tmem_o, tmem_p + ks * 8,
+                                     make_smem_desc_sw128(v_addr + ks * (16 * 128), 1024, kTileKV * 128), idesc_pv,
+                                     ks != 0 ? 1u : 0u);
+                    umma_commit(&pv_done[g]);
+                }
+            }
+        }
+    } else {
+        setmaxnreg_inc<224>();
+        const int g = warp_idx >> 2;
+        const int n = n_of(g);
+        const int quad = warp_idx & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const uint32_t tmem_s = lane_base + g * 128;
+        const uint32_t tmem_o = lane_base + 256 + g * 64;
+        const uint32_t tmem_p = lane_base + 384 + g * 64;
+        const float c = p.scale * kLog2e;
+        const uint64_t c2 = pack_f32x2(c, c);
+        const uint64_t one2 = pack_f32x2(1.0f, 1.0f);
+        for (int j = 0; j < n; ++j) {
+            uint32_t s0[32], s1[32], s2[32], s3[32];
+            warp_mbar_wait(&s_full[g], j & 1, lane);
+            tcgen05_fence_after();
+            tmem_ld_32x32b_x32(tmem_s + 0, s0);
+            tmem_ld_32x32b_x32(tmem_s + 32, s1);
+            tmem_ld_32x32b_x32(tmem_s + 64, s2);
+            tmem_ld_32x32b_x32(tmem_s + 96, s3);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            warp_mbar_arrive(&s_free[g], lane);
+            // t = s * scale*log2e + bias*log2e  (bias: additive key mask, -inf beyond the last key), in place
+            auto prep = [&](uint32_t (&r)[32], int col0) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + i);
+                    float x0, x1, x2, x3;
+                    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, pack_f32x2(b.x, b.y)), x0, x1);
+                    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, pack_f32x2(b.z, b.w)), x2, x3);
+                    r[i] = __float_as_uint(x0);
+                    r[i + 1] = __float_as_uint(x1);
+                    r[i + 2] = __float_as_uint(x2);
+                    r[i + 3] = __float_as_uint(x3);
+                }
+            };
+            prep(s0, 0);
+            prep(s1, 32);
+            prep(s2, 64);
+            prep(s3, 96);
+            const float mx = fmaxf(fmaxf(max32_v3<false>(s0, 0, 128), max32_v3<false>(s1, 0, 128)),
+                                   fmaxf(max32_v3<false>(s2, 0, 128), max32_v3<false>(s3, 0, 128)));
+            const uint64_t negm2 = pack_f32x2(-mx, -mx);
+            uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+            uint32_t pk[32];
+            exp_chunk_v3(s0, one2, negm2, l2a, l2b, pk);
+            exp_chunk_v3(s1, one2, negm2, l2a, l2b, pk + 16);
+            tmem_st_32x32b_x32(tmem_p, pk);
+            exp_chunk_v3(s2, one2, negm2, l2a, l2b, pk);
+            exp_chunk_v3(s3, one2, negm2, l2a, l2b, pk + 16);
+            tmem_st_32x32b_x32(tmem_p + 32, pk);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            warp_mbar_arrive(&p_full[g], lane);
+            float la, lb, lc, ld;
+            unpack_f32x2(l2a, la, lb);
+            unpack_f32x2(l2b, lc, ld);
+            const float inv_l = 1.0f / ((la + lb) + (lc + ld));
+            const int qrow = (qt0 + 2 * j + g) * kTileQ + row;
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                  (static_cast<int64_t>(batch) * p.Sq + (qrow < p.Sq ? qrow : 0)) * p.ldo + head * D;
+            warp_mbar_wait(&pv_done[g], j & 1, lane);
+            tcgen05_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32b_x32(tmem_o, o0);
+            tmem_ld_32x32b_x32(tmem_o + 32, o1);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            warp_mbar_arrive(&o_free[g], lane);
+            if (qrow < p.Sq) {
+                store_row_bf16(orow, o0, inv_l);
+                store_row_bf16(orow + 32, o1, inv_l);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 11) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 std::atomic<uint64_t> g_attn_launches{0};
 
 // per-device scratch for the tail split (148 work items x 256 rows x 17 float4 = 10.3 MB) + ticket counters
@@ -1103,6 +1324,38 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+
+cudaError_t launch_cross_attn_impl(const AttnParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    static int num_sms = 148;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    CUtensorMap tq, tk, tv;
+    cudaError_t e = make_tensor_map_3d_bf16(&tq, p.q, p.B, p.Sq, p.ldq, kTileQ, 64, p.ldq, p.ldq * (int64_t)p.Sq);
+    if (e != cudaSuccess) return e;
+    e = make_tensor_map_3d_bf16(&tk, p.k, p.B, p.Skv, p.ldk, kTileKV, 64, p.ldk, p.ldk * (int64_t)p.Skv);
+    if (e != cudaSuccess) return e;
+    e = make_tensor_map_3d_bf16(&tv, p.v, p.B, p.Skv, p.ldv, kTileKV, 64, p.ldv, p.ldv * (int64_t)p.Skv);
+    if (e != cudaSuccess) return e;
+    const int nq = (p.Sq + kTileQ - 1) / kTileQ;
+    int cph = num_sms / (p.B * p.H);  // CTAs per (batch, head): fill the SMs in one wave
+    if (cph < 1) cph = 1;
+    if (cph > (nq + 1) / 2) cph = (nq + 1) / 2;  // at least one tile pair per CTA
+    if (cph < 1) cph = 1;
+    {
+        ProfScope prof(PROF_ATTN_CROSS, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 64, stream);
+        cross_attn_kernel<<<p.B * p.H * cph, kXThreads, kXSmemBytes, stream>>>(tq, tk, tv, p, cph);
+    }
+    g_attn_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 template <int D>
 cudaError_t launch_attn_impl(const AttnParams& p, cudaStream_t stream) {
     using C = ACfg<D>;
@@ -1144,6 +1397,8 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Skv <= 0) return cudaErrorInvalidValue;
     if (p.D == 64 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && getenv("LTXV_ATTN_V1") == nullptr)
         return launch_attn3_impl(p, stream);
+    if (p.D == 64 && p.Skv <= kTileKV && p.out_rows_per_peer == 0 && getenv("LTXV_ATTN_V1") == nullptr)
+        return launch_cross_attn_impl(p, stream);  // one key tile: text cross-attention
     if (p.D == 64) return launch_attn_impl<64>(p, stream);
     if (p.D == 128) return launch_attn_impl<128>(p, stream);
     return cudaErrorInvalidValue;

@@ -24,6 +24,8 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kEpiRowFloats = 36;                              // 32 columns + 4 pad: conflict-free 128-bit smem rows
+constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;     // one 32x32 f32 transpose tile per epilogue warp
 
 template <int BLOCK_N>
 struct Cfg {
@@ -32,7 +34,7 @@ struct Cfg {
     static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 192) ? 5 : (BLOCK_N >= 128) ? 6 : 8;
     static constexpr int kTmemStride = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128) ? 128 : 256;
     static constexpr int kTmemCols = 2 * kTmemStride;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiStageBytes;
     static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
 };
@@ -219,6 +221,79 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const RowCtx
 }
 
 // ------------------------------------------------------------------------------------------------
+// Coalesced epilogue for the plain (non-conv) GEMMs.  tcgen05.ld hands every thread ONE accumulator row, so direct
+// stores touch 32 different rows per warp instruction (32 LSU wavefronts, 16 useful bytes each): at K = 2048 the
+// f32 residual epilogue (read x, write x, write the bf16 copy) then costs more than the whole main loop
+// (measured 634 TFLOP/s for the [4992,2048]x[2048,2048] projections vs 1.0-1.1 PFLOP/s for the others).  Here each
+// 32x32 chunk goes through a per-warp shared-memory tile and comes back transposed: a lane holds 4 consecutive
+// columns of rows (4i + lane/8), so one warp instruction covers 4 rows x 128 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+// residual rows of one 32x32 chunk in the transposed (coalesced) ownership; issued one chunk AHEAD of its use so the
+// global round trip overlaps the TMEM load / transpose / stores of the previous chunk
+__device__ __forceinline__ void epilogue_load_residual(const GemmParams& p, int m_warp0, int col0, int lane,
+                                                       float4 (&res)[8]) {
+    const int col = col0 + (lane & 7) * 4;
+    const int rsub = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m_warp0 + 4 * i + rsub;
+        res[i] = (m < p.M && col < p.N) ? *reinterpret_cast<const float4*>(p.res_f32 + m * p.ldo + col)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, int m_warp0, int col0, int lane,
+                                                         float (&v)[32], float* stage, const float4 (&res)[8]) {
+    float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiRowFloats);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    __syncwarp();
+    const int cq = (lane & 7) * 4;
+    const int rsub = lane >> 3;
+    const int col = col0 + cq;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    if (p.epi == EPI_RESIDUAL_F32 && p.gate != nullptr) g = __ldg(reinterpret_cast<const float4*>(p.gate + col));
+    // all loads first (the residual rows arrive prefetched in `res`): the stores below go to rows whose addresses the
+    // compiler cannot disambiguate from the next row's loads, so interleaving them would serialise 8 global round trips
+    float4 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(stage + (4 * i + rsub) * kEpiRowFloats + cq);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m_warp0 + 4 * i + rsub;
+        float4 v4 = x[i];
+        v4.x += b.x;
+        v4.y += b.y;
+        v4.z += b.z;
+        v4.w += b.w;
+        if (m >= p.M) continue;
+        if (p.epi == EPI_STORE_BF16) {
+            if (p.act == ACT_GELU_TANH) {
+                v4.x = gelu_tanh_f32(v4.x);
+                v4.y = gelu_tanh_f32(v4.y);
+                v4.z = gelu_tanh_f32(v4.z);
+                v4.w = gelu_tanh_f32(v4.w);
+            }
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col) =
+                make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+        } else if (p.epi == EPI_STORE_F32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + col) = v4;
+        } else {  // EPI_RESIDUAL_F32: gate * y, then + x: two roundings like the reference's ops
+            v4.x = __fadd_rn(__fmul_rn(v4.x, g.x), res[i].x);
+            v4.y = __fadd_rn(__fmul_rn(v4.y, g.y), res[i].y);
+            v4.z = __fadd_rn(__fmul_rn(v4.z, g.z), res[i].z);
+            v4.w = __fadd_rn(__fmul_rn(v4.w, g.w), res[i].w);
+            *reinterpret_cast<float4*>(p.res_f32 + m * p.ldo + col) = v4;
+            if (p.out != nullptr)
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col) =
+                    make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+        }
+    }
+    __syncwarp();  // the tile is rewritten by the next chunk
+}
+
+// ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK_N>
@@ -334,6 +409,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp_idx >= 4) {
         // ===================== epilogue =====================
         const int quad = warp_idx & 3;
+        float* stage = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256) + quad * (32 * kEpiRowFloats);
+        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32) &&
+                               (p.N % 32 == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -341,11 +419,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n0 = t.n0 * BLOCK_N;
             const int m = t.m0 + quad * 32 + lane;
             const RowCtx rc = make_row_ctx(p, m);
+            float4 res_a[8], res_b[8];  // residual rows, double-buffered one chunk ahead (EPI_RESIDUAL_F32)
+            const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
+            const int m_warp0 = t.m0 + quad * 32;
+            if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);  // before the MMAs finish
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * C::kTmemStride;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            auto chunk = [&](int c, const float4 (&res)[8]) {
+                const int col0 = n0 + c * 32;
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, r);
                 tmem_ld_wait();
@@ -355,13 +437,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 }
-                const int col0 = n0 + c * 32;
                 if (col0 < p.N) {
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    epilogue_chunk(p, rc, col0, v);
+                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage, res);
+                    else epilogue_chunk(p, rc, col0, v);
                 }
+            };
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                if (prefetch_res) epilogue_load_residual(p, m_warp0, n0 + (c + 1) * 32, lane, res_b);
+                chunk(c, res_a);
+                if (prefetch_res && c + 2 < BLOCK_N / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
+                chunk(c + 1, res_b);
             }
             if (++acc == 2) {
                 acc = 0;

@@ -237,6 +237,15 @@ static int test_conv(int T, int H, int W, int Cin, int Cout, bool timing) {
 int main(int argc, char** argv) {
     bool big = argc > 1 && atoi(argv[1]) > 0;
     int fails = 0;
+    if (argc > 1 && atoi(argv[1]) == 2) {  // epilogue comparison at the out-projection shape
+        test_gemm(4992, 2048, 2048, EPI_STORE_BF16, 0, 0, true);
+        test_gemm(4992, 2048, 2048, EPI_STORE_F32, 0, 0, true);
+        test_gemm(4992, 2048, 2048, EPI_RESIDUAL_F32, 0, 0, true);
+        test_gemm(4992, 2048, 2048, EPI_RESIDUAL_F32, 0, 128, true);
+        test_gemm(4992, 2048, 2048, EPI_STORE_BF16, 0, 128, true);
+        test_gemm(4992, 2048, 2048, EPI_STORE_BF16, 0, 256, true);
+        return 0;
+    }
     // correctness: small and ragged shapes, every tile width
     fails += test_gemm(128, 64, 64, EPI_STORE_F32, 0, 64, false);
     fails += test_gemm(128, 128, 128, EPI_STORE_F32, 0, 128, false);
