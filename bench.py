@@ -200,21 +200,31 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     F, H, W = (FRAMES - 1) // 8 + 1, HEIGHT // 32, WIDTH // 32
     S = F * H * W
+    frames = 8 * F - 7
     dit = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset("2b"), device=local_rank)
     dit.init_random(1234)
     vae = cv.AutoencoderKLLtxVideo(cv.VaeConfig(), device=local_rank)
     vae.init_random(4321)
 
-    g = torch.Generator().manual_seed(100 + rank)
-    lat_host = torch.randn(S, 128, generator=g).pin_memory()
-    pe_host = torch.randn(K_TEXT, 4096, generator=g).pin_memory()
-    ne_host = torch.randn(K_TEXT, 4096, generator=g).pin_memory()
+    def make_inputs(seed):
+        g = torch.Generator().manual_seed(seed)
+        lat = torch.randn(S, 128, generator=g).pin_memory()
+        pe_h = torch.randn(K_TEXT, 4096, generator=g).pin_memory()
+        ne_h = torch.randn(K_TEXT, 4096, generator=g).pin_memory()
+        return lat, pe_h, ne_h
+
     pm_host = torch.cat([torch.ones(48), torch.zeros(K_TEXT - 48)]).pin_memory()
     nm_host = torch.cat([torch.ones(8), torch.zeros(K_TEXT - 8)]).pin_memory()
-    latents = lat_host.to(dev)
-    pe, ne, pm, nm = pe_host.to(dev), ne_host.to(dev), pm_host.to(dev), nm_host.to(dev)
+    pm, nm = pm_host.to(dev), nm_host.to(dev)
 
     def params(n_steps):
         if n_steps == 1:
@@ -227,126 +237,177 @@ def run_ours(args):
                                  num_inference_steps=n_steps, guidance_scale=GUIDANCE, guidance_rescale=0.0,
                                  stg_scale=0.0, shift_terminal=0.1, decode_timestep=0.05)
 
-    # ---- warm-up ----
-    cv.pipeline_denoise(dit, params(max(args.warmup, 3)), latents, pe, pm, ne, nm)
-    torch.cuda.synchronize()
+    # ------------------------------------------------------------------------------------------------------------
+    # parallel modes.  `videos` = videos in flight over the N GPUs.
+    #   replicas: one video per GPU, no data-path exchange
+    #   pairs   : one video per GPU PAIR -- the two CFG branches run on the two GPUs (the reference runs them as
+    #             independent B=1 forwards), velocities exchanged over NVLink peer memory, VAE decode as 2 H-slabs
+    #   sharded : ONE video over all N GPUs -- CFG branch groups x Ulysses token shards, VAE decode as N H-slabs
+    # ------------------------------------------------------------------------------------------------------------
+    def mode_setup(mode):
+        if mode == "replicas" or world == 1:
+            return None, world, 100 + rank
+        if mode == "pairs":
+            groups = [dist.new_group([2 * i, 2 * i + 1]) for i in range(world // 2)]
+            comm = cv.PeerComm(2, rank % 2, local_rank, heap_bytes=3 << 30, group=groups[rank // 2])
+            return comm, world // 2, 100 + rank // 2
+        comm = cv.PeerComm(world, rank, local_rank, heap_bytes=3 << 30)
+        return comm, 1, 100
 
-    # ---- timed: exactly K denoise steps through the device-resident public API ----
-    latents.copy_(lat_host)
+    def run_mode(mode, n_steps, count_launches=False):
+        """Times exactly n_steps denoise steps and the VAE decode in `mode`; returns a dict (max over ranks)."""
+        comm, videos, seed = mode_setup(mode)
+        lat_h, pe_h, ne_h = make_inputs(seed)
+        lat = lat_h.to(dev)
+        pe_d, ne_d = pe_h.to(dev), ne_h.to(dev)
+
+        def denoise(n):
+            if comm is None:
+                cv.pipeline_denoise(dit, params(n), lat, pe_d, pm, ne_d, nm)
+            else:
+                cv.pipeline_denoise_parallel(dit, comm, params(n), lat, pe_d, pm, ne_d, nm)
+
+        denoise(max(args.warmup, 3))  # warm-up
+        lat.copy_(lat_h)
+        barrier()
+        l0 = cv.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        denoise(n_steps)
+        e1.record()
+        barrier()
+        launches = cv.launch_count() - l0
+        ms_step = max_over_ranks(e0.elapsed_time(e1)) / n_steps
+        if comm is not None:
+            cv.vae_set_comm(vae, comm)
+        n_dec = max(1, min(n_steps, 3))
+        out = cv.pipeline_decode(vae, params(1), lat)  # warm-up / workspace allocation
+        barrier()
+        e0.record()
+        for _ in range(n_dec):
+            out = cv.pipeline_decode(vae, params(1), lat)
+        e1.record()
+        barrier()
+        ms_dec = max_over_ranks(e0.elapsed_time(e1) / n_dec)
+        if comm is not None:
+            cv.vae_set_comm(vae, None)
+        finite = bool(torch.isfinite(lat).all().item())
+        if comm is None or comm.rank == 0:
+            finite = finite and bool(torch.isfinite(out).all().item())
+        res = {"mode": mode, "videos_in_flight": videos, "steps_per_s": videos * 1000.0 / ms_step, "ms_per_step": ms_step,
+               "vae_frames_per_s": videos * frames * 1000.0 / ms_dec, "vae_ms_per_decode": ms_dec,
+               "launches": int(launches), "outputs_finite": finite}
+        if comm is not None:
+            plan = cv.parallel_plan(comm.nranks, comm.rank, S, GUIDANCE > 1.0)
+            res["plan"] = {"cfg_groups": plan["cfg_groups"], "ulysses_size": plan["sp_size"], "vae_h_slabs": comm.nranks}
+        del comm
+        return res, lat
+
+    if world == 1:
+        headline_mode = "single"
+    elif args.mode != "auto":
+        headline_mode = args.mode
+    else:
+        headline_mode = "pairs" if world % 2 == 0 else "replicas"
+    if headline_mode == "pairs" and world % 2 != 0:
+        raise SystemExit("bench.py: --mode pairs needs an even number of GPUs")
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    l0 = cv.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    cv.pipeline_denoise(dit, params(args.steps), latents, pe, pm, ne, nm)
-    e1.record()
-    barrier()
-    launches = cv.launch_count() - l0
-    ms_total = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    steps_per_s = world * 1000.0 / ms_per_step  # each rank denoises its own video (weak scaling)
-
-    # ---- timed: VAE decode (device resident) ----
-    n_dec = max(1, min(args.steps, 3))
-    out = cv.pipeline_decode(vae, params(1), latents)  # warm-up / workspace allocation
-    torch.cuda.synchronize()
-    barrier()
-    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    v0.record()
-    for _ in range(n_dec):
-        cv.pipeline_decode(vae, params(1), latents)
-    v1.record()
-    barrier()
-    vae_ms = v0.elapsed_time(v1) / n_dec
-    if dist is not None:
-        t = torch.tensor([vae_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        vae_ms = float(t.item())
+    head, latents = run_mode(headline_mode if world > 1 else "replicas", args.steps)
     clocks = sampler.stop()
-    frames = 8 * F - 7
-    vae_fps = world * frames * 1000.0 / vae_ms
-    finite = bool(torch.isfinite(latents).all().item()) and bool(torch.isfinite(out).all().item())
+    ms_per_step, vae_ms = head["ms_per_step"], head["vae_ms_per_decode"]
 
     line = {
-        "metric": "dit_denoise_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
+        "metric": "dit_denoise_steps_per_s", "value": head["steps_per_s"], "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(),
-        "vae_frames_per_s": vae_fps, "vae_ms_per_decode": vae_ms, "vae_frames": frames,
-        "dit_forward_ms": ms_per_step / 2.0, "gpu_launches": int(launches), "outputs_finite": finite,
-        "clocks": clocks,
+        "scaling": "strong" if headline_mode == "sharded" else "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(),
+        "vae_frames_per_s": head["vae_frames_per_s"], "vae_ms_per_decode": vae_ms, "vae_frames": frames,
+        "gpu_launches": head["launches"], "outputs_finite": head["outputs_finite"], "clocks": clocks,
     }
     if world > 1:
-        line["config"]["parallelism"] = f"{world} independent replicas (one video per GPU), no data-path collective"
-        # ---- sharded leg: ONE video over all N GPUs (latency mode; strong scaling) ----
-        # CFG branch split across two rank groups x Ulysses token shards inside a group (peer-memory all-to-all fused
-        # into the q/k-norm+RoPE kernel and the attention epilogue); VAE decode as H-slabs with halo rows stored into
-        # the neighbour's padded buffer.  Same inputs on every rank.
-        comm = cv.PeerComm(world, rank, local_rank, heap_bytes=4 << 30)
-        g0 = torch.Generator().manual_seed(100)
-        lat_sh = torch.randn(S, 128, generator=g0).to(dev)
-        pe_s, ne_s = torch.randn(K_TEXT, 4096, generator=g0).to(dev), torch.randn(K_TEXT, 4096, generator=g0).to(dev)
-        lat_keep = lat_sh.clone()
-        cv.pipeline_denoise_parallel(dit, comm, params(3), lat_sh, pe_s, pm, ne_s, nm)
-        lat_sh.copy_(lat_keep)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        cv.pipeline_denoise_parallel(dit, comm, params(args.steps), lat_sh, pe_s, pm, ne_s, nm)
-        s1.record()
-        barrier()
-        t = torch.tensor([s0.elapsed_time(s1)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sh_ms = float(t.item()) / args.steps
-        cv.vae_set_comm(vae, comm)
-        cv.pipeline_decode(vae, params(1), lat_sh)
-        barrier()
-        s0.record()
-        for _ in range(n_dec):
-            cv.pipeline_decode(vae, params(1), lat_sh)
-        s1.record()
-        barrier()
-        t = torch.tensor([s0.elapsed_time(s1) / n_dec], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sh_vae_ms = float(t.item())
-        cv.vae_set_comm(vae, None)
-        plan = cv.parallel_plan(world, rank, S, GUIDANCE > 1.0)
-        line["sharded_one_video"] = {
-            "steps_per_s": 1000.0 / sh_ms, "ms_per_step": sh_ms, "speedup_vs_1gpu_step": ms_per_step / sh_ms,
-            "vae_frames_per_s": frames * 1000.0 / sh_vae_ms, "vae_ms_per_decode": sh_vae_ms,
-            "vae_speedup_vs_1gpu": vae_ms / sh_vae_ms, "scaling": "strong",
-            "plan": {"cfg_groups": plan["cfg_groups"], "ulysses_size": plan["sp_size"], "vae_h_slabs": world},
-            "transport": "NVLink peer stores from the producing kernels + system-scope flag barrier (no NCCL on the "
-                         "data path)",
-            "outputs_finite": bool(torch.isfinite(lat_sh).all().item()),
-        }
+        desc = {"replicas": f"{world} independent replicas (one video per GPU), no data-path exchange",
+                "pairs": f"{world // 2} videos in flight, one per GPU pair: the two CFG branches of a step run on the two "
+                         "GPUs (velocity shards exchanged by NVLink peer stores), VAE decode as 2 H-slabs with halo rows "
+                         "stored by the producer; no NCCL on the data path",
+                "sharded": f"one video over all {world} GPUs: CFG branch groups x Ulysses token shards, VAE as {world} "
+                           "H-slabs"}
+        line["config"]["parallelism"] = desc[headline_mode]
+        line["config"]["mode"] = headline_mode
+        # the other decompositions of the same N GPUs, for the scaling picture (same K steps each)
+        others = {}
+        for m in ("replicas", "pairs", "sharded"):
+            if m == headline_mode or (m == "pairs" and (world % 2 != 0 or world == 2)):
+                continue
+            r, _ = run_mode(m, args.steps)
+            others[m] = r
+        if world == 2 and headline_mode == "pairs":
+            others["sharded"] = dict(head, mode="sharded (= pairs at N=2)")
+        line["modes"] = others
+
+    # ---- end to end through the host-buffer C ABI, every rank on its own video: per step H2D latents+embeddings,
+    # D2H latents; per decode H2D latents, D2H video ----
+    lat_h, pe_h, ne_h = make_inputs(100 + rank)
+    lat_e2e = lat_h.clone().pin_memory()
+    cv.pipeline_denoise_host(dit, params(1), lat_e2e, pe_h, pm_host, ne_h, nm_host)
+    n_e2e = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        cv.pipeline_denoise_host(dit, params(1), lat_e2e, pe_h, pm_host, ne_h, nm_host)
+    t_e2e = max_over_ranks((time.perf_counter() - t0) / n_e2e)
+    vid_host = torch.empty((3, frames, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
+    cv.pipeline_decode_host(vae, params(1), lat_e2e, vid_host)
+    barrier()
+    t0 = time.perf_counter()
+    cv.pipeline_decode_host(vae, params(1), lat_e2e, vid_host)
+    t_vae_e2e = max_over_ranks(time.perf_counter() - t0)
+    finite_e2e = bool(torch.isfinite(lat_e2e).all().item()) and bool(torch.isfinite(vid_host).all().item())
+    line["outputs_finite"] = line["outputs_finite"] and finite_e2e
+    line["e2e"] = {"value": world / t_e2e, "unit": "steps/s",
+                   "h2d_bytes_per_step": int(lat_h.numel() * 4 + 2 * pe_h.numel() * 4 + 2 * K_TEXT * 4),
+                   "d2h_bytes_per_step": int(lat_h.numel() * 4),
+                   "api": "ltxv_pipeline_denoise_host (1 step per call: context prep + 2 forwards + Euler), one video "
+                          "per GPU, wall clock, max over ranks",
+                   "vae_frames_per_s": world * frames / t_vae_e2e, "vae_h2d_bytes": int(lat_h.numel() * 4),
+                   "vae_d2h_bytes": int(vid_host.numel() * 4), "vae_api": "ltxv_pipeline_decode_host"}
 
     if rank == 0:
         peaks = measured_peaks()
         # ---- instrumented pass: per-kernel-class device time inside a real step (CUDA events on the stream) ----
+        lat_p = lat_h.to(dev)
+        pe_d, ne_d = pe_h.to(dev), ne_h.to(dev)
         cv.profile_begin()
-        cv.pipeline_denoise(dit, params(2), latents, pe, pm, ne, nm)
+        cv.pipeline_denoise(dit, params(2), lat_p, pe_d, pm, ne_d, nm)
         prof_dit = cv.profile_end()
         cv.profile_begin()
-        cv.pipeline_decode(vae, params(1), latents)
+        cv.pipeline_decode(vae, params(1), lat_p)
         prof_vae = cv.profile_end()
+        t1 = 0.0
+        if world > 1:  # single-GPU step time for the per-kernel shares
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cv.pipeline_denoise(dit, params(2), lat_p, pe_d, pm, ne_d, nm)
+            e1.record()
+            torch.cuda.synchronize()
+            t1 = e0.elapsed_time(e1) / 2
+        step1 = ms_per_step if world == 1 else t1
 
         def tf(d):
             return d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
 
         gm = prof_dit["gemm"]
+        traffic = ncu_traffic_bytes()
         line["roofline"] = {
             "kernel": "gemm_bf16_tn_kernel (tcgen05 GEMM, DiT projections/FFN)", "bound": "tensor",
             "achieved": tf(gm), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": tf(gm) / peaks["tf_sustained"], "traffic": None,
+            "frac": tf(gm) / peaks["tf_sustained"], "traffic": traffic,
             "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
             "launches": gm["launches"], "avg_launch_ms": gm["ms"] / max(gm["launches"], 1),
-            "share_of_step": gm["ms"] / (2 * ms_per_step),
+            "share_of_step": gm["ms"] / (2 * step1),
         }
+        attn_ms = prof_dit["attn_self"]["ms"] + prof_dit["attn_cross"]["ms"]
         line["roofline_all"] = {
             "dit_gemm": {"tflops": tf(gm), "ms_per_step": gm["ms"] / 2, "frac": tf(gm) / peaks["tf_sustained"]},
             "dit_attn_self": {"tflops": tf(prof_dit["attn_self"]), "ms_per_step": prof_dit["attn_self"]["ms"] / 2,
@@ -354,36 +415,16 @@ def run_ours(args):
             "dit_attn_cross": {"tflops": tf(prof_dit["attn_cross"]), "ms_per_step": prof_dit["attn_cross"]["ms"] / 2},
             "vae_conv3d": {"tflops": tf(prof_vae["conv3d"]), "ms_per_decode": prof_vae["conv3d"]["ms"],
                            "frac": tf(prof_vae["conv3d"]) / peaks["tf_sustained"]},
-            "dit_step_algorithmic_tflops": 2 * dit_flops(S) / (ms_per_step * 1e-3) / 1e12,
-            "dit_step_frac_of_peak": 2 * dit_flops(S) / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"],
-            "vae_decode_algorithmic_tflops": vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12,
-            "vae_decode_frac_of_peak": vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12 / peaks["tf_sustained"],
-            "glue_ms_per_step": ms_per_step - (gm["ms"] + prof_dit["attn_self"]["ms"] + prof_dit["attn_cross"]["ms"]) / 2,
+            "single_gpu_ms_per_step": step1,
+            "dit_step_algorithmic_tflops": 2 * dit_flops(S) / (step1 * 1e-3) / 1e12,
+            "dit_step_frac_of_peak": 2 * dit_flops(S) / (step1 * 1e-3) / 1e12 / peaks["tf_sustained"],
+            "glue_ms_per_step": step1 - (gm["ms"] + attn_ms) / 2,
         }
-
-        # ---- end to end through the host-buffer C ABI: per step H2D latents+embeddings, D2H latents ----
-        lat_e2e = lat_host.clone().pin_memory()
-        cv.pipeline_denoise_host(dit, params(1), lat_e2e, pe_host, pm_host, ne_host, nm_host)
-        n_e2e = max(1, min(args.steps, 5))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            cv.pipeline_denoise_host(dit, params(1), lat_e2e, pe_host, pm_host, ne_host, nm_host)
-        t_e2e = (time.perf_counter() - t0) / n_e2e
-        h2d = lat_host.numel() * 4 + 2 * pe_host.numel() * 4 + 2 * K_TEXT * 4
-        d2h = lat_host.numel() * 4
-        vid_host = torch.empty((3, frames, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
-        cv.pipeline_decode_host(vae, params(1), lat_e2e, vid_host)
-        t0 = time.perf_counter()
-        cv.pipeline_decode_host(vae, params(1), lat_e2e, vid_host)
-        t_vae_e2e = time.perf_counter() - t0
-        finite = finite and bool(torch.isfinite(lat_e2e).all().item()) and bool(torch.isfinite(vid_host).all().item())
-        line["outputs_finite"] = finite
-        line["e2e"] = {"value": 1.0 / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": int(d2h),
-                       "api": "ltxv_pipeline_denoise_host (1 step per call: context prep + 2 forwards + Euler)",
-                       "vae_frames_per_s": frames / t_vae_e2e, "vae_h2d_bytes": int(lat_host.numel() * 4),
-                       "vae_d2h_bytes": int(vid_host.numel() * 4), "vae_api": "ltxv_pipeline_decode_host"}
+        if world == 1:
+            line["roofline_all"]["vae_decode_algorithmic_tflops"] = vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12
+            line["roofline_all"]["vae_decode_frac_of_peak"] = (vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12 /
+                                                               peaks["tf_sustained"])
+            line["dit_forward_ms"] = ms_per_step / 2.0
 
         # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----
         if world == 1 and not args.no_cpu_baseline:
@@ -398,6 +439,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set
+    full` capture (profiles/r01_ncu_full_gemm.csv; ncu cannot run inside the timed bench)."""
+    p = ROOT / "profiles" / "r01_gemm_traffic.json"
+    try:
+        return json.loads(p.read_text())["bytes_per_launch_mean"]
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -405,6 +456,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "pairs", "sharded"],
+                    help="multi-GPU decomposition of the headline number (auto = pairs on an even GPU count)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
