@@ -397,6 +397,12 @@ def run_ours(args):
         def tf(d):
             return d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
 
+        def hbm(d, per):
+            """HBM-bound glue class: achieved algorithmic GB/s against the measured copy bandwidth."""
+            gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+            return {"gb_per_s": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"], "ms": d["ms"] / per,
+                    "launches": d["launches"] // per}
+
         gm = prof_dit["gemm"]
         traffic = ncu_traffic_bytes()
         line["roofline"] = {
@@ -415,10 +421,15 @@ def run_ours(args):
             "dit_attn_cross": {"tflops": tf(prof_dit["attn_cross"]), "ms_per_step": prof_dit["attn_cross"]["ms"] / 2},
             "vae_conv3d": {"tflops": tf(prof_vae["conv3d"]), "ms_per_decode": prof_vae["conv3d"]["ms"],
                            "frac": tf(prof_vae["conv3d"]) / peaks["tf_sustained"]},
+            "dit_norm_modulate": hbm(prof_dit["norm_modulate"], 2),
+            "dit_qk_norm_rope": hbm(prof_dit["qk_norm_rope"], 2),
+            "vae_prep": hbm(prof_vae["vae_prep"], 1),
             "single_gpu_ms_per_step": step1,
             "dit_step_algorithmic_tflops": 2 * dit_flops(S) / (step1 * 1e-3) / 1e12,
             "dit_step_frac_of_peak": 2 * dit_flops(S) / (step1 * 1e-3) / 1e12 / peaks["tf_sustained"],
             "glue_ms_per_step": step1 - (gm["ms"] + attn_ms) / 2,
+            "unattributed_ms_per_step": step1 - (gm["ms"] + attn_ms + prof_dit["norm_modulate"]["ms"] +
+                                                 prof_dit["qk_norm_rope"]["ms"]) / 2,
         }
         if world == 1:
             line["roofline_all"]["vae_decode_algorithmic_tflops"] = vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12

@@ -609,7 +609,7 @@ def pipeline_decode_host(vae: AutoencoderKLLtxVideo, params: PipelineParams, lat
     return out
 
 
-PROFILE_CLASSES = ("gemm", "conv3d", "attn_self", "attn_cross")
+PROFILE_CLASSES = ("gemm", "conv3d", "attn_self", "attn_cross", "norm_modulate", "qk_norm_rope", "vae_prep", "other")
 
 
 def profile_begin() -> None:
@@ -617,11 +617,13 @@ def profile_begin() -> None:
 
 
 def profile_end() -> Dict[str, Dict[str, float]]:
-    n = (C.c_uint64 * 4)()
-    ms = (C.c_double * 4)()
-    fl = (C.c_double * 4)()
+    n = (C.c_uint64 * 8)()
+    ms = (C.c_double * 8)()
+    fl = (C.c_double * 8)()
     _check(lib().ltxv_profile_end(n, ms, fl))
-    return {PROFILE_CLASSES[i]: {"launches": int(n[i]), "ms": float(ms[i]), "flops": float(fl[i])} for i in range(4)}
+    # classes 4-7 are HBM-bound glue kernels: "flops" holds their algorithmic bytes (also exposed as "bytes")
+    return {PROFILE_CLASSES[i]: {"launches": int(n[i]), "ms": float(ms[i]), "flops": float(fl[i]), "bytes": float(fl[i])}
+            for i in range(8)}
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 // For D = 64 two CTAs are resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps
 // the other's MMAs.
 #include "attention.h"
+#include "launch.h"
 #include "common.cuh"
 #include "tensormap.h"
 #include "profile.h"
@@ -113,6 +114,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();
 
     if (warp_idx == 0) {
         // ===================== TMA producer =====================
@@ -631,6 +634,8 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();
 #ifdef LTXV_ATTN_TRACE
     if (threadIdx.x == 0 && qb == 3 && head == 5 && split == 0) {
         g_attn_trace[10][39][0] = t_entry;
@@ -1092,6 +1097,8 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
         fence_barrier_init();
     }
+    griddep_launch_dependents();
+    griddep_wait();  // the key bias / Q / K / V come from earlier kernels of the stream
     if (threadIdx.x < 128) {
         const int k = threadIdx.x;
         float b = (k < p.Skv) ? 0.f : -INFINITY;
@@ -1318,7 +1325,8 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     const int n_items = sp.n_units - sp.n_split_units + sp.n_split_units * sp.nsplit;
     {
         ProfScope prof(PROF_ATTN_SELF, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 64, stream);
-        flash_attn3_kernel<<<n_items, kV3Threads, kV3SmemBytes, stream>>>(tq, tk, tv, p, sp);
+        cudaError_t le = launch_pdl(flash_attn3_kernel, dim3(n_items), dim3(kV3Threads), kV3SmemBytes, stream, tq, tk, tv, p, sp);
+        if (le != cudaSuccess) return le;
     }
     g_attn_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
@@ -1350,7 +1358,8 @@ cudaError_t launch_cross_attn_impl(const AttnParams& p, cudaStream_t stream) {
     if (cph < 1) cph = 1;
     {
         ProfScope prof(PROF_ATTN_CROSS, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 64, stream);
-        cross_attn_kernel<<<p.B * p.H * cph, kXThreads, kXSmemBytes, stream>>>(tq, tk, tv, p, cph);
+        cudaError_t le = launch_pdl(cross_attn_kernel, dim3(p.B * p.H * cph), dim3(kXThreads), kXSmemBytes, stream, tq, tk, tv, p, cph);
+        if (le != cudaSuccess) return le;
     }
     g_attn_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
@@ -1377,7 +1386,8 @@ cudaError_t launch_attn_impl(const AttnParams& p, cudaStream_t stream) {
     {
         ProfScope prof(p.kv_bias != nullptr || p.Skv != p.Sq ? PROF_ATTN_CROSS : PROF_ATTN_SELF,
                        4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * D, stream);
-        flash_attn_kernel<D><<<grid, kAttnThreads, C::kSmemBytes, stream>>>(tq, tk, tv, p);
+        cudaError_t le = launch_pdl(flash_attn_kernel<D>, grid, dim3(kAttnThreads), C::kSmemBytes, stream, tq, tk, tv, p);
+        if (le != cudaSuccess) return le;
     }
     g_attn_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();

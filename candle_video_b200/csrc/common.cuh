@@ -34,6 +34,16 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): the kernels of the per-step chain (about 400 per DiT forward) are launched
+// with programmatic stream serialisation, call griddep_launch_dependents() at entry and griddep_wait() before the
+// first access to memory an earlier kernel may have written.  The next kernel's CTAs are then scheduled while the
+// current grid drains: its prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail instead of
+// adding a ~4 us grid-boundary bubble per launch.  Both instructions are no-ops under an ordinary launch.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -263,6 +273,15 @@ __device__ __forceinline__ float gelu_tanh_f32(float x) {
     return 0.5f * x * (1.0f + th);
 }
 __device__ __forceinline__ float silu_f32(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) = h + h * tanh(h), h = x/2: ONE MUFU op (tanh.approx, rel. error ~2^-11, below the bf16 rounding of the
+// stored activation) instead of ex2 + IEEE division.  For the bandwidth-bound VAE pixel-norm kernel, where the exact
+// form made the kernel ALU-bound.
+__device__ __forceinline__ float silu_fast_f32(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

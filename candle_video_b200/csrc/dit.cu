@@ -360,8 +360,8 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
         gemm(h_.p, S, b.qkv1, S, EPI_STORE_BF16, ACT_NONE, qkv_.p, nullptr, nullptr, s);
         const void* attn1_out = attn_.p;
         if (!sp) {
-            LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, 0, S, D, b.norm_q1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
-            LTXV_CUDA(launch_qk_norm_rope(qkv_.p, 3 * D, D, S, D, b.norm_k1, 1e-5f, cos_.as<float>(), sin_.as<float>(), s));
+            LTXV_CUDA(launch_qk_pair_norm_rope(qkv_.p, 3 * D, S, D, b.norm_q1, b.norm_k1, 1e-5f, cos_.as<float>(),
+                                               sin_.as<float>(), s));
             AttnParams ap{};
             ap.q = ap.k = ap.v = qkv_.p;
             ap.ldq = ap.ldk = ap.ldv = 3 * D;

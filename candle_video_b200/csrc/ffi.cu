@@ -60,10 +60,10 @@ int ltxv_profile_begin(void) {
     profiling_begin();
     return 0;
 }
-int ltxv_profile_end(uint64_t* launches4, double* ms4, double* flops4) {
+int ltxv_profile_end(uint64_t* launches8, double* ms8, double* work8) {
     LTXV_TRY
-    if (launches4 == nullptr || ms4 == nullptr || flops4 == nullptr) fail("null argument");
-    profiling_end(launches4, ms4, flops4);
+    if (launches8 == nullptr || ms8 == nullptr || work8 == nullptr) fail("null argument");
+    profiling_end(launches8, ms8, work8);
     LTXV_CATCH
 }
 

@@ -10,6 +10,7 @@
 //   warps 4-7: epilogue; warp w owns TMEM lanes 32*(w%4) .. +31, one accumulator row per thread
 #include "common.cuh"
 #include "gemm.h"
+#include "launch.h"
 #include "tensormap.h"
 #include "profile.h"
 
@@ -343,6 +344,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();  // A (and the residual / conv inputs) may come from the previous kernel of the stream
 
     if (warp_idx == 0) {
         // ===================== TMA producer =====================
@@ -496,7 +499,8 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
         double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
         if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;  // unpadded voxels
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
-        gemm_bf16_tn_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, p);
+        cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BLOCK_N>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, ta, tb, p);
+        if (le != cudaSuccess) return le;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();

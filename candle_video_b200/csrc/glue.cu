@@ -2,6 +2,8 @@
 // warp-shuffle reductions; nothing here is shaped into a GEMM.
 #include "common.cuh"
 #include "glue.h"
+#include "launch.h"
+#include "profile.h"
 
 #include <atomic>
 
@@ -22,6 +24,8 @@ template <int KIND>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
                      const float* __restrict__ shift, int rows, int D, float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -76,6 +80,8 @@ norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ ou
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int rows, int D, const float* __restrict__ w,
                     float eps, const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -118,6 +124,69 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int row
         o.z = pack_bf16x2(f[4], f[5]);
         o.w = pack_bf16x2(f[6], f[7]);
         xr[i] = o;
+    }
+}
+
+// q AND k of the fused self-attention projection in one launch (x = [rows, >= 2D] with q at col 0, k at col D): one
+// pass over the token's cos/sin row serves both (the two separate launches read the 2 x 20 MB f32 tables twice)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+qk_pair_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, int D, const float* __restrict__ wq,
+                         const float* __restrict__ wk, float eps, const float* __restrict__ cos_t,
+                         const float* __restrict__ sin_t) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = D >> 3;
+    uint4* xq = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
+    uint4* xk = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + D);
+    const float4* c4 = reinterpret_cast<const float4*>(cos_t + static_cast<int64_t>(row) * (D >> 1));
+    const float4* s4 = reinterpret_cast<const float4*>(sin_t + static_cast<int64_t>(row) * (D >> 1));
+    float sq = 0.f, sk = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+        const uint4 a = xq[i], b = xk[i];
+        const float fa[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y),
+                             bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
+        const float fb[8] = {bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y),
+                             bf16_lo(b.z), bf16_hi(b.z), bf16_lo(b.w), bf16_hi(b.w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sq += fa[j] * fa[j];
+            sk += fb[j] * fb[j];
+        }
+    }
+    sq = warp_sum(sq);
+    sk = warp_sum(sk);
+    const float rq = rsqrtf(sq * (1.0f / D) + eps), rk = rsqrtf(sk * (1.0f / D) + eps);
+    for (int i = lane; i < nv; i += 32) {
+        const float4 cc = __ldg(c4 + i), ss = __ldg(s4 + i);
+        const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            uint4* xr = which == 0 ? xq : xk;
+            const float* w = which == 0 ? wq : wk;
+            const float rinv = which == 0 ? rq : rk;
+            uint4 u = xr[i];
+            float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                          bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * i);
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+            const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = f[j] * rinv * ww[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float re = f[2 * j], im = f[2 * j + 1];
+                f[2 * j] = re * cv[j] - im * sv[j];
+                f[2 * j + 1] = im * cv[j] + re * sv[j];
+            }
+            u.x = pack_bf16x2(f[0], f[1]);
+            u.y = pack_bf16x2(f[2], f[3]);
+            u.z = pack_bf16x2(f[4], f[5]);
+            u.w = pack_bf16x2(f[6], f[7]);
+            xr[i] = u;
+        }
     }
 }
 
@@ -438,20 +507,31 @@ cudaError_t launch_norm_modulate(const float* x, void* out, const float* scale, 
                                  float eps, int kind, cudaStream_t s) {
     if (D % 4 != 0 || (scale == nullptr) != (shift == nullptr)) return cudaErrorInvalidValue;
     const int grid = blocks_for(rows, kWarpsPerBlock);
+    ProfScope prof(PROF_NORM_MOD, 6.0 * rows * D, s);  // f32 in, bf16 out
     if (kind == NORM_LAYER)
-        norm_modulate_kernel<NORM_LAYER><<<grid, kWarpsPerBlock * 32, 0, s>>>(
-            x, reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, D, eps);
+        launch_pdl(norm_modulate_kernel<NORM_LAYER>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, x,
+                   reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, D, eps);
     else
-        norm_modulate_kernel<NORM_RMS><<<grid, kWarpsPerBlock * 32, 0, s>>>(
-            x, reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, D, eps);
+        launch_pdl(norm_modulate_kernel<NORM_RMS>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, x,
+                   reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, D, eps);
     return done();
 }
 
 cudaError_t launch_qk_norm_rope(void* x, int64_t ld, int col0, int rows, int D, const float* w, float eps,
                                 const float* cos_t, const float* sin_t, cudaStream_t s) {
     if (D % 8 != 0 || ld % 8 != 0 || col0 % 8 != 0) return cudaErrorInvalidValue;
-    qk_norm_rope_kernel<<<blocks_for(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-        reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, D, w, eps, cos_t, sin_t);
+    ProfScope prof(PROF_QK_ROPE, 4.0 * rows * D + (cos_t ? 2.0 * rows * (D / 2) * 4 : 0.0), s);
+    launch_pdl(qk_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+               reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, D, w, eps, cos_t, sin_t);
+    return done();
+}
+
+cudaError_t launch_qk_pair_norm_rope(void* x, int64_t ld, int rows, int D, const float* wq, const float* wk, float eps,
+                                     const float* cos_t, const float* sin_t, cudaStream_t s) {
+    if (D % 8 != 0 || ld % 8 != 0 || ld < 2 * D || cos_t == nullptr || sin_t == nullptr) return cudaErrorInvalidValue;
+    ProfScope prof(PROF_QK_ROPE, 2.0 * rows * D * 4 + 2.0 * rows * (D / 2) * 4, s);  // q,k bf16 in+out, cos/sin f32 once
+    launch_pdl(qk_pair_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+               reinterpret_cast<__nv_bfloat16*>(x), ld, rows, D, wq, wk, eps, cos_t, sin_t);
     return done();
 }
 

@@ -25,6 +25,11 @@ cudaError_t launch_qk_norm_rope(void* x_bf16, int64_t ld, int col0, int rows, in
 cudaError_t launch_rope_table(const float* coords, int F, int H, int W, const float* scale3_host, int S, int D,
                               float theta, float* cos_t, float* sin_t, cudaStream_t s, int token0 = 0);
 
+// q (cols [0,D)) and k (cols [D,2D)) of a fused projection buffer in ONE launch: same math as two launch_qk_norm_rope
+// calls, the cos/sin row of a token is read once for both.
+cudaError_t launch_qk_pair_norm_rope(void* x_bf16, int64_t ld, int rows, int D, const float* wq, const float* wk,
+                                     float eps, const float* cos_t, const float* sin_t, cudaStream_t s);
+
 // Ulysses scatter fused with q/k RMS-norm + RoPE: local fused projections x [rows, 3D] (q | k | v) are normed /
 // rotated (q, k) or copied (v) and written head-group-wise into the peers' [S_total, 3*D/nranks] buffers:
 // columns of head group g go to dst[g] at row (row0 + r), column (which * D/nranks + col % (D/nranks)).

@@ -1,0 +1,32 @@
+// Host-side launch helper: cudaLaunchKernelEx with programmatic stream serialisation (PDL), see common.cuh.
+// Only kernels that call griddep_wait() before touching global memory may be launched through it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include <utility>
+
+namespace ltxv {
+
+inline bool pdl_enabled() {
+    static const bool on = getenv("LTXV_NO_PDL") == nullptr;
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+}  // namespace ltxv

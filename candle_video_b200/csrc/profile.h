@@ -6,7 +6,11 @@
 
 namespace ltxv {
 
-enum ProfClass : int { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN_SELF = 2, PROF_ATTN_CROSS = 3, PROF_NUM = 4 };
+// classes 4-7 are HBM-bound glue kernels: their `flops` field carries ALGORITHMIC BYTES instead
+enum ProfClass : int {
+    PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN_SELF = 2, PROF_ATTN_CROSS = 3,
+    PROF_NORM_MOD = 4, PROF_QK_ROPE = 5, PROF_VAE_PREP = 6, PROF_OTHER = 7, PROF_NUM = 8
+};
 
 bool profiling_enabled();
 void profiling_begin();

@@ -1,5 +1,7 @@
 #include "common.cuh"
 #include "vae_glue.h"
+#include "launch.h"
+#include "profile.h"
 
 #include <atomic>
 
@@ -45,6 +47,8 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
     constexpr int LPV = (C / 8 < 32) ? C / 8 : 32;  // lanes per voxel
     constexpr int VPW = 32 / LPV;                    // voxels per warp
     constexpr int CPL = (C / 8) / LPV;               // chunks per lane
+    griddep_launch_dependents();
+    griddep_wait();
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPV, l = lane % LPV;
     const int64_t nvox = static_cast<int64_t>(T) * H * W;
@@ -67,17 +71,19 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             sh[k][4] = d.x; sh[k][5] = d.y; sh[k][6] = d.z; sh[k][7] = d.w;
         }
     }
-    for (int64_t base = warp0; base < nvox; base += stride) {
-        const int64_t vox_raw = base + sub;
-        const bool valid = vox_raw < nvox;
-        const int64_t vox = valid ? vox_raw : nvox - 1;
-        float v[CPL][8];
+    // two voxel groups per iteration: both 16-byte loads are in flight before either is consumed; all index math in
+    // 32 bits (64-bit div/mod per voxel made the previous version ALU-bound: 2.2 TB/s)
+    const int nv32 = static_cast<int>(nvox);
+    const int hw = H * W;
+    auto load = [&](int vox, float (&v)[CPL][8]) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-            const uint4 u = *reinterpret_cast<const uint4*>(x + vox * C + (k * LPV + l) * 8);
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(vox) * C + (k * LPV + l) * 8));
             v[k][0] = bf16_lo(u.x); v[k][1] = bf16_hi(u.x); v[k][2] = bf16_lo(u.y); v[k][3] = bf16_hi(u.y);
             v[k][4] = bf16_lo(u.z); v[k][5] = bf16_hi(u.z); v[k][6] = bf16_lo(u.w); v[k][7] = bf16_hi(u.w);
         }
+    };
+    auto finish = [&](int vox, bool valid, float (&v)[CPL][8]) {
         if (do_norm) {
             float s2 = 0.f;
 #pragma unroll
@@ -102,10 +108,14 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 #pragma unroll
             for (int k = 0; k < CPL; ++k)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[k][i] = silu_f32(v[k][i]);
+                for (int i = 0; i < 8; ++i) v[k][i] = silu_fast_f32(v[k][i]);
         }
-        if (!valid) continue;
-        const int w = static_cast<int>(vox % W), h = static_cast<int>((vox / W) % H), t = static_cast<int>(vox / (W * H));
+        if (!valid) return;
+        const int t = vox / hw;
+        const int rem = vox - t * hw;
+        const int h = rem / W;
+        const int w = rem - h * W;
+        const int64_t plane = static_cast<int64_t>(Hp) * Wp;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
             uint4 o;
@@ -114,7 +124,6 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             o.z = pack_bf16x2(v[k][4], v[k][5]);
             o.w = pack_bf16x2(v[k][6], v[k][7]);
             const int c0 = (k * LPV + l) * 8;
-            const int64_t plane = static_cast<int64_t>(Hp) * Wp;
             auto put = [&](__nv_bfloat16* base, int hp) {
                 const int64_t row = (static_cast<int64_t>(t + 1) * Hp + hp) * Wp + (w + 1);
                 *reinterpret_cast<uint4*>(base + row * C + c0) = o;
@@ -125,6 +134,17 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             if (halo_up != nullptr && h == 0) put(halo_up, H + 1);   // my first row = bottom halo of the slab above
             if (halo_dn != nullptr && h == H - 1) put(halo_dn, 0);   // my last row  = top halo of the slab below
         }
+    };
+    const int istride = static_cast<int>(stride);
+    for (int base = static_cast<int>(warp0); base < nv32; base += 2 * istride) {
+        const int va_raw = base + sub, vb_raw = base + istride + sub;
+        const bool a_ok = va_raw < nv32, b_ok = vb_raw < nv32;  // b_ok is warp-uniform only per half: keep shuffles full
+        const int va = a_ok ? va_raw : nv32 - 1, vb = b_ok ? vb_raw : nv32 - 1;
+        float xa[CPL][8], xb[CPL][8];
+        load(va, xa);
+        load(vb, xb);
+        finish(va, a_ok, xa);
+        finish(vb, b_ok, xb);
     }
 }
 
@@ -188,16 +208,18 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
     __nv_bfloat16* hu = reinterpret_cast<__nv_bfloat16*>(halo_up);
     __nv_bfloat16* hd = reinterpret_cast<__nv_bfloat16*>(halo_dn);
     const int64_t nvox = static_cast<int64_t>(T) * H * W;
+    if (nvox >= (1ll << 31) - 148 * 8 * 4) return cudaErrorInvalidValue;  // the kernel indexes voxels in 32 bits
     const int vpb = 8 * (C == 128 ? 2 : 1);  // voxels per block pass
     int64_t want = (nvox + vpb - 1) / vpb;
     const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
+    ProfScope prof(PROF_VAE_PREP, 4.0 * static_cast<double>(nvox) * C, s);  // bf16 in, bf16 out
     switch (C) {
-        case 128: vae_prep_kernel<128><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
-        case 256: vae_prep_kernel<256><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
-        case 512: vae_prep_kernel<512><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
-        case 1024: vae_prep_kernel<1024><<<grid, 256, 0, s>>>(xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 128: launch_pdl(vae_prep_kernel<128>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 256: launch_pdl(vae_prep_kernel<256>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 512: launch_pdl(vae_prep_kernel<512>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 1024: launch_pdl(vae_prep_kernel<1024>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
         default: return cudaErrorInvalidValue;
     }
     return done();

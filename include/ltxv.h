@@ -49,10 +49,12 @@ const char* ltxv_version(void);
 uint64_t ltxv_launch_count(void);
 
 /* Measurement hook (bench.py): between begin/end every GEMM / conv3d / attention launch is bracketed by CUDA events
- * on its stream.  end() synchronises and returns per class {0 GEMM, 1 conv3d, 2 self-attention, 3 cross-attention}:
- * launches, summed device milliseconds, summed algorithmic FLOPs.  Not part of the reference interface. */
+ * on its stream.  end() synchronises and returns per class {0 GEMM, 1 conv3d, 2 self-attention, 3 cross-attention,
+ * 4 norm+modulate, 5 q/k norm+RoPE, 6 VAE pixel-norm/modulate/SiLU, 7 reserved}: launches, summed device
+ * milliseconds, and summed algorithmic FLOPs (classes 0-3) or algorithmic BYTES (classes 4-7).  All three arrays
+ * have 8 entries.  Not part of the reference interface. */
 int ltxv_profile_begin(void);
-int ltxv_profile_end(uint64_t* launches4, double* ms4, double* flops4);
+int ltxv_profile_end(uint64_t* launches8, double* ms8, double* work8);
 
 /* ------------------------------------------------------------------ DiT ------------------------------------------ */
 /* LtxVideoTransformer3DModelConfig, ltx_transformer.rs:22-59 */
