@@ -40,6 +40,8 @@ EXPORTED_SYMBOLS = [
     "ltxv_profile_begin", "ltxv_profile_end",
     "ltxv_comm_create", "ltxv_comm_destroy", "ltxv_comm_get_handle", "ltxv_comm_open", "ltxv_comm_barrier",
     "ltxv_parallel_plan", "ltxv_pipeline_denoise_parallel", "ltxv_vae_set_comm",
+    "ltxv_remap_official_key_raw", "ltxv_remap_official_key", "ltxv_safetensors_list",
+    "ltxv_dit_load_safetensors", "ltxv_vae_load_safetensors",
 ]
 
 
@@ -133,6 +135,11 @@ def _load() -> C.CDLL:
     l.ltxv_parallel_plan.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int32)]
     l.ltxv_pipeline_denoise_parallel.argtypes = [vp, vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32, vp]
     l.ltxv_vae_set_comm.argtypes = [vp, vp]
+    l.ltxv_remap_official_key_raw.argtypes = [C.c_char_p, C.c_char_p, u64]
+    l.ltxv_remap_official_key.argtypes = [C.c_char_p, C.c_char_p, u64, C.POINTER(C.c_int32)]
+    l.ltxv_safetensors_list.argtypes = [C.c_char_p, C.c_char_p, u64, C.POINTER(C.c_int32)]
+    l.ltxv_dit_load_safetensors.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    l.ltxv_vae_load_safetensors.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     l.ltxv_profile_begin.argtypes = []
     l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return l
@@ -262,6 +269,14 @@ class LtxVideoTransformer3DModel:
         _load_state_dict(lib().ltxv_dit_load_tensor, self._h, sd)
         _check(lib().ltxv_dit_finalize(self._h))
 
+    def load_safetensors(self, path, official: bool = False):
+        """Load a .safetensors file / diffusers directory / sharded directory; official=True remaps the unified-file
+        key names (weight_format.rs) and takes the transformer tensors only.  Returns (loaded, ignored)."""
+        a, b = C.c_int32(), C.c_int32()
+        _check(lib().ltxv_dit_load_safetensors(self._h, str(path).encode(), int(official), C.byref(a), C.byref(b)))
+        _check(lib().ltxv_dit_finalize(self._h))
+        return a.value, b.value
+
     def init_random(self, seed: int = 0) -> None:
         _check(lib().ltxv_dit_init_random(self._h, seed))
 
@@ -388,6 +403,12 @@ class AutoencoderKLLtxVideo:
     def load_state_dict(self, sd) -> None:
         _load_state_dict(lib().ltxv_vae_load_tensor, self._h, sd)
         _check(lib().ltxv_vae_finalize(self._h))
+
+    def load_safetensors(self, path, official: bool = False):
+        a, b = C.c_int32(), C.c_int32()
+        _check(lib().ltxv_vae_load_safetensors(self._h, str(path).encode(), int(official), C.byref(a), C.byref(b)))
+        _check(lib().ltxv_vae_finalize(self._h))
+        return a.value, b.value
 
     def init_random(self, seed: int = 0) -> None:
         _check(lib().ltxv_vae_init_random(self._h, seed))
@@ -624,6 +645,40 @@ def profile_end() -> Dict[str, Dict[str, float]]:
     # classes 4-7 are HBM-bound glue kernels: "flops" holds their algorithmic bytes (also exposed as "bytes")
     return {PROFILE_CLASSES[i]: {"launches": int(n[i]), "ms": float(ms[i]), "flops": float(fl[i]), "bytes": float(fl[i])}
             for i in range(8)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# weight files (host only)
+# ------------------------------------------------------------------------------------------------------------
+def remap_official_key_raw(key: str) -> str:
+    """KeyRemapper::remap_key (weight_format.rs:55-143)."""
+    buf = C.create_string_buffer(1024)
+    _check(lib().ltxv_remap_official_key_raw(key.encode(), buf, 1024))
+    return buf.value.decode()
+
+
+def remap_official_key(key: str):
+    """(model key, component) as examples/ltx-video/main.rs:480-497 routes a unified-file tensor; component in
+    {"other", "transformer", "vae"}."""
+    buf = C.create_string_buffer(1024)
+    c = C.c_int32()
+    _check(lib().ltxv_remap_official_key(key.encode(), buf, 1024, C.byref(c)))
+    return buf.value.decode(), ("other", "transformer", "vae")[c.value]
+
+
+def safetensors_list(path) -> list:
+    """[(name, dtype, shape, nbytes)] of a safetensors file / directory / sharded directory, sorted by name."""
+    cap = 1 << 24
+    buf = C.create_string_buffer(cap)
+    n = C.c_int32()
+    _check(lib().ltxv_safetensors_list(str(path).encode(), buf, cap, C.byref(n)))
+    out = []
+    for ln in buf.value.decode().splitlines():
+        name, dtype, shape, nbytes = ln.rsplit(" ", 3)
+        dims = [int(v) for v in shape.strip("[]").split(",") if v]
+        out.append((name, dtype, dims, int(nbytes)))
+    assert len(out) == n.value
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -35,6 +35,7 @@ LIB_SOURCES = [
     "vae.cu",
     "pipeline.cu",
     "comm.cu",
+    "weights.cc",
     "ffi.cu",
     "model_common.cu",
     "tensormap.cc",

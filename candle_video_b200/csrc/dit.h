@@ -47,6 +47,7 @@ public:
     int inner_dim() const { return cfg_.num_attention_heads * cfg_.attention_head_dim; }
 
     void load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape, int rank);
+    bool has_key(const std::string& key) const { return slots_.count(key) != 0; }
     void init_random(uint64_t seed);
     void finalize();
     void set_skip_block_list(const int32_t* idx, int n);  // ltx_transformer.rs:1024

@@ -9,6 +9,7 @@
 #include "pipeline.h"
 #include "profile.h"
 #include "vae.h"
+#include "weights.h"
 #include "vae_glue.h"
 
 using namespace ltxv;
@@ -67,6 +68,44 @@ int ltxv_profile_end(uint64_t* launches8, double* ms8, double* work8) {
     LTXV_CATCH
 }
 
+int ltxv_remap_official_key(const char* key, char* out, uint64_t out_cap, int32_t* component) {
+    LTXV_TRY
+    if (key == nullptr || out == nullptr) fail("null argument");
+    int c = WEIGHT_OTHER;
+    const std::string r = official_key_to_model_key(key, &c);
+    if (r.size() + 1 > out_cap) fail("output buffer too small for the remapped key (%zu bytes needed)", r.size() + 1);
+    memcpy(out, r.c_str(), r.size() + 1);
+    if (component) *component = c;
+    LTXV_CATCH
+}
+int ltxv_remap_official_key_raw(const char* key, char* out, uint64_t out_cap) {
+    LTXV_TRY
+    if (key == nullptr || out == nullptr) fail("null argument");
+    const std::string r = remap_official_key(key);
+    if (r.size() + 1 > out_cap) fail("output buffer too small for the remapped key (%zu bytes needed)", r.size() + 1);
+    memcpy(out, r.c_str(), r.size() + 1);
+    LTXV_CATCH
+}
+int ltxv_safetensors_list(const char* path, char* out, uint64_t out_cap, int32_t* n_tensors) {
+    LTXV_TRY
+    if (path == nullptr || out == nullptr) fail("null argument");
+    std::string text;
+    int n = 0;
+    for (const std::string& f : resolve_safetensors_files(path)) {
+        SafeTensorsFile st(f);
+        for (const SafeTensorInfo& t : st.tensors()) {
+            text += t.name + " " + t.dtype + " [";
+            for (size_t i = 0; i < t.shape.size(); ++i) text += (i ? "," : "") + std::to_string(t.shape[i]);
+            text += "] " + std::to_string(t.bytes) + "\n";
+            ++n;
+        }
+    }
+    if (text.size() + 1 > out_cap) fail("output buffer too small for the tensor list (%zu bytes needed)", text.size() + 1);
+    memcpy(out, text.c_str(), text.size() + 1);
+    if (n_tensors) *n_tensors = n;
+    LTXV_CATCH
+}
+
 int ltxv_dit_config_preset(const char* name, ltxv_dit_config* out) {
     LTXV_TRY
     if (out == nullptr || name == nullptr) fail("null argument");
@@ -96,6 +135,20 @@ int ltxv_dit_load_tensor(ltxv_dit* m, const char* key, const void* data, int dty
     LTXV_TRY
     if (m == nullptr || key == nullptr || data == nullptr) fail("null argument");
     m->model.load_tensor(key, data, dtype, shape, rank);
+    LTXV_CATCH
+}
+int ltxv_dit_load_safetensors(ltxv_dit* m, const char* path, int official, int32_t* n_loaded, int32_t* n_ignored) {
+    LTXV_TRY
+    if (m == nullptr || path == nullptr) fail("null argument");
+    WeightSink sink;
+    sink.wants = [m](const std::string& k) { return m->model.has_key(k); };
+    sink.load = [m](const std::string& k, const void* d, int dt, const int64_t* sh, int r) {
+        m->model.load_tensor(k, d, dt, sh, r);
+    };
+    int a = 0, b = 0;
+    load_safetensors(path, official != 0, WEIGHT_TRANSFORMER, sink, &a, &b);
+    if (n_loaded) *n_loaded = a;
+    if (n_ignored) *n_ignored = b;
     LTXV_CATCH
 }
 int ltxv_dit_init_random(ltxv_dit* m, uint64_t seed) {
@@ -215,6 +268,20 @@ int ltxv_vae_load_tensor(ltxv_vae* m, const char* key, const void* data, int dty
     LTXV_TRY
     if (m == nullptr || key == nullptr || data == nullptr) fail("null argument");
     m->model.load_tensor(key, data, dtype, shape, rank);
+    LTXV_CATCH
+}
+int ltxv_vae_load_safetensors(ltxv_vae* m, const char* path, int official, int32_t* n_loaded, int32_t* n_ignored) {
+    LTXV_TRY
+    if (m == nullptr || path == nullptr) fail("null argument");
+    WeightSink sink;
+    sink.wants = [m](const std::string& k) { return m->model.has_key(k); };
+    sink.load = [m](const std::string& k, const void* d, int dt, const int64_t* sh, int r) {
+        m->model.load_tensor(k, d, dt, sh, r);
+    };
+    int a = 0, b = 0;
+    load_safetensors(path, official != 0, WEIGHT_VAE, sink, &a, &b);
+    if (n_loaded) *n_loaded = a;
+    if (n_ignored) *n_ignored = b;
     LTXV_CATCH
 }
 int ltxv_vae_init_random(ltxv_vae* m, uint64_t seed) {

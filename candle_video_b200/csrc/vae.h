@@ -33,6 +33,7 @@ public:
 
     const ltxv_vae_config& config() const { return cfg_; }
     void load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape, int rank);
+    bool has_key(const std::string& key) const { return slots_.count(key) != 0; }
     void init_random(uint64_t seed);
     void finalize();
     const float* latents_mean() const { return latents_mean_; }

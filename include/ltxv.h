@@ -56,6 +56,18 @@ uint64_t ltxv_launch_count(void);
 int ltxv_profile_begin(void);
 int ltxv_profile_end(uint64_t* launches8, double* ms8, double* work8);
 
+/* --------------------------------------------------------------- weight files ------------------------------------- */
+/* Official single-file checkpoints (e.g. ltx-video-2b-v0.9.5.safetensors) name tensors differently from the diffusers
+ * layout the models consume.  ltxv_remap_official_key_raw = KeyRemapper::remap_key (weight_format.rs:55-143);
+ * ltxv_remap_official_key additionally strips the "vae." / "model.diffusion_model." / "transformer." prefix and
+ * reports the component (0 other, 1 transformer, 2 VAE) exactly as examples/ltx-video/main.rs:480-497 routes tensors. */
+int ltxv_remap_official_key_raw(const char* key, char* out, uint64_t out_cap);
+int ltxv_remap_official_key(const char* key, char* out, uint64_t out_cap, int32_t* component);
+/* Tensor index of a safetensors file / directory, one line per tensor: "<name> <dtype> [d0,d1,...] <bytes>\n", sorted
+ * by name.  `path`: a .safetensors file, a directory holding one, or a directory with `*.safetensors.index.json` and
+ * its shards (loader.rs:341-371; a shard named by the index but missing on disk is an error). */
+int ltxv_safetensors_list(const char* path, char* out, uint64_t out_cap, int32_t* n_tensors);
+
 /* ------------------------------------------------------------------ DiT ------------------------------------------ */
 /* LtxVideoTransformer3DModelConfig, ltx_transformer.rs:22-59 */
 typedef struct ltxv_dit_config {
@@ -81,6 +93,10 @@ void ltxv_dit_destroy(ltxv_dit* m);
  * host or a device pointer, dtype f32 or bf16; the shape must match the reference's. */
 int ltxv_dit_load_tensor(ltxv_dit* m, const char* key, const void* data, int dtype, const int64_t* shape, int rank);
 /* Synthetic random-init weights of the configured architecture, generated on the device (benchmarks). */
+/* Loads every tensor of `path` (see ltxv_safetensors_list) the model has a slot for: F32 / BF16 / F16 sources, cast on
+ * load.  official = 1: keys go through the official->diffusers remap first and only transformer tensors are taken.
+ * Still requires ltxv_dit_finalize (which reports tensors that were never loaded). */
+int ltxv_dit_load_safetensors(ltxv_dit* m, const char* path, int official, int32_t* n_loaded, int32_t* n_ignored);
 int ltxv_dit_init_random(ltxv_dit* m, uint64_t seed);
 /* Fails (listing the missing keys) unless every tensor of the architecture has been loaded. */
 int ltxv_dit_finalize(ltxv_dit* m);
@@ -131,6 +147,7 @@ void ltxv_vae_destroy(ltxv_vae* m);
 /* keys carry the reference's `decoder.` prefix; `latents_mean` / `latents_std` (top level) are optional.
  * `encoder.*` and other unknown keys are accepted and ignored (the reference builds an encoder the t2v path never runs). */
 int ltxv_vae_load_tensor(ltxv_vae* m, const char* key, const void* data, int dtype, const int64_t* shape, int rank);
+int ltxv_vae_load_safetensors(ltxv_vae* m, const char* path, int official, int32_t* n_loaded, int32_t* n_ignored);
 int ltxv_vae_init_random(ltxv_vae* m, uint64_t seed);
 int ltxv_vae_finalize(ltxv_vae* m);
 /* VaeLtxVideo accessors (t2v_pipeline.rs:91-99): 128-entry f32 device vectors, ratios 32 / 8 */
