@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = [
     "ltxv_parallel_plan", "ltxv_pipeline_denoise_parallel", "ltxv_vae_set_comm",
     "ltxv_remap_official_key_raw", "ltxv_remap_official_key", "ltxv_safetensors_list",
     "ltxv_dit_load_safetensors", "ltxv_vae_load_safetensors",
+    "ltxv_vae_tiling_default", "ltxv_vae_decode_tiled",
 ]
 
 
@@ -140,6 +141,8 @@ def _load() -> C.CDLL:
     l.ltxv_safetensors_list.argtypes = [C.c_char_p, C.c_char_p, u64, C.POINTER(C.c_int32)]
     l.ltxv_dit_load_safetensors.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     l.ltxv_vae_load_safetensors.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    l.ltxv_vae_tiling_default.argtypes = [C.POINTER(_VaeTilingC)]
+    l.ltxv_vae_decode_tiled.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, C.POINTER(_VaeTilingC), vp, i32, i32, vp]
     l.ltxv_profile_begin.argtypes = []
     l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return l
@@ -383,6 +386,32 @@ class VaeConfig:
                            int(self.timestep_conditioning), self.scaling_factor)
 
 
+class _VaeTilingC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "use_tiling", "use_framewise_decoding", "tile_sample_min_height", "tile_sample_min_width",
+        "tile_sample_min_num_frames", "tile_sample_stride_height", "tile_sample_stride_width",
+        "tile_sample_stride_num_frames")]
+
+
+@dataclass
+class VaeTiling:
+    """Tiling knobs of AutoencoderKLLtxVideo (vae.rs:1848-1861 defaults, enable_tiling :1870-1898), sample space."""
+    use_tiling: bool = True
+    use_framewise_decoding: bool = True
+    tile_sample_min_height: int = 512
+    tile_sample_min_width: int = 512
+    tile_sample_min_num_frames: int = 16
+    tile_sample_stride_height: int = 384
+    tile_sample_stride_width: int = 384
+    tile_sample_stride_num_frames: int = 8
+
+    def to_c(self) -> _VaeTilingC:
+        return _VaeTilingC(int(self.use_tiling), int(self.use_framewise_decoding), self.tile_sample_min_height,
+                           self.tile_sample_min_width, self.tile_sample_min_num_frames,
+                           self.tile_sample_stride_height, self.tile_sample_stride_width,
+                           self.tile_sample_stride_num_frames)
+
+
 class AutoencoderKLLtxVideo:
     """Binds `ltxv_vae_*`; mirrors AutoencoderKLLtxVideo::decode + trait VaeLtxVideo (vae.rs:2101, :2437-2463)."""
 
@@ -431,6 +460,21 @@ class AutoencoderKLLtxVideo:
         out = torch.empty((B, 3, 8 * F - 7, 32 * H, 32 * W), dtype=odt, device=z.device)
         _check(lib().ltxv_vae_decode(self._h, _ptr(z), _dtype_code(z), _ptr(ts), B, F, H, W, _ptr(out),
                                      _dtype_code(out), int(postprocess), _stream()))
+        return out
+
+    def decode_tiled(self, latents, timestep=None, tiling: "Optional[VaeTiling]" = None, postprocess: bool = False,
+                     out_dtype=None):
+        """decode_z of the reference with its tiling dispatch (vae.rs:2037-2066); tiling=None is the library default
+        (512/384 px tiles, 16/8 frames)."""
+        torch = _torch()
+        z = _dev(latents, "latents")
+        B, _, F, H, W = z.shape
+        ts = None if timestep is None else _dev(timestep, "timestep").to(torch.float32).reshape(-1).contiguous()
+        odt = torch.float32 if out_dtype is None else out_dtype
+        out = torch.empty((B, 3, 8 * F - 7, 32 * H, 32 * W), dtype=odt, device=z.device)
+        tp = (tiling or VaeTiling()).to_c()
+        _check(lib().ltxv_vae_decode_tiled(self._h, _ptr(z), _dtype_code(z), _ptr(ts), B, F, H, W, C.byref(tp),
+                                           _ptr(out), _dtype_code(out), int(postprocess), _stream()))
         return out
 
     def decode_host(self, latents, timestep=None, postprocess: bool = False):

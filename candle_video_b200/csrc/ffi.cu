@@ -308,6 +308,20 @@ int ltxv_vae_decode(ltxv_vae* m, const void* z, int z_dtype, const float* timest
     m->model.decode(z, z_dtype, timestep, B, F, H, W, out, out_dtype, postprocess, static_cast<cudaStream_t>(stream));
     LTXV_CATCH
 }
+int ltxv_vae_tiling_default(ltxv_vae_tiling* out) {
+    LTXV_TRY
+    if (out == nullptr) fail("null argument");
+    *out = ltxv_vae_tiling{1, 1, 512, 512, 16, 384, 384, 8};  // vae.rs:1848-1861
+    LTXV_CATCH
+}
+int ltxv_vae_decode_tiled(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
+                          const ltxv_vae_tiling* tiling, void* out, int out_dtype, int postprocess, void* stream) {
+    LTXV_TRY
+    if (m == nullptr || z == nullptr || out == nullptr) fail("null argument");
+    m->model.decode_z(z, z_dtype, timestep, B, F, H, W, out, out_dtype, postprocess, tiling,
+                      static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
 int ltxv_vae_decode_host(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
                          void* out, int out_dtype, int postprocess) {
     LTXV_TRY

@@ -10,6 +10,9 @@
 // writes bias (+ residual), the depth-to-space scatter of the upsamplers, or the unpatchified f32 pixels.
 #include "vae.h"
 
+#include <algorithm>
+#include <memory>
+
 #include <math.h>
 
 #include "gemm.h"
@@ -413,6 +416,156 @@ void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* time
         if (out_dtype == LTXV_BF16)
             LTXV_CUDA(launch_f32_to_bf16(o32, static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(b) * out_elems,
                                          out_elems, s));
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// tiled decode (compatibility mode)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct TileBuf {
+    DevBuf buf;
+    int T = 0, H = 0, W = 0;
+    float* p() const { return buf.as<float>(); }
+    void shape(int t, int h, int w) {
+        T = t;
+        H = h;
+        W = w;
+        buf.ensure(static_cast<size_t>(3) * t * h * w * 4);
+    }
+};
+}  // namespace
+
+void AutoencoderKLLtxVideo::tiled_decode(const void* z, int z_dtype, const float* ts_b, int T, int H, int W, float* dst,
+                                         const ltxv_vae_tiling& tp, cudaStream_t s) {
+    const int sr = spatial_compression_ratio(), C = cfg_.latent_channels;
+    const int esz = z_dtype == LTXV_F32 ? 4 : 2;
+    const int Td = 8 * T - 7, Hs = H * sr, Ws = W * sr;
+    const int tl_min_h = tp.tile_sample_min_height / sr, tl_min_w = tp.tile_sample_min_width / sr;
+    const int tl_str_h = tp.tile_sample_stride_height / sr, tl_str_w = tp.tile_sample_stride_width / sr;
+    if (tl_min_h < 1 || tl_min_w < 1 || tl_str_h < 1 || tl_str_w < 1)
+        fail("tile sizes and strides must be at least %d pixels", sr);
+    const int blend_h = std::max(tp.tile_sample_min_height - tp.tile_sample_stride_height, 0);
+    const int blend_w = std::max(tp.tile_sample_min_width - tp.tile_sample_stride_width, 0);
+    const int ncols = (W + tl_str_w - 1) / tl_str_w;
+    std::unique_ptr<TileBuf[]> row_a(new TileBuf[ncols]), row_b(new TileBuf[ncols]);
+    TileBuf* prev = row_a.get();
+    TileBuf* cur = row_b.get();
+    int ri = 0;
+    for (int i = 0; i < H; i += tl_str_h, ++ri) {
+        const int th = std::min(i + tl_min_h, H) - i;
+        int cj = 0;
+        for (int j = 0; j < W; j += tl_str_w, ++cj) {
+            const int tw = std::min(j + tl_min_w, W) - j;
+            tz_sp_.ensure(static_cast<size_t>(C) * T * th * tw * esz);
+            LTXV_CUDA(launch_copy_box(z, esz, C, T, H, W, 0, i, j, tz_sp_.p, T, th, tw, 0, 0, 0, T, th, tw, s));
+            TileBuf& tile = cur[cj];
+            tile.shape(Td, th * sr, tw * sr);
+            decode(tz_sp_.p, z_dtype, ts_b, 1, T, th, tw, tile.p(), LTXV_F32, 0, s);
+            if (ri > 0)  // blend_v: seam with the (already blended) tile above, along H
+                LTXV_CUDA(launch_blend_axis(prev[cj].p(), prev[cj].T, prev[cj].H, prev[cj].W, tile.p(), tile.T, tile.H,
+                                            tile.W, 3, 2, blend_h, s));
+            if (cj > 0)  // blend_h: seam with the (already blended) left neighbour, along W
+                LTXV_CUDA(launch_blend_axis(cur[cj - 1].p(), cur[cj - 1].T, cur[cj - 1].H, cur[cj - 1].W, tile.p(), tile.T,
+                                            tile.H, tile.W, 3, 3, blend_w, s));
+            // keep the first stride rows / columns, cropped to the sample size (:2279-2289)
+            const int y0 = ri * tp.tile_sample_stride_height, x0 = cj * tp.tile_sample_stride_width;
+            const int hs = std::min(std::min(tp.tile_sample_stride_height, tile.H), Hs - y0);
+            const int ws = std::min(std::min(tp.tile_sample_stride_width, tile.W), Ws - x0);
+            LTXV_CUDA(launch_copy_box(tile.p(), 4, 3, tile.T, tile.H, tile.W, 0, 0, 0, dst, Td, Hs, Ws, 0, y0, x0, Td, hs,
+                                      ws, s));
+        }
+        std::swap(prev, cur);
+    }
+    LTXV_CUDA(cudaStreamSynchronize(s));  // the tile buffers die with this frame
+}
+
+void AutoencoderKLLtxVideo::temporal_tiled_decode(const void* z, int z_dtype, const float* ts_b, int F, int H, int W,
+                                                  float* dst, const ltxv_vae_tiling& tp, cudaStream_t s) {
+    const int sr = spatial_compression_ratio(), tr = temporal_compression_ratio(), C = cfg_.latent_channels;
+    const int esz = z_dtype == LTXV_F32 ? 4 : 2;
+    const int Hs = H * sr, Ws = W * sr, n_sample = (F - 1) * tr + 1;
+    const int tl_min_h = tp.tile_sample_min_height / sr, tl_min_w = tp.tile_sample_min_width / sr;
+    const int tl_min_t = tp.tile_sample_min_num_frames / tr, tl_str_t = tp.tile_sample_stride_num_frames / tr;
+    if (tl_str_t < 1) fail("tile_sample_stride_num_frames must be at least %d", tr);
+    const int blend_t = std::max(tp.tile_sample_min_num_frames - tp.tile_sample_stride_num_frames, 0);
+    const size_t plane = static_cast<size_t>(Hs) * Ws;
+    int prev_T = 0, fo = 0, idx = 0;
+    for (int i = 0; i < F && fo < n_sample; i += tl_str_t, ++idx) {
+        const int Tl = std::min(i + tl_min_t + 1, F) - i;
+        const int Tfull = 8 * Tl - 7;
+        tz_tm_.ensure(static_cast<size_t>(C) * Tl * H * W * esz);
+        LTXV_CUDA(launch_copy_box(z, esz, C, F, H, W, i, 0, 0, tz_tm_.p, Tl, H, W, 0, 0, 0, Tl, H, W, s));
+        t_dec_.ensure(3 * static_cast<size_t>(Tfull) * plane * 4);
+        if (tp.use_tiling && (H > tl_min_h || W > tl_min_w))
+            tiled_decode(tz_tm_.p, z_dtype, ts_b, Tl, H, W, t_dec_.as<float>(), tp, s);
+        else
+            decode(tz_tm_.p, z_dtype, ts_b, 1, Tl, H, W, t_dec_.p, LTXV_F32, 0, s);
+        // every tile but the first loses its last sample frame (:2398-2408); compact into t_cur_
+        const int Td = (idx > 0 && Tfull > 1) ? Tfull - 1 : Tfull;
+        t_cur_.ensure(3 * static_cast<size_t>(Td) * plane * 4);
+        LTXV_CUDA(launch_copy_box(t_dec_.p, 4, 3, Tfull, Hs, Ws, 0, 0, 0, t_cur_.p, Td, Hs, Ws, 0, 0, 0, Td, Hs, Ws, s));
+        int take;
+        const float* src = t_cur_.as<float>();
+        if (idx > 0) {
+            // blend with the UNBLENDED previous tile (row[idx - 1], :2420), then keep the first `stride` frames
+            t_work_.ensure(3 * static_cast<size_t>(Td) * plane * 4);
+            LTXV_CUDA(cudaMemcpyAsync(t_work_.p, t_cur_.p, 3 * static_cast<size_t>(Td) * plane * 4,
+                                      cudaMemcpyDeviceToDevice, s));
+            LTXV_CUDA(launch_blend_axis(t_prev_.as<float>(), prev_T, Hs, Ws, t_work_.as<float>(), Td, Hs, Ws, 3, 1, blend_t, s));
+            take = std::min(tp.tile_sample_stride_num_frames, Td);
+            src = t_work_.as<float>();
+        } else {
+            take = std::min(tp.tile_sample_stride_num_frames + 1, Td);
+        }
+        take = std::min(take, n_sample - fo);  // final crop to (F-1)*8+1 frames (:2433)
+        LTXV_CUDA(launch_copy_box(src, 4, 3, Td, Hs, Ws, 0, 0, 0, dst, n_sample, Hs, Ws, fo, 0, 0, take, Hs, Ws, s));
+        fo += take;
+        std::swap(t_prev_.p, t_cur_.p);
+        std::swap(t_prev_.bytes, t_cur_.bytes);
+        prev_T = Td;
+    }
+    if (fo != n_sample) fail("temporal tiling produced %d of %d frames (stride larger than the tile?)", fo, n_sample);
+}
+
+void AutoencoderKLLtxVideo::decode_z(const void* z, int z_dtype, const float* timestep_dev, int B, int F, int H, int W,
+                                     void* out, int out_dtype, int postprocess, const ltxv_vae_tiling* tiling,
+                                     cudaStream_t s) {
+    const int sr = spatial_compression_ratio(), tr = temporal_compression_ratio();
+    bool temporal = false, spatial = false;
+    if (tiling != nullptr) {
+        const ltxv_vae_tiling& tp = *tiling;
+        if (tp.tile_sample_min_height < sr || tp.tile_sample_min_width < sr || tp.tile_sample_min_num_frames < tr ||
+            tp.tile_sample_stride_height < sr || tp.tile_sample_stride_width < sr || tp.tile_sample_stride_num_frames < tr)
+            fail("tile sizes / strides must be at least %d pixels and %d frames", sr, tr);
+        temporal = tp.use_framewise_decoding && F > tp.tile_sample_min_num_frames / tr;
+        spatial = !temporal && tp.use_tiling && (W > tp.tile_sample_min_width / sr || H > tp.tile_sample_min_height / sr);
+    }
+    if (!temporal && !spatial) {
+        decode(z, z_dtype, timestep_dev, B, F, H, W, out, out_dtype, postprocess, s);
+        return;
+    }
+    if (comm_ != nullptr) fail("tiled decode is a single-GPU compatibility mode: clear the communicator first");
+    if (z_dtype != LTXV_F32 && z_dtype != LTXV_BF16) fail("unsupported latent dtype %d", z_dtype);
+    if (out_dtype != LTXV_F32 && out_dtype != LTXV_BF16) fail("unsupported output dtype %d", out_dtype);
+    const size_t zsz = z_dtype == LTXV_F32 ? 4 : 2;
+    const int64_t z_elems = static_cast<int64_t>(cfg_.latent_channels) * F * H * W;
+    const int64_t out_elems = 3ll * (8 * F - 7) * (sr * H) * (sr * W);
+    DevBuf assembled;
+    if (out_dtype == LTXV_BF16) assembled.ensure(static_cast<size_t>(out_elems) * 4);
+    for (int b = 0; b < B; ++b) {
+        const char* zb = static_cast<const char*>(z) + static_cast<size_t>(b) * z_elems * zsz;
+        const float* ts_b = timestep_dev ? timestep_dev + b : nullptr;
+        float* dst = out_dtype == LTXV_F32 ? static_cast<float*>(out) + static_cast<size_t>(b) * out_elems
+                                           : assembled.as<float>();
+        if (temporal) temporal_tiled_decode(zb, z_dtype, ts_b, F, H, W, dst, *tiling, s);
+        else tiled_decode(zb, z_dtype, ts_b, F, H, W, dst, *tiling, s);
+        if (postprocess) LTXV_CUDA(launch_postprocess(dst, dst, out_elems, s));
+        if (out_dtype == LTXV_BF16)
+            LTXV_CUDA(launch_f32_to_bf16(dst, static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(b) * out_elems,
+                                         out_elems, s));
+        LTXV_CUDA(cudaStreamSynchronize(s));
     }
 }
 

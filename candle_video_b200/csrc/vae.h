@@ -50,6 +50,12 @@ public:
     // z [B, C, F, H, W] -> out f32/bf16 [B, 3, 8F-7, 32H, 32W]
     void decode(const void* z, int z_dtype, const float* timestep_dev, int B, int F, int H, int W, void* out,
                 int out_dtype, int postprocess, cudaStream_t s);
+    // decode_z dispatch of the reference (vae.rs:2037-2066) with its tiling knobs: temporal tiling first
+    // (:2358-2434), then spatial tiling (:2225-2290), each tile decoded by decode() and the seams blended linearly
+    // (:1927-2006).  tiling == nullptr or no branch taken -> plain decode().  Compatibility mode for --vae-tiling
+    // users: the slab decode above makes tiling unnecessary on B200, but its output differs from the blended one.
+    void decode_z(const void* z, int z_dtype, const float* timestep_dev, int B, int F, int H, int W, void* out,
+                  int out_dtype, int postprocess, const ltxv_vae_tiling* tiling, cudaStream_t s);
 
 private:
     enum SlotKind { PLAIN = 0, CONV_W = 1, CONV_B = 2 };
@@ -66,6 +72,10 @@ private:
     void conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out, const void* res, int post,
               cudaStream_t s);
     void resnet(const ResnetW& rw, int level, const float* ss, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s);
+    void tiled_decode(const void* z, int z_dtype, const float* ts_b, int T, int H, int W, float* dst,
+                      const ltxv_vae_tiling& tp, cudaStream_t s);
+    void temporal_tiled_decode(const void* z, int z_dtype, const float* ts_b, int F, int H, int W, float* dst,
+                               const ltxv_vae_tiling& tp, cudaStream_t s);
     // pixel-norm / modulate / SiLU into the level's padded conv input (+ halo exchange and barrier when sharded)
     void* prep(const void* x, int level, const float* scale, const float* shift, int do_norm, int do_silu, cudaStream_t s);
 
@@ -88,6 +98,7 @@ private:
     int wsF_ = 0, wsH_ = 0, wsW_ = 0;
     int T_[4], H_[4], W_[4];
     DevBuf a0_, p_[4], xa_, xb_, hb_, cond_, out_f32_;
+    DevBuf tz_sp_, tz_tm_, t_dec_, t_prev_, t_cur_, t_work_;  // tiled decode: sub-latents and decoded tiles
     // sharded decode
     PeerComm* comm_ = nullptr;
     int Hfull_[4] = {0, 0, 0, 0};

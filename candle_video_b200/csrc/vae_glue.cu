@@ -184,6 +184,47 @@ __global__ void conv_bias_relayout_kernel(const TIn* __restrict__ b, float* __re
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// tiled-decode helpers (vae.rs:1927-2006, :2225-2290, :2358-2434): box copies and linear seam blends on NCDHW volumes
+// ------------------------------------------------------------------------------------------------
+struct Vol {
+    int C, T, H, W;
+};
+template <typename E>
+__global__ void copy_box_kernel(const E* __restrict__ src, Vol sv, int st0, int sh0, int sw0, E* __restrict__ dst, Vol dv,
+                                int dt0, int dh0, int dw0, int bT, int bH, int bW) {
+    const int64_t n = static_cast<int64_t>(sv.C) * bT * bH * bW;
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const int w = static_cast<int>(i % bW);
+    const int h = static_cast<int>((i / bW) % bH);
+    const int t = static_cast<int>((i / (static_cast<int64_t>(bW) * bH)) % bT);
+    const int c = static_cast<int>(i / (static_cast<int64_t>(bW) * bH * bT));
+    dst[((static_cast<int64_t>(c) * dv.T + dt0 + t) * dv.H + dh0 + h) * dv.W + dw0 + w] =
+        src[((static_cast<int64_t>(c) * sv.T + st0 + t) * sv.H + sh0 + h) * sv.W + sw0 + w];
+}
+// b[.., x along axis] = a[.., La - blend + x] * (1 - x * f32(1/blend)) + b[.., x] * (x * f32(1/blend)), x < blend;
+// a and b agree in every other extent.  axis: 1 = T, 2 = H, 3 = W.
+__global__ void blend_axis_kernel(const float* __restrict__ a, Vol av, float* __restrict__ b, Vol bv, int axis,
+                                  int blend, float inv_blend) {
+    const int eT = axis == 1 ? blend : bv.T, eH = axis == 2 ? blend : bv.H, eW = axis == 3 ? blend : bv.W;
+    const int64_t n = static_cast<int64_t>(bv.C) * eT * eH * eW;
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const int w = static_cast<int>(i % eW);
+    const int h = static_cast<int>((i / eW) % eH);
+    const int t = static_cast<int>((i / (static_cast<int64_t>(eW) * eH)) % eT);
+    const int c = static_cast<int>(i / (static_cast<int64_t>(eW) * eH * eT));
+    const int x = axis == 1 ? t : (axis == 2 ? h : w);
+    const int at = axis == 1 ? av.T - blend + t : t, ah = axis == 2 ? av.H - blend + h : h,
+              aw = axis == 3 ? av.W - blend + w : w;
+    const float wgt = __fmul_rn(static_cast<float>(x), inv_blend);
+    const float om = __fsub_rn(1.0f, wgt);
+    const float va = a[((static_cast<int64_t>(c) * av.T + at) * av.H + ah) * av.W + aw];
+    float* pb = b + ((static_cast<int64_t>(c) * bv.T + t) * bv.H + h) * bv.W + w;
+    *pb = __fadd_rn(__fmul_rn(va, om), __fmul_rn(*pb, wgt));
+}
+
 uint64_t vae_glue_launch_count() { return g_vae_glue_launches.load(); }
 
 cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out, int C, int F, int H, int W, cudaStream_t s) {
@@ -247,6 +288,44 @@ cudaError_t launch_conv_bias_relayout(const void* b, int b_is_bf16, float* out, 
     else
         conv_bias_relayout_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(b), out, Cout, rows_out,
                                                               d2s_perm);
+    return done();
+}
+
+
+cudaError_t launch_copy_box(const void* src, int elem_bytes, int C, int sT, int sH, int sW, int st0, int sh0, int sw0,
+                            void* dst, int dT, int dH, int dW, int dt0, int dh0, int dw0, int bT, int bH, int bW,
+                            cudaStream_t s) {
+    if (bT <= 0 || bH <= 0 || bW <= 0) return cudaSuccess;
+    if (st0 < 0 || sh0 < 0 || sw0 < 0 || dt0 < 0 || dh0 < 0 || dw0 < 0 || st0 + bT > sT || sh0 + bH > sH ||
+        sw0 + bW > sW || dt0 + bT > dT || dh0 + bH > dH || dw0 + bW > dW)
+        return cudaErrorInvalidValue;
+    const int64_t n = static_cast<int64_t>(C) * bT * bH * bW;
+    const int grid = static_cast<int>((n + 255) / 256);
+    const Vol sv{C, sT, sH, sW}, dv{C, dT, dH, dW};
+    if (elem_bytes == 4)
+        copy_box_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), sv, st0, sh0, sw0,
+                                                    static_cast<float*>(dst), dv, dt0, dh0, dw0, bT, bH, bW);
+    else if (elem_bytes == 2)
+        copy_box_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), sv, st0, sh0, sw0,
+                                                       static_cast<uint16_t*>(dst), dv, dt0, dh0, dw0, bT, bH, bW);
+    else
+        return cudaErrorInvalidValue;
+    return done();
+}
+
+cudaError_t launch_blend_axis(const float* a, int aT, int aH, int aW, float* b, int bT, int bH, int bW, int C, int axis,
+                              int blend_extent, cudaStream_t s) {
+    if (axis < 1 || axis > 3) return cudaErrorInvalidValue;
+    const int la = axis == 1 ? aT : (axis == 2 ? aH : aW), lb = axis == 1 ? bT : (axis == 2 ? bH : bW);
+    int blend = blend_extent < la ? blend_extent : la;
+    if (lb < blend) blend = lb;
+    if (blend <= 0) return cudaSuccess;
+    if ((axis != 1 && aT != bT) || (axis != 2 && aH != bH) || (axis != 3 && aW != bW)) return cudaErrorInvalidValue;
+    const int eT = axis == 1 ? blend : bT, eH = axis == 2 ? blend : bH, eW = axis == 3 ? blend : bW;
+    const int64_t n = static_cast<int64_t>(C) * eT * eH * eW;
+    const float inv = static_cast<float>(1.0 / static_cast<double>(blend));  // affine(1/blend) of an f32 arange
+    blend_axis_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(a, Vol{C, aT, aH, aW}, b, Vol{C, bT, bH, bW}, axis,
+                                                                        blend, inv);
     return done();
 }
 

@@ -33,6 +33,15 @@ cudaError_t launch_conv_weight_relayout(const void* w, int w_is_bf16, void* out,
 cudaError_t launch_conv_bias_relayout(const void* b, int b_is_bf16, float* out, int Cout, int rows_out, int d2s_perm,
                                       cudaStream_t s);
 
+// Tiled decode (vae.rs:2225-2434): copy a [C, bT, bH, bW] box between two NCDHW volumes (2- or 4-byte elements) ...
+cudaError_t launch_copy_box(const void* src, int elem_bytes, int C, int sT, int sH, int sW, int st0, int sh0, int sw0,
+                            void* dst, int dT, int dH, int dW, int dt0, int dh0, int dw0, int bT, int bH, int bW,
+                            cudaStream_t s);
+// ... and blend the leading `blend` slices of b along axis (1 T, 2 H, 3 W) with the trailing slices of a, in place
+// (blend_t / blend_v / blend_h, vae.rs:1927-2006; blend = min(blend_extent, extent of a, extent of b)).
+cudaError_t launch_blend_axis(const float* a, int aT, int aH, int aW, float* b, int bT, int bH, int bW, int C, int axis,
+                              int blend_extent, cudaStream_t s);
+
 uint64_t vae_glue_launch_count();
 
 }  // namespace ltxv

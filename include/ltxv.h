@@ -161,6 +161,23 @@ int ltxv_vae_temporal_compression_ratio(const ltxv_vae* m);
  * (clamp(0.5x+0.5,0,1)*255, t2v_pipeline.rs:147-155) in the last kernel's epilogue. */
 int ltxv_vae_decode(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
                     void* out, int out_dtype, int postprocess, void* stream);
+/* Tiling knobs of AutoencoderKLLtxVideo (vae.rs:1848-1861, enable_tiling :1870-1898), all in SAMPLE space. */
+typedef struct ltxv_vae_tiling {
+    int32_t use_tiling;                    /* 1 */
+    int32_t use_framewise_decoding;        /* 1 */
+    int32_t tile_sample_min_height;        /* 512 */
+    int32_t tile_sample_min_width;         /* 512 */
+    int32_t tile_sample_min_num_frames;    /* 16 */
+    int32_t tile_sample_stride_height;     /* 384 */
+    int32_t tile_sample_stride_width;      /* 384 */
+    int32_t tile_sample_stride_num_frames; /* 8 */
+} ltxv_vae_tiling;
+int ltxv_vae_tiling_default(ltxv_vae_tiling* out);
+/* decode_z of the reference with its tiling dispatch (vae.rs:2037-2066): temporal tiling when F > min_frames/8, else
+ * spatial tiling when H or W exceed the minimum tile, else the plain decoder; seams blended linearly in f32.
+ * tiling == NULL is ltxv_vae_decode.  Single-GPU only (H-slab decode already removes the need for tiles). */
+int ltxv_vae_decode_tiled(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
+                          const ltxv_vae_tiling* tiling, void* out, int out_dtype, int postprocess, void* stream);
 int ltxv_vae_decode_host(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
                          void* out, int out_dtype, int postprocess);
 

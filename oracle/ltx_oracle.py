@@ -477,6 +477,113 @@ def vae_decode(w: Dict[str, Tensor], cfg: VaeConfig, z: Tensor, timestep: Option
     return unpatchify(h, cfg.patch_size, cfg.patch_size_t)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# tiled / temporal-tiled decode (the LIBRARY default of the reference: use_tiling = use_framewise_decoding = true,
+# vae.rs:1848-1861; the example binary only enables it with --vae-tiling, main.rs:516-518)
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class VaeTiling:
+    """vae.rs:1848-1861 (defaults) / enable_tiling :1870-1898; all sizes in SAMPLE space (pixels / frames)."""
+    use_tiling: bool = True
+    use_framewise_decoding: bool = True
+    tile_sample_min_height: int = 512
+    tile_sample_min_width: int = 512
+    tile_sample_min_num_frames: int = 16
+    tile_sample_stride_height: int = 384
+    tile_sample_stride_width: int = 384
+    tile_sample_stride_num_frames: int = 8
+
+
+def _blend(a: Tensor, b: Tensor, blend_extent: int, dim: int) -> Tensor:
+    """blend_h / blend_v / blend_t, vae.rs:1927-2006: the first `blend` slices of b along `dim` become
+    a[-blend + x] * (1 - x/blend) + b[x] * (x/blend), w = x * f32(1/blend)."""
+    blend = min(blend_extent, a.shape[dim], b.shape[dim])
+    if blend == 0:
+        return b.clone()
+    w = torch.arange(blend, dtype=F32) * torch.tensor(1.0 / blend, dtype=F32)
+    shape = [1] * b.dim()
+    shape[dim] = blend
+    w = w.reshape(shape)
+    one_minus = 1.0 - w
+    b_head = b.narrow(dim, 0, blend)
+    b_tail = b.narrow(dim, blend, b.shape[dim] - blend)
+    a_tail = a.narrow(dim, a.shape[dim] - blend, blend)
+    mixed = a_tail * one_minus + b_head * w
+    return torch.cat([mixed, b_tail], dim=dim)
+
+
+def vae_tiled_decode(w, cfg: VaeConfig, z: Tensor, timestep, tp: VaeTiling, sr: int = 32) -> Tensor:
+    """AutoencoderKLLtxVideo::tiled_decode, vae.rs:2225-2290."""
+    height, width = z.shape[3], z.shape[4]
+    sample_h, sample_w = height * sr, width * sr
+    tl_min_h, tl_min_w = tp.tile_sample_min_height // sr, tp.tile_sample_min_width // sr
+    tl_str_h, tl_str_w = tp.tile_sample_stride_height // sr, tp.tile_sample_stride_width // sr
+    blend_h = max(tp.tile_sample_min_height - tp.tile_sample_stride_height, 0)
+    blend_w = max(tp.tile_sample_min_width - tp.tile_sample_stride_width, 0)
+    rows = []
+    for i in range(0, height, tl_str_h):
+        row = []
+        for j in range(0, width, tl_str_w):
+            tile = z[:, :, :, i:min(i + tl_min_h, height), j:min(j + tl_min_w, width)]
+            row.append(vae_decode(w, cfg, tile, timestep))
+        rows.append(row)
+    prev_row, result_rows = [], []
+    for ri, row in enumerate(rows):
+        result_row, cur_row = [], []
+        for cj, tile in enumerate(row):
+            if ri > 0:
+                tile = _blend(prev_row[cj], tile, blend_h, 3)   # blend_v acts on H (dim 3)
+            if cj > 0:
+                tile = _blend(cur_row[cj - 1], tile, blend_w, 4)  # blend_h acts on W (dim 4)
+            cur_row.append(tile)
+            hs = min(tp.tile_sample_stride_height, tile.shape[3])
+            ws = min(tp.tile_sample_stride_width, tile.shape[4])
+            result_row.append(tile[:, :, :, :hs, :ws])
+        result_rows.append(torch.cat(result_row, dim=4))
+        prev_row = cur_row
+    return torch.cat(result_rows, dim=3)[:, :, :, :sample_h, :sample_w]
+
+
+def vae_temporal_tiled_decode(w, cfg: VaeConfig, z: Tensor, timestep, tp: VaeTiling, sr: int = 32, tr: int = 8) -> Tensor:
+    """AutoencoderKLLtxVideo::temporal_tiled_decode, vae.rs:2358-2434."""
+    num_frames = z.shape[2]
+    num_sample_frames = (num_frames - 1) * tr + 1
+    tl_min_h, tl_min_w = tp.tile_sample_min_height // sr, tp.tile_sample_min_width // sr
+    tl_min_t = tp.tile_sample_min_num_frames // tr
+    tl_str_t = tp.tile_sample_stride_num_frames // tr
+    blend_t = max(tp.tile_sample_min_num_frames - tp.tile_sample_stride_num_frames, 0)
+    row = []
+    for loop_idx, i in enumerate(range(0, num_frames, tl_str_t)):
+        tile = z[:, :, i:min(i + tl_min_t + 1, num_frames)]
+        if tp.use_tiling and (tile.shape[3] > tl_min_h or tile.shape[4] > tl_min_w):
+            dec = vae_tiled_decode(w, cfg, tile, timestep, tp, sr)
+        else:
+            dec = vae_decode(w, cfg, tile, timestep)
+        if loop_idx > 0 and dec.shape[2] > 1:
+            dec = dec[:, :, :-1]
+        row.append(dec)
+    out = []
+    for idx, tile in enumerate(row):
+        if idx > 0:
+            blended = _blend(row[idx - 1], tile, blend_t, 2)
+            out.append(blended[:, :, :min(tp.tile_sample_stride_num_frames, blended.shape[2])])
+        else:
+            out.append(tile[:, :, :min(tp.tile_sample_stride_num_frames + 1, tile.shape[2])])
+    return torch.cat(out, dim=2)[:, :, :num_sample_frames]
+
+
+def vae_decode_z(w, cfg: VaeConfig, z: Tensor, timestep, tp: Optional[VaeTiling], sr: int = 32, tr: int = 8) -> Tensor:
+    """decode_z dispatch, vae.rs:2037-2066: framewise first, then spatial tiling, else the plain decoder."""
+    if tp is None:
+        return vae_decode(w, cfg, z, timestep)
+    t, h, wd = z.shape[2], z.shape[3], z.shape[4]
+    if tp.use_framewise_decoding and t > tp.tile_sample_min_num_frames // tr:
+        return vae_temporal_tiled_decode(w, cfg, z, timestep, tp, sr, tr)
+    if tp.use_tiling and (wd > tp.tile_sample_min_width // sr or h > tp.tile_sample_min_height // sr):
+        return vae_tiled_decode(w, cfg, z, timestep, tp, sr)
+    return vae_decode(w, cfg, z, timestep)
+
+
 def vae_weight_shapes(cfg: VaeConfig) -> Dict[str, Tuple[int, ...]]:
     """Decoder keys / shapes (vae.rs:323-335, :983-987, :1070-1079, :1257-1263, :1583-1604)."""
     ch = cfg.stage_channels()  # [1024, 512, 256, 128]

@@ -220,3 +220,33 @@ def test_euler_and_schedule_closed_forms():
     s8 = [1.0, 0.9937, 0.9875, 0.9812, 0.975, 0.9094, 0.725, 0.4219]
     sig2, ts2 = O.scheduler_set_timesteps(8, 0.0, sigmas=s8, shift_terminal=None)
     assert np.allclose(sig2[:-1], s8, atol=1e-6) and ts2[0] == 1000
+
+
+# ---- tiled decode restatement: blend weights and dispatch (vae.rs:1927-2066) ----
+def test_blend_weights_and_extent():
+    a = torch.ones(1, 1, 1, 1, 6)
+    b = torch.zeros(1, 1, 1, 1, 5)
+    out = O._blend(a, b, 4, 4)
+    # b[x] = a[-4+x]*(1-x/4) + b[x]*(x/4): 1, .75, .5, .25 then b's own tail
+    assert torch.equal(out.flatten(), torch.tensor([1.0, 0.75, 0.5, 0.25, 0.0]))
+    # the blend is clipped to both extents (min(blend, a, b), :1931)
+    out = O._blend(torch.full((1, 1, 2, 1, 1), 2.0), torch.zeros(1, 1, 3, 1, 1), 8, 2)
+    assert torch.equal(out.flatten(), torch.tensor([2.0, 1.0, 0.0]))
+    assert torch.equal(O._blend(a, b, 0, 4), b)
+
+
+def test_tiling_dispatch_and_frame_count():
+    cfg = O.VaeConfig(decoder_layers_per_block=(1, 1, 1, 1))
+    w = O.init_vae_weights(cfg, 7)
+    z = torch.randn(1, 128, 3, 2, 2, generator=torch.Generator().manual_seed(0))
+    ts = torch.tensor([0.05])
+    plain = O.vae_decode(w, cfg, z, ts)
+    # defaults: 3 latent frames > 16/8 = 2 -> temporal tiling; result keeps (F-1)*8+1 frames (:2433)
+    tiled = O.vae_decode_z(w, cfg, z, ts, O.VaeTiling())
+    assert tiled.shape == plain.shape == (1, 3, 17, 64, 64)
+    # both switches off, or a volume below every threshold: the plain decoder (:2055-2065)
+    assert torch.equal(O.vae_decode_z(w, cfg, z, ts, O.VaeTiling(use_tiling=False, use_framewise_decoding=False)), plain)
+    assert torch.equal(O.vae_decode_z(w, cfg, z[:, :, :2], ts, O.VaeTiling()), O.vae_decode(w, cfg, z[:, :, :2], ts))
+    # the first temporal tile contributes its first stride+1 = 9 frames unchanged (:2426-2429)
+    first = O.vae_decode(w, cfg, z[:, :, :3], ts)
+    assert torch.equal(tiled[:, :, :9], first[:, :, :9])
