@@ -43,6 +43,8 @@ EXPORTED_SYMBOLS = [
     "ltxv_remap_official_key_raw", "ltxv_remap_official_key", "ltxv_safetensors_list",
     "ltxv_dit_load_safetensors", "ltxv_vae_load_safetensors",
     "ltxv_vae_tiling_default", "ltxv_vae_decode_tiled",
+    "ltxv_scheduler_step_stochastic", "ltxv_decode_noise_blend", "ltxv_pipeline_denoise_stochastic",
+    "ltxv_pipeline_decode_noisy",
 ]
 
 
@@ -141,6 +143,10 @@ def _load() -> C.CDLL:
     l.ltxv_safetensors_list.argtypes = [C.c_char_p, C.c_char_p, u64, C.POINTER(C.c_int32)]
     l.ltxv_dit_load_safetensors.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     l.ltxv_vae_load_safetensors.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    l.ltxv_scheduler_step_stochastic.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp]
+    l.ltxv_decode_noise_blend.argtypes = [vp, vp, C.c_float, C.c_int64, vp]
+    l.ltxv_pipeline_denoise_stochastic.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    l.ltxv_pipeline_decode_noisy.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, C.c_float, vp, vp]
     l.ltxv_vae_tiling_default.argtypes = [C.POINTER(_VaeTilingC)]
     l.ltxv_vae_decode_tiled.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, C.POINTER(_VaeTilingC), vp, i32, i32, vp]
     l.ltxv_profile_begin.argtypes = []
@@ -636,13 +642,50 @@ def pipeline_denoise(dit: LtxVideoTransformer3DModel, params: PipelineParams, la
     return latents
 
 
-def pipeline_decode(vae: AutoencoderKLLtxVideo, params: PipelineParams, latents):
+def pipeline_decode(vae: AutoencoderKLLtxVideo, params: PipelineParams, latents, decode_noise=None,
+                    decode_noise_scale: float = 0.0):
+    """Decode branch (t2v_pipeline.rs:1000-1072).  decode_noise: f32 CUDA [128, F, H, W] drawn by the caller, blended
+    as (1 - scale) latents + scale noise before the VAE (:1049-1062)."""
     torch = _torch()
     p, keep = params.to_c()
     f = (params.num_frames - 1) // 8 + 1
     out = torch.empty((3, 8 * f - 7, params.height, params.width), dtype=torch.float32, device=latents.device)
-    _check(lib().ltxv_pipeline_decode(vae._h, C.byref(p), _ptr(latents), _ptr(out), _stream()))
+    if decode_noise is None and decode_noise_scale == 0.0:
+        _check(lib().ltxv_pipeline_decode(vae._h, C.byref(p), _ptr(latents), _ptr(out), _stream()))
+    else:
+        nz = None if decode_noise is None else _dev(decode_noise, "decode_noise").to(torch.float32).contiguous()
+        _check(lib().ltxv_pipeline_decode_noisy(vae._h, C.byref(p), _ptr(latents), _ptr(nz), float(decode_noise_scale),
+                                                _ptr(out), _stream()))
     return out
+
+
+def scheduler_step_stochastic(latents, model_output, noise, sigma: float, sigma_next: float):
+    """In place: x <- (1 - sigma_next) (x - sigma v) + sigma_next noise (scheduler.rs:557-575); f32 CUDA tensors."""
+    _check(lib().ltxv_scheduler_step_stochastic(_ptr(latents), _ptr(model_output), _ptr(noise), latents.numel(),
+                                                float(sigma), float(sigma_next), _stream()))
+    return latents
+
+
+def pipeline_denoise_stochastic(dit: LtxVideoTransformer3DModel, params: PipelineParams, latents, prompt_embeds,
+                                prompt_mask, step_noise, negative_embeds=None, negative_mask=None):
+    """pipeline_denoise with stochastic_sampling = true; step_noise f32 CUDA [num_inference_steps, S, 128]."""
+    torch = _torch()
+    p, keep = params.to_c()
+    pe = _dev(prompt_embeds, "prompt_embeds")
+    pe = pe[0] if pe.dim() == 3 else pe
+    ne = _dev(negative_embeds, "negative_embeds")
+    if ne is not None and ne.dim() == 3:
+        ne = ne[0]
+    pm = None if prompt_mask is None else _dev(prompt_mask, "prompt_mask").to(torch.float32).reshape(-1).contiguous()
+    nm = None if negative_mask is None else _dev(negative_mask, "negative_mask").to(torch.float32).reshape(-1).contiguous()
+    sn = _dev(step_noise, "step_noise")
+    if sn.dtype != torch.float32 or not sn.is_contiguous() or sn.numel() != params.num_inference_steps * latents.numel():
+        raise LtxvError("step_noise must be a contiguous float32 CUDA tensor [num_inference_steps, S, C]")
+    if latents.dtype != torch.float32 or not latents.is_cuda or not latents.is_contiguous():
+        raise LtxvError("latents must be a contiguous float32 CUDA tensor")
+    _check(lib().ltxv_pipeline_denoise_stochastic(dit._h, C.byref(p), _ptr(latents), _ptr(pe), _ptr(pm), _ptr(ne),
+                                                  _ptr(nm), _dtype_code(pe), pe.shape[0], _ptr(sn), _stream()))
+    return latents
 
 
 def pipeline_denoise_host(dit: LtxVideoTransformer3DModel, params: PipelineParams, latents, prompt_embeds, prompt_mask,

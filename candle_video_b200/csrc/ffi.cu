@@ -390,6 +390,19 @@ int ltxv_guidance_euler_step(const float* cond, const float* uncond, const float
                                         static_cast<cudaStream_t>(stream)));
     LTXV_CATCH
 }
+int ltxv_scheduler_step_stochastic(float* latents, const float* model_output, const float* noise, int64_t n, float sigma,
+                                   float sigma_next, void* stream) {
+    LTXV_TRY
+    if (latents == nullptr || model_output == nullptr || noise == nullptr) fail("null argument");
+    LTXV_CUDA(launch_stochastic_step(latents, model_output, noise, sigma, sigma_next, n, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_decode_noise_blend(float* latents, const float* noise, float scale, int64_t n, void* stream) {
+    LTXV_TRY
+    if (latents == nullptr || noise == nullptr) fail("null argument");
+    LTXV_CUDA(launch_noise_blend(latents, noise, scale, n, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
 int ltxv_denormalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,
                              int B, int C, int64_t n_per_channel, void* stream) {
     LTXV_TRY
@@ -434,6 +447,27 @@ int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const flo
     LTXV_TRY
     if (vae == nullptr || p == nullptr || latents == nullptr || out == nullptr) fail("null argument");
     pipeline_decode(vae->model, *p, latents, out, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+int ltxv_pipeline_denoise_stochastic(ltxv_dit* dit, const ltxv_pipeline_params* p, float* latents,
+                                     const void* prompt_embeds, const float* prompt_mask, const void* negative_embeds,
+                                     const float* negative_mask, int embeds_dtype, int K, const float* step_noise,
+                                     void* stream) {
+    LTXV_TRY
+    if (dit == nullptr || p == nullptr || latents == nullptr || prompt_embeds == nullptr || step_noise == nullptr)
+        fail("null argument");
+    pipeline_denoise(dit->model, *p, latents, prompt_embeds, prompt_mask, negative_embeds, negative_mask, embeds_dtype, K,
+                     static_cast<cudaStream_t>(stream), step_noise);
+    LTXV_CATCH
+}
+int ltxv_pipeline_decode_noisy(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, const float* noise,
+                               float decode_noise_scale, float* out, void* stream) {
+    LTXV_TRY
+    if (vae == nullptr || p == nullptr || latents == nullptr || out == nullptr) fail("null argument");
+    if (noise == nullptr && decode_noise_scale != 0.0f)
+        fail("decode_noise_scale = %g needs a noise tensor (the library has no RNG of its own)", decode_noise_scale);
+    pipeline_decode(vae->model, *p, latents, out, static_cast<cudaStream_t>(stream), noise, decode_noise_scale);
     LTXV_CATCH
 }
 

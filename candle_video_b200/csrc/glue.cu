@@ -476,6 +476,24 @@ __global__ void guidance_euler_kernel(const float* __restrict__ cond, const floa
     if (latents != nullptr) latents[i] = __fadd_rn(latents[i], __fmul_rn(m, dt));
 }
 
+// stochastic branch of FlowMatchEulerDiscreteScheduler::step (scheduler.rs:557-575), noise supplied by the caller:
+//   x0 = x - sigma * v ;  x <- (1 - sigma_next) * x0 + sigma_next * noise      (every op rounded to f32 like the tensor ops)
+__global__ void stochastic_step_kernel(float* __restrict__ latents, const float* __restrict__ v,
+                                       const float* __restrict__ noise, float sigma, float sigma_next, int64_t n) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float x0 = __fsub_rn(latents[i], __fmul_rn(sigma, v[i]));
+    const float om = __fadd_rn(__fmul_rn(sigma_next, -1.0f), 1.0f);  // ns.affine(-1, 1)
+    latents[i] = __fadd_rn(__fmul_rn(om, x0), __fmul_rn(sigma_next, noise[i]));
+}
+// decode-noise blend (t2v_pipeline.rs:1055-1062): x <- x * (1 - s) + noise * s
+__global__ void noise_blend_kernel(float* __restrict__ x, const float* __restrict__ noise, float scale, int64_t n) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float om = __fadd_rn(__fmul_rn(scale, -1.0f), 1.0f);
+    x[i] = __fadd_rn(__fmul_rn(x[i], om), __fmul_rn(noise[i], scale));
+}
+
 __global__ void denorm_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ mean,
                               const float* __restrict__ std, float inv_sf, int C, int64_t n_per_c) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -662,6 +680,18 @@ cudaError_t launch_guidance_euler(const float* cond, const float* uncond, const 
         parts.n_total = n;
     }
     return launch_guidance_euler_parts(cond, uncond, pert, latents, noise_out, n, g, r, s_stg, dt, parts, s);
+}
+
+cudaError_t launch_stochastic_step(float* latents, const float* v, const float* noise, float sigma, float sigma_next,
+                                   int64_t n, cudaStream_t s) {
+    if (latents == nullptr || v == nullptr || noise == nullptr) return cudaErrorInvalidValue;
+    stochastic_step_kernel<<<blocks_for(n, 256), 256, 0, s>>>(latents, v, noise, sigma, sigma_next, n);
+    return done();
+}
+cudaError_t launch_noise_blend(float* x, const float* noise, float scale, int64_t n, cudaStream_t s) {
+    if (x == nullptr || noise == nullptr) return cudaErrorInvalidValue;
+    noise_blend_kernel<<<blocks_for(n, 256), 256, 0, s>>>(x, noise, scale, n);
+    return done();
 }
 
 cudaError_t launch_denormalize(const float* in, float* out, const float* mean, const float* std, float inv_sf, int C,

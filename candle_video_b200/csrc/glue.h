@@ -94,6 +94,14 @@ cudaError_t launch_guidance_euler_parts(const float* cond, const float* uncond, 
                                         float* noise_pred_out, int64_t n, float guidance_scale, float guidance_rescale,
                                         float stg_scale, float dt, const StatParts& parts, cudaStream_t s);
 
+// Stochastic scheduler step with CALLER-SUPPLIED noise (scheduler.rs:557-575: x0 = x - sigma v;
+// x <- (1 - sigma_next) x0 + sigma_next noise) and the decode-noise blend (t2v_pipeline.rs:1055-1062:
+// x <- x (1 - s) + noise s).  The reference draws the noise from the device RNG (Tensor::randn -> cuRAND); the drop-in
+// keeps that RNG on the Rust side and hands the tensor in, which is what makes the result reproducible.
+cudaError_t launch_stochastic_step(float* latents, const float* v, const float* noise, float sigma, float sigma_next,
+                                   int64_t n, cudaStream_t s);
+cudaError_t launch_noise_blend(float* x, const float* noise, float scale, int64_t n, cudaStream_t s);
+
 // x*std_c*(1/sf)+mean_c on [C, N] (per-channel), f32  (:573-594)
 cudaError_t launch_denormalize(const float* in, float* out, const float* mean, const float* std, float inv_sf, int C,
                                int64_t n_per_c, cudaStream_t s);

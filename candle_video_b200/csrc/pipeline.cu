@@ -57,7 +57,7 @@ void scheduler_set_timesteps(int n, const float* custom_sigmas, float mu, bool h
 
 namespace {
 struct PipeWs {
-    DevBuf cond, uncond, pert, coords, ts, scratch, unpacked, denorm, tdec;
+    DevBuf cond, uncond, pert, comb, coords, ts, scratch, unpacked, denorm, tdec;
 };
 PipeWs& ws() {
     static PipeWs w;
@@ -67,7 +67,7 @@ PipeWs& ws() {
 
 void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_params& p, float* latents,
                       const void* prompt, const float* prompt_mask, const void* negative, const float* negative_mask,
-                      int embeds_dtype, int K, cudaStream_t s) {
+                      int embeds_dtype, int K, cudaStream_t s, const float* step_noise) {
     // check_inputs (t2v_pipeline.rs:323-327)
     if (p.height % 32 != 0 || p.width % 32 != 0)
         fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
@@ -96,6 +96,7 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
     w.cond.ensure(out_bytes);
     if (do_cfg) w.uncond.ensure(out_bytes);
     if (do_stg) w.pert.ensure(out_bytes);
+    if (step_noise != nullptr) w.comb.ensure(out_bytes);
     w.coords.ensure(static_cast<size_t>(S) * 3 * 4);
     w.ts.ensure(static_cast<size_t>(n) * 4);
     w.scratch.ensure(64);
@@ -125,10 +126,21 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
             dit.forward_ctx(0, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, stg_mask.data(), 1, w.pert.p,
                             LTXV_F32, s);
         const float dt = sigmas[i + 1] - sigmas[i];  // scheduler.rs:544-549
-        LTXV_CUDA(launch_guidance_euler(w.cond.as<float>(), do_cfg ? w.uncond.as<float>() : nullptr,
-                                        do_stg ? w.pert.as<float>() : nullptr, latents, nullptr,
-                                        static_cast<int64_t>(S) * C, p.guidance_scale, p.guidance_rescale, p.stg_scale,
-                                        dt, w.scratch.as<double>(), s));
+        if (step_noise == nullptr) {
+            LTXV_CUDA(launch_guidance_euler(w.cond.as<float>(), do_cfg ? w.uncond.as<float>() : nullptr,
+                                            do_stg ? w.pert.as<float>() : nullptr, latents, nullptr,
+                                            static_cast<int64_t>(S) * C, p.guidance_scale, p.guidance_rescale,
+                                            p.stg_scale, dt, w.scratch.as<double>(), s));
+        } else {
+            // stochastic_sampling = true (scheduler.rs:557-575; preset 0.9.8-distilled, configs.rs:210): the combined
+            // velocity is materialised (in place of the conditional output), then x <- (1-s')(x - s v) + s' noise_i
+            LTXV_CUDA(launch_guidance_euler(w.cond.as<float>(), do_cfg ? w.uncond.as<float>() : nullptr,
+                                            do_stg ? w.pert.as<float>() : nullptr, nullptr, w.comb.as<float>(),
+                                            static_cast<int64_t>(S) * C, p.guidance_scale, p.guidance_rescale,
+                                            p.stg_scale, dt, w.scratch.as<double>(), s));
+            LTXV_CUDA(launch_stochastic_step(latents, w.comb.as<float>(), step_noise + static_cast<size_t>(i) * S * C,
+                                             sigmas[i], sigmas[i + 1], static_cast<int64_t>(S) * C, s));
+        }
     }
 }
 
@@ -271,7 +283,7 @@ void pipeline_denoise_parallel(LtxVideoTransformer3DModel& dit, PeerComm& comm, 
 }
 
 void pipeline_decode(AutoencoderKLLtxVideo& vae, const ltxv_pipeline_params& p, const float* latents, float* out,
-                     cudaStream_t s) {
+                     cudaStream_t s, const float* decode_noise, float decode_noise_scale) {
     if (p.height % 32 != 0 || p.width % 32 != 0)
         fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
     const int F = (p.num_frames - 1) / 8 + 1, H = p.height / 32, W = p.width / 32;
@@ -291,7 +303,10 @@ void pipeline_decode(AutoencoderKLLtxVideo& vae, const ltxv_pipeline_params& p, 
         LTXV_CUDA(cudaStreamSynchronize(s));
         t_dev = w.tdec.as<float>();
     }
-    // decode_noise_scale = 0 (the reference's device-RNG noise blend, :1055-1062, is not reproduced here)
+    // decode-noise blend (:1049-1062) with the caller's noise tensor; without one, decode_noise_scale = 0
+    if (decode_noise != nullptr && decode_noise_scale != 0.0f)
+        LTXV_CUDA(launch_noise_blend(w.denorm.as<float>(), decode_noise, decode_noise_scale,
+                                     static_cast<int64_t>(C) * F * H * W, s));
     vae.decode(w.denorm.p, LTXV_F32, t_dev, 1, F, H, W, out, LTXV_F32, /*postprocess=*/1, s);  // :1069-1070
 }
 

@@ -227,6 +227,25 @@ int ltxv_pipeline_denoise(ltxv_dit* dit, const ltxv_pipeline_params* p, float* l
  * postprocess.  latents: device f32 [S,128]; out: device f32 [3, num_frames, height, width] in 0..255. */
 int ltxv_pipeline_decode(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out, void* stream);
 
+/* ---- stochastic sampling and decode noise with CALLER-SUPPLIED noise -----------------------------
+ * The reference draws both from the device RNG (Tensor::randn -> cuRAND, scheduler.rs:566, t2v_pipeline.rs:1055); the
+ * library has no RNG of its own: the caller (the Rust pipeline, still holding Candle's generator) passes the tensors,
+ * so a run is reproducible bit for bit.  All f32, every arithmetic op rounded like the reference's tensor ops. */
+/* x0 = x - sigma v; x <- (1 - sigma_next) x0 + sigma_next noise   (scheduler.rs:557-575) */
+int ltxv_scheduler_step_stochastic(float* latents, const float* model_output, const float* noise, int64_t n, float sigma,
+                                   float sigma_next, void* stream);
+/* x <- x (1 - scale) + noise scale   (t2v_pipeline.rs:1049-1062) */
+int ltxv_decode_noise_blend(float* latents, const float* noise, float scale, int64_t n, void* stream);
+/* ltxv_pipeline_denoise with stochastic_sampling = true (preset 0.9.8-distilled, configs.rs:210):
+ * step_noise = device f32 [num_inference_steps, S, 128], slice i used by step i. */
+int ltxv_pipeline_denoise_stochastic(ltxv_dit* dit, const ltxv_pipeline_params* p, float* latents,
+                                     const void* prompt_embeds, const float* prompt_mask, const void* negative_embeds,
+                                     const float* negative_mask, int embeds_dtype, int K, const float* step_noise,
+                                     void* stream);
+/* ltxv_pipeline_decode with the decode-noise blend: noise = device f32 [128, F, H, W] (NULL only with scale 0). */
+int ltxv_pipeline_decode_noisy(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, const float* noise,
+                               float decode_noise_scale, float* out, void* stream);
+
 /* ------------------------------------------------------------- multi-GPU ------------------------------------------ */
 /* One process per GPU.  The reference has no distributed code at all; these entry
  * points add the sharding BASELINE.json's north_star names: CFG cond/uncond split across two rank groups, Ulysses

@@ -693,6 +693,24 @@ def euler_step(sample: Tensor, model_output: Tensor, sigma: float, sigma_next: f
     return sample.to(F32) + model_output.to(F32) * dt
 
 
+def stochastic_step(sample: Tensor, model_output: Tensor, noise: Tensor, sigma: float, sigma_next: float) -> Tensor:
+    """FlowMatchEulerDiscreteScheduler::step, stochastic branch (scheduler.rs:557-575) with the noise passed in
+    (the reference draws it with Tensor::randn on the device): x0 = x - sigma v; (1 - sigma_next) x0 + sigma_next n."""
+    sample = sample.to(F32)
+    cs = torch.tensor(sigma, dtype=F32)
+    ns = torch.tensor(sigma_next, dtype=F32)
+    x0 = sample - cs * model_output.to(F32)
+    one_minus = ns * -1.0 + 1.0
+    return one_minus * x0 + ns * noise.to(F32)
+
+
+def decode_noise_blend(latents: Tensor, noise: Tensor, scale: float) -> Tensor:
+    """t2v_pipeline.rs:1049-1062: latents * (1 - scale) + noise * scale (f32 here; model dtype in a bf16 run)."""
+    sc = torch.tensor(scale, dtype=F32)
+    one_minus = sc * -1.0 + 1.0
+    return latents.to(F32) * one_minus + noise.to(F32) * sc
+
+
 def denormalize_latents(latents: Tensor, mean: Tensor, std: Tensor, scaling_factor: float) -> Tensor:
     """t2v_pipeline.rs:573-594."""
     c = latents.shape[1]

@@ -75,3 +75,19 @@ def test_denormalize_and_postprocess_bit_exact(cuda):
         assert torch.equal(out.cpu(), ref)
     v = torch.randn(1, 3, 9, 64, 96, generator=gen) * 1.5
     assert torch.equal(cv.postprocess_video(v.to(cuda)).cpu(), O.postprocess_video(v))
+
+
+def test_stochastic_step_and_decode_noise_bit_exact(cuda):
+    """scheduler.rs:557-575 and t2v_pipeline.rs:1049-1062 with caller-supplied noise: f32, bit-exact vs the oracle."""
+    import candle_video_b200 as cv
+    g = torch.Generator().manual_seed(21)
+    x, v, n = (torch.randn(4992, 128, generator=g) for _ in range(3))
+    for sigma, sigma_next in [(1.0, 0.9375), (0.421, 0.25), (0.1, 0.0)]:
+        ref = O.stochastic_step(x, v, n, sigma, sigma_next)
+        out = cv.scheduler_step_stochastic(x.to(cuda).clone(), v.to(cuda), n.to(cuda), sigma, sigma_next)
+        assert torch.equal(out.cpu(), ref)
+    ref = O.decode_noise_blend(x, n, 0.025)
+    out = x.to(cuda).clone()
+    import ctypes as C
+    cv._check(cv.lib().ltxv_decode_noise_blend(cv._ptr(out), cv._ptr(n.to(cuda)), 0.025, out.numel(), cv._stream()))
+    assert torch.equal(out.cpu(), ref)

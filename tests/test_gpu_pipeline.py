@@ -95,3 +95,52 @@ def test_pipeline_rejects_bad_resolution(cuda):
     params = cv.PipelineParams(height=250, width=256, num_frames=9, num_inference_steps=2, guidance_scale=1.0)
     with pytest.raises(cv.LtxvError, match="divisible by 32"):
         cv.pipeline_denoise(m, params, torch.zeros(64, 128, device=cuda), torch.zeros(4, 256, device=cuda), None)
+
+
+def test_stochastic_denoise_and_noisy_decode_match_oracle(cuda):
+    """stochastic_sampling = true (preset 0.9.8-distilled, configs.rs:210) and decode_noise_scale = 0.025
+    (configs.rs:234) with the noise tensors injected on both sides."""
+    import candle_video_b200 as cv
+    from tests.test_gpu_dit import build, small_cfg
+    cfg = small_cfg(layers=2)
+    m, w = build(cfg)
+    m.set_skip_block_list([])
+    height, width, frames, fps, K, n_steps = 128, 160, 9, 25, 16, 3
+    F, H, W = 2, 4, 5
+    S = F * H * W
+    gen = torch.Generator().manual_seed(31)
+    lat = torch.randn(1, S, 128, generator=gen)
+    pe = torch.randn(1, K, 256, generator=gen)
+    pm = torch.ones(1, K)
+    noise = torch.randn(n_steps, S, 128, generator=gen)
+    sig, ts = O.scheduler_set_timesteps(n_steps, O.calculate_shift(S), None, 0.1)
+    coords = O.video_coords(1, F, H, W, fps)
+    ref = lat.clone()
+    for i, t in enumerate(ts):  # distilled: guidance 1 -> one forward per step
+        v = O.dit_forward(w, cfg, ref, pe, torch.tensor([float(t)]), pm, num_frames=F, height=H, width=W,
+                          video_coords=coords, timestep_to_bf16=True)
+        ref = O.stochastic_step(ref, v, noise[i][None], sig[i], sig[i + 1])
+    params = cv.PipelineParams(height=height, width=width, num_frames=frames, frame_rate=fps,
+                               num_inference_steps=n_steps, guidance_scale=1.0, guidance_rescale=0.0, stg_scale=0.0)
+    out = lat[0].to(cuda).contiguous()
+    cv.pipeline_denoise_stochastic(m, params, out, pe.to(cuda), pm.to(cuda), noise.to(cuda).contiguous())
+    e = rel_l2(out, ref[0])
+    print(f"stochastic denoise rel_l2={e:.3e}")
+    assert e <= 2e-2
+    # noisy decode
+    from tests.test_gpu_vae import build as build_vae
+    vm, vw, vcfg = build_vae()
+    dn = torch.randn(128, F, H, W, generator=gen)
+    z = O.denormalize_latents(O.unpack_latents(lat, F, H, W), torch.zeros(128), torch.ones(128), 1.0)
+    z = O.decode_noise_blend(z, dn[None], 0.025)
+    vref = O.postprocess_video(O.vae_decode(vw, vcfg, z, torch.tensor([0.05])))
+    vout = cv.pipeline_decode(vm, cv.PipelineParams(height=height, width=width, num_frames=frames, decode_timestep=0.05),
+                              lat[0].to(cuda).contiguous(), decode_noise=dn.to(cuda), decode_noise_scale=0.025)
+    mse = float(((vout.cpu().double() - vref[0].double()) ** 2).mean())
+    import math
+    psnr = 99.0 if mse == 0 else 10 * math.log10(255.0 ** 2 / mse)
+    print(f"noisy decode PSNR = {psnr:.1f} dB")
+    assert psnr >= 35.0
+    with pytest.raises(cv.LtxvError, match="noise tensor"):
+        cv.pipeline_decode(vm, cv.PipelineParams(height=height, width=width, num_frames=frames), lat[0].to(cuda).contiguous(),
+                           decode_noise_scale=0.025)
