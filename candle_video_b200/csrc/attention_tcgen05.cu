@@ -1258,7 +1258,7 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 
 std::atomic<uint64_t> g_attn_launches{0};
 
-// per-device scratch for the tail split (148 work items x 256 rows x 17 float4 = 10.3 MB) + ticket counters
+// per-device scratch for the tail split + ticket counters
 struct SplitScratch {
     float* scratch = nullptr;
     int* counters = nullptr;
@@ -1274,7 +1274,8 @@ cudaError_t split_scratch(SplitScratch** out) {
     if (s.scratch == nullptr) {
         e = cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        e = cudaMalloc(&s.scratch, static_cast<size_t>(s.n_sm) * 256 * kSplitCols4 * sizeof(float4));
+        // up to (n_sm - 1) tail units x kMaxSplit key ranges x 256 rows x 17 float4 = 82 MB on a 148-SM part
+        e = cudaMalloc(&s.scratch, static_cast<size_t>(s.n_sm) * kMaxSplit * 256 * kSplitCols4 * sizeof(float4));
         if (e != cudaSuccess) return e;
         e = cudaMalloc(&s.counters, static_cast<size_t>(s.n_sm) * sizeof(int));
         if (e != cudaSuccess) return e;
@@ -1313,12 +1314,23 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     const int n_tiles = (p.Skv + kTileKV - 1) / kTileKV;
     const int rem = sp.n_units % ss->n_sm;
     if (rem != 0 && getenv("LTXV_ATTN_NOSPLIT") == nullptr) {
-        int ns = ss->n_sm / rem;                // key ranges per tail unit so that the tail wave fills the SMs
-        if (ns > n_tiles / 4) ns = n_tiles / 4;  // keep >= 4 key tiles per range (pipeline fill / drain)
-        if (ns > kMaxSplit) ns = kMaxSplit;
-        if (const char* ev = getenv("LTXV_ATTN_NSPLIT")) ns = atoi(ev) < ns ? atoi(ev) : ns;  // experiment knob
-        if (ns >= 2) {
-            sp.nsplit = ns;
+        // key ranges per tail unit: minimise the length of the tail, ceil(rem * ns / SMs) rounds of 1/ns unit each
+        // (plus a few percent per extra range for its pipeline fill and the merge), keeping >= 4 key tiles per range
+        int max_ns = n_tiles / 4;
+        if (max_ns > kMaxSplit) max_ns = kMaxSplit;
+        if (const char* ev = getenv("LTXV_ATTN_NSPLIT")) max_ns = atoi(ev) < max_ns ? atoi(ev) : max_ns;  // experiment knob
+        int best_ns = 1;
+        double best = 1.0;
+        for (int ns = 2; ns <= max_ns; ++ns) {
+            const double rounds = static_cast<double>((rem * ns + ss->n_sm - 1) / ss->n_sm);
+            const double cost = rounds / ns + 0.03 * (ns - 1);
+            if (cost < best - 1e-9) {
+                best = cost;
+                best_ns = ns;
+            }
+        }
+        if (best_ns >= 2) {
+            sp.nsplit = best_ns;
             sp.n_split_units = rem;
         }
     }

@@ -284,17 +284,68 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
                                              void* out, int out_dtype, cudaStream_t s) {
     if (!finalized_) finalize();
     if (slot < 0 || slot > kNumSlots || !ctx_[slot].valid) fail("context slot %d has not been prepared", slot);
+    forward_impl(&ctx_[slot], 1, hidden, hidden_dtype, timestep_dev, S, F, H, W, rope_scale3_host, video_coords, skip_mask,
+                 skip_mask_stride, out, out_dtype, s);
+}
+
+void LtxVideoTransformer3DModel::prepare_pair(int slot_a, int slot_b, cudaStream_t s) {
+    if (slot_a < 0 || slot_a > kNumSlots || slot_b < 0 || slot_b > kNumSlots || !ctx_[slot_a].valid || !ctx_[slot_b].valid)
+        fail("both context slots of a pair must have been prepared");
+    const DitContext& a = ctx_[slot_a];
+    const DitContext& b = ctx_[slot_b];
+    if (a.K != b.K) fail("the two contexts of a pair must have the same text length (%d vs %d)", a.K, b.K);
+    LTXV_CUDA(cudaSetDevice(device_));
+    const int D = inner_dim(), L = cfg_.num_layers, K = a.K;
+    const size_t per = static_cast<size_t>(K) * 2 * D * 2;  // bytes of one [K, 2D] bf16 block
+    pair_kv_.ensure(static_cast<size_t>(L) * 2 * per);
+    for (int l = 0; l < L; ++l) {
+        char* dst = static_cast<char*>(pair_kv_.p) + static_cast<size_t>(l) * 2 * per;
+        LTXV_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(a.kv.p) + l * per, per, cudaMemcpyDeviceToDevice, s));
+        LTXV_CUDA(cudaMemcpyAsync(dst + per, static_cast<const char*>(b.kv.p) + l * per, per, cudaMemcpyDeviceToDevice, s));
+    }
+    pair_has_mask_ = a.has_mask || b.has_mask;
+    if (pair_has_mask_) {
+        pair_bias_.ensure(static_cast<size_t>(2) * K * 4);
+        const DitContext* c2[2] = {&a, &b};
+        for (int i = 0; i < 2; ++i) {
+            float* dst = pair_bias_.as<float>() + static_cast<size_t>(i) * K;
+            if (c2[i]->has_mask) LTXV_CUDA(cudaMemcpyAsync(dst, c2[i]->mask_bias.p, K * 4, cudaMemcpyDeviceToDevice, s));
+            else LTXV_CUDA(cudaMemsetAsync(dst, 0, K * 4, s));
+        }
+    }
+    pair_K_ = K;
+    pair_valid_ = true;
+}
+
+void LtxVideoTransformer3DModel::forward_pair(const void* hidden, int hidden_dtype, const float* timestep_dev, int S,
+                                              int F, int H, int W, const float* rope_scale3_host,
+                                              const float* video_coords, void* out, int out_dtype, cudaStream_t s) {
+    if (!finalized_) finalize();
+    if (!pair_valid_) fail("prepare_pair has not been called");
+    if (comm_ != nullptr) fail("the batched CFG pair forward is a single-GPU path (the ranks split the branches instead)");
+    forward_impl(nullptr, 2, hidden, hidden_dtype, timestep_dev, S, F, H, W, rope_scale3_host, video_coords, nullptr, 0, out,
+                 out_dtype, s);
+}
+
+// nb = 1: one batch entry against `ctx1`.  nb = 2: the CFG pair (pair_kv_ / pair_bias_); the two entries share hidden
+// states, timestep (hence the AdaLN modulation) and the RoPE table; all token-local kernels simply see M = 2S rows.
+void LtxVideoTransformer3DModel::forward_impl(const DitContext* ctx1, int nb, const void* hidden, int hidden_dtype,
+                                              const float* timestep_dev, int S, int F, int H, int W,
+                                              const float* rope_scale3_host, const float* video_coords,
+                                              const float* skip_mask, int skip_mask_stride, void* out, int out_dtype,
+                                              cudaStream_t s) {
     if (S <= 0) fail("sequence length must be positive");
     if (video_coords == nullptr && static_cast<int64_t>(F) * H * W != static_cast<int64_t>(S) * sp_count_)
         fail("num_frames*height*width (%d*%d*%d) must equal the sequence length %d when video_coords is not given", F, H,
              W, S * sp_count_);
     if (out_dtype != LTXV_F32 && out_dtype != LTXV_BF16) fail("unsupported output dtype %d", out_dtype);
     LTXV_CUDA(cudaSetDevice(device_));
-    const DitContext& ctx = ctx_[slot];
     const int D = inner_dim();
     const int L = cfg_.num_layers;
     const int heads = cfg_.num_attention_heads, hd = cfg_.attention_head_dim;
-    ensure_workspace(S);
+    const int M = nb * S;  // rows of every token-local kernel
+    const int ctxK = nb == 1 ? ctx1->K : pair_K_;
+    ensure_workspace(M);
 
     float* sm = small_.as<float>();
     float* tp = sm;                    // [256]
@@ -337,7 +388,8 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
         fail("unsupported hidden_states dtype %d", hidden_dtype);
     }
     float* x = x_.as<float>();
-    gemm(a_in, S, proj_in_, S, EPI_STORE_F32, ACT_NONE, x, nullptr, nullptr, s);
+    for (int i = 0; i < nb; ++i)  // the pair shares its hidden states: same projection into both halves of x
+        gemm(a_in, S, proj_in_, S, EPI_STORE_F32, ACT_NONE, x + static_cast<size_t>(i) * S * D, nullptr, nullptr, s);
 
     const float attn_scale = 1.0f / sqrtf(static_cast<float>(hd));
     for (int l = 0; l < L; ++l) {
@@ -349,19 +401,19 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
         if (m == 1.0f) continue;  // x*(1-1) + orig*1 == orig  (:1112-1123)
         const bool blend = (m != 0.0f);
         if (blend) {
-            orig_.ensure(static_cast<size_t>(S) * D * 4);
-            LTXV_CUDA(cudaMemcpyAsync(orig_.p, x, static_cast<size_t>(S) * D * 4, cudaMemcpyDeviceToDevice, s));
+            orig_.ensure(static_cast<size_t>(M) * D * 4);
+            LTXV_CUDA(cudaMemcpyAsync(orig_.p, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
         }
         const DitBlockW& b = blocks_[l];
         const float* a6 = ada + static_cast<size_t>(l) * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
 
         // --- self-attention ---
-        LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 1 * D, a6 + 0 * D, S, D, cfg_.norm_eps, NORM_RMS, s));
-        gemm(h_.p, S, b.qkv1, S, EPI_STORE_BF16, ACT_NONE, qkv_.p, nullptr, nullptr, s);
+        LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 1 * D, a6 + 0 * D, M, D, cfg_.norm_eps, NORM_RMS, s));
+        gemm(h_.p, M, b.qkv1, M, EPI_STORE_BF16, ACT_NONE, qkv_.p, nullptr, nullptr, s);
         const void* attn1_out = attn_.p;
         if (!sp) {
-            LTXV_CUDA(launch_qk_pair_norm_rope(qkv_.p, 3 * D, S, D, b.norm_q1, b.norm_k1, 1e-5f, cos_.as<float>(),
-                                               sin_.as<float>(), s));
+            LTXV_CUDA(launch_qk_pair_norm_rope(qkv_.p, 3 * D, M, D, b.norm_q1, b.norm_k1, 1e-5f, cos_.as<float>(),
+                                               sin_.as<float>(), s, S));
             AttnParams ap{};
             ap.q = ap.k = ap.v = qkv_.p;
             ap.ldq = ap.ldk = ap.ldv = 3 * D;
@@ -371,7 +423,7 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
             ap.out = attn_.p;
             ap.ldo = D;
             ap.kv_bias = nullptr;
-            ap.B = 1;
+            ap.B = nb;
             ap.H = heads;
             ap.Sq = S;
             ap.Skv = S;
@@ -409,13 +461,15 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
             comm_->barrier(s, 1, sp_first_, spn);
             attn1_out = comm_->local(sp_attn_off_);
         }
-        gemm(attn1_out, S, b.out1, S, EPI_RESIDUAL_F32, ACT_NONE, xb_.p, x, a6 + 2 * D, s);  // x += gate_msa * attn1
+        gemm(attn1_out, M, b.out1, M, EPI_RESIDUAL_F32, ACT_NONE, xb_.p, x, a6 + 2 * D, s);  // x += gate_msa * attn1
 
         // --- cross-attention (no norm, no gate, no RoPE; :903-909) ---
-        gemm(xb_.p, S, b.q2, S, EPI_STORE_BF16, ACT_NONE, q2_.p, nullptr, nullptr, s);
-        LTXV_CUDA(launch_qk_norm_rope(q2_.p, D, 0, S, D, b.norm_q2, 1e-5f, nullptr, nullptr, s));
+        gemm(xb_.p, M, b.q2, M, EPI_STORE_BF16, ACT_NONE, q2_.p, nullptr, nullptr, s);
+        LTXV_CUDA(launch_qk_norm_rope(q2_.p, D, 0, M, D, b.norm_q2, 1e-5f, nullptr, nullptr, s));
         {
-            const __nv_bfloat16* kv = ctx.kv.as<__nv_bfloat16>() + static_cast<size_t>(l) * ctx.K * 2 * D;
+            const __nv_bfloat16* kv =
+                nb == 1 ? ctx1->kv.as<__nv_bfloat16>() + static_cast<size_t>(l) * ctxK * 2 * D
+                        : pair_kv_.as<__nv_bfloat16>() + static_cast<size_t>(l) * 2 * ctxK * 2 * D;  // [2][K, 2D]
             AttnParams ap{};
             ap.q = q2_.p;
             ap.k = ap.v = kv;
@@ -426,31 +480,32 @@ void LtxVideoTransformer3DModel::forward_ctx(int slot, const void* hidden, int h
             ap.v_col0 = D;
             ap.out = attn_.p;
             ap.ldo = D;
-            ap.kv_bias = ctx.has_mask ? ctx.mask_bias.as<float>() : nullptr;
-            ap.B = 1;
+            ap.kv_bias = nb == 1 ? (ctx1->has_mask ? ctx1->mask_bias.as<float>() : nullptr)
+                                 : (pair_has_mask_ ? pair_bias_.as<float>() : nullptr);
+            ap.B = nb;
             ap.H = heads;
             ap.Sq = S;
-            ap.Skv = ctx.K;
+            ap.Skv = ctxK;
             ap.D = hd;
             ap.scale = attn_scale;
             LTXV_CUDA(launch_attention(ap, s));
         }
-        gemm(attn_.p, S, b.out2, S, EPI_RESIDUAL_F32, ACT_NONE, nullptr, x, nullptr, s);  // x += attn2
+        gemm(attn_.p, M, b.out2, M, EPI_RESIDUAL_F32, ACT_NONE, nullptr, x, nullptr, s);  // x += attn2
 
         // --- feed-forward ---
-        LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 4 * D, a6 + 3 * D, S, D, cfg_.norm_eps, NORM_RMS, s));
-        gemm(h_.p, S, b.ff1, S, EPI_STORE_BF16, ACT_GELU_TANH, ff_.p, nullptr, nullptr, s);
-        gemm(ff_.p, S, b.ff2, S, EPI_RESIDUAL_F32, ACT_NONE, nullptr, x, a6 + 5 * D, s);  // x += gate_mlp * ff
+        LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 4 * D, a6 + 3 * D, M, D, cfg_.norm_eps, NORM_RMS, s));
+        gemm(h_.p, M, b.ff1, M, EPI_STORE_BF16, ACT_GELU_TANH, ff_.p, nullptr, nullptr, s);
+        gemm(ff_.p, M, b.ff2, M, EPI_RESIDUAL_F32, ACT_NONE, nullptr, x, a6 + 5 * D, s);  // x += gate_mlp * ff
 
-        if (blend) LTXV_CUDA(launch_blend(x, orig_.as<float>(), m, static_cast<int64_t>(S) * D, s));
+        if (blend) LTXV_CUDA(launch_blend(x, orig_.as<float>(), m, static_cast<int64_t>(M) * D, s));
     }
 
     // ---- output head (:1126-1163): LayerNorm (no affine) -> (1+scale) x + shift -> proj_out ----
-    LTXV_CUDA(launch_norm_modulate(x, h_.p, fin + D, fin, S, D, 1e-6f, NORM_LAYER, s));
+    LTXV_CUDA(launch_norm_modulate(x, h_.p, fin + D, fin, M, D, 1e-6f, NORM_LAYER, s));
     if (out_dtype == LTXV_F32) {
-        gemm(h_.p, S, proj_out_, S, EPI_STORE_F32, ACT_NONE, out, nullptr, nullptr, s);
+        gemm(h_.p, M, proj_out_, M, EPI_STORE_F32, ACT_NONE, out, nullptr, nullptr, s);
     } else {
-        gemm(h_.p, S, proj_out_, S, EPI_STORE_BF16, ACT_NONE, out, nullptr, nullptr, s);
+        gemm(h_.p, M, proj_out_, M, EPI_STORE_BF16, ACT_NONE, out, nullptr, nullptr, s);
     }
 }
 

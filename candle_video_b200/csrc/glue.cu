@@ -132,7 +132,7 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int row
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 qk_pair_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, int D, const float* __restrict__ wq,
                          const float* __restrict__ wk, float eps, const float* __restrict__ cos_t,
-                         const float* __restrict__ sin_t) {
+                         const float* __restrict__ sin_t, int table_rows) {
     griddep_launch_dependents();
     griddep_wait();
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -141,8 +141,9 @@ qk_pair_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, in
     const int nv = D >> 3;
     uint4* xq = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
     uint4* xk = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + D);
-    const float4* c4 = reinterpret_cast<const float4*>(cos_t + static_cast<int64_t>(row) * (D >> 1));
-    const float4* s4 = reinterpret_cast<const float4*>(sin_t + static_cast<int64_t>(row) * (D >> 1));
+    const int trow = row % table_rows;  // batch entries share one [table_rows, D/2] table
+    const float4* c4 = reinterpret_cast<const float4*>(cos_t + static_cast<int64_t>(trow) * (D >> 1));
+    const float4* s4 = reinterpret_cast<const float4*>(sin_t + static_cast<int64_t>(trow) * (D >> 1));
     float sq = 0.f, sk = 0.f;
     for (int i = lane; i < nv; i += 32) {
         const uint4 a = xq[i], b = xk[i];
@@ -545,11 +546,12 @@ cudaError_t launch_qk_norm_rope(void* x, int64_t ld, int col0, int rows, int D, 
 }
 
 cudaError_t launch_qk_pair_norm_rope(void* x, int64_t ld, int rows, int D, const float* wq, const float* wk, float eps,
-                                     const float* cos_t, const float* sin_t, cudaStream_t s) {
+                                     const float* cos_t, const float* sin_t, cudaStream_t s, int table_rows) {
     if (D % 8 != 0 || ld % 8 != 0 || ld < 2 * D || cos_t == nullptr || sin_t == nullptr) return cudaErrorInvalidValue;
+    if (table_rows <= 0) table_rows = rows;
     ProfScope prof(PROF_QK_ROPE, 2.0 * rows * D * 4 + 2.0 * rows * (D / 2) * 4, s);  // q,k bf16 in+out, cos/sin f32 once
     launch_pdl(qk_pair_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
-               reinterpret_cast<__nv_bfloat16*>(x), ld, rows, D, wq, wk, eps, cos_t, sin_t);
+               reinterpret_cast<__nv_bfloat16*>(x), ld, rows, D, wq, wk, eps, cos_t, sin_t, table_rows);
     return done();
 }
 

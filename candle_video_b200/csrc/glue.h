@@ -28,7 +28,8 @@ cudaError_t launch_rope_table(const float* coords, int F, int H, int W, const fl
 // q (cols [0,D)) and k (cols [D,2D)) of a fused projection buffer in ONE launch: same math as two launch_qk_norm_rope
 // calls, the cos/sin row of a token is read once for both.
 cudaError_t launch_qk_pair_norm_rope(void* x_bf16, int64_t ld, int rows, int D, const float* wq, const float* wk,
-                                     float eps, const float* cos_t, const float* sin_t, cudaStream_t s);
+                                     float eps, const float* cos_t, const float* sin_t, cudaStream_t s,
+                                     int table_rows = 0 /* rows of the cos/sin table (batch entries share it); 0 = rows */);
 
 // Ulysses scatter fused with q/k RMS-norm + RoPE: local fused projections x [rows, 3D] (q | k | v) are normed /
 // rotated (q, k) or copied (v) and written head-group-wise into the peers' [S_total, 3*D/nranks] buffers:

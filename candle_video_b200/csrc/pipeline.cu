@@ -57,7 +57,7 @@ void scheduler_set_timesteps(int n, const float* custom_sigmas, float mu, bool h
 
 namespace {
 struct PipeWs {
-    DevBuf cond, uncond, pert, comb, coords, ts, scratch, unpacked, denorm, tdec;
+    DevBuf cond, uncond, pert, comb, pair, coords, ts, scratch, unpacked, denorm, tdec;
 };
 PipeWs& ws() {
     static PipeWs w;
@@ -108,6 +108,19 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
 
     dit.prepare_context(0, prompt, embeds_dtype, prompt_mask, K, s);
     if (do_cfg) dit.prepare_context(1, negative, embeds_dtype, negative_mask, K, s);
+    // The reference runs the CFG branches as sequential B = 1 forwards (:878-907).  They share latents, timestep and
+    // coordinates, so here they run as ONE forward over 2S tokens (uncond rows first): same per-row arithmetic, better
+    // tile occupancy, weights streamed once.  LTXV_NO_CFG_BATCH=1 restores the sequential order.
+    static const bool batch_cfg = getenv("LTXV_NO_CFG_BATCH") == nullptr;
+    const bool pair = do_cfg && batch_cfg;
+    float* out_uncond = do_cfg ? w.uncond.as<float>() : nullptr;
+    float* out_cond = w.cond.as<float>();
+    if (pair) {
+        dit.prepare_pair(1, 0, s);
+        w.pair.ensure(2 * out_bytes);
+        out_uncond = w.pair.as<float>();
+        out_cond = w.pair.as<float>() + static_cast<size_t>(S) * C;
+    }
 
     std::vector<float> stg_mask;
     if (do_stg) {  // :911-923, mask [num_layers, b=1]: 1 = skip
@@ -119,22 +132,26 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
     const float* coords = w.coords.as<float>();
     for (int i = 0; i < n; ++i) {
         const float* t_dev = w.ts.as<float>() + i;
-        if (do_cfg)
-            dit.forward_ctx(1, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, nullptr, 1, w.uncond.p, LTXV_F32, s);
-        dit.forward_ctx(0, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, nullptr, 1, w.cond.p, LTXV_F32, s);
+        if (pair) {
+            dit.forward_pair(latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, w.pair.p, LTXV_F32, s);
+        } else {
+            if (do_cfg)
+                dit.forward_ctx(1, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, nullptr, 1, out_uncond, LTXV_F32, s);
+            dit.forward_ctx(0, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, nullptr, 1, out_cond, LTXV_F32, s);
+        }
         if (do_stg)
             dit.forward_ctx(0, latents, LTXV_F32, t_dev, S, F, H, W, nullptr, coords, stg_mask.data(), 1, w.pert.p,
                             LTXV_F32, s);
         const float dt = sigmas[i + 1] - sigmas[i];  // scheduler.rs:544-549
         if (step_noise == nullptr) {
-            LTXV_CUDA(launch_guidance_euler(w.cond.as<float>(), do_cfg ? w.uncond.as<float>() : nullptr,
+            LTXV_CUDA(launch_guidance_euler(out_cond, out_uncond,
                                             do_stg ? w.pert.as<float>() : nullptr, latents, nullptr,
                                             static_cast<int64_t>(S) * C, p.guidance_scale, p.guidance_rescale,
                                             p.stg_scale, dt, w.scratch.as<double>(), s));
         } else {
             // stochastic_sampling = true (scheduler.rs:557-575; preset 0.9.8-distilled, configs.rs:210): the combined
             // velocity is materialised (in place of the conditional output), then x <- (1-s')(x - s v) + s' noise_i
-            LTXV_CUDA(launch_guidance_euler(w.cond.as<float>(), do_cfg ? w.uncond.as<float>() : nullptr,
+            LTXV_CUDA(launch_guidance_euler(out_cond, out_uncond,
                                             do_stg ? w.pert.as<float>() : nullptr, nullptr, w.comb.as<float>(),
                                             static_cast<int64_t>(S) * C, p.guidance_scale, p.guidance_rescale,
                                             p.stg_scale, dt, w.scratch.as<double>(), s));
