@@ -15,6 +15,7 @@
 #include "profile.h"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace ltxv {
 
@@ -470,6 +471,201 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
+
+// ================================================================================================
+// CTA-pair variant: one 256 x 256 output tile per cluster of two CTAs (cta_group::2).
+// The single-CTA kernel above moves 48 KB of operands through shared memory per 128x256x64 step twice (TMA write,
+// UMMA read): ~190 B/clk against ~128 B/clk of shared-memory bandwidth, i.e. it is shared-memory bound at ~2/3 of the
+// tensor peak (ncu: tensor pipe 63-69 % active).  In a pair each CTA stages 128 rows of A and HALF of the 256 B rows
+// (32 KB per step) and the pair's tensor cores share the B halves: per-CTA traffic drops by a third and six stages fit.
+// Roles per CTA as above; only the leader CTA's warp 1 issues MMAs; both CTAs run TMA producers and epilogues.
+// ================================================================================================
+template <int BN>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
+struct PairCfg {
+    static constexpr int kBBytes = (BN / 2) * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;  // 32 KB (BN = 256) / 24 KB (BN = 128)
+    static constexpr int kStages = BN == 256 ? 6 : 8;
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiStageBytes;
+    static_assert(BN == 256 || BN == 128, "pair tile width");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ GemmParams p) {
+    using PC = PairCfg<BN>;
+    constexpr int kPairBlockN = BN;
+    constexpr int kPairBBytes = PC::kBBytes;
+    constexpr int kPairStageBytes = PC::kStageBytes;
+    constexpr int kPairStages = PC::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kPairStages * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+    uint64_t* full_bar = bars;                       // leader's copy is the live one (tx from both CTAs)
+    uint64_t* empty_bar = bars + kPairStages;        // both copies live (multicast commit)
+    uint64_t* tmem_full_bar = bars + 2 * kPairStages;      // [2] both copies live (multicast commit)
+    uint64_t* tmem_empty_bar = bars + 2 * kPairStages + 2;  // [2] leader's copy: 8 arrivals (4 epilogue warps x 2 CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    const int num_m = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row tiles
+    const int num_n = (p.N + kPairBlockN - 1) / kPairBlockN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = p.num_k_blocks;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int i = 0; i < kPairStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc_2sm<PC::kTmemCols>(tmem_slot);
+    tcgen05_fence_before();
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = (tile % num_m) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
+                const int n0 = (tile / num_m) * kPairBlockN + static_cast<int>(rank) * (kPairBlockN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);  // bytes of BOTH CTAs
+                    int a_row = m0, a_col = kb * kBlockK;
+                    if (p.conv) {
+                        const int tap = kb / p.cin_blocks;
+                        a_row += p.tap_off[tap];
+                        a_col = (kb - tap * p.cin_blocks) * kBlockK;
+                    }
+                    tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], a_col, a_row);
+                    tma_load_2d_2sm(smem_b + stage * kPairBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
+                    if (++stage == kPairStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== UMMA issuer (leader CTA only) =====================
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, kPairBlockN, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kPairBlockN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * kPairBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(a_addr + k * kUmmaK * 2, 1024, 0);
+                        const uint64_t db = make_smem_desc_sw128(b_addr + k * kUmmaK * 2, 1024, 0);
+                        umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty_bar[stage]);  // frees the stage in BOTH CTAs once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit_2sm(&tmem_full_bar[acc]);
+                    if (++stage == kPairStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue (both CTAs: this CTA's 128 rows of the tile) =====================
+        const int quad = warp_idx & 3;
+        float* stage_buf = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + 256) + quad * (32 * kEpiRowFloats);
+        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32) &&
+                               (p.N % 32 == 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_cta0 = (tile % num_m) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
+            const int n0 = (tile / num_m) * kPairBlockN;
+            const int m_warp0 = m_cta0 + quad * 32;
+            const RowCtx rc = make_row_ctx(p, m_warp0 + lane);
+            float4 res_a[8], res_b[8];
+            const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
+            if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kPairBlockN;
+            auto chunk = [&](int c, const float4 (&res)[8]) {
+                const int col0 = n0 + c * 32;
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (c == kPairBlockN / 32 - 1) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+                }
+                if (col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage_buf, res);
+                    else epilogue_chunk(p, rc, col0, v);
+                }
+            };
+#pragma unroll 1
+            for (int c = 0; c < kPairBlockN / 32; c += 2) {
+                if (prefetch_res) epilogue_load_residual(p, m_warp0, n0 + (c + 1) * 32, lane, res_b);
+                chunk(c, res_a);
+                if (prefetch_res && c + 2 < kPairBlockN / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
+                chunk(c + 1, res_b);
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();  // neither CTA leaves while its peer may still touch its barriers / shared memory
+    if (warp_idx == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm<PC::kTmemCols>(tmem_base);
+    }
+}
+
 std::atomic<uint64_t> g_launches{0};
 
 template <int BLOCK_N>
@@ -506,21 +702,60 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
     return cudaGetLastError();
 }
 
+
+template <int BN>
+cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
+    using PC = PairCfg<BN>;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             PC::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    CUtensorMap ta, tb;
+    cudaError_t e = make_tensor_map_2d_bf16(&ta, ops.a, ops.a_rows, ops.a_cols, kBlockM, kBlockK);
+    if (e != cudaSuccess) return e;
+    e = make_tensor_map_2d_bf16(&tb, ops.b, ops.b_rows, ops.b_cols, BN / 2, kBlockK);
+    if (e != cudaSuccess) return e;
+    const int num_m = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
+    const int num_n = (p.N + BN - 1) / BN;
+    const int tiles = num_m * num_n;
+    const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+    {
+        double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
+        if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;
+        ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
+        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN>, dim3(2 * clusters), dim3(kThreads), PC::kSmemBytes, stream,
+                                    ta, tb, p);
+        if (le != cudaSuccess) return le;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 uint64_t gemm_launch_count() { return g_launches.load(); }
 
 cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int block_n, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
+    if (block_n == -2) return launch_pair_impl<256>(ops, p, stream);
+    if (block_n == -3) return launch_pair_impl<128>(ops, p, stream);
     if (block_n == 0) {
-        // pick the tile width that minimises (rounds over 148 SMs) x (tile cost ~ BLOCK_N)
+        // Pick the kernel / tile width that minimises (rounds over the SMs) x (per-SM tile area) / (relative rate of
+        // that tile shape).  Rates from the isolated measurements at K = 8192 (profiles/r01_gemm_*): the CTA-pair
+        // kernel (256x256 per cluster = 128x256 per SM) 1.00, single-CTA 128x256 0.94, 128x192 0.88, 128x128 0.75
+        // (shared-memory bound), 128x64 0.50.
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int cands[4] = {256, 192, 128, 64};
-        // relative cost of one tile per k-block, from the measured tensor-pipe activity of each width
-        // (profiles/r01_ncu_full_*.csv: 63 % at 256, 57 % at 192, 43 % at 128: narrow tiles are smem-bandwidth bound)
-        const double tile_cost[4] = {1.00, 0.83, 0.73, 0.50};
+        const double rate[4] = {0.94, 0.88, 0.75, 0.50};
         double best = 1e30;
         const int num_m = (p.M + kBlockM - 1) / kBlockM;
         for (int i = 0; i < 4; ++i) {
@@ -528,11 +763,31 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             if (c > 64 && p.N <= c / 2) continue;
             const int tiles = num_m * ((p.N + c - 1) / c);
             const int rounds = (tiles + sms - 1) / sms;
-            const double cost = rounds * tile_cost[i];
+            const double cost = rounds * static_cast<double>(c) / rate[i];
             if (cost < best) {
                 best = cost;
                 block_n = c;
             }
+        }
+        if (p.M > 2 * kBlockM && getenv("LTXV_GEMM_NO_PAIR") == nullptr) {
+            const int num_mp = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
+            int pair_bn = 0;
+            if (p.N % 256 == 0) {
+                const int rounds = (num_mp * (p.N / 256) + sms / 2 - 1) / (sms / 2);
+                if (rounds * 256.0 / 1.00 <= best) {
+                    best = rounds * 256.0;
+                    pair_bn = 256;
+                }
+            }
+            if (p.N % 128 == 0) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
+                const int rounds = (num_mp * (p.N / 128) + sms / 2 - 1) / (sms / 2);
+                if (rounds * 128.0 / 0.80 < best) {
+                    best = rounds * 128.0 / 0.80;
+                    pair_bn = 128;
+                }
+            }
+            if (pair_bn == 256) return launch_pair_impl<256>(ops, p, stream);
+            if (pair_bn == 128) return launch_pair_impl<128>(ops, p, stream);
         }
     }
     switch (block_n) {
