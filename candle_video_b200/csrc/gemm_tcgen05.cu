@@ -480,29 +480,45 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // (32 KB per step) and the pair's tensor cores share the B halves: per-CTA traffic drops by a third and six stages fit.
 // Roles per CTA as above; only the leader CTA's warp 1 issues MMAs; both CTAs run TMA producers and epilogues.
 // ================================================================================================
-template <int BN>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
+//
+// KW3 (conv3d only): one pipeline step covers the THREE kw taps of a (kt, kh, channel-block).  The taps read the same
+// rows of the padded volume shifted by -1 / 0 / +1, so the step loads ONE box of 128 + 8 rows and the three MMAs start
+// their A descriptor 0 / 1 / 2 rows (128 B each) into it; the swizzle phase follows the absolute smem address.  The A
+// traffic from L2 drops 3x -- at Cin = Cout = 128 the conv re-read 1.7 MB of operands per 128x128 tile and was
+// L2-bandwidth bound at ~1.0 PFLOP/s.
+constexpr int kBoxRows3 = kBlockM + 8;                 // rows per KW3 A box (needs 130, keeps the 8-row swizzle atom)
+constexpr int kABytes3 = 18 * 1024;                    // 136 x 128 B = 17 408, padded to a 1024-byte multiple
+constexpr int kABoxBytes3 = kBoxRows3 * kBlockK * 2;   // bytes one KW3 A box transfers
+
+template <int BN, bool KW3>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
 struct PairCfg {
-    static constexpr int kBBytes = (BN / 2) * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;  // 32 KB (BN = 256) / 24 KB (BN = 128)
-    static constexpr int kStages = BN == 256 ? 6 : 8;
+    static constexpr int kBBytes = (BN / 2) * kBlockK * 2;          // one tap's B half: 16 KB / 8 KB
+    static constexpr int kAStage = KW3 ? kABytes3 : kABytes;
+    static constexpr int kBStage = KW3 ? 3 * kBBytes : kBBytes;
+    static constexpr int kStageBytes = kAStage + kBStage;
+    static constexpr int kTxBytes = (KW3 ? kABoxBytes3 : kABytes) + kBStage;  // bytes ONE CTA's loads credit per stage
+    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 6 : 8);
     static constexpr int kTmemCols = 2 * BN;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiStageBytes;
     static_assert(BN == 256 || BN == 128, "pair tile width");
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN>
+template <int BN, bool KW3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ GemmParams p) {
-    using PC = PairCfg<BN>;
+    using PC = PairCfg<BN, KW3>;
     constexpr int kPairBlockN = BN;
     constexpr int kPairBBytes = PC::kBBytes;
     constexpr int kPairStageBytes = PC::kStageBytes;
     constexpr int kPairStages = PC::kStages;
+    constexpr int kAStage = PC::kAStage;
+    constexpr int kBStage = PC::kBStage;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kPairStages * kABytes;
+    uint8_t* smem_b = smem + kPairStages * kAStage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
     uint64_t* full_bar = bars;                       // leader's copy is the live one (tx from both CTAs)
     uint64_t* empty_bar = bars + kPairStages;        // both copies live (multicast commit)
@@ -520,7 +536,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int num_m = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row tiles
     const int num_n = (p.N + kPairBlockN - 1) / kPairBlockN;
     const int num_tiles = num_m * num_n;
-    const int num_kb = p.num_k_blocks;
+    const int num_kb = KW3 ? p.num_k_blocks / 3 : p.num_k_blocks;  // KW3: steps over (kt, kh, channel block)
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -555,15 +571,27 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int n0 = (tile / num_m) * kPairBlockN + static_cast<int>(rank) * (kPairBlockN / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);  // bytes of BOTH CTAs
-                    int a_row = m0, a_col = kb * kBlockK;
-                    if (p.conv) {
-                        const int tap = kb / p.cin_blocks;
-                        a_row += p.tap_off[tap];
-                        a_col = (kb - tap * p.cin_blocks) * kBlockK;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PC::kTxBytes);  // bytes of BOTH CTAs
+                    if (KW3) {
+                        const int th = kb / p.cin_blocks;  // kt * 3 + kh
+                        const int cb = kb - th * p.cin_blocks;
+                        // rows of tap kw = 0 (shift -1); kw = 1, 2 start one / two rows further into the same box
+                        tma_load_2d_2sm(smem_a + stage * kAStage, &tmap_a, &full_bar[stage], cb * kBlockK,
+                                        m0 + p.tap_off[th * 3]);
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+                            tma_load_2d_2sm(smem_b + stage * kBStage + kw * kPairBBytes, &tmap_b, &full_bar[stage],
+                                            ((th * 3 + kw) * p.cin_blocks + cb) * kBlockK, n0);
+                    } else {
+                        int a_row = m0, a_col = kb * kBlockK;
+                        if (p.conv) {
+                            const int tap = kb / p.cin_blocks;
+                            a_row += p.tap_off[tap];
+                            a_col = (kb - tap * p.cin_blocks) * kBlockK;
+                        }
+                        tma_load_2d_2sm(smem_a + stage * kAStage, &tmap_a, &full_bar[stage], a_col, a_row);
+                        tma_load_2d_2sm(smem_b + stage * kBStage, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
                     }
-                    tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], a_col, a_row);
-                    tma_load_2d_2sm(smem_b + stage * kPairBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
                     if (++stage == kPairStages) {
                         stage = 0;
                         phase ^= 1;
@@ -586,13 +614,17 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * kPairBBytes);
+                    const uint32_t a_addr = smem_u32(smem_a + stage * kAStage);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * kBStage);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        const uint64_t da = make_smem_desc_sw128(a_addr + k * kUmmaK * 2, 1024, 0);
-                        const uint64_t db = make_smem_desc_sw128(b_addr + k * kUmmaK * 2, 1024, 0);
-                        umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int kw = 0; kw < (KW3 ? 3 : 1); ++kw) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // KW3: tap kw reads the box from row kw on (one row = 128 B)
+                            const uint64_t da = make_smem_desc_sw128(a_addr + kw * 128 + k * kUmmaK * 2, 1024, 0);
+                            const uint64_t db = make_smem_desc_sw128(b_addr + kw * kPairBBytes + k * kUmmaK * 2, 1024, 0);
+                            umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | kw | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit_2sm(&empty_bar[stage]);  // frees the stage in BOTH CTAs once these MMAs retire
                     if (kb == num_kb - 1) umma_commit_2sm(&tmem_full_bar[acc]);
@@ -703,13 +735,13 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
 }
 
 
-template <int BN>
+template <int BN, bool KW3>
 cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
-    using PC = PairCfg<BN>;
+    using PC = PairCfg<BN, KW3>;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, KW3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PC::kSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -717,8 +749,9 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
+    if (KW3 && (!p.conv || p.num_k_blocks != 27 * p.cin_blocks)) return cudaErrorInvalidValue;
     CUtensorMap ta, tb;
-    cudaError_t e = make_tensor_map_2d_bf16(&ta, ops.a, ops.a_rows, ops.a_cols, kBlockM, kBlockK);
+    cudaError_t e = make_tensor_map_2d_bf16(&ta, ops.a, ops.a_rows, ops.a_cols, KW3 ? kBoxRows3 : kBlockM, kBlockK);
     if (e != cudaSuccess) return e;
     e = make_tensor_map_2d_bf16(&tb, ops.b, ops.b_rows, ops.b_cols, BN / 2, kBlockK);
     if (e != cudaSuccess) return e;
@@ -730,8 +763,8 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
         if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
-        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN>, dim3(2 * clusters), dim3(kThreads), PC::kSmemBytes, stream,
-                                    ta, tb, p);
+        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, KW3>, dim3(2 * clusters), dim3(kThreads), PC::kSmemBytes,
+                                    stream, ta, tb, p);
         if (le != cudaSuccess) return le;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -744,8 +777,10 @@ uint64_t gemm_launch_count() { return g_launches.load(); }
 
 cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int block_n, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
-    if (block_n == -2) return launch_pair_impl<256>(ops, p, stream);
-    if (block_n == -3) return launch_pair_impl<128>(ops, p, stream);
+    if (block_n == -2) return launch_pair_impl<256, false>(ops, p, stream);
+    if (block_n == -3) return launch_pair_impl<128, false>(ops, p, stream);
+    if (block_n == -4) return launch_pair_impl<256, true>(ops, p, stream);   // conv3d, three kw taps per step
+    if (block_n == -5) return launch_pair_impl<128, true>(ops, p, stream);
     if (block_n == 0) {
         // Pick the kernel / tile width that minimises (rounds over the SMs) x (per-SM tile area) / (relative rate of
         // that tile shape).  Rates from the isolated measurements at K = 8192 (profiles/r01_gemm_*): the CTA-pair
@@ -786,8 +821,9 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
                     pair_bn = 128;
                 }
             }
-            if (pair_bn == 256) return launch_pair_impl<256>(ops, p, stream);
-            if (pair_bn == 128) return launch_pair_impl<128>(ops, p, stream);
+            const bool kw3 = p.conv && p.num_k_blocks == 27 * p.cin_blocks && getenv("LTXV_CONV_NO_KW3") == nullptr;
+            if (pair_bn == 256) return kw3 ? launch_pair_impl<256, true>(ops, p, stream) : launch_pair_impl<256, false>(ops, p, stream);
+            if (pair_bn == 128) return kw3 ? launch_pair_impl<128, true>(ops, p, stream) : launch_pair_impl<128, false>(ops, p, stream);
         }
     }
     switch (block_n) {
