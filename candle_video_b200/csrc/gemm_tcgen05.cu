@@ -490,25 +490,31 @@ constexpr int kBoxRows3 = kBlockM + 8;                 // rows per KW3 A box (ne
 constexpr int kABytes3 = 18 * 1024;                    // 136 x 128 B = 17 408, padded to a 1024-byte multiple
 constexpr int kABoxBytes3 = kBoxRows3 * kBlockK * 2;   // bytes one KW3 A box transfers
 
-template <int BN, bool KW3>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
+// MODE 0: one 64-wide k-block per pipeline stage; MODE 1: KW3 (above); MODE 2: TWO k-blocks per stage (8 MMAs per
+// full/empty barrier round trip instead of 4 -- the plain GEMMs ran at 71 % tensor-pipe activity against 99 % for KW3).
+template <int BN, int MODE>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
 struct PairCfg {
-    static constexpr int kBBytes = (BN / 2) * kBlockK * 2;          // one tap's B half: 16 KB / 8 KB
-    static constexpr int kAStage = KW3 ? kABytes3 : kABytes;
-    static constexpr int kBStage = KW3 ? 3 * kBBytes : kBBytes;
+    static constexpr bool KW3 = MODE == 1;
+    static constexpr int kKbPerStage = MODE == 2 ? 2 : 1;
+    static constexpr int kBBytes = (BN / 2) * kBlockK * 2;          // one k-block's / tap's B half: 16 KB / 8 KB
+    static constexpr int kAStage = KW3 ? kABytes3 : kKbPerStage * kABytes;
+    static constexpr int kBStage = KW3 ? 3 * kBBytes : kKbPerStage * kBBytes;
     static constexpr int kStageBytes = kAStage + kBStage;
-    static constexpr int kTxBytes = (KW3 ? kABoxBytes3 : kABytes) + kBStage;  // bytes ONE CTA's loads credit per stage
-    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 6 : 8);
+    static constexpr int kTxBytes = (KW3 ? kABoxBytes3 : kKbPerStage * kABytes) + kBStage;  // bytes ONE CTA credits per stage
+    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 6 : 8) / kKbPerStage;
     static constexpr int kTmemCols = 2 * BN;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiStageBytes;
     static_assert(BN == 256 || BN == 128, "pair tile width");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, bool KW3>
+template <int BN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ GemmParams p) {
-    using PC = PairCfg<BN, KW3>;
+    using PC = PairCfg<BN, MODE>;
+    constexpr bool KW3 = PC::KW3;
+    constexpr int kKbPerStage = PC::kKbPerStage;
     constexpr int kPairBlockN = BN;
     constexpr int kPairBBytes = PC::kBBytes;
     constexpr int kPairStageBytes = PC::kStageBytes;
@@ -536,7 +542,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int num_m = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row tiles
     const int num_n = (p.N + kPairBlockN - 1) / kPairBlockN;
     const int num_tiles = num_m * num_n;
-    const int num_kb = KW3 ? p.num_k_blocks / 3 : p.num_k_blocks;  // KW3: steps over (kt, kh, channel block)
+    const int num_kb = KW3 ? p.num_k_blocks / 3 : p.num_k_blocks / kKbPerStage;  // pipeline steps per tile
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -583,14 +589,19 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             tma_load_2d_2sm(smem_b + stage * kBStage + kw * kPairBBytes, &tmap_b, &full_bar[stage],
                                             ((th * 3 + kw) * p.cin_blocks + cb) * kBlockK, n0);
                     } else {
-                        int a_row = m0, a_col = kb * kBlockK;
-                        if (p.conv) {
-                            const int tap = kb / p.cin_blocks;
-                            a_row += p.tap_off[tap];
-                            a_col = (kb - tap * p.cin_blocks) * kBlockK;
+#pragma unroll
+                        for (int j = 0; j < kKbPerStage; ++j) {
+                            const int kbj = kb * kKbPerStage + j;
+                            int a_row = m0, a_col = kbj * kBlockK;
+                            if (p.conv) {
+                                const int tap = kbj / p.cin_blocks;
+                                a_row += p.tap_off[tap];
+                                a_col = (kbj - tap * p.cin_blocks) * kBlockK;
+                            }
+                            tma_load_2d_2sm(smem_a + stage * kAStage + j * kABytes, &tmap_a, &full_bar[stage], a_col, a_row);
+                            tma_load_2d_2sm(smem_b + stage * kBStage + j * kPairBBytes, &tmap_b, &full_bar[stage],
+                                            kbj * kBlockK, n0);
                         }
-                        tma_load_2d_2sm(smem_a + stage * kAStage, &tmap_a, &full_bar[stage], a_col, a_row);
-                        tma_load_2d_2sm(smem_b + stage * kBStage, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
                     }
                     if (++stage == kPairStages) {
                         stage = 0;
@@ -617,11 +628,12 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const uint32_t a_addr = smem_u32(smem_a + stage * kAStage);
                     const uint32_t b_addr = smem_u32(smem_b + stage * kBStage);
 #pragma unroll
-                    for (int kw = 0; kw < (KW3 ? 3 : 1); ++kw) {
+                    for (int kw = 0; kw < (KW3 ? 3 : kKbPerStage); ++kw) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            // KW3: tap kw reads the box from row kw on (one row = 128 B)
-                            const uint64_t da = make_smem_desc_sw128(a_addr + kw * 128 + k * kUmmaK * 2, 1024, 0);
+                            // KW3: tap kw reads the SAME box from row kw on (one row = 128 B); otherwise sub-block kw
+                            const uint32_t a_off = KW3 ? kw * 128 : kw * kABytes;
+                            const uint64_t da = make_smem_desc_sw128(a_addr + a_off + k * kUmmaK * 2, 1024, 0);
                             const uint64_t db = make_smem_desc_sw128(b_addr + kw * kPairBBytes + k * kUmmaK * 2, 1024, 0);
                             umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | kw | k) != 0 ? 1u : 0u);
                         }
@@ -735,13 +747,14 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
 }
 
 
-template <int BN, bool KW3>
+template <int BN, int MODE>
 cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
-    using PC = PairCfg<BN, KW3>;
+    using PC = PairCfg<BN, MODE>;
+    constexpr bool KW3 = PC::KW3;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, KW3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PC::kSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -750,6 +763,7 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         configured = true;
     }
     if (KW3 && (!p.conv || p.num_k_blocks != 27 * p.cin_blocks)) return cudaErrorInvalidValue;
+    if (MODE == 2 && p.num_k_blocks % 2 != 0) return cudaErrorInvalidValue;
     CUtensorMap ta, tb;
     cudaError_t e = make_tensor_map_2d_bf16(&ta, ops.a, ops.a_rows, ops.a_cols, KW3 ? kBoxRows3 : kBlockM, kBlockK);
     if (e != cudaSuccess) return e;
@@ -763,7 +777,7 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
         if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
-        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, KW3>, dim3(2 * clusters), dim3(kThreads), PC::kSmemBytes,
+        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE>, dim3(2 * clusters), dim3(kThreads), PC::kSmemBytes,
                                     stream, ta, tb, p);
         if (le != cudaSuccess) return le;
     }
@@ -777,10 +791,11 @@ uint64_t gemm_launch_count() { return g_launches.load(); }
 
 cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int block_n, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
-    if (block_n == -2) return launch_pair_impl<256, false>(ops, p, stream);
-    if (block_n == -3) return launch_pair_impl<128, false>(ops, p, stream);
-    if (block_n == -4) return launch_pair_impl<256, true>(ops, p, stream);   // conv3d, three kw taps per step
-    if (block_n == -5) return launch_pair_impl<128, true>(ops, p, stream);
+    if (block_n == -2) return launch_pair_impl<256, 0>(ops, p, stream);
+    if (block_n == -3) return launch_pair_impl<128, 0>(ops, p, stream);
+    if (block_n == -4) return launch_pair_impl<256, 1>(ops, p, stream);   // conv3d, three kw taps per step
+    if (block_n == -5) return launch_pair_impl<128, 1>(ops, p, stream);
+    if (block_n == -6) return launch_pair_impl<256, 2>(ops, p, stream);   // two k-blocks per stage
     if (block_n == 0) {
         // Pick the kernel / tile width that minimises (rounds over the SMs) x (per-SM tile area) / (relative rate of
         // that tile shape).  Rates from the isolated measurements at K = 8192 (profiles/r01_gemm_*): the CTA-pair
@@ -822,8 +837,12 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
                 }
             }
             const bool kw3 = p.conv && p.num_k_blocks == 27 * p.cin_blocks && getenv("LTXV_CONV_NO_KW3") == nullptr;
-            if (pair_bn == 256) return kw3 ? launch_pair_impl<256, true>(ops, p, stream) : launch_pair_impl<256, false>(ops, p, stream);
-            if (pair_bn == 128) return kw3 ? launch_pair_impl<128, true>(ops, p, stream) : launch_pair_impl<128, false>(ops, p, stream);
+            // two k-blocks per stage measured neutral (1341 vs 1353 TFLOP/s on the QKV shape): opt-in only
+            const bool k2 = !p.conv && p.num_k_blocks % 2 == 0 && getenv("LTXV_GEMM_K2") != nullptr;
+            if (pair_bn == 256)
+                return kw3 ? launch_pair_impl<256, 1>(ops, p, stream)
+                           : (k2 ? launch_pair_impl<256, 2>(ops, p, stream) : launch_pair_impl<256, 0>(ops, p, stream));
+            if (pair_bn == 128) return kw3 ? launch_pair_impl<128, 1>(ops, p, stream) : launch_pair_impl<128, 0>(ops, p, stream);
         }
     }
     switch (block_n) {

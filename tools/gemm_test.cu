@@ -240,14 +240,18 @@ int main(int argc, char** argv) {
     if (argc > 1 && atoi(argv[1]) == 2) {  // epilogue comparison at the out-projection shape
         test_gemm(9984, 6144, 2048, EPI_STORE_BF16, 0, 256, true);
         test_gemm(9984, 6144, 2048, EPI_STORE_BF16, 0, -2, true);
+        test_gemm(9984, 6144, 2048, EPI_STORE_BF16, 0, -6, true);
         test_gemm(9984, 8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH, 256, true);
         test_gemm(9984, 8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH, -2, true);
+        test_gemm(9984, 8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH, -6, true);
         test_gemm(9984, 2048, 8192, EPI_RESIDUAL_F32, 0, 192, true);
         test_gemm(9984, 2048, 8192, EPI_RESIDUAL_F32, 0, -2, true);
+        test_gemm(9984, 2048, 8192, EPI_RESIDUAL_F32, 0, -6, true);
         test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, 192, true);
         test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, -2, true);
         test_gemm(8192, 8192, 8192, EPI_STORE_BF16, 0, 256, true);
         test_gemm(8192, 8192, 8192, EPI_STORE_BF16, 0, -2, true);
+        test_gemm(8192, 8192, 8192, EPI_STORE_BF16, 0, -6, true);
         test_gemm(4992, 2048, 2048, EPI_STORE_BF16, 0, 0, true);
         test_gemm(4992, 2048, 2048, EPI_STORE_F32, 0, 0, true);
         test_gemm(4992, 2048, 2048, EPI_RESIDUAL_F32, 0, 0, true);
@@ -271,6 +275,7 @@ int main(int argc, char** argv) {
     fails += test_gemm(384, 512, 320, EPI_STORE_BF16, ACT_GELU_TANH, -2, false);
     fails += test_gemm(1000, 768, 1024, EPI_RESIDUAL_F32, 0, -2, false);
     fails += test_gemm(4992, 2048, 2048, EPI_RESIDUAL_F32, 0, -2, false);
+    fails += test_gemm(1000, 768, 1024, EPI_RESIDUAL_F32, 0, -6, false);  // two k-blocks per stage
     fails += test_gemm(1000, 384, 1024, EPI_RESIDUAL_F32, 0, -3, false);  // 256x128 cluster tiles
     fails += test_gemm(700, 128, 320, EPI_STORE_BF16, ACT_GELU_TANH, -3, false);
     fails += test_conv(3, 6, 10, 128, 128, false);
