@@ -295,6 +295,20 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
     __syncwarp();  // the tile is rewritten by the next chunk
 }
 
+// conv3d k-block order: (kt, kh) outermost, then the 64-channel block, then kw -- the SAME accumulation order as the
+// KW3 pair kernel (three kw taps per pipeline step), so every kernel variant produces identical bits and the result
+// does not depend on which one the tile heuristic picks (single GPU vs H-slabs pick differently).
+__device__ __forceinline__ void conv_kblock(const GemmParams& p, int kb, int& a_row, int& a_col, int& b_col) {
+    const int per_th = 3 * p.cin_blocks;
+    const int th = kb / per_th;  // kt * 3 + kh
+    const int r = kb - th * per_th;
+    const int cb = r / 3, kw = r - cb * 3;
+    const int tap = th * 3 + kw;
+    a_row += p.tap_off[tap];
+    a_col = cb * kBlockK;
+    b_col = (tap * p.cin_blocks + cb) * kBlockK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
@@ -359,14 +373,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-                    int a_row = t.m0, a_col = kb * kBlockK;
-                    if (p.conv) {
-                        const int tap = kb / p.cin_blocks;
-                        a_row += p.tap_off[tap];
-                        a_col = (kb - tap * p.cin_blocks) * kBlockK;
-                    }
+                    int a_row = t.m0, a_col = kb * kBlockK, b_col = kb * kBlockK;
+                    if (p.conv) conv_kblock(p, kb, a_row, a_col, b_col);
                     tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], a_col, a_row);
-                    tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
+                    tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], b_col, n0);
                     if (++stage == C::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -592,15 +602,10 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                         for (int j = 0; j < kKbPerStage; ++j) {
                             const int kbj = kb * kKbPerStage + j;
-                            int a_row = m0, a_col = kbj * kBlockK;
-                            if (p.conv) {
-                                const int tap = kbj / p.cin_blocks;
-                                a_row += p.tap_off[tap];
-                                a_col = (kbj - tap * p.cin_blocks) * kBlockK;
-                            }
+                            int a_row = m0, a_col = kbj * kBlockK, b_col = kbj * kBlockK;
+                            if (p.conv) conv_kblock(p, kbj, a_row, a_col, b_col);
                             tma_load_2d_2sm(smem_a + stage * kAStage + j * kABytes, &tmap_a, &full_bar[stage], a_col, a_row);
-                            tma_load_2d_2sm(smem_b + stage * kBStage + j * kPairBBytes, &tmap_b, &full_bar[stage],
-                                            kbj * kBlockK, n0);
+                            tma_load_2d_2sm(smem_b + stage * kBStage + j * kPairBBytes, &tmap_b, &full_bar[stage], b_col, n0);
                         }
                     }
                     if (++stage == kPairStages) {
