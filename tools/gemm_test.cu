@@ -237,6 +237,12 @@ static int test_conv(int T, int H, int W, int Cin, int Cout, bool timing) {
 int main(int argc, char** argv) {
     bool big = argc > 1 && atoi(argv[1]) > 0;
     int fails = 0;
+    if (argc > 1 && atoi(argv[1]) == 3) {  // every kernel variant at the [9984, 2048] x [2048, 2048] projections
+        for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, bn, true);
+        for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_STORE_BF16, 0, bn, true);
+        for (int bn : {192, 256, -2, -3}) test_gemm(4992, 2048, 2048, EPI_RESIDUAL_F32, 0, bn, true);
+        return 0;
+    }
     if (argc > 1 && atoi(argv[1]) == 2) {  // epilogue comparison at the out-projection shape
         test_gemm(9984, 6144, 2048, EPI_STORE_BF16, 0, 256, true);
         test_gemm(9984, 6144, 2048, EPI_STORE_BF16, 0, -2, true);
