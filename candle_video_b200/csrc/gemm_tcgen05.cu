@@ -371,7 +371,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const Tile t = tile_coords(tile, num_m);
                 const int n0 = t.n0 * BLOCK_N;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_sleep(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
                     int a_row = t.m0, a_col = kb * kBlockK, b_col = kb * kBlockK;
                     if (p.conv) conv_kblock(p, kb, a_row, a_col, b_col);
@@ -393,11 +393,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                mbar_wait_sleep(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * C::kTmemStride;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_sleep(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
                     const uint32_t b_addr = smem_u32(smem_b + stage * C::kBBytes);
@@ -437,7 +437,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
             const int m_warp0 = t.m0 + quad * 32;
             if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);  // before the MMAs finish
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            mbar_wait_sleep(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * C::kTmemStride;
             auto chunk = [&](int c, const float4 (&res)[8]) {
@@ -586,7 +586,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int m0 = (tile % num_m) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
                 const int n0 = (tile / num_m) * kPairBlockN + static_cast<int>(rank) * (kPairBlockN / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_sleep(&empty_bar[stage], phase ^ 1);
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PC::kTxBytes);  // bytes of BOTH CTAs
                     if (KW3) {
                         const int th = kb / p.cin_blocks;  // kt * 3 + kh
@@ -624,11 +624,11 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                mbar_wait_sleep(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kPairBlockN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_sleep(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * kAStage);
                     const uint32_t b_addr = smem_u32(smem_b + stage * kBStage);
@@ -672,7 +672,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             float4 res_a[8], res_b[8];
             const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
             if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            mbar_wait_sleep(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kPairBlockN;
             auto chunk = [&](int c, const float4 (&res)[8]) {
