@@ -74,6 +74,48 @@ norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ ou
     }
 }
 
+// RMS variant with the whole row register-resident (D = 128 * VPL): one pass over x, every load of the row in flight
+// before the first is consumed (the generic kernel above reads the row twice with 4 loads in flight per lane)
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rms_modulate_row_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int rows, float eps) {
+    constexpr int D = VPL * 128;
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * D);
+    float4 v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = xr[lane + 32 * i];
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s2 += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    s2 = warp_sum(s2);
+    const float rinv = rsqrtf(s2 * (1.0f / D) + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(row) * D);
+    const float4* sc4 = reinterpret_cast<const float4*>(scale);
+    const float4* sh4 = reinterpret_cast<const float4*>(shift);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        float a = v[i].x * rinv, b = v[i].y * rinv, c = v[i].z * rinv, d = v[i].w * rinv;
+        if (scale != nullptr) {
+            const float4 sc = __ldg(sc4 + idx), sh = __ldg(sh4 + idx);
+            a = a * (1.0f + sc.x) + sh.x;
+            b = b * (1.0f + sc.y) + sh.y;
+            c = c * (1.0f + sc.z) + sh.z;
+            d = d * (1.0f + sc.w) + sh.w;
+        }
+        uint2 o;
+        o.x = pack_bf16x2(a, b);
+        o.y = pack_bf16x2(c, d);
+        orow[idx] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // q/k RMS norm across heads (+ RoPE), in place on bf16
 // ------------------------------------------------------------------------------------------------
@@ -188,6 +230,121 @@ qk_pair_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, in
             u.w = pack_bf16x2(f[6], f[7]);
             xr[i] = u;
         }
+    }
+}
+
+// register-resident variant of qk_pair_norm_rope_kernel for D = 256 * VPL: q and k of the token are loaded once (all 2*VPL
+// 16-byte loads in flight), normed, rotated and stored; one pass over the activations and over the cos/sin row
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+qk_pair_norm_rope_row_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, const float* __restrict__ wq,
+                             const float* __restrict__ wk, float eps, const float* __restrict__ cos_t,
+                             const float* __restrict__ sin_t, int table_rows) {
+    constexpr int D = VPL * 256;
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    uint4* xq = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
+    uint4* xk = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + D);
+    const int trow = row % table_rows;
+    const float4* c4 = reinterpret_cast<const float4*>(cos_t + static_cast<int64_t>(trow) * (D >> 1));
+    const float4* s4 = reinterpret_cast<const float4*>(sin_t + static_cast<int64_t>(trow) * (D >> 1));
+    uint4 q[VPL], k[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        q[i] = xq[lane + 32 * i];
+        k[i] = xk[lane + 32 * i];
+    }
+    float sq = 0.f, sk = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float fa[8] = {bf16_lo(q[i].x), bf16_hi(q[i].x), bf16_lo(q[i].y), bf16_hi(q[i].y),
+                             bf16_lo(q[i].z), bf16_hi(q[i].z), bf16_lo(q[i].w), bf16_hi(q[i].w)};
+        const float fb[8] = {bf16_lo(k[i].x), bf16_hi(k[i].x), bf16_lo(k[i].y), bf16_hi(k[i].y),
+                             bf16_lo(k[i].z), bf16_hi(k[i].z), bf16_lo(k[i].w), bf16_hi(k[i].w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sq += fa[j] * fa[j];
+            sk += fb[j] * fb[j];
+        }
+    }
+    sq = warp_sum(sq);
+    sk = warp_sum(sk);
+    const float rq = rsqrtf(sq * (1.0f / D) + eps), rk = rsqrtf(sk * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        const float4 cc = __ldg(c4 + idx), ss = __ldg(s4 + idx);
+        const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            uint4 u = which == 0 ? q[i] : k[i];
+            const float* w = which == 0 ? wq : wk;
+            const float rinv = which == 0 ? rq : rk;
+            float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                          bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx);
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx + 1);
+            const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = f[j] * rinv * ww[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float re = f[2 * j], im = f[2 * j + 1];
+                f[2 * j] = re * cv[j] - im * sv[j];
+                f[2 * j + 1] = im * cv[j] + re * sv[j];
+            }
+            u.x = pack_bf16x2(f[0], f[1]);
+            u.y = pack_bf16x2(f[2], f[3]);
+            u.z = pack_bf16x2(f[4], f[5]);
+            u.w = pack_bf16x2(f[6], f[7]);
+            (which == 0 ? xq : xk)[idx] = u;
+        }
+    }
+}
+
+// register-resident RMS norm x weight of ONE tensor, in place (the cross-attention queries: no RoPE), D = 256 * VPL
+template <int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rms_weight_row_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int rows, const float* __restrict__ w, float eps) {
+    constexpr int D = VPL * 256;
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + col0);
+    uint4 q[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) q[i] = xr[lane + 32 * i];
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float f[8] = {bf16_lo(q[i].x), bf16_hi(q[i].x), bf16_lo(q[i].y), bf16_hi(q[i].y),
+                            bf16_lo(q[i].z), bf16_hi(q[i].z), bf16_lo(q[i].w), bf16_hi(q[i].w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2 += f[j] * f[j];
+    }
+    s2 = warp_sum(s2);
+    const float rinv = rsqrtf(s2 * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        float f[8] = {bf16_lo(q[i].x), bf16_hi(q[i].x), bf16_lo(q[i].y), bf16_hi(q[i].y),
+                      bf16_lo(q[i].z), bf16_hi(q[i].z), bf16_lo(q[i].w), bf16_hi(q[i].w)};
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx);
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx + 1);
+        const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] * rinv * ww[j];
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        xr[idx] = o;
     }
 }
 
@@ -527,7 +684,13 @@ cudaError_t launch_norm_modulate(const float* x, void* out, const float* scale, 
     if (D % 4 != 0 || (scale == nullptr) != (shift == nullptr)) return cudaErrorInvalidValue;
     const int grid = blocks_for(rows, kWarpsPerBlock);
     ProfScope prof(PROF_NORM_MOD, 6.0 * rows * D, s);  // f32 in, bf16 out
-    if (kind == NORM_LAYER)
+    if (kind == NORM_RMS && D == 2048)
+        launch_pdl(rms_modulate_row_kernel<16>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, x,
+                   reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, eps);
+    else if (kind == NORM_RMS && D == 4096)
+        launch_pdl(rms_modulate_row_kernel<32>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, x,
+                   reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, eps);
+    else if (kind == NORM_LAYER)
         launch_pdl(norm_modulate_kernel<NORM_LAYER>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, x,
                    reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, D, eps);
     else
@@ -540,8 +703,15 @@ cudaError_t launch_qk_norm_rope(void* x, int64_t ld, int col0, int rows, int D, 
                                 const float* cos_t, const float* sin_t, cudaStream_t s) {
     if (D % 8 != 0 || ld % 8 != 0 || col0 % 8 != 0) return cudaErrorInvalidValue;
     ProfScope prof(PROF_QK_ROPE, 4.0 * rows * D + (cos_t ? 2.0 * rows * (D / 2) * 4 : 0.0), s);
-    launch_pdl(qk_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
-               reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, D, w, eps, cos_t, sin_t);
+    if (cos_t == nullptr && D == 2048)
+        launch_pdl(rms_weight_row_kernel<8>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+                   reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, w, eps);
+    else if (cos_t == nullptr && D == 4096)
+        launch_pdl(rms_weight_row_kernel<16>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+                   reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, w, eps);
+    else
+        launch_pdl(qk_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+                   reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, D, w, eps, cos_t, sin_t);
     return done();
 }
 
@@ -550,8 +720,15 @@ cudaError_t launch_qk_pair_norm_rope(void* x, int64_t ld, int rows, int D, const
     if (D % 8 != 0 || ld % 8 != 0 || ld < 2 * D || cos_t == nullptr || sin_t == nullptr) return cudaErrorInvalidValue;
     if (table_rows <= 0) table_rows = rows;
     ProfScope prof(PROF_QK_ROPE, 2.0 * rows * D * 4 + 2.0 * rows * (D / 2) * 4, s);  // q,k bf16 in+out, cos/sin f32 once
-    launch_pdl(qk_pair_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
-               reinterpret_cast<__nv_bfloat16*>(x), ld, rows, D, wq, wk, eps, cos_t, sin_t, table_rows);
+    if (D == 2048)
+        launch_pdl(qk_pair_norm_rope_row_kernel<8>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+                   reinterpret_cast<__nv_bfloat16*>(x), ld, rows, wq, wk, eps, cos_t, sin_t, table_rows);
+    else if (D == 4096)
+        launch_pdl(qk_pair_norm_rope_row_kernel<16>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+                   reinterpret_cast<__nv_bfloat16*>(x), ld, rows, wq, wk, eps, cos_t, sin_t, table_rows);
+    else
+        launch_pdl(qk_pair_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+                   reinterpret_cast<__nv_bfloat16*>(x), ld, rows, D, wq, wk, eps, cos_t, sin_t, table_rows);
     return done();
 }
 
