@@ -45,6 +45,8 @@ EXPORTED_SYMBOLS = [
     "ltxv_vae_tiling_default", "ltxv_vae_decode_tiled",
     "ltxv_scheduler_step_stochastic", "ltxv_decode_noise_blend", "ltxv_pipeline_denoise_stochastic",
     "ltxv_pipeline_decode_noisy",
+    "ltxv_vae_encoder_config_default", "ltxv_vae_enable_encoder", "ltxv_vae_encode_dims", "ltxv_vae_encode",
+    "ltxv_vae_encode_host", "ltxv_normalize_latents",
 ]
 
 
@@ -67,6 +69,11 @@ class _VaeConfigC(C.Structure):
     _fields_ = [("latent_channels", C.c_int32), ("out_channels", C.c_int32),
                 ("decoder_block_out_channels", C.c_int32 * 3), ("decoder_layers_per_block", C.c_int32 * 4),
                 ("patch_size", C.c_int32), ("timestep_conditioning", C.c_int32), ("scaling_factor", C.c_float)]
+
+
+class _VaeEncoderConfigC(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("latent_channels", C.c_int32), ("block_out_channels", C.c_int32 * 5),
+                ("layers_per_block", C.c_int32 * 5), ("downsample_types", C.c_int32 * 4), ("patch_size", C.c_int32)]
 
 
 class _PipelineParamsC(C.Structure):
@@ -149,6 +156,12 @@ def _load() -> C.CDLL:
     l.ltxv_pipeline_decode_noisy.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp, C.c_float, vp, vp]
     l.ltxv_vae_tiling_default.argtypes = [C.POINTER(_VaeTilingC)]
     l.ltxv_vae_decode_tiled.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, C.POINTER(_VaeTilingC), vp, i32, i32, vp]
+    l.ltxv_vae_encoder_config_default.argtypes = [C.POINTER(_VaeEncoderConfigC)]
+    l.ltxv_vae_enable_encoder.argtypes = [vp, C.POINTER(_VaeEncoderConfigC)]
+    l.ltxv_vae_encode_dims.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    l.ltxv_vae_encode.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    l.ltxv_vae_encode_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    l.ltxv_normalize_latents.argtypes = [vp, vp, vp, vp, f32, i32, i32, i64, vp]
     l.ltxv_profile_begin.argtypes = []
     l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return l
@@ -392,6 +405,28 @@ class VaeConfig:
                            int(self.timestep_conditioning), self.scaling_factor)
 
 
+DOWNSAMPLE_CODES = {"spatial": 1, "temporal": 2, "spatiotemporal": 3}  # LTXV_DOWN_*, DownsampleType (vae.rs:469-493)
+
+
+@dataclass
+class VaeEncoderConfig:
+    """AutoencoderKLLtxVideoConfig, encoder fields (vae.rs:30-103); the LTX-Video 0.9.5 layout."""
+    in_channels: int = 3
+    latent_channels: int = 128
+    block_out_channels: Tuple[int, int, int, int, int] = (128, 256, 512, 1024, 2048)
+    layers_per_block: Tuple[int, int, int, int, int] = (4, 6, 6, 2, 2)
+    downsample_types: Tuple[str, str, str, str] = ("spatial", "temporal", "spatiotemporal", "spatiotemporal")
+    patch_size: int = 4
+
+    def to_c(self) -> _VaeEncoderConfigC:
+        try:
+            codes = [DOWNSAMPLE_CODES[t] for t in self.downsample_types]
+        except KeyError as e:
+            raise LtxvError(f"unsupported downsample type {e}; pixel-unshuffle types only (spatial/temporal/spatiotemporal)")
+        return _VaeEncoderConfigC(self.in_channels, self.latent_channels, (C.c_int32 * 5)(*self.block_out_channels),
+                                  (C.c_int32 * 5)(*self.layers_per_block), (C.c_int32 * 4)(*codes), self.patch_size)
+
+
 class _VaeTilingC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "use_tiling", "use_framewise_decoding", "tile_sample_min_height", "tile_sample_min_width",
@@ -483,6 +518,42 @@ class AutoencoderKLLtxVideo:
                                            _ptr(out), _dtype_code(out), int(postprocess), _stream()))
         return out
 
+    # ---- encoder half ----
+    def enable_encoder(self, config: "Optional[VaeEncoderConfig]" = None) -> None:
+        """Build the encoder (vae.rs:1772-1784): `encoder.*` keys are then loaded instead of ignored."""
+        self.encoder_config = config or VaeEncoderConfig()
+        cc = self.encoder_config.to_c()
+        _check(lib().ltxv_vae_enable_encoder(self._h, C.byref(cc)))
+
+    def encode_dims(self, num_frames: int, height: int, width: int) -> Tuple[int, int, int]:
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().ltxv_vae_encode_dims(self._h, num_frames, height, width, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def encode(self, video):
+        """AutoencoderKLLtxVideo::encode (vae.rs:2070-2099): [B,3,F,H,W] in [-1,1] (CUDA, f32/bf16) -> moments f32
+        [B, 2*latent, F', H', W']; `moments[:, :latent]` is the posterior mean (`.mode()`), the rest the logvar."""
+        torch = _torch()
+        x = _dev(video, "video")
+        B, Cin, F, H, W = x.shape
+        if Cin != 3:
+            raise LtxvError("video must have 3 channels")
+        fl, hl, wl = self.encode_dims(F, H, W)
+        out = torch.empty((B, 2 * self.config.latent_channels, fl, hl, wl), dtype=torch.float32, device=x.device)
+        _check(lib().ltxv_vae_encode(self._h, _ptr(x), _dtype_code(x), B, F, H, W, _ptr(out), _stream()))
+        return out
+
+    def encode_host(self, video):
+        torch = _torch()
+        x = video.contiguous()
+        B, Cin, F, H, W = x.shape
+        if Cin != 3:
+            raise LtxvError("video must have 3 channels")
+        fl, hl, wl = self.encode_dims(F, H, W)
+        out = torch.empty((B, 2 * self.config.latent_channels, fl, hl, wl), dtype=torch.float32)
+        _check(lib().ltxv_vae_encode_host(self._h, _ptr(x), _dtype_code(x), B, F, H, W, _ptr(out)))
+        return out
+
     def decode_host(self, latents, timestep=None, postprocess: bool = False):
         torch = _torch()
         z = latents.contiguous()
@@ -560,6 +631,19 @@ def denormalize_latents(latents, mean, std, scaling_factor: float):
     out = torch.empty_like(x)
     _check(lib().ltxv_denormalize_latents(_ptr(x), _ptr(out), _ptr(m), _ptr(s), scaling_factor, B, Cc,
                                           x[0, 0].numel(), _stream()))
+    return out
+
+
+def normalize_latents(latents, mean, std, scaling_factor: float):
+    """LtxPipeline::normalize_latents (t2v_pipeline.rs:552-571)."""
+    torch = _torch()
+    x = _dev(latents, "latents").to(torch.float32).contiguous()
+    B, Cc = x.shape[:2]
+    m = _dev(mean, "mean").to(torch.float32).contiguous()
+    s = _dev(std, "std").to(torch.float32).contiguous()
+    out = torch.empty_like(x)
+    _check(lib().ltxv_normalize_latents(_ptr(x), _ptr(out), _ptr(m), _ptr(s), scaling_factor, B, Cc,
+                                        x[0, 0].numel(), _stream()))
     return out
 
 

@@ -33,6 +33,7 @@ LIB_SOURCES = [
     "vae_glue.cu",
     "dit.cu",
     "vae.cu",
+    "vae_encoder.cu",
     "pipeline.cu",
     "comm.cu",
     "weights.cc",

@@ -9,6 +9,7 @@
 #include "pipeline.h"
 #include "profile.h"
 #include "vae.h"
+#include "vae_encoder.h"
 #include "weights.h"
 #include "vae_glue.h"
 
@@ -308,6 +309,57 @@ int ltxv_vae_decode(ltxv_vae* m, const void* z, int z_dtype, const float* timest
     m->model.decode(z, z_dtype, timestep, B, F, H, W, out, out_dtype, postprocess, static_cast<cudaStream_t>(stream));
     LTXV_CATCH
 }
+int ltxv_vae_encoder_config_default(ltxv_vae_encoder_config* out) {
+    LTXV_TRY
+    if (out == nullptr) fail("null argument");
+    // AutoencoderKLLtxVideoConfig::default (vae.rs:68-103)
+    const ltxv_vae_encoder_config c = {3, 128, {128, 256, 512, 1024, 2048}, {4, 6, 6, 2, 2},
+        {LTXV_DOWN_SPATIAL, LTXV_DOWN_TEMPORAL, LTXV_DOWN_SPATIOTEMPORAL, LTXV_DOWN_SPATIOTEMPORAL}, 4};
+    *out = c;
+    LTXV_CATCH
+}
+int ltxv_vae_enable_encoder(ltxv_vae* m, const ltxv_vae_encoder_config* cfg) {
+    LTXV_TRY
+    if (m == nullptr || cfg == nullptr) fail("null argument");
+    m->model.enable_encoder(*cfg);
+    LTXV_CATCH
+}
+static LtxVideoEncoder3d& encoder_of(const ltxv_vae* m) {
+    if (m == nullptr) fail("null handle");
+    if (m->model.encoder() == nullptr) fail("this VAE has no encoder: call ltxv_vae_enable_encoder first");
+    return *m->model.encoder();
+}
+int ltxv_vae_encode_dims(const ltxv_vae* m, int F, int H, int W, int32_t* Fl, int32_t* Hl, int32_t* Wl) {
+    LTXV_TRY
+    if (Fl == nullptr || Hl == nullptr || Wl == nullptr) fail("null argument");
+    int a, b, c;
+    encoder_of(m).latent_dims(F, H, W, &a, &b, &c);
+    *Fl = a;
+    *Hl = b;
+    *Wl = c;
+    LTXV_CATCH
+}
+int ltxv_vae_encode(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W, float* moments, void* stream) {
+    LTXV_TRY
+    if (x == nullptr || moments == nullptr) fail("null argument");
+    encoder_of(m).encode(x, x_dtype, B, F, H, W, moments, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+int ltxv_vae_encode_host(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W, float* moments) {
+    LTXV_TRY
+    if (x == nullptr || moments == nullptr) fail("null argument");
+    LtxVideoEncoder3d& e = encoder_of(m);
+    int fl, hl, wl;
+    e.latent_dims(F, H, W, &fl, &hl, &wl);
+    const size_t in_bytes = static_cast<size_t>(B) * 3 * F * H * W * dsize(x_dtype);
+    const size_t out_bytes = static_cast<size_t>(B) * 2 * e.config().latent_channels * fl * hl * wl * 4;
+    m->h_z.ensure(in_bytes);
+    m->h_out.ensure(out_bytes);
+    LTXV_CUDA(cudaMemcpy(m->h_z.p, x, in_bytes, cudaMemcpyHostToDevice));
+    e.encode(m->h_z.p, x_dtype, B, F, H, W, m->h_out.as<float>(), 0);
+    LTXV_CUDA(cudaMemcpy(moments, m->h_out.p, out_bytes, cudaMemcpyDeviceToHost));
+    LTXV_CATCH
+}
 int ltxv_vae_tiling_default(ltxv_vae_tiling* out) {
     LTXV_TRY
     if (out == nullptr) fail("null argument");
@@ -401,6 +453,14 @@ int ltxv_decode_noise_blend(float* latents, const float* noise, float scale, int
     LTXV_TRY
     if (latents == nullptr || noise == nullptr) fail("null argument");
     LTXV_CUDA(launch_noise_blend(latents, noise, scale, n, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_normalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,
+                           int B, int C, int64_t n_per_channel, void* stream) {
+    LTXV_TRY
+    if (in == nullptr || out == nullptr || mean == nullptr || std == nullptr) fail("null argument");
+    LTXV_CUDA(launch_normalize_latents(in, mean, std, scaling_factor, out, B, C, n_per_channel,
+                                       static_cast<cudaStream_t>(stream)));
     LTXV_CATCH
 }
 int ltxv_denormalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,

@@ -17,6 +17,7 @@
 
 #include "gemm.h"
 #include "glue.h"
+#include "vae_encoder.h"
 #include "vae_glue.h"
 
 namespace ltxv {
@@ -128,9 +129,24 @@ AutoencoderKLLtxVideo::AutoencoderKLLtxVideo(const ltxv_vae_config& cfg, int dev
 
 AutoencoderKLLtxVideo::~AutoencoderKLLtxVideo() = default;
 
+bool AutoencoderKLLtxVideo::has_key(const std::string& key) const {
+    return slots_.count(key) != 0 || (enc_ && enc_->has_key(key));
+}
+
+void AutoencoderKLLtxVideo::enable_encoder(const ltxv_vae_encoder_config& cfg) {
+    if (cfg.latent_channels != cfg_.latent_channels)
+        fail("encoder latent_channels %d != decoder latent_channels %d", cfg.latent_channels, cfg_.latent_channels);
+    enc_.reset(new LtxVideoEncoder3d(cfg, device_));
+    finalized_ = false;
+}
+
 void AutoencoderKLLtxVideo::load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape,
                                         int rank) {
     auto it = slots_.find(key);
+    if (it == slots_.end() && enc_ && key.rfind("encoder.", 0) == 0) {
+        enc_->load_tensor(key, data, dtype, shape, rank);
+        return;
+    }
     if (it == slots_.end()) {
         // The reference also builds an encoder / quant convs the t2v path never runs (vae.rs:1772-1808): ignore.
         if (key.rfind("encoder.", 0) == 0 || key.rfind("quant_conv", 0) == 0 || key.rfind("post_quant_conv", 0) == 0)
@@ -188,6 +204,7 @@ void AutoencoderKLLtxVideo::init_random(uint64_t seed) {
         v.ps.loaded = true;
     }
     LTXV_CUDA(cudaDeviceSynchronize());
+    if (enc_) enc_->init_random(seed);
     finalized_ = true;
 }
 
@@ -208,6 +225,7 @@ void AutoencoderKLLtxVideo::finalize() {
         ++n;
     }
     if (n) fail("%d VAE decoder tensors were never loaded (first: %s)", n, missing.c_str());
+    if (enc_) enc_->finalize();
     finalized_ = true;
 }
 

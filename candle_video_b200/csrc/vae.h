@@ -26,6 +26,8 @@ struct TimeEmbW {
     int dim = 0;
 };
 
+class LtxVideoEncoder3d;
+
 class AutoencoderKLLtxVideo {
 public:
     AutoencoderKLLtxVideo(const ltxv_vae_config& cfg, int device);
@@ -33,7 +35,10 @@ public:
 
     const ltxv_vae_config& config() const { return cfg_; }
     void load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape, int rank);
-    bool has_key(const std::string& key) const { return slots_.count(key) != 0; }
+    bool has_key(const std::string& key) const;
+    // encoder half (vae_encoder.h); without it `encoder.*` keys are ignored like in a decode-only deployment
+    void enable_encoder(const ltxv_vae_encoder_config& cfg);
+    LtxVideoEncoder3d* encoder() const { return enc_.get(); }
     void init_random(uint64_t seed);
     void finalize();
     const float* latents_mean() const { return latents_mean_; }
@@ -81,6 +86,7 @@ private:
 
     ltxv_vae_config cfg_;
     int device_;
+    std::unique_ptr<LtxVideoEncoder3d> enc_;
     bool finalized_ = false;
     std::vector<std::unique_ptr<DevBuf>> storage_;
     std::map<std::string, VSlot> slots_;

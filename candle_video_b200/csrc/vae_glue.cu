@@ -42,8 +42,12 @@ __global__ void vae_input_kernel(const TIn* __restrict__ z, __nv_bfloat16* __res
 template <int C>
 __global__ void __launch_bounds__(256)
 vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
-                const float* __restrict__ shift, int do_norm, int do_silu, int T, int H, int W,
+                const float* __restrict__ shift, int do_norm, int do_silu, int T, int H, int W, int tf,
                 __nv_bfloat16* __restrict__ halo_up, __nv_bfloat16* __restrict__ halo_dn) {
+    // tf = replicated frames in front of the volume: 1 = the decoder's non-causal padding (one more copy of the last
+    // frame behind it), 2 = the encoder's causal padding (vae.rs:383-387), 3 = causal padding of a volume whose first
+    // frame is duplicated once more by the temporal downsampler (vae.rs:539-544)
+    constexpr bool kMod = C <= 1024;  // C = 2048 (encoder mid block) is never modulated: keep its registers free
     constexpr int LPV = (C / 8 < 32) ? C / 8 : 32;  // lanes per voxel
     constexpr int VPW = 32 / LPV;                    // voxels per warp
     constexpr int CPL = (C / 8) / LPV;               // chunks per lane
@@ -56,10 +60,10 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
     const int64_t stride = static_cast<int64_t>(gridDim.x) * 8 * VPW;
     const int Hp = H + 2, Wp = W + 2;
 
-    float sc[CPL][8], sh[CPL][8];
-    if (scale != nullptr) {
+    float sc[kMod ? CPL : 1][8], sh[kMod ? CPL : 1][8];
+    if (kMod && scale != nullptr) {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
+        for (int k = 0; k < (kMod ? CPL : 1); ++k) {
             const int c0 = (k * LPV + l) * 8;
             const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c0));
             const float4 b = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
@@ -98,9 +102,9 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[k][i] *= rinv;
         }
-        if (scale != nullptr) {
+        if (kMod && scale != nullptr) {
 #pragma unroll
-            for (int k = 0; k < CPL; ++k)
+            for (int k = 0; k < (kMod ? CPL : 1); ++k)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[k][i] = v[k][i] * sc[k][i] + sh[k][i];
         }
@@ -125,10 +129,11 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             o.w = pack_bf16x2(v[k][6], v[k][7]);
             const int c0 = (k * LPV + l) * 8;
             auto put = [&](__nv_bfloat16* base, int hp) {
-                const int64_t row = (static_cast<int64_t>(t + 1) * Hp + hp) * Wp + (w + 1);
+                const int64_t row = (static_cast<int64_t>(t + tf) * Hp + hp) * Wp + (w + 1);
                 *reinterpret_cast<uint4*>(base + row * C + c0) = o;
-                if (t == 0) *reinterpret_cast<uint4*>(base + (row - plane) * C + c0) = o;      // replicate frame 0
-                if (t == T - 1) *reinterpret_cast<uint4*>(base + (row + plane) * C + c0) = o;  // replicate frame T-1
+                if (t == 0)  // replicate frame 0
+                    for (int q = 1; q <= tf; ++q) *reinterpret_cast<uint4*>(base + (row - q * plane) * C + c0) = o;
+                if (tf == 1 && t == T - 1) *reinterpret_cast<uint4*>(base + (row + plane) * C + c0) = o;  // frame T-1
             };
             put(out, h + 1);
             if (halo_up != nullptr && h == 0) put(halo_up, H + 1);   // my first row = bottom halo of the slab above
@@ -138,7 +143,7 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
     const int istride = static_cast<int>(stride);
     // U voxel groups per iteration, all loads issued before the first is consumed: with 16-byte loads the kernel needs
     // ~8 MB in flight chip-wide to cover HBM latency (Little's law at 6.5 TB/s x 1.2 us)
-    constexpr int U = 2;  // U = 4 measured slower at C = 128 (76 registers: one resident CTA fewer per SM)
+    constexpr int U = C <= 1024 ? 2 : 1;  // U = 4 measured slower at C = 128 (76 registers: one resident CTA fewer per SM)
     for (int base = static_cast<int>(warp0); base < nv32; base += U * istride) {
         int vox[U];
         bool ok[U];
@@ -157,8 +162,8 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 
 template <typename TIn>
 __global__ void conv_weight_relayout_kernel(const TIn* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
-                                            int Cin, int rows_out, int d2s_perm) {
-    // out[r, tap*Cin + c]
+                                            int Cin, int rows_out, int d2s_perm, int cin_src) {
+    // out[r, tap*Cin + c]; the source has cin_src <= Cin input channels (the rest of the K row is zero)
     const int64_t K = 27ll * Cin;
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (idx >= rows_out * K) return;
@@ -172,7 +177,7 @@ __global__ void conv_weight_relayout_kernel(const TIn* __restrict__ w, __nv_bflo
         co = c1 * 8 + sub;
     }
     float v = 0.f;
-    if (r < Cout) v = static_cast<float>(w[(static_cast<int64_t>(co) * Cin + c) * 27 + tap]);
+    if (r < Cout && c < cin_src) v = static_cast<float>(w[(static_cast<int64_t>(co) * cin_src + c) * 27 + tap]);
     out[idx] = __float2bfloat16(v);
 }
 template <typename TIn>
@@ -187,6 +192,103 @@ __global__ void conv_bias_relayout_kernel(const TIn* __restrict__ b, float* __re
         co = c1 * 8 + sub;
     }
     out[r] = (r < Cout) ? static_cast<float>(b[co]) : 0.f;
+}
+
+// ---- encoder-side glue ----
+// One thread per (patch voxel, colour plane slot): 4 rows x 4 pixels of one plane become 16 consecutive channels
+// c*16 + pw*4 + ph (vae.rs:1427-1445); slot 3 writes the 16 zero channels that pad 48 -> 64.
+template <typename TIn>
+__global__ void vae_patchify_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int F, int H, int W) {
+    const int Hq = H >> 2, Wq = W >> 2;
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t n = static_cast<int64_t>(F) * Hq * Wq * 4;
+    if (idx >= n) return;
+    const int c = static_cast<int>(idx & 3);
+    const int64_t vox = idx >> 2;
+    const int w = static_cast<int>(vox % Wq), h = static_cast<int>((vox / Wq) % Hq),
+              f = static_cast<int>(vox / (static_cast<int64_t>(Wq) * Hq));
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    if (c < 3) {
+        const TIn* src = x + ((static_cast<int64_t>(c) * F + f) * H + 4 * h) * W + 4 * w;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+            for (int pw = 0; pw < 4; ++pw) v[pw * 4 + ph] = static_cast<float>(src[static_cast<int64_t>(ph) * W + pw]);
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);   o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    const int Hp = Hq + 2, Wp = Wq + 2;
+    const int64_t plane = static_cast<int64_t>(Hp) * Wp;
+    const int64_t row = (static_cast<int64_t>(f + 2) * Hp + (h + 1)) * Wp + (w + 1);  // causal: two frames in front
+    for (int q = 0; q <= (f == 0 ? 2 : 0); ++q) {
+        uint4* d = reinterpret_cast<uint4*>(out + (row - q * plane) * 64 + c * 16);
+        d[0] = o0;
+        d[1] = o1;
+    }
+}
+
+// LtxVideoDownsampler3d tail (vae.rs:549-581): out[t,h,w, oc] = conv[t*st+i, h*sh+j, w*sw+k, oc / S]  (sub = oc % S)
+//   + mean_{g < G} xdup[.., (oc*G + g) / S] at sub-voxel (oc*G + g) % S,   xdup[t] = x[max(t - (st-1), 0)].
+// One thread per (output voxel, 8 consecutive channels); all operands NDHWC bf16.
+__global__ void vae_unshuffle_add_kernel(const __nv_bfloat16* __restrict__ conv, const __nv_bfloat16* __restrict__ x,
+                                         __nv_bfloat16* __restrict__ out, int To, int Ho, int Wo, int st, int sh, int sw,
+                                         int C, int Cc, int G) {
+    const int S = st * sh * sw;
+    const int Cout = Cc * S;
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t n = static_cast<int64_t>(To) * Ho * Wo * (Cout >> 3);
+    if (idx >= n) return;
+    const int oc0 = static_cast<int>(idx % (Cout >> 3)) * 8;
+    const int64_t vox = idx / (Cout >> 3);
+    const int w = static_cast<int>(vox % Wo), h = static_cast<int>((vox / Wo) % Ho),
+              t = static_cast<int>(vox / (static_cast<int64_t>(Wo) * Ho));
+    const int Hi = Ho * sh, Wi = Wo * sw;
+    const float inv_g = 1.0f / static_cast<float>(G);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int oc = oc0 + e;
+        const int sub = oc % S, cc = oc / S;
+        const int i = sub / (sh * sw), j = (sub / sw) % sh, k = sub % sw;
+        const int64_t cv = (static_cast<int64_t>(t * st + i) * Hi + (h * sh + j)) * Wi + (w * sw + k);
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const int u = oc * G + g;
+            const int ci = u / S, su = u % S;
+            const int i2 = su / (sh * sw), j2 = (su / sw) % sh, k2 = su % sw;
+            int ts = t * st + i2 - (st - 1);
+            ts = ts < 0 ? 0 : ts;
+            const int64_t xv = (static_cast<int64_t>(ts) * Hi + (h * sh + j2)) * Wi + (w * sw + k2);
+            acc += __bfloat162float(x[xv * C + ci]);
+        }
+        v[e] = __bfloat162float(conv[cv * Cc + cc]) + acc * inv_g;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + vox * Cout + oc0) = o;
+}
+
+// conv_out rows [voxel, ld] f32 (columns 0..L = mean channels + one logvar channel) -> moments [2L, T*H*W] f32 with
+// the last conv channel replicated over [L, 2L) (vae.rs:1462-1467)
+__global__ void vae_moments_kernel(const float* __restrict__ h, float* __restrict__ out, int64_t nvox, int L, int ld) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= nvox * 2 * L) return;
+    const int64_t v = idx % nvox;
+    const int c = static_cast<int>(idx / nvox);
+    out[idx] = h[v * ld + (c < L ? c : L)];
+}
+
+// normalize_latents (t2v_pipeline.rs:552-571): (x - mean[c]) * scaling_factor / std[c] on [B, C, inner] f32
+__global__ void normalize_latents_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                         const float* __restrict__ std, float sf, float* __restrict__ out, int C,
+                                         int64_t inner, int64_t n) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= n) return;
+    const int c = static_cast<int>((idx / inner) % C);
+    out[idx] = __fdiv_rn(__fmul_rn(__fsub_rn(x[idx], mean[c]), sf), std[c]);
 }
 
 }  // namespace
@@ -252,7 +354,8 @@ cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out, int C, int
 }
 
 cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const float* shift, int do_norm, int do_silu,
-                            int T, int H, int W, int C, cudaStream_t s, void* halo_up, void* halo_dn) {
+                            int T, int H, int W, int C, cudaStream_t s, void* halo_up, void* halo_dn, int tf) {
+    if (tf < 1 || tf > 3 || (C > 1024 && scale != nullptr)) return cudaErrorInvalidValue;
     __nv_bfloat16* hu = reinterpret_cast<__nv_bfloat16*>(halo_up);
     __nv_bfloat16* hd = reinterpret_cast<__nv_bfloat16*>(halo_dn);
     const int64_t nvox = static_cast<int64_t>(T) * H * W;
@@ -264,26 +367,69 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
     __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
     ProfScope prof(PROF_VAE_PREP, 4.0 * static_cast<double>(nvox) * C, s);  // bf16 in, bf16 out
     switch (C) {
-        case 128: launch_pdl(vae_prep_kernel<128>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
-        case 256: launch_pdl(vae_prep_kernel<256>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
-        case 512: launch_pdl(vae_prep_kernel<512>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
-        case 1024: launch_pdl(vae_prep_kernel<1024>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, hu, hd); break;
+        case 128: launch_pdl(vae_prep_kernel<128>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
+        case 256: launch_pdl(vae_prep_kernel<256>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
+        case 512: launch_pdl(vae_prep_kernel<512>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
+        case 1024: launch_pdl(vae_prep_kernel<1024>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
+        case 2048: launch_pdl(vae_prep_kernel<2048>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
         default: return cudaErrorInvalidValue;
     }
     return done();
 }
 
+cudaError_t launch_vae_patchify(const void* x, int x_is_bf16, void* out_padded, int F, int H, int W, cudaStream_t s) {
+    if ((H & 3) || (W & 3)) return cudaErrorInvalidValue;
+    const int64_t n = static_cast<int64_t>(F) * (H >> 2) * (W >> 2) * 4;
+    const int grid = static_cast<int>((n + 255) / 256);
+    if (x_is_bf16)
+        vae_patchify_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                reinterpret_cast<__nv_bfloat16*>(out_padded), F, H, W);
+    else
+        vae_patchify_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x),
+                                                        reinterpret_cast<__nv_bfloat16*>(out_padded), F, H, W);
+    return done();
+}
+
+cudaError_t launch_vae_unshuffle_add(const void* conv, const void* x, void* out, int To, int Ho, int Wo, int st, int sh,
+                                     int sw, int C, int Cc, cudaStream_t s) {
+    const int S = st * sh * sw;
+    const int Cout = Cc * S;
+    if (Cout % 8 != 0 || (C * S) % Cout != 0) return cudaErrorInvalidValue;
+    const int G = C * S / Cout;
+    const int64_t n = static_cast<int64_t>(To) * Ho * Wo * (Cout >> 3);
+    vae_unshuffle_add_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(conv), reinterpret_cast<const __nv_bfloat16*>(x),
+        reinterpret_cast<__nv_bfloat16*>(out), To, Ho, Wo, st, sh, sw, C, Cc, G);
+    return done();
+}
+
+cudaError_t launch_vae_moments(const float* h, float* out, int64_t nvox, int L, int ld, cudaStream_t s) {
+    const int64_t n = nvox * 2 * L;
+    vae_moments_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(h, out, nvox, L, ld);
+    return done();
+}
+
+cudaError_t launch_normalize_latents(const float* x, const float* mean, const float* std, float scaling_factor,
+                                     float* out, int B, int C, int64_t inner, cudaStream_t s) {
+    const int64_t n = static_cast<int64_t>(B) * C * inner;
+    if (n <= 0) return cudaSuccess;
+    normalize_latents_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(x, mean, std, scaling_factor, out, C, inner, n);
+    return done();
+}
+
 cudaError_t launch_conv_weight_relayout(const void* w, int w_is_bf16, void* out, int Cout, int Cin, int rows_out,
-                                        int d2s_perm, cudaStream_t s) {
+                                        int d2s_perm, cudaStream_t s, int cin_src) {
+    if (cin_src <= 0) cin_src = Cin;
     const int64_t n = static_cast<int64_t>(rows_out) * 27 * Cin;
     const int grid = static_cast<int>((n + 255) / 256);
     if (w_is_bf16)
         conv_weight_relayout_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
-            reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(out), Cout, Cin, rows_out, d2s_perm);
+            reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(out), Cout, Cin, rows_out, d2s_perm,
+            cin_src);
     else
         conv_weight_relayout_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(w),
                                                                 reinterpret_cast<__nv_bfloat16*>(out), Cout, Cin,
-                                                                rows_out, d2s_perm);
+                                                                rows_out, d2s_perm, cin_src);
     return done();
 }
 cudaError_t launch_conv_bias_relayout(const void* b, int b_is_bf16, float* out, int Cout, int rows_out, int d2s_perm,

@@ -145,7 +145,8 @@ int ltxv_vae_config_default(ltxv_vae_config* out);
 int ltxv_vae_create(const ltxv_vae_config* cfg, int device, ltxv_vae** out);
 void ltxv_vae_destroy(ltxv_vae* m);
 /* keys carry the reference's `decoder.` prefix; `latents_mean` / `latents_std` (top level) are optional.
- * `encoder.*` and other unknown keys are accepted and ignored (the reference builds an encoder the t2v path never runs). */
+ * `encoder.*` keys are ignored unless ltxv_vae_enable_encoder was called (the reference builds an encoder the t2v
+ * path never runs); quant_conv / post_quant_conv keys are always ignored. */
 int ltxv_vae_load_tensor(ltxv_vae* m, const char* key, const void* data, int dtype, const int64_t* shape, int rank);
 int ltxv_vae_load_safetensors(ltxv_vae* m, const char* path, int official, int32_t* n_loaded, int32_t* n_ignored);
 int ltxv_vae_init_random(ltxv_vae* m, uint64_t seed);
@@ -181,6 +182,31 @@ int ltxv_vae_decode_tiled(ltxv_vae* m, const void* z, int z_dtype, const float* 
 int ltxv_vae_decode_host(ltxv_vae* m, const void* z, int z_dtype, const float* timestep, int B, int F, int H, int W,
                          void* out, int out_dtype, int postprocess);
 
+/* ---- encoder half: `AutoencoderKLLtxVideo::encode` (vae.rs:2070-2099) -> LtxVideoEncoder3d
+ * (vae.rs:1315-1469).  The reference's t2v path never calls it; it is here for image/video conditioning callers.
+ * Encoder-relevant fields of AutoencoderKLLtxVideoConfig (vae.rs:30-103); LTX-Video 0.9.5 layout only. */
+enum { LTXV_DOWN_SPATIAL = 1, LTXV_DOWN_TEMPORAL = 2, LTXV_DOWN_SPATIOTEMPORAL = 3 }; /* DownsampleType, vae.rs:469-493 */
+typedef struct ltxv_vae_encoder_config {
+    int32_t in_channels;           /* 3 */
+    int32_t latent_channels;       /* 128 */
+    int32_t block_out_channels[5]; /* 128, 256, 512, 1024, 2048 */
+    int32_t layers_per_block[5];   /* 4, 6, 6, 2, 2 (the last entry counts the mid block: layers - 1 resnets) */
+    int32_t downsample_types[4];   /* spatial, temporal, spatiotemporal, spatiotemporal */
+    int32_t patch_size;            /* 4 */
+} ltxv_vae_encoder_config;
+int ltxv_vae_encoder_config_default(ltxv_vae_encoder_config* out);
+/* Builds the encoder inside `m`: from here on `encoder.*` keys are loaded (and required by ltxv_vae_finalize) instead
+ * of ignored, and ltxv_vae_init_random also fills the encoder. */
+int ltxv_vae_enable_encoder(ltxv_vae* m, const ltxv_vae_encoder_config* cfg);
+/* latent extent (F', H', W') of an [F, H, W] video; fails when the extent does not divide through the downsamplers */
+int ltxv_vae_encode_dims(const ltxv_vae* m, int F, int H, int W, int32_t* Fl, int32_t* Hl, int32_t* Wl);
+/* x [B,3,F,H,W] NCDHW in [-1,1] (x_dtype, device) -> moments f32 [B, 2*latent, F', H', W'] (device): channels
+ * [0, latent) are the posterior mean (DiagonalGaussianDistribution::mode, vae.rs:135), [latent, 2*latent) the
+ * log-variance.  Untiled (encode_z with use_tiling / use_framewise_encoding off), no quant_conv. */
+int ltxv_vae_encode(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W, float* moments, void* stream);
+/* same with HOST buffers (copies inside) */
+int ltxv_vae_encode_host(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W, float* moments);
+
 /* ------------------------------------------------------------- pipeline glue -------------------------------------- */
 /* f32 device tensors.  pack: [B,C,F,H,W] -> [B,S,C*pt*p*p]; unpack is the inverse (F,H,W = unpacked dims). */
 int ltxv_pack_latents(const float* in, float* out, int B, int C, int F, int H, int W, int p, int pt, void* stream);
@@ -195,6 +221,9 @@ int ltxv_guidance_euler_step(const float* cond, const float* uncond, const float
 /* in/out f32 [B,C,n_per_channel]; mean/std device f32 [C] */
 int ltxv_denormalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,
                              int B, int C, int64_t n_per_channel, void* stream);
+/* normalize_latents (t2v_pipeline.rs:552-571): (x - mean) * scaling_factor / std, same layout */
+int ltxv_normalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,
+                           int B, int C, int64_t n_per_channel, void* stream);
 int ltxv_postprocess_video(const float* in, float* out, int64_t n, void* stream);
 
 /* Host-only schedule math (stays as in the reference): writes num_steps+1 sigmas (terminal 0 appended) and num_steps

@@ -390,8 +390,9 @@ def causal_conv3d(x: Tensor, weight: Tensor, bias: Tensor, is_causal: bool = Fal
     return F.conv3d(x, weight, bias, stride=1, padding=(0, kh // 2, kh // 2))
 
 
-def resnet_block(w: Dict[str, Tensor], prefix: str, x: Tensor, temb: Optional[Tensor]) -> Tensor:
-    """LtxVideoResnetBlock3d::forward (decoder variant, in == out), vae.rs:711-821."""
+def resnet_block(w: Dict[str, Tensor], prefix: str, x: Tensor, temb: Optional[Tensor], is_causal: bool = False) -> Tensor:
+    """LtxVideoResnetBlock3d::forward (in == out), vae.rs:711-821.  Decoder: non-causal convs, optional timestep
+    conditioning; encoder: causal convs, no conditioning (vae.rs:863-876)."""
     b, c = x.shape[:2]
     tbl = w.get(prefix + "scale_shift_table")
     ss = None
@@ -401,12 +402,12 @@ def resnet_block(w: Dict[str, Tensor], prefix: str, x: Tensor, temb: Optional[Te
     if ss is not None:
         h = h * (1.0 + ss[:, 1]) + ss[:, 0]
     h = F.silu(h)
-    h = causal_conv3d(h, w[prefix + "conv1.conv.weight"], w[prefix + "conv1.conv.bias"])
+    h = causal_conv3d(h, w[prefix + "conv1.conv.weight"], w[prefix + "conv1.conv.bias"], is_causal)
     h = pixel_norm(h)
     if ss is not None:
         h = h * (1.0 + ss[:, 3]) + ss[:, 2]
     h = F.silu(h)
-    h = causal_conv3d(h, w[prefix + "conv2.conv.weight"], w[prefix + "conv2.conv.bias"])
+    h = causal_conv3d(h, w[prefix + "conv2.conv.weight"], w[prefix + "conv2.conv.bias"], is_causal)
     return h + x
 
 
@@ -475,6 +476,114 @@ def vae_decode(w: Dict[str, Tensor], cfg: VaeConfig, z: Tensor, timestep: Option
     h = F.silu(h)
     h = causal_conv3d(h, w[P + "conv_out.conv.weight"], w[P + "conv_out.conv.bias"])
     return unpatchify(h, cfg.patch_size, cfg.patch_size_t)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# encoder: LtxVideoEncoder3d / AutoencoderKLLtxVideo::encode, vae.rs:496-582, :841-948, :1315-1469,
+# :2017-2099.  0.9.5 layout only: pixel-unshuffle downsamplers (the stride-2 "conv" type of 0.9.0 is not restated).
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class VaeEncoderConfig:  # AutoencoderKLLtxVideoConfig defaults, vae.rs:68-103
+    in_channels: int = 3
+    latent_channels: int = 128
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 1024, 2048)
+    layers_per_block: Tuple[int, ...] = (4, 6, 6, 2, 2)
+    downsample_types: Tuple[str, ...] = ("spatial", "temporal", "spatiotemporal", "spatiotemporal")
+    patch_size: int = 4
+    patch_size_t: int = 1
+
+
+DOWNSAMPLE_STRIDE = {"spatial": (1, 2, 2), "temporal": (2, 1, 1), "spatiotemporal": (2, 2, 2)}  # vae.rs:484-493
+
+
+def patchify(x: Tensor, p: int = 4, pt: int = 1) -> Tensor:
+    """LtxVideoEncoder3d::patchify, vae.rs:1427-1445: channel = ((c*pt + it)*p + iw)*p + ih."""
+    b, c, f, h, w = x.shape
+    if f % pt or h % p or w % p:
+        raise ValueError("input not divisible by patch sizes")
+    x = x.reshape(b, c, f // pt, pt, h // p, p, w // p, p).permute(0, 1, 3, 7, 5, 2, 4, 6).contiguous()
+    return x.reshape(b, c * pt * p * p, f // pt, h // p, w // p)
+
+
+def space_to_depth(x: Tensor, st: int, sh: int, sw: int) -> Tensor:
+    """vae.rs:553-556 / :574-577: out[b, ((c*st+i)*sh+j)*sw+k, t, h, w] = x[b, c, t*st+i, h*sh+j, w*sw+k]."""
+    b, c, t, h, w = x.shape
+    x = x.reshape(b, c, t // st, st, h // sh, sh, w // sw, sw).permute(0, 1, 3, 5, 7, 2, 4, 6).contiguous()
+    return x.reshape(b, c * st * sh * sw, t // st, h // sh, w // sw)
+
+
+def downsampler(w: Dict[str, Tensor], prefix: str, x: Tensor, stride: Tuple[int, int, int], out_channels: int) -> Tensor:
+    """LtxVideoDownsampler3d::forward, vae.rs:534-582: duplicate the first st-1 frames, causal conv to
+    out_channels/(st*sh*sw), pixel-unshuffle; residual = pixel-unshuffled input averaged in channel groups."""
+    st, sh, sw = stride
+    c = x.shape[1]
+    group = (c * st * sh * sw) // out_channels
+    if st > 1:
+        x = torch.cat([x[:, :, : st - 1], x], dim=2)
+    res = space_to_depth(x, st, sh, sw)
+    b, cr, t, h, wd = res.shape
+    res = res.reshape(b, cr // group, group, t, h, wd).mean(dim=2)
+    h_ = causal_conv3d(x, w[prefix + "conv.conv.weight"], w[prefix + "conv.conv.bias"], is_causal=True)
+    return space_to_depth(h_, st, sh, sw) + res
+
+
+def vae_encode(w: Dict[str, Tensor], cfg: VaeEncoderConfig, x: Tensor) -> Tensor:
+    """AutoencoderKLLtxVideo::encode -> encode_z (untiled, no quant_conv) -> LtxVideoEncoder3d::forward,
+    vae.rs:2070, :2017-2034, :1447-1468.  x [B,3,F,H,W] in [-1,1] -> moments [B, 2*latent, F', H', W']:
+    channels [0,latent) = mean, [latent, 2*latent) = logvar (one conv channel replicated, :1462-1467)."""
+    x = x.to(F32)
+    P = "encoder."
+    h = patchify(x, cfg.patch_size, cfg.patch_size_t)
+    h = causal_conv3d(h, w[P + "conv_in.conv.weight"], w[P + "conv_in.conv.bias"], is_causal=True)
+    boc = cfg.block_out_channels
+    for bi in range(len(boc) - 1):
+        bp = P + f"down_blocks.{bi}."
+        for i in range(cfg.layers_per_block[bi]):
+            h = resnet_block(w, bp + f"resnets.{i}.", h, None, is_causal=True)
+        h = downsampler(w, bp + "downsamplers.0.", h, DOWNSAMPLE_STRIDE[cfg.downsample_types[bi]], boc[bi + 1])
+    for i in range(cfg.layers_per_block[-1] - 1):  # vae.rs:1383-1386
+        h = resnet_block(w, P + f"mid_block.resnets.{i}.", h, None, is_causal=True)
+    h = F.silu(pixel_norm(h))
+    h = causal_conv3d(h, w[P + "conv_out.conv.weight"], w[P + "conv_out.conv.bias"], is_causal=True)
+    ch = h.shape[1]
+    return torch.cat([h, h[:, -1:].repeat(1, ch - 2, 1, 1, 1)], dim=1)
+
+
+def vae_encoder_weight_shapes(cfg: VaeEncoderConfig) -> Dict[str, Tuple[int, ...]]:
+    """Appendix A (encoder half): keys as consumed by VarBuilder at vae.rs:1342-1412, :863-905, :513-524."""
+    s: Dict[str, Tuple[int, ...]] = {}
+    P = "encoder."
+
+    def conv(prefix: str, cin: int, cout: int) -> None:
+        s[prefix + ".conv.weight"] = (cout, cin, 3, 3, 3)
+        s[prefix + ".conv.bias"] = (cout,)
+
+    boc = cfg.block_out_channels
+    conv(P + "conv_in", cfg.in_channels * cfg.patch_size_t * cfg.patch_size ** 2, boc[0])
+    for bi in range(len(boc) - 1):
+        c = boc[bi]
+        for i in range(cfg.layers_per_block[bi]):
+            conv(P + f"down_blocks.{bi}.resnets.{i}.conv1", c, c)
+            conv(P + f"down_blocks.{bi}.resnets.{i}.conv2", c, c)
+        st, sh, sw = DOWNSAMPLE_STRIDE[cfg.downsample_types[bi]]
+        conv(P + f"down_blocks.{bi}.downsamplers.0.conv", c, boc[bi + 1] // (st * sh * sw))
+    c = boc[-1]
+    for i in range(cfg.layers_per_block[-1] - 1):
+        conv(P + f"mid_block.resnets.{i}.conv1", c, c)
+        conv(P + f"mid_block.resnets.{i}.conv2", c, c)
+    conv(P + "conv_out", c, cfg.latent_channels + 1)
+    return s
+
+
+def init_vae_encoder_weights(cfg: VaeEncoderConfig, seed: int = 43) -> Dict[str, Tensor]:
+    gen = torch.Generator().manual_seed(seed)
+    return {k: _init_tensor(k, shp, gen) for k, shp in vae_encoder_weight_shapes(cfg).items()}
+
+
+def normalize_latents(latents: Tensor, mean: Tensor, std: Tensor, scaling_factor: float) -> Tensor:
+    """t2v_pipeline.rs:552-571: (x - mean) * scaling_factor / std per channel."""
+    c = latents.shape[1]
+    return (latents - mean.reshape(1, c, 1, 1, 1)) * scaling_factor / std.reshape(1, c, 1, 1, 1)
 
 
 # ---------------------------------------------------------------------------------------------------------------

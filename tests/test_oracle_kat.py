@@ -250,3 +250,75 @@ def test_tiling_dispatch_and_frame_count():
     # the first temporal tile contributes its first stride+1 = 9 frames unchanged (:2426-2429)
     first = O.vae_decode(w, cfg, z[:, :, :3], ts)
     assert torch.equal(tiled[:, :, :9], first[:, :, :9])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# encoder restatement
+# ---------------------------------------------------------------------------------------------------------------
+def test_patchify_index_map_and_unpatchify_inverse():
+    """vae.rs:1427-1445: out[b, (c*pt + it)*p*p + iw*p + ih, f, h, w] = x[b, c, f*pt + it, h*p + ih, w*p + iw];
+    the decoder's unpatchify (vae.rs:1626-1654) is its inverse."""
+    x = torch.arange(2 * 3 * 2 * 8 * 12, dtype=torch.float32).reshape(2, 3, 2, 8, 12)
+    y = O.patchify(x, 4, 1)
+    assert y.shape == (2, 48, 2, 2, 3)
+    for (b, c, f, h, w, ih, iw) in [(0, 0, 0, 0, 0, 0, 0), (1, 2, 1, 1, 2, 3, 1), (0, 1, 1, 0, 1, 2, 3)]:
+        assert y[b, c * 16 + iw * 4 + ih, f, h, w] == x[b, c, f, h * 4 + ih, w * 4 + iw]
+    assert torch.equal(O.unpatchify(y, 4, 1), x)
+    with pytest.raises(ValueError):
+        O.patchify(torch.zeros(1, 3, 1, 6, 8), 4, 1)
+
+
+def test_space_to_depth_closed_form_and_inverse():
+    x = torch.randn(1, 3, 4, 6, 8, generator=torch.Generator().manual_seed(0))
+    for st, sh, sw in O.DOWNSAMPLE_STRIDE.values():
+        y = O.space_to_depth(x, st, sh, sw)
+        assert y.shape == (1, 3 * st * sh * sw, 4 // st, 6 // sh, 8 // sw)
+        c, i, j, k, t, h, w = 2, st - 1, sh - 1, 0, 1, 2, 3
+        assert y[0, ((c * st + i) * sh + j) * sw + k, t, h, w] == x[0, c, t * st + i, h * sh + j, w * sw + k]
+        assert torch.equal(O.depth_to_space(y, st, sh, sw), x)
+
+
+def test_downsampler_constant_input():
+    """With zero conv weights the downsampler is the group-mean of the unshuffled input (+ bias): a constant volume
+    stays constant, and the temporal variants turn T frames into (T+1)/2 (first frame duplicated, vae.rs:539-544)."""
+    for name, (st, sh, sw) in O.DOWNSAMPLE_STRIDE.items():
+        cin, cout = 8, 16
+        cc = cout // (st * sh * sw)
+        w = {"d.conv.conv.weight": torch.zeros(cc, cin, 3, 3, 3), "d.conv.conv.bias": torch.full((cc,), 0.25)}
+        x = torch.full((1, cin, 5, 4, 4), 2.0)
+        y = O.downsampler(w, "d.", x, (st, sh, sw), cout)
+        assert y.shape == (1, cout, (5 + st - 1) // st, 4 // sh, 4 // sw), name
+        assert torch.allclose(y, torch.full_like(y, 2.25))
+
+
+def test_encoder_shapes_keys_and_logvar_replication():
+    cfg = O.VaeEncoderConfig(block_out_channels=(64, 64, 128, 128, 256), layers_per_block=(1, 1, 1, 1, 2))
+    shapes = O.vae_encoder_weight_shapes(cfg)
+    # key names as consumed by VarBuilder (vae.rs:1342-1412, :863-905, :513-524)
+    assert shapes["encoder.conv_in.conv.weight"] == (64, 48, 3, 3, 3)
+    assert shapes["encoder.down_blocks.0.downsamplers.0.conv.conv.weight"] == (16, 64, 3, 3, 3)   # spatial: 64/4
+    assert shapes["encoder.down_blocks.1.downsamplers.0.conv.conv.weight"] == (64, 64, 3, 3, 3)   # temporal: 128/2
+    assert shapes["encoder.down_blocks.3.downsamplers.0.conv.conv.weight"] == (32, 128, 3, 3, 3)  # 256/8
+    assert shapes["encoder.conv_out.conv.weight"] == (129, 256, 3, 3, 3)
+    assert "encoder.mid_block.resnets.0.conv1.conv.weight" in shapes
+    assert "encoder.mid_block.resnets.1.conv1.conv.weight" not in shapes  # layers - 1 resnets (vae.rs:1383-1386)
+    full = O.vae_encoder_weight_shapes(O.VaeEncoderConfig())
+    assert sum(1 for k in full if k.endswith("conv1.conv.weight")) == 4 + 6 + 6 + 2 + 1
+    w = O.init_vae_encoder_weights(cfg)
+    x = torch.randn(2, 3, 9, 64, 96, generator=torch.Generator().manual_seed(1))
+    m = O.vae_encode(w, cfg, x)
+    assert m.shape == (2, 256, 2, 2, 3)
+    assert torch.equal(m[:, 128:], m[:, 128:129].expand(-1, 128, -1, -1, -1))
+    # causal: latent frame 0 only sees video frame 0
+    y = x.clone()
+    y[:, :, 1:] = 0
+    assert torch.allclose(O.vae_encode(w, cfg, y)[:, :, 0], m[:, :, 0], atol=1e-6)
+
+
+def test_normalize_denormalize_round_trip():
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(1, 8, 2, 3, 4, generator=g)
+    mean, std = torch.randn(8, generator=g), torch.rand(8, generator=g) + 0.5
+    n = O.normalize_latents(z, mean, std, 0.5)
+    assert torch.allclose(n[0, 3], (z[0, 3] - mean[3]) * 0.5 / std[3])
+    assert torch.allclose(O.denormalize_latents(n, mean, std, 0.5), z, atol=1e-5)
