@@ -48,6 +48,23 @@ def vae_flops(F, H, W):
     return tot
 
 
+def vae_encode_flops(frames, height, width):
+    """Sum over the 0.9.5 encoder's convs of 2*Cin*Cout*27*T*H*W (vae.rs:68-103 defaults; conv_in counted at its
+    algorithmic 48 input channels, conv_out at 129 outputs; the temporal downsamplers run on T+1 frames)."""
+    ch, layers = [128, 256, 512, 1024, 2048], [4, 6, 6, 2, 1]
+    strides = [(1, 2, 2), (2, 1, 1), (2, 2, 2), (2, 2, 2)]
+    T, h, w = frames, height // 4, width // 4
+    tot = 2 * 48 * ch[0] * 27 * T * h * w
+    for l in range(5):
+        tot += layers[l] * 2 * 2 * ch[l] * ch[l] * 27 * T * h * w
+        if l < 4:
+            st, sh, sw = strides[l]
+            tot += 2 * ch[l] * (ch[l + 1] // (st * sh * sw)) * 27 * (T + st - 1) * h * w
+            T, h, w = (T + st - 1) // st, h // sh, w // sw
+    tot += 2 * ch[4] * 129 * 27 * T * h * w
+    return tot
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
 
@@ -434,6 +451,29 @@ def run_ours(args):
             "unattributed_ms_per_step": step1 - (gm["ms"] + attn_ms + prof_dit["norm_modulate"]["ms"] +
                                                  prof_dit["qk_norm_rope"]["ms"]) / 2,
         }
+        if world == 1 and not args.no_encode:
+            # row f-4 (next row of the path): the VAE encoder on the clip the decoder produces, same conv3d kernel
+            venc = cv.AutoencoderKLLtxVideo(cv.VaeConfig(), device=local_rank)
+            venc.enable_encoder()
+            venc.init_random(99)
+            clip = torch.tanh(torch.randn(1, 3, FRAMES, HEIGHT, WIDTH, device=dev))
+            venc.encode(clip)  # workspace + warm-up
+            torch.cuda.synchronize()
+            cv.profile_begin()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                venc.encode(clip)
+            e1.record()
+            torch.cuda.synchronize()
+            prof_enc = cv.profile_end()
+            enc_ms = e0.elapsed_time(e1) / 2
+            line["roofline_all"]["vae_encode"] = {
+                "ms_per_encode": enc_ms, "frames_per_s": FRAMES * 1000.0 / enc_ms,
+                "algorithmic_tflops": vae_encode_flops(FRAMES, HEIGHT, WIDTH) / (enc_ms * 1e-3) / 1e12,
+                "conv3d_tflops": tf(prof_enc["conv3d"]), "conv3d_ms": prof_enc["conv3d"]["ms"] / 2,
+                "prep": hbm(prof_enc["vae_prep"], 2), "api": "ltxv_vae_encode (device buffers)"}
+            del venc, clip
         if world == 1:
             line["roofline_all"]["vae_decode_algorithmic_tflops"] = vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12
             line["roofline_all"]["vae_decode_frac_of_peak"] = (vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12 /
@@ -470,6 +510,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encode", action="store_true", help="skip the VAE encoder measurement (roofline_all.vae_encode)")
     ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "pairs", "sharded"],
                     help="multi-GPU decomposition of the headline number (auto = replicas, the throughput-optimal one)")
     args = ap.parse_args()
