@@ -1033,6 +1033,276 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 
+// ================================================================================================
+// Self-attention, head_dim 128 (the 13B preset: 32 heads x 128).  Same organisation as flash_attn3_kernel (two query
+// tiles per CTA sharing every K/V tile, register-resident scores, P in TMEM, one UMMA issuer per tile), with the
+// differences head_dim 128 forces:
+//   * TMEM is full with S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512): P_t (64 packed bf16x2 columns) ALIASES the
+//     first half of S_t.  A softmax thread holds its whole S row in registers before it writes P, and the issuer emits
+//     QK^T(j+1) of a tile only after P_t V(j) in program order (the tensor pipe executes one thread's MMAs in order),
+//     so S_t is overwritten only after P_t has been consumed; the OTHER tile's MMAs fill the pipe meanwhile.
+//   * s_full(j+1) is committed after P V(j), hence also signals "O_t may be rescaled": no pv_done wait in the loop.
+//   * K / V tiles are 32 KB (two 64-column swizzle atoms, 16 KB apart): 2-stage rings, Q 2 x 32 KB -> 192 KB smem.
+//   * MUFU is no longer the bound (twice the FLOPs per exponential): per key tile 1024 clk of tensor work against
+//     768 clk of exp2 per query tile.
+// No tail splitting (c4 runs 2432 units = 16.4 waves).
+// ================================================================================================
+constexpr int kV5Threads = 384;
+constexpr int kV5Stages = 2;
+constexpr int kV5QBytes = kTileQ * 128 * 2;    // 32 KB per query tile
+constexpr int kV5KVBytes = kTileKV * 128 * 2;  // 32 KB per K or V tile
+constexpr int kV5SmemBytes = 2 * kV5QBytes + 2 * kV5Stages * kV5KVBytes + 512;
+
+__global__ void __launch_bounds__(kV5Threads, 1)
+flash_attn3_d128_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ AttnParams p, const int n_qb) {
+    constexpr int D = 128;
+    constexpr int kHalf = kTileKV * 128;  // bytes of one 64-column atom of a 128-row tile
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sq = smem;
+    uint8_t* sk = sq + 2 * kV5QBytes;
+    uint8_t* sv = sk + kV5Stages * kV5KVBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sv + kV5Stages * kV5KVBytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = bars + 1 + kV5Stages;
+    uint64_t* v_full = bars + 1 + 2 * kV5Stages;
+    uint64_t* v_empty = bars + 1 + 3 * kV5Stages;
+    uint64_t* s_full = bars + 1 + 4 * kV5Stages;  // [2]
+    uint64_t* p_full = s_full + 2;                // [2]
+    uint64_t* pv_done = p_full + 2;               // [2] last P V of the tile retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x;
+    const int qb = unit % n_qb;
+    const int head = (unit / n_qb) % p.H;
+    const int batch = unit / (n_qb * p.H);
+    const int q0 = qb * (2 * kTileQ);
+    const int n_tiles = (p.Skv + kTileKV - 1) / kTileKV;
+    const bool two = (q0 + kTileQ) < p.Sq;
+    const int nt = two ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {
+            printf("ltxv attention d128: dynamic smem base not 1024B aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < kV5Stages; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], nt);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], nt);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&p_full[t], 4);  // one arrival per softmax warp
+            mbar_init(&pv_done[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 11) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();
+
+    if (warp_idx >= 8) {
+        setmaxnreg_dec<48>();
+        if (warp_idx == 8) {
+            // ===================== TMA producer =====================
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, nt * kV5QBytes);
+                for (int t = 0; t < nt; ++t)
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_3d(sq + t * kV5QBytes + h * kHalf, &tm_q, q_full, p.q_col0 + head * D + h * 64,
+                                    q0 + t * kTileQ, batch);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_tiles; ++j) {
+                    const int kv0 = j * kTileKV;
+                    if (j + kV5Stages + 1 < n_tiles) {
+                        const int kvp = kv0 + (kV5Stages + 1) * kTileKV;
+                        for (int h = 0; h < 2; ++h) {
+                            tma_prefetch_3d(&tm_k, p.k_col0 + head * D + h * 64, kvp, batch);
+                            tma_prefetch_3d(&tm_v, p.v_col0 + head * D + h * 64, kvp, batch);
+                        }
+                    }
+                    mbar_wait_sleep(&k_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&k_full[stage], kV5KVBytes);
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_3d(sk + stage * kV5KVBytes + h * kHalf, &tm_k, &k_full[stage],
+                                    p.k_col0 + head * D + h * 64, kv0, batch);
+                    mbar_wait_sleep(&v_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&v_full[stage], kV5KVBytes);
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_3d(sv + stage * kV5KVBytes + h * kHalf, &tm_v, &v_full[stage],
+                                    p.v_col0 + head * D + h * 64, kv0, batch);
+                    if (++stage == kV5Stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        } else if (warp_idx == 9 || (warp_idx == 10 && two)) {
+            // ===================== UMMA issuer of query tile t =====================
+            const int t = warp_idx - 9;
+            if (elect_one()) {
+                constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, false, false);
+                constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, D, false, true);  // B = V is MN-major
+                const uint32_t qa = smem_u32(sq) + t * kV5QBytes;
+                const uint32_t tmem_s = tmem_base + t * 128;
+                const uint32_t tmem_o = tmem_base + 256 + t * 128;
+                const uint32_t tmem_p = tmem_s;  // aliases S_t columns [0, 64)
+                auto issue_s = [&](int stage) {
+                    const uint32_t k_addr = smem_u32(sk + stage * kV5KVBytes);
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks) {
+                        const uint32_t off = (ks >> 2) * kHalf + (ks & 3) * 32;
+                        umma_bf16_ss(tmem_s, make_smem_desc_sw128(qa + off, 1024, 0),
+                                     make_smem_desc_sw128(k_addr + off, 1024, 0), idesc_s, ks != 0 ? 1u : 0u);
+                    }
+                };
+                mbar_wait_sleep(q_full, 0);
+                mbar_wait_sleep(&k_full[0], 0);
+                tcgen05_fence_after();
+                issue_s(0);
+                umma_commit(&s_full[t]);
+                umma_commit(&k_empty[0]);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_tiles; ++j) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == kV5Stages) {
+                        nstage = 0;
+                        nphase ^= 1;
+                    }
+                    mbar_wait_sleep(&v_full[stage], phase);
+                    mbar_wait_sleep(&p_full[t], j & 1);
+                    tcgen05_fence_after();
+                    const uint32_t v_addr = smem_u32(sv + stage * kV5KVBytes);
+#pragma unroll
+                    for (int ks = 0; ks < kTileKV / 16; ++ks)
+                        umma_bf16_ts(tmem_o, tmem_p + ks * 8,
+                                     make_smem_desc_sw128(v_addr + ks * (16 * 128), 1024, kHalf), idesc_pv,
+                                     (j | ks) != 0 ? 1u : 0u);
+                    umma_commit(&v_empty[stage]);
+                    if (j + 1 < n_tiles) {
+                        // S_t(j+1) overwrites S_t / P_t: in program order behind P_t V(j)
+                        mbar_wait_sleep(&k_full[nstage], nphase);
+                        tcgen05_fence_after();
+                        issue_s(nstage);
+                        umma_commit(&s_full[t]);
+                        umma_commit(&k_empty[nstage]);
+                    } else {
+                        umma_commit(&pv_done[t]);
+                    }
+                    stage = nstage;
+                    phase = nphase;
+                }
+            }
+        }
+    } else {
+        setmaxnreg_inc<224>();
+        const int t = warp_idx >> 2;
+        if (t == 0 || two) {
+            const int quad = warp_idx & 3;
+            const int row = quad * 32 + lane;
+            const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+            const uint32_t tmem_s = lane_base + t * 128;
+            const uint32_t tmem_o = lane_base + 256 + t * 128;
+            const uint32_t tmem_p = tmem_s;
+            const float c = p.scale * kLog2e;
+            const uint64_t c2 = pack_f32x2(c, c);
+            float m_used = -INFINITY;
+            uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+            auto tile = [&](int j, auto tail_tag) {
+                constexpr bool TAIL = decltype(tail_tag)::value;
+                const int kv0 = j * kTileKV;
+                uint32_t s0[32], s1[32], s2[32], s3[32];
+                warp_mbar_wait(&s_full[t], j & 1, lane);  // also: P_t V(j-1) retired, O_t is quiescent
+                tcgen05_fence_after();
+                tmem_ld_32x32b_x32(tmem_s + 0, s0);
+                tmem_ld_32x32b_x32(tmem_s + 32, s1);
+                tmem_ld_32x32b_x32(tmem_s + 64, s2);
+                tmem_ld_32x32b_x32(tmem_s + 96, s3);
+                tmem_ld_wait();
+                float mx = fmaxf(fmaxf(max32_v3<TAIL>(s0, kv0, p.Skv), max32_v3<TAIL>(s1, kv0 + 32, p.Skv)),
+                                 fmaxf(max32_v3<TAIL>(s2, kv0 + 64, p.Skv), max32_v3<TAIL>(s3, kv0 + 96, p.Skv)));
+                mx *= c;
+                if (j == 0) {
+                    m_used = mx;
+                } else {
+                    const float m_new = fmaxf(m_used, mx);
+                    if (__any_sync(0xffffffffu, (m_new - m_used) > kRescaleThreshold)) {
+                        const float alpha = ex2_approx(m_used - m_new);
+#pragma unroll 1
+                        for (int dc = 0; dc < D / 32; ++dc) {
+                            uint32_t r[32];
+                            tmem_ld_32x32b_x32(tmem_o + dc * 32, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st_32x32b_x32(tmem_o + dc * 32, r);
+                        }
+                        tmem_st_wait();
+                        const uint64_t a2 = pack_f32x2(alpha, alpha), z2 = pack_f32x2(0.f, 0.f);
+                        l2a = fma_f32x2(l2a, a2, z2);
+                        l2b = fma_f32x2(l2b, a2, z2);
+                        m_used = m_new;
+                    }
+                }
+                const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
+                uint32_t pk[32];
+                exp_chunk_v3(s0, c2, negm2, l2a, l2b, pk);
+                exp_chunk_v3(s1, c2, negm2, l2a, l2b, pk + 16);
+                tmem_st_32x32b_x32(tmem_p, pk);       // keys  0..63  -> P columns  0..31 (over S columns 0..31)
+                exp_chunk_v3(s2, c2, negm2, l2a, l2b, pk);
+                exp_chunk_v3(s3, c2, negm2, l2a, l2b, pk + 16);
+                tmem_st_32x32b_x32(tmem_p + 32, pk);  // keys 64..127 -> P columns 32..63
+                tmem_st_wait();
+                tcgen05_fence_before();
+                warp_mbar_arrive(&p_full[t], lane);
+            };
+            const bool ragged = (p.Skv % kTileKV != 0);
+            const int n_full = n_tiles - (ragged ? 1 : 0);
+            for (int j = 0; j < n_full; ++j) tile(j, std::false_type{});
+            if (ragged) tile(n_full, std::true_type{});
+            warp_mbar_wait(&pv_done[t], 0, lane);
+            tcgen05_fence_after();
+            float la, lb, lc, ld;
+            unpack_f32x2(l2a, la, lb);
+            unpack_f32x2(l2b, lc, ld);
+            const float inv_l = 1.0f / ((la + lb) + (lc + ld));
+            const int qrow = q0 + t * kTileQ + row;
+            __nv_bfloat16* orow = attn_out_row(p, batch, qrow < p.Sq ? qrow : 0, head, D);
+#pragma unroll 1
+            for (int dc = 0; dc < D / 32; ++dc) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_o + dc * 32, r);
+                tmem_ld_wait();
+                if (qrow < p.Sq) store_row_bf16(orow + dc * 32, r, inv_l);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 11) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+
 
 // ================================================================================================
 // Cross-attention (head_dim 64, <= 128 keys: the T5 text tokens).  The whole key axis is ONE tile, so there is no online
@@ -1345,6 +1615,32 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
 }
 
 
+cudaError_t launch_attn3_d128_impl(const AttnParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(flash_attn3_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kV5SmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    CUtensorMap tq, tk, tv;
+    cudaError_t e = make_tensor_map_3d_bf16(&tq, p.q, p.B, p.Sq, p.ldq, kTileQ, 64, p.ldq, p.ldq * (int64_t)p.Sq);
+    if (e != cudaSuccess) return e;
+    e = make_tensor_map_3d_bf16(&tk, p.k, p.B, p.Skv, p.ldk, kTileKV, 64, p.ldk, p.ldk * (int64_t)p.Skv);
+    if (e != cudaSuccess) return e;
+    e = make_tensor_map_3d_bf16(&tv, p.v, p.B, p.Skv, p.ldv, kTileKV, 64, p.ldv, p.ldv * (int64_t)p.Skv);
+    if (e != cudaSuccess) return e;
+    const int n_qb = (p.Sq + 2 * kTileQ - 1) / (2 * kTileQ);
+    {
+        ProfScope prof(PROF_ATTN_SELF, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 128, stream);
+        cudaError_t le = launch_pdl(flash_attn3_d128_kernel, dim3(p.B * p.H * n_qb), dim3(kV5Threads), kV5SmemBytes, stream,
+                                    tq, tk, tv, p, n_qb);
+        if (le != cudaSuccess) return le;
+    }
+    g_attn_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cross_attn_impl(const AttnParams& p, cudaStream_t stream) {
     static bool configured = false;
     static int num_sms = 148;
@@ -1421,6 +1717,8 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
         return launch_attn3_impl(p, stream);
     if (p.D == 64 && p.Skv <= kTileKV && p.out_rows_per_peer == 0 && getenv("LTXV_ATTN_V1") == nullptr)
         return launch_cross_attn_impl(p, stream);  // one key tile: text cross-attention
+    if (p.D == 128 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && getenv("LTXV_ATTN_V1") == nullptr)
+        return launch_attn3_d128_impl(p, stream);
     if (p.D == 64) return launch_attn_impl<64>(p, stream);
     if (p.D == 128) return launch_attn_impl<128>(p, stream);
     return cudaErrorInvalidValue;

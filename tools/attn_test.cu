@@ -157,6 +157,9 @@ int main(int argc, char** argv) {
     fails += run(1, 4, 300, 77, 64, false, true, false, 1.0f);    // ragged text length
     fails += run(1, 2, 256, 256, 128, true, false, false, 1.0f);  // 13B head_dim
     fails += run(1, 2, 300, 128, 128, false, true, false, 1.0f);
+    fails += run(1, 2, 384, 384, 128, true, false, false, 2.0f);    // head_dim-128 two-tile kernel: odd tile count
+    fails += run(2, 3, 640, 1300, 128, false, false, false, 5.0f);  // batch, ragged kv tail, peaky softmax (rescale path)
+    fails += run(1, 2, 1000, 1000, 128, true, false, false, 6.0f);
     if (big) {
         fails += run(1, 32, 4992, 4992, 64, true, false, true, 1.0f);
         fails += run(1, 32, 4992, 128, 64, false, true, true, 1.0f);
@@ -164,6 +167,7 @@ int main(int argc, char** argv) {
         fails += run(1, 16, 4992, 4992, 64, true, false, true, 1.0f);  // Ulysses shard at 4 GPUs
         fails += run(1, 32, 13376, 13376, 64, true, false, true, 1.0f);
         fails += run(1, 32, 4992, 4992, 128, true, false, true, 1.0f);
+        fails += run(1, 32, 19320, 19320, 128, true, false, true, 1.0f);  // c4: 13B at 736x1280x161
     }
     printf("%s (%d failing cases)\n", fails ? "ATTN_TEST_FAIL" : "ATTN_TEST_OK", fails);
     return fails ? 1 : 0;
