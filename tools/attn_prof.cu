@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../candle_video_b200/csrc/attention.h"
 using namespace ltxv;
 namespace ltxv { void attention_debug_timing(long long* out32); void attention_debug_trace(long long* out); }
@@ -10,13 +11,15 @@ __global__ void fill(__nv_bfloat16* p, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) { uint32_t x = (uint32_t)i * 2654435761u; x ^= x >> 15; p[i] = __float2bfloat16(((x >> 8) * (1.0f / 16777216.0f) - 0.5f) * 2.f); }
 }
-int main() {
-    const int S = 4992, H = 32, D = 64, HD = H * D;
+int main(int argc, char** argv) {
+    // usage: attn_prof [S] [H] [D]   (defaults: the c2 shape; `attn_prof 4992 32 128` = the 13B head layout)
+    const int S = argc > 1 ? atoi(argv[1]) : 4992, H = argc > 2 ? atoi(argv[2]) : 32, D = argc > 3 ? atoi(argv[3]) : 64;
+    const int HD = H * D;
     __nv_bfloat16 *q, *o;
     cudaMalloc(&q, (size_t)S * 3 * HD * 2); cudaMalloc(&o, (size_t)S * HD * 2);
     fill<<<((size_t)S * 3 * HD + 255) / 256, 256>>>(q, (size_t)S * 3 * HD);
     AttnParams p{}; p.q = p.k = p.v = q; p.ldq = p.ldk = p.ldv = 3 * HD; p.k_col0 = HD; p.v_col0 = 2 * HD; p.out = o; p.ldo = HD;
-    p.B = 1; p.H = H; p.Sq = S; p.Skv = S; p.D = D; p.scale = 0.125f;
+    p.B = 1; p.H = H; p.Sq = S; p.Skv = S; p.D = D; p.scale = 1.0f / sqrtf((float)D);
     for (int i = 0; i < 3; ++i) launch_attention(p, 0);
     cudaDeviceSynchronize();
     printf("done %s\n", cudaGetErrorString(cudaGetLastError()));
