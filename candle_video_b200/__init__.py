@@ -727,13 +727,19 @@ def pipeline_denoise(dit: LtxVideoTransformer3DModel, params: PipelineParams, la
 
 
 def pipeline_decode(vae: AutoencoderKLLtxVideo, params: PipelineParams, latents, decode_noise=None,
-                    decode_noise_scale: float = 0.0):
+                    decode_noise_scale: float = 0.0, out=None):
     """Decode branch (t2v_pipeline.rs:1000-1072).  decode_noise: f32 CUDA [128, F, H, W] drawn by the caller, blended
-    as (1 - scale) latents + scale noise before the VAE (:1049-1062)."""
+    as (1 - scale) latents + scale noise before the VAE (:1049-1062).  out: optional preallocated f32 CUDA
+    [3, frames, height, width] (a fresh 458 MB tensor per call otherwise costs a cudaMalloc when the caching
+    allocator has no free block)."""
     torch = _torch()
     p, keep = params.to_c()
     f = (params.num_frames - 1) // 8 + 1
-    out = torch.empty((3, 8 * f - 7, params.height, params.width), dtype=torch.float32, device=latents.device)
+    shape = (3, 8 * f - 7, params.height, params.width)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=latents.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+        raise LtxvError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
     if decode_noise is None and decode_noise_scale == 0.0:
         _check(lib().ltxv_pipeline_decode(vae._h, C.byref(p), _ptr(latents), _ptr(out), _stream()))
     else:

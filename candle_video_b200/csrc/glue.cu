@@ -235,72 +235,97 @@ qk_pair_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, in
 
 // register-resident variant of qk_pair_norm_rope_kernel for D = 256 * VPL: q and k of the token are loaded once (all 2*VPL
 // 16-byte loads in flight), normed, rotated and stored; one pass over the activations and over the cos/sin row
-template <int VPL>
+template <int VPL, bool SHARE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 qk_pair_norm_rope_row_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, const float* __restrict__ wq,
                              const float* __restrict__ wk, float eps, const float* __restrict__ cos_t,
                              const float* __restrict__ sin_t, int table_rows) {
+    // SHARE: one warp per TABLE row: with the two CFG branches batched (rows = 2 * table_rows) the warp keeps the
+    // cos/sin row in registers and applies it to token t of both branches, so the f32 tables cross HBM once instead of
+    // twice.  !SHARE (D = 4096: the tables do not fit next to a row): one warp per activation row.
     constexpr int D = VPL * 256;
     griddep_launch_dependents();
     griddep_wait();
-    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int w_row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    uint4* xq = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
-    uint4* xk = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + D);
-    const int trow = row % table_rows;
+    if (w_row >= (SHARE ? table_rows : rows)) return;
+    const int trow = SHARE ? w_row : w_row % table_rows;
+    const int row_step = SHARE ? table_rows : rows;
     const float4* c4 = reinterpret_cast<const float4*>(cos_t + static_cast<int64_t>(trow) * (D >> 1));
     const float4* s4 = reinterpret_cast<const float4*>(sin_t + static_cast<int64_t>(trow) * (D >> 1));
+    float4 cc[SHARE ? VPL : 1], ss[SHARE ? VPL : 1];
     uint4 q[VPL], k[VPL];
+    {
+        const uint4* xq = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(w_row) * ld);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        q[i] = xq[lane + 32 * i];
-        k[i] = xk[lane + 32 * i];
-    }
-    float sq = 0.f, sk = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const float fa[8] = {bf16_lo(q[i].x), bf16_hi(q[i].x), bf16_lo(q[i].y), bf16_hi(q[i].y),
-                             bf16_lo(q[i].z), bf16_hi(q[i].z), bf16_lo(q[i].w), bf16_hi(q[i].w)};
-        const float fb[8] = {bf16_lo(k[i].x), bf16_hi(k[i].x), bf16_lo(k[i].y), bf16_hi(k[i].y),
-                             bf16_lo(k[i].z), bf16_hi(k[i].z), bf16_lo(k[i].w), bf16_hi(k[i].w)};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sq += fa[j] * fa[j];
-            sk += fb[j] * fb[j];
+        for (int i = 0; i < VPL; ++i) {
+            q[i] = xq[lane + 32 * i];
+            k[i] = xq[lane + 32 * i + (D >> 3)];
         }
     }
-    sq = warp_sum(sq);
-    sk = warp_sum(sk);
-    const float rq = rsqrtf(sq * (1.0f / D) + eps), rk = rsqrtf(sk * (1.0f / D) + eps);
+    if (SHARE) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        const float4 cc = __ldg(c4 + idx), ss = __ldg(s4 + idx);
-        const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+        for (int i = 0; i < (SHARE ? VPL : 1); ++i) {
+            cc[i] = __ldg(c4 + lane + 32 * i);
+            ss[i] = __ldg(s4 + lane + 32 * i);
+        }
+    }
+    for (int row = w_row; row < rows; row += row_step) {
+        uint4* xq = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld);
+        uint4* xk = xq + (D >> 3);
+        float sq = 0.f, sk = 0.f;
 #pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            uint4 u = which == 0 ? q[i] : k[i];
-            const float* w = which == 0 ? wq : wk;
-            const float rinv = which == 0 ? rq : rk;
-            float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                          bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-            const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx);
-            const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx + 1);
-            const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        for (int i = 0; i < VPL; ++i) {
+            const float fa[8] = {bf16_lo(q[i].x), bf16_hi(q[i].x), bf16_lo(q[i].y), bf16_hi(q[i].y),
+                                 bf16_lo(q[i].z), bf16_hi(q[i].z), bf16_lo(q[i].w), bf16_hi(q[i].w)};
+            const float fb[8] = {bf16_lo(k[i].x), bf16_hi(k[i].x), bf16_lo(k[i].y), bf16_hi(k[i].y),
+                                 bf16_lo(k[i].z), bf16_hi(k[i].z), bf16_lo(k[i].w), bf16_hi(k[i].w)};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = f[j] * rinv * ww[j];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float re = f[2 * j], im = f[2 * j + 1];
-                f[2 * j] = re * cv[j] - im * sv[j];
-                f[2 * j + 1] = im * cv[j] + re * sv[j];
+            for (int j = 0; j < 8; ++j) {
+                sq += fa[j] * fa[j];
+                sk += fb[j] * fb[j];
             }
-            u.x = pack_bf16x2(f[0], f[1]);
-            u.y = pack_bf16x2(f[2], f[3]);
-            u.z = pack_bf16x2(f[4], f[5]);
-            u.w = pack_bf16x2(f[6], f[7]);
-            (which == 0 ? xq : xk)[idx] = u;
+        }
+        sq = warp_sum(sq);
+        sk = warp_sum(sk);
+        const float rq = rsqrtf(sq * (1.0f / D) + eps), rk = rsqrtf(sk * (1.0f / D) + eps);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int idx = lane + 32 * i;
+            const float4 c_i = SHARE ? cc[SHARE ? i : 0] : __ldg(c4 + idx), s_i = SHARE ? ss[SHARE ? i : 0] : __ldg(s4 + idx);
+            const float cv[4] = {c_i.x, c_i.y, c_i.z, c_i.w}, sv[4] = {s_i.x, s_i.y, s_i.z, s_i.w};
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                uint4 u = which == 0 ? q[i] : k[i];
+                const float* w = which == 0 ? wq : wk;
+                const float rinv = which == 0 ? rq : rk;
+                float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                              bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx);
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * idx + 1);
+                const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = f[j] * rinv * ww[j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float re = f[2 * j], im = f[2 * j + 1];
+                    f[2 * j] = re * cv[j] - im * sv[j];
+                    f[2 * j + 1] = im * cv[j] + re * sv[j];
+                }
+                u.x = pack_bf16x2(f[0], f[1]);
+                u.y = pack_bf16x2(f[2], f[3]);
+                u.z = pack_bf16x2(f[4], f[5]);
+                u.w = pack_bf16x2(f[6], f[7]);
+                (which == 0 ? xq : xk)[idx] = u;
+            }
+        }
+        if (SHARE && row + row_step < rows) {
+            const uint4* nq = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row + row_step) * ld);
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                q[i] = nq[lane + 32 * i];
+                k[i] = nq[lane + 32 * i + (D >> 3)];
+            }
         }
     }
 }
@@ -719,12 +744,17 @@ cudaError_t launch_qk_pair_norm_rope(void* x, int64_t ld, int rows, int D, const
                                      const float* cos_t, const float* sin_t, cudaStream_t s, int table_rows) {
     if (D % 8 != 0 || ld % 8 != 0 || ld < 2 * D || cos_t == nullptr || sin_t == nullptr) return cudaErrorInvalidValue;
     if (table_rows <= 0) table_rows = rows;
-    ProfScope prof(PROF_QK_ROPE, 2.0 * rows * D * 4 + 2.0 * rows * (D / 2) * 4, s);  // q,k bf16 in+out, cos/sin f32 once
-    if (D == 2048)
-        launch_pdl(qk_pair_norm_rope_row_kernel<8>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+    // q,k bf16 in+out for every row; the f32 cos/sin rows once per TABLE row on the register-resident path
+    const bool share = D == 2048 && rows % table_rows == 0 && rows > table_rows;
+    ProfScope prof(PROF_QK_ROPE, 2.0 * rows * D * 4 + 2.0 * (share ? table_rows : rows) * (D / 2) * 4, s);
+    if (share)
+        launch_pdl(qk_pair_norm_rope_row_kernel<8, true>, dim3(blocks_for(table_rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+                   reinterpret_cast<__nv_bfloat16*>(x), ld, rows, wq, wk, eps, cos_t, sin_t, table_rows);
+    else if (D == 2048)
+        launch_pdl(qk_pair_norm_rope_row_kernel<8, false>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
                    reinterpret_cast<__nv_bfloat16*>(x), ld, rows, wq, wk, eps, cos_t, sin_t, table_rows);
     else if (D == 4096)
-        launch_pdl(qk_pair_norm_rope_row_kernel<16>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+        launch_pdl(qk_pair_norm_rope_row_kernel<16, false>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
                    reinterpret_cast<__nv_bfloat16*>(x), ld, rows, wq, wk, eps, cos_t, sin_t, table_rows);
     else
         launch_pdl(qk_pair_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
