@@ -17,6 +17,10 @@ enum EpiMode : int {
     EPI_CONV_NDHWC = 3,       // out_bf16[voxel, col] = acc + bias (+ residual_bf16[voxel, col]); unpadded NDHWC
     EPI_CONV_D2S = 4,         // upsampler: depth-to-space(2,2,2) + channel-tiled residual + drop frame 0
     EPI_CONV_UNPATCHIFY = 5,  // conv_out: f32 NCDHW pixels through the p=4 unpatchify index map
+    // conv + the NEXT conv's input producer in one epilogue (N <= 256 so one tile holds every channel of a voxel):
+    // x = bf16(acc + bias (+ residual)) is stored to `out` if non-null, then pixel-norm / (1+scale)x+shift / SiLU of x
+    // goes to the zero-bordered, T-replicated padded volume `norm_out` (what vae_prep_kernel would have produced).
+    EPI_CONV_NORM_PAD = 6,
 };
 
 enum ActMode : int { ACT_NONE = 0, ACT_GELU_TANH = 1 };
@@ -44,6 +48,15 @@ struct GemmParams {
     int post_u8_scale;  // EPI_CONV_UNPATCHIFY: 1 => also apply clamp(0.5x+0.5,0,1)*255 (t2v_pipeline.rs:147-155)
     int out_h0;         // EPI_CONV_UNPATCHIFY, H-slab decode: first pixel row of this slab in the full frame
     int out_h_full;     // ... and the full frame height in pixels (0 = 4*H, single slab)
+
+    // ---- EPI_CONV_NORM_PAD ----
+    void* norm_out;            // padded bf16 [(T + tf + (tf == 1)), H+2, W+2, N] of the SAME T, H, W (must not be `a_ptr`)
+    const float* norm_scale;   // f32 [N] or null
+    const float* norm_shift;   // f32 [N] or null
+    int norm_do, norm_silu;    // pixel norm (RMS over N, eps 1e-8) / SiLU on or off
+    int norm_tf;               // replicated front frames of norm_out: 1 non-causal (+1 behind), 2 causal, 3 causal + dup
+    void* norm_halo_up;        // H-slab decode: neighbour buffers receiving this slab's first / last row, or null
+    void* norm_halo_dn;
 };
 
 // A: [rows_a, K_a] bf16 row-major (K contiguous). B: [N, K] bf16 row-major (nn.Linear weight layout).

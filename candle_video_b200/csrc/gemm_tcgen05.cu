@@ -295,6 +295,169 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
     __syncwarp();  // the tile is rewritten by the next chunk
 }
 
+// ------------------------------------------------------------------------------------------------
+// EPI_CONV_NORM_PAD: the conv epilogue is also the producer of the next conv's input.  One thread owns one voxel and the
+// tile holds all N <= BN channels, so the row is rounded to bf16 once (the value `x` every consumer sees), kept in
+// registers as BN/2 packed words while the RMS accumulates, then normalised / modulated / SiLU'd and stored at the
+// voxel's place in the padded volume (plus the replicated frames and the neighbours' halo rows).  Same arithmetic as
+// vae_prep_kernel on the stored x; removes that kernel's read of x and, for a resnet's first conv, the write of x too.
+// ------------------------------------------------------------------------------------------------
+// Two passes over the accumulator row in TMEM, 32 columns at a time (loops kept rolled: a fully unrolled version is
+// ~200 KB of code and thrashes the instruction cache of the whole CTA): pass 1 accumulates the RMS of the bf16-rounded
+// row, pass 2 recomputes the same rounded values, stores x and the normalised / modulated / SiLU'd padded copy.
+template <int BN>
+__device__ __noinline__ void epilogue_conv_norm_pad(const GemmParams& p, const RowCtx rc, uint32_t taddr,
+                                                    uint64_t* tmem_empty, int arrive_on_leader, int lane) {
+    const int N = p.N;
+    const float* bias = p.bias;
+    const __nv_bfloat16* res =
+        (p.res_bf16 != nullptr && rc.valid) ? reinterpret_cast<const __nv_bfloat16*>(p.res_bf16) + rc.out_row * p.ldo : nullptr;
+    // x (bf16-rounded acc + bias + residual) of one 32-column chunk as 16 packed words
+    auto load_chunk = [&](int c, uint32_t (&w)[16]) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+        const float4* b4 = reinterpret_cast<const float4*>(bias + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b.x;
+            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b.z;
+            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b.w;
+        }
+        if (res != nullptr) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(res + c * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(r4 + i);
+                v[8 * i + 0] += bf16_lo(u.x);
+                v[8 * i + 1] += bf16_hi(u.x);
+                v[8 * i + 2] += bf16_lo(u.y);
+                v[8 * i + 3] += bf16_hi(u.y);
+                v[8 * i + 4] += bf16_lo(u.z);
+                v[8 * i + 5] += bf16_hi(u.z);
+                v[8 * i + 6] += bf16_lo(u.w);
+                v[8 * i + 7] += bf16_hi(u.w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    };
+    const int n_chunks = (N < BN ? N : BN) / 32;
+    __nv_bfloat16* xdst =
+        (p.out != nullptr && rc.valid) ? reinterpret_cast<__nv_bfloat16*>(p.out) + rc.out_row * p.ldo : nullptr;
+    // When x itself is stored (a resnet's second conv) pass 1 stores it and hands the accumulator back at once; pass 2
+    // then re-reads the thread's own 64-byte pieces of x (L1/L2 hits) instead of TMEM + bias + residual.
+    const bool reread = p.out != nullptr;
+    auto release_tmem = [&] {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (arrive_on_leader) mbar_arrive_leader(tmem_empty);
+            else mbar_arrive(tmem_empty);
+        }
+    };
+    float s2 = 0.f;
+    if (p.norm_do || reread) {
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+            uint32_t w[16];
+            load_chunk(c, w);
+            if (reread && c == n_chunks - 1) release_tmem();
+            if (xdst != nullptr) {
+                uint4* d4 = reinterpret_cast<uint4*>(xdst + c * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d4[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a = bf16_lo(w[i]), b = bf16_hi(w[i]);
+                s2 = fmaf(a, a, s2);
+                s2 = fmaf(b, b, s2);
+            }
+        }
+    }
+    if (reread && !rc.valid) return;
+    const float rinv = p.norm_do ? rsqrtf(s2 / static_cast<float>(N) + 1e-8f) : 1.0f;
+    const int Hp = p.H + 2, Wp = p.W + 2, tf = p.norm_tf;
+    const int64_t plane_elems = static_cast<int64_t>(Hp) * Wp * N;
+    const bool mod = p.norm_scale != nullptr;
+    const int silu = p.norm_silu;
+    // destinations of this voxel: its place in the padded volume, the replicated frames when it lies in the first /
+    // last frame, and the neighbours' halo rows when it lies in the first / last row of an H-slab
+    const int64_t row0 = (static_cast<int64_t>(rc.t + tf) * Hp) * Wp + (rc.w + 1);
+    __nv_bfloat16* d_main = reinterpret_cast<__nv_bfloat16*>(p.norm_out) + (row0 + static_cast<int64_t>(rc.h + 1) * Wp) * N;
+    __nv_bfloat16* d_up = (p.norm_halo_up != nullptr && rc.h == 0)
+                              ? reinterpret_cast<__nv_bfloat16*>(p.norm_halo_up) + (row0 + static_cast<int64_t>(p.H + 1) * Wp) * N
+                              : nullptr;
+    __nv_bfloat16* d_dn = (p.norm_halo_dn != nullptr && rc.h == p.H - 1)
+                              ? reinterpret_cast<__nv_bfloat16*>(p.norm_halo_dn) + row0 * N
+                              : nullptr;
+    const int n_front = rc.t == 0 ? tf : 0;
+    const bool back = tf == 1 && rc.t == p.T - 1;
+    const bool simple = rc.valid && n_front == 0 && !back && d_up == nullptr && d_dn == nullptr;
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+        uint32_t w[16];
+        if (reread) {
+            const uint4* x4 = reinterpret_cast<const uint4*>(xdst + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 u = x4[q];
+                w[4 * q] = u.x; w[4 * q + 1] = u.y; w[4 * q + 2] = u.z; w[4 * q + 3] = u.w;
+            }
+        } else {
+            load_chunk(c, w);
+            if (c == n_chunks - 1) release_tmem();  // accumulator drained for the second time
+            if (!rc.valid) continue;
+        }
+        uint32_t o[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                f[2 * i] = bf16_lo(w[4 * q + i]) * rinv;
+                f[2 * i + 1] = bf16_hi(w[4 * q + i]) * rinv;
+            }
+            if (mod) {
+                const float4* sc4 = reinterpret_cast<const float4*>(p.norm_scale + c * 32 + q * 8);
+                const float4* sh4 = reinterpret_cast<const float4*>(p.norm_shift + c * 32 + q * 8);
+                const float4 sa = __ldg(sc4), sb = __ldg(sc4 + 1), ta = __ldg(sh4), tb = __ldg(sh4 + 1);
+                f[0] = f[0] * (1.f + sa.x) + ta.x; f[1] = f[1] * (1.f + sa.y) + ta.y;
+                f[2] = f[2] * (1.f + sa.z) + ta.z; f[3] = f[3] * (1.f + sa.w) + ta.w;
+                f[4] = f[4] * (1.f + sb.x) + tb.x; f[5] = f[5] * (1.f + sb.y) + tb.y;
+                f[6] = f[6] * (1.f + sb.z) + tb.z; f[7] = f[7] * (1.f + sb.w) + tb.w;
+            }
+            if (silu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = silu_fast_f32(f[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[4 * q + i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+        }
+        auto put = [&](__nv_bfloat16* d) {
+            uint4* d4 = reinterpret_cast<uint4*>(d + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d4[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        };
+        put(d_main);
+        if (!simple) {
+#pragma unroll 1
+            for (int which = 0; which < 3; ++which) {
+                __nv_bfloat16* d = which == 0 ? d_main : (which == 1 ? d_up : d_dn);
+                if (d == nullptr) continue;
+                if (which != 0) put(d);
+#pragma unroll 1
+                for (int k = 1; k <= n_front; ++k) put(d - k * plane_elems);
+                if (back) put(d + plane_elems);
+            }
+        }
+    }
+}
+
 // conv3d k-block order: (kt, kh) outermost, then the 64-channel block, then kw -- the SAME accumulation order as the
 // KW3 pair kernel (three kw taps per pipeline step), so every kernel variant produces identical bits and the result
 // does not depend on which one the tile heuristic picks (single GPU vs H-slabs pick differently).
@@ -459,12 +622,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
+            if (p.epi == EPI_CONV_NORM_PAD) {
+                if constexpr (BLOCK_N == 128 || BLOCK_N == 256) epilogue_conv_norm_pad<BLOCK_N>(p, rc, taddr, &tmem_empty_bar[acc], 0, lane);
+            } else {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; c += 2) {
-                if (prefetch_res) epilogue_load_residual(p, m_warp0, n0 + (c + 1) * 32, lane, res_b);
-                chunk(c, res_a);
-                if (prefetch_res && c + 2 < BLOCK_N / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
-                chunk(c + 1, res_b);
+                for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                    if (prefetch_res) epilogue_load_residual(p, m_warp0, n0 + (c + 1) * 32, lane, res_b);
+                    chunk(c, res_a);
+                    if (prefetch_res && c + 2 < BLOCK_N / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
+                    chunk(c + 1, res_b);
+                }
             }
             if (++acc == 2) {
                 acc = 0;
@@ -693,12 +860,16 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
+            if (p.epi == EPI_CONV_NORM_PAD) {
+                if constexpr (MODE == 1) epilogue_conv_norm_pad<kPairBlockN>(p, rc, taddr, &tmem_empty_bar[acc], 1, lane);
+            } else {
 #pragma unroll 1
-            for (int c = 0; c < kPairBlockN / 32; c += 2) {
-                if (prefetch_res) epilogue_load_residual(p, m_warp0, n0 + (c + 1) * 32, lane, res_b);
-                chunk(c, res_a);
-                if (prefetch_res && c + 2 < kPairBlockN / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
-                chunk(c + 1, res_b);
+                for (int c = 0; c < kPairBlockN / 32; c += 2) {
+                    if (prefetch_res) epilogue_load_residual(p, m_warp0, n0 + (c + 1) * 32, lane, res_b);
+                    chunk(c, res_a);
+                    if (prefetch_res && c + 2 < kPairBlockN / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
+                    chunk(c + 1, res_b);
+                }
             }
             if (++acc == 2) {
                 acc = 0;
@@ -796,6 +967,11 @@ uint64_t gemm_launch_count() { return g_launches.load(); }
 
 cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int block_n, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
+    const bool norm_pad = p.epi == EPI_CONV_NORM_PAD;  // one tile must hold every channel of a voxel
+    if (norm_pad && (!p.conv || p.N > 256 || p.N % 32 != 0 || p.bias == nullptr || p.norm_out == nullptr ||
+                     p.norm_out == p.a_ptr || p.norm_tf < 1 || p.norm_tf > 3 ||
+                     (p.norm_scale == nullptr) != (p.norm_shift == nullptr)))
+        return cudaErrorInvalidValue;
     if (block_n == -2) return launch_pair_impl<256, 0>(ops, p, stream);
     if (block_n == -3) return launch_pair_impl<128, 0>(ops, p, stream);
     if (block_n == -4) return launch_pair_impl<256, 1>(ops, p, stream);   // conv3d, three kw taps per step
@@ -816,6 +992,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         for (int i = 0; i < 4; ++i) {
             const int c = cands[i];
             if (c > 64 && p.N <= c / 2) continue;
+            if (norm_pad && (c < p.N || (c != 128 && c != 256))) continue;
             const int tiles = num_m * ((p.N + c - 1) / c);
             const int rounds = (tiles + sms - 1) / sms;
             const double cost = rounds * static_cast<double>(c) / rate[i];
@@ -834,7 +1011,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
                     pair_bn = 256;
                 }
             }
-            if (p.N % 128 == 0) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
+            if (p.N % 128 == 0 && !(norm_pad && p.N > 128)) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
                 const int rounds = (num_mp * (p.N / 128) + sms / 2 - 1) / (sms / 2);
                 if (rounds * 128.0 / 0.80 < best) {
                     best = rounds * 128.0 / 0.80;
@@ -842,6 +1019,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
                 }
             }
             const bool kw3 = p.conv && p.num_k_blocks == 27 * p.cin_blocks && getenv("LTXV_CONV_NO_KW3") == nullptr;
+            if (norm_pad && !kw3) pair_bn = 0;  // only the KW3 pair kernels carry the fused producer epilogue
             // two k-blocks per stage measured neutral (1341 vs 1353 TFLOP/s on the QKV shape): opt-in only
             const bool k2 = !p.conv && p.num_k_blocks % 2 == 0 && getenv("LTXV_GEMM_K2") != nullptr;
             if (pair_bn == 256)

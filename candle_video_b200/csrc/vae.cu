@@ -255,6 +255,9 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
             // geometry changed: the zero border must be re-established
             p_[l].release();
             p_[l].ensure(padded, true);
+            p2_[l].release();
+            p2_[l].ensure(padded, true);
+            pp_[l] = 0;
         } else {
             for (int k = 0; k < 2; ++k) {
                 p_off_[l][k] = comm_->alloc(padded);
@@ -289,13 +292,23 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
     wsW_ = W;
 }
 
+bool AutoencoderKLLtxVideo::fusable(int l) const {
+    static const bool off = getenv("LTXV_VAE_NO_FUSED_PREP") != nullptr;
+    return !off && ch_[l] <= 256;
+}
+
+void* AutoencoderKLLtxVideo::pad_buf(int l, int k) const {
+    if (comm_ != nullptr) return comm_->local(p_off_[l][k]);
+    return k ? p2_[l].p : p_[l].p;
+}
+
 void* AutoencoderKLLtxVideo::prep(const void* x, int l, const float* scale, const float* shift, int do_norm,
                                   int do_silu, cudaStream_t s) {
+    pp_[l] ^= 1;  // padded inputs are double-buffered: a producer never writes the volume a conv may still be reading
     if (comm_ == nullptr) {
-        LTXV_CUDA(launch_vae_prep(x, p_[l].p, scale, shift, do_norm, do_silu, T_[l], H_[l], W_[l], ch_[l], s));
-        return p_[l].p;
+        LTXV_CUDA(launch_vae_prep(x, pad_buf(l, pp_[l]), scale, shift, do_norm, do_silu, T_[l], H_[l], W_[l], ch_[l], s));
+        return pad_buf(l, pp_[l]);
     }
-    pp_[l] ^= 1;
     const size_t off = p_off_[l][pp_[l]];
     const int r = comm_->rank(), N = comm_->nranks();
     void* up = r > 0 ? comm_->peer(r - 1, off) : nullptr;
@@ -306,7 +319,7 @@ void* AutoencoderKLLtxVideo::prep(const void* x, int l, const float* scale, cons
 }
 
 void AutoencoderKLLtxVideo::conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out,
-                                 const void* res, int post, cudaStream_t s) {
+                                 const void* res, int post, cudaStream_t s, int fuse_level, const Producer* next) {
     const int Wp = W + 2, plane = (H + 2) * Wp;
     GemmOperands ops{a_padded, static_cast<int64_t>(T + 2) * plane, cw.Cin, cw.w, cw.rows_out, 27ll * cw.Cin};
     GemmParams p{};
@@ -332,19 +345,57 @@ void AutoencoderKLLtxVideo::conv(const ConvW& cw, const void* a_padded, int T, i
     for (int kt = 0; kt < 3; ++kt)
         for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) p.tap_off[(kt * 3 + kh) * 3 + kw] = kt * plane + (kh - 1) * Wp + (kw - 1);
+    if (next != nullptr) {
+        // the epilogue is also the producer of the next conv's input (same level, other padded buffer)
+        const int l = fuse_level;
+        pp_[l] ^= 1;
+        p.epi = EPI_CONV_NORM_PAD;
+        p.norm_out = pad_buf(l, pp_[l]);
+        p.norm_scale = next->scale;
+        p.norm_shift = next->shift;
+        p.norm_do = next->do_norm;
+        p.norm_silu = next->do_silu;
+        p.norm_tf = 1;
+        if (comm_ != nullptr) {
+            const int r = comm_->rank(), N = comm_->nranks();
+            p.norm_halo_up = r > 0 ? comm_->peer(r - 1, p_off_[l][pp_[l]]) : nullptr;
+            p.norm_halo_dn = r < N - 1 ? comm_->peer(r + 1, p_off_[l][pp_[l]]) : nullptr;
+        }
+    }
     LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
+    if (next != nullptr && comm_ != nullptr) comm_->barrier(s, 0);  // halo rows from both neighbours have landed
 }
 
 // LtxVideoResnetBlock3d::forward (vae.rs:755-821), in == out
 void AutoencoderKLLtxVideo::resnet(const ResnetW& rw, int l, const float* ss, __nv_bfloat16*& x, __nv_bfloat16*& x_alt,
-                                   cudaStream_t s) {
+                                   cudaStream_t s, const Producer* next, void** ready) {
     const int C = ch_[l], T = T_[l], H = H_[l], W = W_[l];
     // ss = [shift1, scale1, shift2, scale2] (vae.rs:734-735)
-    void* a1 = prep(x, l, ss ? ss + C : nullptr, ss ? ss : nullptr, 1, 1, s);
-    conv(rw.conv1, a1, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, 0, s);
-    void* a2 = prep(hb_.p, l, ss ? ss + 3 * C : nullptr, ss ? ss + 2 * C : nullptr, 1, 1, s);
-    conv(rw.conv2, a2, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s);
+    if (!fusable(l)) {
+        void* a1 = prep(x, l, ss ? ss + C : nullptr, ss ? ss : nullptr, 1, 1, s);
+        conv(rw.conv1, a1, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, 0, s);
+        void* a2 = prep(hb_.p, l, ss ? ss + 3 * C : nullptr, ss ? ss + 2 * C : nullptr, 1, 1, s);
+        conv(rw.conv2, a2, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s);
+        std::swap(x, x_alt);
+        if (ready) *ready = nullptr;
+        return;
+    }
+    // narrow level: conv1's epilogue produces conv2's input (norm2 / scale2 / shift2 / SiLU; its raw output is never
+    // stored), conv2's epilogue stores the new residual stream AND produces the next consumer's input
+    void* a1 = (ready && *ready) ? *ready : prep(x, l, ss ? ss + C : nullptr, ss ? ss : nullptr, 1, 1, s);
+    Producer mid;
+    mid.scale = ss ? ss + 3 * C : nullptr;
+    mid.shift = ss ? ss + 2 * C : nullptr;
+    conv(rw.conv1, a1, T, H, W, EPI_CONV_NDHWC, nullptr, nullptr, 0, s, l, &mid);
+    void* a2 = pad_buf(l, pp_[l]);
+    // Fusing conv2's consumer as well (store x AND the next padded input from one epilogue) measured SLOWER on B200:
+    // conv3d 33.5 -> 38.8 ms per c2 decode for 2.3 ms of saved prep time, whereas the conv1 fusion above is free
+    // (33.5 -> 33.9 ms, prep 5.8 -> 3.4 ms).  Opt-in for experiments only.
+    static const bool fuse_conv2 = getenv("LTXV_VAE_FUSE_CONV2") != nullptr;
+    if (!fuse_conv2) next = nullptr;
+    conv(rw.conv2, a2, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s, next ? l : -1, next);
     std::swap(x, x_alt);
+    if (ready) *ready = next ? pad_buf(l, pp_[l]) : nullptr;
 }
 
 void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* timestep_dev, int B, int F, int H, int W,
@@ -399,21 +450,37 @@ void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* time
         __nv_bfloat16* x = xa_.as<__nv_bfloat16>();
         __nv_bfloat16* x_alt = xb_.as<__nv_bfloat16>();
         conv(conv_in_, a0, T_[0], H_[0], W_[0], EPI_CONV_NDHWC, x, nullptr, 0, s);
+        void* ready = nullptr;  // padded buffer already filled by the previous conv's fused producer epilogue
         for (int l = 0; l < 4; ++l) {
             if (l > 0) {
                 // LtxVideoUpsampler3d (vae.rs:1090-1169): conv on the raw x, depth-to-space + residual in the epilogue
                 const int lp = l - 1;
-                void* au = prep(x, lp, nullptr, nullptr, 0, 0, s);
+                void* au = ready ? ready : prep(x, lp, nullptr, nullptr, 0, 0, s);
+                ready = nullptr;
                 conv(ups_[lp], au, T_[lp], H_[lp], W_[lp], EPI_CONV_D2S, x_alt, nullptr, 0, s);
                 std::swap(x, x_alt);
             }
             const int C = ch_[l];
-            for (size_t i = 0; i < res_[l].size(); ++i)
-                resnet(res_[l][i], l, cond ? ss[l] + i * 4 * C : nullptr, x, x_alt, s);
+            const size_t n_res = res_[l].size();
+            for (size_t i = 0; i < n_res; ++i) {
+                // who consumes this resnet's output: the next resnet's norm1, the upsampler (raw x) or norm_out
+                Producer next;
+                if (i + 1 < n_res) {
+                    const float* ssn = cond ? ss[l] + (i + 1) * 4 * C : nullptr;
+                    next.scale = ssn ? ssn + C : nullptr;
+                    next.shift = ssn;
+                } else if (l < 3) {
+                    next.do_norm = next.do_silu = 0;
+                } else {
+                    next.scale = cond ? ssf + C : nullptr;
+                    next.shift = cond ? ssf : nullptr;
+                }
+                resnet(res_[l][i], l, cond ? ss[l] + i * 4 * C : nullptr, x, x_alt, s, fusable(l) ? &next : nullptr, &ready);
+            }
         }
         // norm_out -> scale/shift -> SiLU -> conv_out -> unpatchify (vae.rs:1686-1725)
         const int C3 = ch_[3];
-        void* af = prep(x, 3, cond ? ssf + C3 : nullptr, cond ? ssf : nullptr, 1, 1, s);
+        void* af = ready ? ready : prep(x, 3, cond ? ssf + C3 : nullptr, cond ? ssf : nullptr, 1, 1, s);
         float* o32 = out_dtype == LTXV_F32 ? static_cast<float*>(out) + static_cast<size_t>(b) * out_elems
                                            : out_f32_.as<float>();
         if (comm_ == nullptr) {

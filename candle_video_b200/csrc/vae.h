@@ -74,9 +74,21 @@ private:
     void add_time_embedder(const std::string& prefix, TimeEmbW& te, int dim);
     float* vec(int64_t n);
     void ensure_workspace(int F, int H, int W);
+    // what the consumer of a conv's output applies before ITS conv (the job of prep()); when the level is narrow
+    // enough (C <= 256) the producing conv does it in its epilogue (EPI_CONV_NORM_PAD) and prep() is skipped
+    struct Producer {
+        const float* scale = nullptr;
+        const float* shift = nullptr;
+        int do_norm = 1, do_silu = 1;
+    };
     void conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out, const void* res, int post,
-              cudaStream_t s);
-    void resnet(const ResnetW& rw, int level, const float* ss, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s);
+              cudaStream_t s, int fuse_level = -1, const Producer* next = nullptr);
+    // `next`: producer parameters of whatever consumes the resnet's output; `ready`: in/out, the padded buffer that
+    // already holds the (fused) producer output for the next conv, or null
+    void resnet(const ResnetW& rw, int level, const float* ss, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s,
+                const Producer* next = nullptr, void** ready = nullptr);
+    bool fusable(int level) const;
+    void* pad_buf(int level, int k) const;
     void tiled_decode(const void* z, int z_dtype, const float* ts_b, int T, int H, int W, float* dst,
                       const ltxv_vae_tiling& tp, cudaStream_t s);
     void temporal_tiled_decode(const void* z, int z_dtype, const float* ts_b, int F, int H, int W, float* dst,
@@ -103,7 +115,7 @@ private:
     // workspace
     int wsF_ = 0, wsH_ = 0, wsW_ = 0;
     int T_[4], H_[4], W_[4];
-    DevBuf a0_, p_[4], xa_, xb_, hb_, cond_, out_f32_;
+    DevBuf a0_, p_[4], p2_[4], xa_, xb_, hb_, cond_, out_f32_;
     DevBuf tz_sp_, tz_tm_, t_dec_, t_prev_, t_cur_, t_work_;  // tiled decode: sub-latents and decoded tiles
     // sharded decode
     PeerComm* comm_ = nullptr;

@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include <math.h>
+#include <stdlib.h>
 
 #include "gemm.h"
 #include "vae_glue.h"
@@ -184,6 +185,8 @@ void LtxVideoEncoder3d::ensure_workspace(int F, int H, int W) {
         const size_t padded = static_cast<size_t>(T_[l] + 3) * (H_[l] + 2) * (W_[l] + 2) * ch_[l] * 2;
         p_[l].release();  // geometry changed: the zero border must be re-established
         p_[l].ensure(padded, true);
+        q_[l].release();
+        if (ch_[l] <= 256) q_[l].ensure(padded, true);  // second padded volume of the narrow levels (fused conv1 epilogue)
         const size_t un = static_cast<size_t>(T_[l] + 1) * H_[l] * W_[l] * ch_[l] * 2;
         max_unpadded = std::max(max_unpadded, un);
     }
@@ -199,7 +202,7 @@ void LtxVideoEncoder3d::ensure_workspace(int F, int H, int W) {
 }
 
 void LtxVideoEncoder3d::conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out,
-                             const void* res, int n_cols, int ldo, cudaStream_t s) {
+                             const void* res, int n_cols, int ldo, cudaStream_t s, void* fused_norm_out) {
     const int Wp = W + 2, plane = (H + 2) * Wp;
     GemmOperands ops{a_padded, static_cast<int64_t>(T + 2) * plane, cw.Cin, cw.w, cw.rows_out, 27ll * cw.Cin};
     GemmParams p{};
@@ -223,16 +226,31 @@ void LtxVideoEncoder3d::conv(const ConvW& cw, const void* a_padded, int T, int H
     for (int kt = 0; kt < 3; ++kt)
         for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) p.tap_off[(kt * 3 + kh) * 3 + kw] = kt * plane + (kh - 1) * Wp + (kw - 1);
+    if (fused_norm_out != nullptr) {
+        // the epilogue is also the producer of the next conv's input: pixel norm + SiLU into the causally padded volume
+        p.epi = EPI_CONV_NORM_PAD;
+        p.norm_out = fused_norm_out;
+        p.norm_do = p.norm_silu = 1;
+        p.norm_tf = 2;
+    }
     LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
 }
 
 // LtxVideoResnetBlock3d::forward (vae.rs:755-821), in == out, causal, no conditioning
 void LtxVideoEncoder3d::resnet(const ResnetW& rw, int l, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s) {
     const int C = ch_[l], T = T_[l], H = H_[l], W = W_[l];
+    static const bool no_fuse = getenv("LTXV_VAE_NO_FUSED_PREP") != nullptr;
     LTXV_CUDA(launch_vae_prep(x, p_[l].p, nullptr, nullptr, 1, 1, T, H, W, C, s, nullptr, nullptr, 2));
-    conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, C, C, s);
-    LTXV_CUDA(launch_vae_prep(hb_.p, p_[l].p, nullptr, nullptr, 1, 1, T, H, W, C, s, nullptr, nullptr, 2));
-    conv(rw.conv2, p_[l].p, T, H, W, EPI_CONV_NDHWC, x_alt, x, C, C, s);
+    if (C <= 256 && !no_fuse) {
+        // narrow level: conv1's epilogue writes conv2's input (norm2 + SiLU) straight into the second padded volume;
+        // its raw output is never stored (see EPI_CONV_NORM_PAD, gemm.h)
+        conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, nullptr, nullptr, C, C, s, q_[l].p);
+        conv(rw.conv2, q_[l].p, T, H, W, EPI_CONV_NDHWC, x_alt, x, C, C, s);
+    } else {
+        conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, C, C, s);
+        LTXV_CUDA(launch_vae_prep(hb_.p, p_[l].p, nullptr, nullptr, 1, 1, T, H, W, C, s, nullptr, nullptr, 2));
+        conv(rw.conv2, p_[l].p, T, H, W, EPI_CONV_NDHWC, x_alt, x, C, C, s);
+    }
     std::swap(x, x_alt);
 }
 

@@ -39,7 +39,7 @@ private:
     void add_conv(const std::string& prefix, ConvW& cw, int cin_src, int Cin, int Cout, int rows_out);
     void ensure_workspace(int F, int H, int W);
     void conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out, const void* res, int n_cols,
-              int ldo, cudaStream_t s);
+              int ldo, cudaStream_t s, void* fused_norm_out = nullptr);
     void resnet(const ResnetW& rw, int level, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s);
 
     ltxv_vae_encoder_config cfg_;
@@ -55,7 +55,7 @@ private:
 
     int wsF_ = 0, wsH_ = 0, wsW_ = 0;
     int T_[5], H_[5], W_[5];
-    DevBuf a_in_, p_[5], xa_, xb_, hb_, out32_;
+    DevBuf a_in_, p_[5], q_[5], xa_, xb_, hb_, out32_;
 };
 
 }  // namespace ltxv
