@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     "ltxv_scheduler_step_stochastic", "ltxv_decode_noise_blend", "ltxv_pipeline_denoise_stochastic",
     "ltxv_pipeline_decode_noisy",
     "ltxv_vae_encoder_config_default", "ltxv_vae_enable_encoder", "ltxv_vae_encode_dims", "ltxv_vae_encode",
-    "ltxv_vae_encode_host", "ltxv_normalize_latents",
+    "ltxv_vae_encode_host", "ltxv_normalize_latents", "ltxv_frames_to_u8", "ltxv_pipeline_decode_host_u8",
 ]
 
 
@@ -162,6 +162,8 @@ def _load() -> C.CDLL:
     l.ltxv_vae_encode.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     l.ltxv_vae_encode_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     l.ltxv_normalize_latents.argtypes = [vp, vp, vp, vp, f32, i32, i32, i64, vp]
+    l.ltxv_frames_to_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    l.ltxv_pipeline_decode_host_u8.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp]
     l.ltxv_profile_begin.argtypes = []
     l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return l
@@ -804,6 +806,29 @@ def pipeline_decode_host(vae: AutoencoderKLLtxVideo, params: PipelineParams, lat
     if out is None:
         out = torch.empty((3, 8 * f - 7, params.height, params.width), dtype=torch.float32)
     _check(lib().ltxv_pipeline_decode_host(vae._h, C.byref(p), _ptr(latents.contiguous()), _ptr(out)))
+    return out
+
+
+def frames_to_u8(frames):
+    """Output hand-off of the reference's example (main.rs:653-667): f32 CUDA [B,3,F,H,W] in 0..255 -> u8 [B,F,H,W,3]."""
+    torch = _torch()
+    x = _dev(frames, "frames").to(torch.float32).contiguous()
+    B, Cc, F, H, W = x.shape
+    if Cc != 3:
+        raise LtxvError("frames must have 3 channels")
+    out = torch.empty((B, F, H, W, 3), dtype=torch.uint8, device=x.device)
+    _check(lib().ltxv_frames_to_u8(_ptr(x), _ptr(out), B, F, H, W, _stream()))
+    return out
+
+
+def pipeline_decode_host_u8(vae: AutoencoderKLLtxVideo, params: PipelineParams, latents, out=None):
+    """pipeline_decode_host delivering host u8 [frames, height, width, 3] (a quarter of the D2H bytes)."""
+    torch = _torch()
+    p, keep = params.to_c()
+    f = (params.num_frames - 1) // 8 + 1
+    if out is None:
+        out = torch.empty((8 * f - 7, params.height, params.width, 3), dtype=torch.uint8)
+    _check(lib().ltxv_pipeline_decode_host_u8(vae._h, C.byref(p), _ptr(latents.contiguous()), _ptr(out)))
     return out
 
 

@@ -637,4 +637,32 @@ int ltxv_pipeline_decode_host(ltxv_vae* vae, const ltxv_pipeline_params* p, cons
     LTXV_CATCH
 }
 
+int ltxv_frames_to_u8(const float* frames, uint8_t* out, int B, int F, int H, int W, void* stream) {
+    LTXV_TRY
+    if (frames == nullptr || out == nullptr) fail("null argument");
+    if (B <= 0 || F <= 0 || H <= 0 || W <= 0) fail("invalid frame extent [%d,3,%d,%d,%d]", B, F, H, W);
+    LTXV_CUDA(launch_frames_to_u8(frames, out, B, F, H, W, static_cast<cudaStream_t>(stream)));
+    LTXV_CATCH
+}
+int ltxv_pipeline_decode_host_u8(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, uint8_t* out) {
+    LTXV_TRY
+    if (vae == nullptr || p == nullptr || latents == nullptr || out == nullptr) fail("null argument");
+    const int C = vae->model.config().latent_channels;
+    const int F = (p->num_frames - 1) / 8 + 1, H = p->height / 32, W = p->width / 32;
+    const int Fo = 8 * F - 7, Ho = 32 * H, Wo = 32 * W;
+    const size_t nl = static_cast<size_t>(F) * H * W * C * 4;
+    const size_t npx = static_cast<size_t>(Fo) * Ho * Wo;
+    cudaStream_t s = 0;
+    static DevBuf d_lat, d_out, d_u8;
+    d_lat.ensure(nl);
+    d_out.ensure(npx * 3 * 4);
+    d_u8.ensure(npx * 3);
+    LTXV_CUDA(cudaMemcpyAsync(d_lat.p, latents, nl, cudaMemcpyHostToDevice, s));
+    pipeline_decode(vae->model, *p, d_lat.as<float>(), d_out.as<float>(), s);
+    LTXV_CUDA(launch_frames_to_u8(d_out.as<float>(), d_u8.as<uint8_t>(), 1, Fo, Ho, Wo, s));
+    LTXV_CUDA(cudaMemcpyAsync(out, d_u8.p, npx * 3, cudaMemcpyDeviceToHost, s));
+    LTXV_CUDA(cudaStreamSynchronize(s));
+    LTXV_CATCH
+}
+
 }  // extern "C"

@@ -908,6 +908,26 @@ cudaError_t launch_denormalize(const float* in, float* out, const float* mean, c
     denorm_kernel<<<blocks_for(C * n_per_c, 256), 256, 0, s>>>(in, out, mean, std, inv_sf, C, n_per_c);
     return done();
 }
+// frames f32 [B, 3, F, H, W] in 0..255 -> u8 [B, F, H, W, 3]: the per-frame permute((1,2,0)).clamp(0,255).to_dtype(U8)
+// of the reference's output hand-off (examples/ltx-video/main.rs:653-667; the cast truncates toward zero).
+__global__ void frames_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int F, int64_t hw,
+                                    int64_t n_px) {
+    const int64_t px = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;  // over B * F * H * W
+    if (px >= n_px) return;
+    const int64_t fhw = static_cast<int64_t>(F) * hw;
+    const int64_t b = px / fhw, r = px - b * fhw;  // r = f * hw + pixel: the offset inside one colour plane
+    const float* src = in + b * 3 * fhw + r;
+    uint8_t* dst = out + px * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[c] = static_cast<uint8_t>(fminf(fmaxf(src[c * fhw], 0.f), 255.f));
+}
+cudaError_t launch_frames_to_u8(const float* in, uint8_t* out, int B, int F, int H, int W, cudaStream_t s) {
+    const int64_t hw = static_cast<int64_t>(H) * W;
+    const int64_t n = static_cast<int64_t>(B) * F * hw;
+    if (n <= 0) return cudaSuccess;
+    frames_to_u8_kernel<<<blocks_for(n, 256), 256, 0, s>>>(in, out, F, hw, n);
+    return done();
+}
 cudaError_t launch_postprocess(const float* in, float* out, int64_t n, cudaStream_t s) {
     postprocess_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(in, out, n);
     return done();

@@ -108,6 +108,8 @@ cudaError_t launch_denormalize(const float* in, float* out, const float* mean, c
                                int64_t n_per_c, cudaStream_t s);
 // clamp(0.5x+0.5,0,1)*255  (:147-155)
 cudaError_t launch_postprocess(const float* in, float* out, int64_t n, cudaStream_t s);
+// f32 frames [B,3,F,H,W] in 0..255 -> u8 [B,F,H,W,3] (main.rs:653-667: permute, clamp, truncating cast)
+cudaError_t launch_frames_to_u8(const float* in, uint8_t* out, int B, int F, int H, int W, cudaStream_t s);
 
 uint64_t glue_launch_count();
 

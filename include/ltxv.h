@@ -225,6 +225,10 @@ int ltxv_denormalize_latents(const float* in, float* out, const float* mean, con
 int ltxv_normalize_latents(const float* in, float* out, const float* mean, const float* std, float scaling_factor,
                            int B, int C, int64_t n_per_channel, void* stream);
 int ltxv_postprocess_video(const float* in, float* out, int64_t n, void* stream);
+/* Output hand-off of the reference's example binary (examples/ltx-video/main.rs:653-667): per frame
+ * permute((1,2,0)).clamp(0,255).to_dtype(U8).  frames: device f32 [B,3,F,H,W] in 0..255 (postprocess_video output);
+ * out: device u8 [B,F,H,W,3] (RGB8 rows as image::save_buffer / the GIF encoder take them). */
+int ltxv_frames_to_u8(const float* frames, uint8_t* out, int B, int F, int H, int W, void* stream);
 
 /* Host-only schedule math (stays as in the reference): writes num_steps+1 sigmas (terminal 0 appended) and num_steps
  * integer-truncated timesteps.  custom_sigmas may be NULL (then linspace(1, 1/n, n) with the SD3 shift mu). */
@@ -306,6 +310,9 @@ int ltxv_pipeline_denoise_host(ltxv_dit* dit, const ltxv_pipeline_params* p, flo
                                const float* prompt_mask, const void* negative_embeds, const float* negative_mask,
                                int embeds_dtype, int K);
 int ltxv_pipeline_decode_host(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, float* out);
+/* same, delivering what the reference's example hands to its image / GIF writers: host u8 [frames, height, width, 3]
+ * (ltxv_frames_to_u8 on the device, so a quarter of the bytes cross PCIe) */
+int ltxv_pipeline_decode_host_u8(ltxv_vae* vae, const ltxv_pipeline_params* p, const float* latents, uint8_t* out);
 
 #ifdef __cplusplus
 }

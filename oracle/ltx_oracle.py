@@ -832,6 +832,12 @@ def postprocess_video(video: Tensor) -> Tensor:
     return (video * 0.5 + 0.5).clamp(0.0, 1.0) * 255.0
 
 
+def frames_to_u8(video: Tensor) -> Tensor:
+    """examples/ltx-video/main.rs:653-667: per frame permute((1,2,0)).clamp(0,255).to_dtype(U8) (truncating cast).
+    [B,3,F,H,W] f32 in 0..255 -> [B,F,H,W,3] u8."""
+    return video.permute(0, 2, 3, 4, 1).clamp(0.0, 255.0).to(torch.uint8).contiguous()
+
+
 def calculate_shift(seq_len: int, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
                     max_shift: float = 1.15) -> float:
     """t2v_pipeline.rs:159-169 (all f32)."""

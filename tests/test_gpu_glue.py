@@ -91,3 +91,15 @@ def test_stochastic_step_and_decode_noise_bit_exact(cuda):
     import ctypes as C
     cv._check(cv.lib().ltxv_decode_noise_blend(cv._ptr(out), cv._ptr(n.to(cuda)), 0.025, out.numel(), cv._stream()))
     assert torch.equal(out.cpu(), ref)
+
+
+def test_frames_to_u8_bit_exact(cuda):
+    """main.rs:653-667 hand-off: permute + clamp + truncating cast, bit-exact vs the oracle incl. out-of-range values."""
+    import candle_video_b200 as cv
+    g = torch.Generator().manual_seed(9)
+    v = torch.rand(2, 3, 5, 6, 10, generator=g) * 300.0 - 20.0   # below 0 and above 255 on purpose
+    v[0, 0, 0, 0, :4] = torch.tensor([0.0, 254.999, 255.0, 0.999])
+    out = cv.frames_to_u8(v.to(cuda)).cpu()
+    assert out.dtype == torch.uint8 and out.shape == (2, 5, 6, 10, 3)
+    assert torch.equal(out, O.frames_to_u8(v))
+    assert out[0, 0, 0, :4, 0].tolist() == [0, 254, 255, 0]

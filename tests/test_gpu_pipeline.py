@@ -195,3 +195,18 @@ def test_kernel_variants_are_bit_identical(cuda, monkeypatch):
     assert torch.isfinite(ref).all()
     assert torch.equal(ref, no_kw3)
     assert torch.equal(ref, single)
+
+
+def test_decode_host_u8_matches_f32_path(cuda):
+    """ltxv_pipeline_decode_host_u8 == frames_to_u8(ltxv_pipeline_decode_host) (same kernels, u8 hand-off on device)."""
+    import candle_video_b200 as cv
+    from tests.test_gpu_vae import build
+    vae, _, _ = build()
+    params = cv.PipelineParams(height=64, width=96, num_frames=9, frame_rate=25, num_inference_steps=1,
+                               custom_sigmas=[0.9], guidance_scale=1.0, guidance_rescale=0.0, stg_scale=0.0,
+                               shift_terminal=None, decode_timestep=0.05)
+    lat = torch.randn(2 * 2 * 3, 128, generator=torch.Generator().manual_seed(4))
+    f32 = cv.pipeline_decode_host(vae, params, lat)
+    u8 = cv.pipeline_decode_host_u8(vae, params, lat)
+    assert u8.shape == (9, 64, 96, 3) and u8.dtype == torch.uint8
+    assert torch.equal(u8, O.frames_to_u8(f32[None])[0])

@@ -322,3 +322,12 @@ def test_normalize_denormalize_round_trip():
     n = O.normalize_latents(z, mean, std, 0.5)
     assert torch.allclose(n[0, 3], (z[0, 3] - mean[3]) * 0.5 / std[3])
     assert torch.allclose(O.denormalize_latents(n, mean, std, 0.5), z, atol=1e-5)
+
+
+def test_frames_to_u8_kat():
+    """main.rs:653-667: channel-last per frame, clamp to [0,255], truncation toward zero."""
+    v = torch.zeros(1, 3, 2, 1, 2)
+    v[0, :, 1, 0, 1] = torch.tensor([12.9, 300.0, -4.0])
+    out = O.frames_to_u8(v)
+    assert out.shape == (1, 2, 1, 2, 3) and out.dtype == torch.uint8
+    assert out[0, 1, 0, 1].tolist() == [12, 255, 0]
