@@ -302,6 +302,15 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
 // voxel's place in the padded volume (plus the replicated frames and the neighbours' halo rows).  Same arithmetic as
 // vae_prep_kernel on the stored x; removes that kernel's read of x and, for a resnet's first conv, the write of x too.
 // ------------------------------------------------------------------------------------------------
+// The residual row of a fused-producer tile is requested into L2 while the tile's main loop still runs (the epilogue
+// warps are idle then): its four dependent 64-byte loads per row otherwise pay the HBM round trip one after the other
+// and, together with the second pass, outlast the main loop of the 128-channel convs (measured: 1.34 -> 1.99 ms).
+__device__ __forceinline__ void prefetch_residual_row_l2(const GemmParams& p, const RowCtx& rc) {
+    if (p.epi != EPI_CONV_NORM_PAD || p.res_bf16 == nullptr || !rc.valid) return;
+    const char* r = reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(p.res_bf16) + rc.out_row * p.ldo);
+    for (int b = 0; b < p.N * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + b));
+}
+
 // Two passes over the accumulator row in TMEM, 32 columns at a time (loops kept rolled: a fully unrolled version is
 // ~200 KB of code and thrashes the instruction cache of the whole CTA): pass 1 accumulates the RMS of the bf16-rounded
 // row, pass 2 recomputes the same rounded values, stores x and the normalised / modulated / SiLU'd padded copy.
@@ -600,6 +609,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
             const int m_warp0 = t.m0 + quad * 32;
             if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);  // before the MMAs finish
+            prefetch_residual_row_l2(p, rc);
             mbar_wait_sleep(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * C::kTmemStride;
@@ -839,6 +849,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             float4 res_a[8], res_b[8];
             const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
             if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);
+            prefetch_residual_row_l2(p, rc);
             mbar_wait_sleep(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kPairBlockN;

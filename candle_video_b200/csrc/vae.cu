@@ -388,11 +388,12 @@ void AutoencoderKLLtxVideo::resnet(const ResnetW& rw, int l, const float* ss, __
     mid.shift = ss ? ss + 2 * C : nullptr;
     conv(rw.conv1, a1, T, H, W, EPI_CONV_NDHWC, nullptr, nullptr, 0, s, l, &mid);
     void* a2 = pad_buf(l, pp_[l]);
-    // Fusing conv2's consumer as well (store x AND the next padded input from one epilogue) measured SLOWER on B200:
-    // conv3d 33.5 -> 38.8 ms per c2 decode for 2.3 ms of saved prep time, whereas the conv1 fusion above is free
-    // (33.5 -> 33.9 ms, prep 5.8 -> 3.4 ms).  Opt-in for experiments only.
-    static const bool fuse_conv2 = getenv("LTXV_VAE_FUSE_CONV2") != nullptr;
-    if (!fuse_conv2) next = nullptr;
+    // conv2's epilogue can also produce the NEXT consumer's input (store x and the padded copy), but that doubles the
+    // epilogue: at C = 128 it then outlasts the 11 us main loop of a tile (ncu: 1.34 -> 1.99 ms per conv for 0.33 ms of
+    // saved prep), at C = 256 the main loop is 4x longer and it stays hidden (0.65 -> 0.67 ms for 0.08 ms saved).
+    static const bool no_conv2 = getenv("LTXV_VAE_NO_FUSE_CONV2") != nullptr;
+    static const bool all_conv2 = getenv("LTXV_VAE_FUSE_CONV2") != nullptr;
+    if (no_conv2 || (C < 256 && !all_conv2)) next = nullptr;
     conv(rw.conv2, a2, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s, next ? l : -1, next);
     std::swap(x, x_alt);
     if (ready) *ready = next ? pad_buf(l, pp_[l]) : nullptr;

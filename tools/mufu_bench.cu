@@ -5,6 +5,7 @@
 
 __device__ __forceinline__ float ex2_f32(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ unsigned ex2_h2(unsigned x) { unsigned y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ unsigned ex2_bf2(unsigned x) { unsigned y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 // 2^x for x <= 0 (x >= -126): Cody-Waite split + degree-3 minimax on [0,1)
 __device__ __forceinline__ float ex2_poly(float x) {
     x = fmaxf(x, -126.0f);
@@ -28,6 +29,7 @@ __global__ void k(float* out, int iters) {
             if (MODE == 0) a[i] = ex2_f32(a[i]) - 1.0f;
             if (MODE == 1) h[i] = ex2_h2(h[i]) ^ 0x80008000u;
             if (MODE == 2) a[i] = ex2_poly(a[i]) - 1.0f;
+            if (MODE == 3) h[i] = ex2_bf2(h[i]) ^ 0x80008000u;
         }
     }
     float s = 0;
@@ -55,5 +57,6 @@ int main() {
     run<0>("ex2.approx.ftz.f32", 1);
     run<1>("ex2.approx.ftz.f16x2", 2);
     run<2>("poly exp2 (FMA pipe)", 1);
+    run<3>("ex2.approx.ftz.bf16x2", 2);
     return 0;
 }
