@@ -159,7 +159,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const RowCtx
                     reinterpret_cast<const __nv_bfloat16*>(p.res_bf16) + rc.out_row * p.ldo + col0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    uint4 u = __ldg(r4 + i);
+                    uint4 u = __ldcs(r4 + i);  // streamed once: keep L2 for the A operand's (kt, kh) reuse
                     v[8 * i + 0] += bf16_lo(u.x);
                     v[8 * i + 1] += bf16_hi(u.x);
                     v[8 * i + 2] += bf16_lo(u.y);
@@ -340,7 +340,7 @@ __device__ __noinline__ void epilogue_conv_norm_pad(const GemmParams& p, const R
             const uint4* r4 = reinterpret_cast<const uint4*>(res + c * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(r4 + i);
+                const uint4 u = __ldcs(r4 + i);  // read once: streaming, evict-first
                 v[8 * i + 0] += bf16_lo(u.x);
                 v[8 * i + 1] += bf16_hi(u.x);
                 v[8 * i + 2] += bf16_lo(u.y);
@@ -378,7 +378,7 @@ __device__ __noinline__ void epilogue_conv_norm_pad(const GemmParams& p, const R
             if (xdst != nullptr) {
                 uint4* d4 = reinterpret_cast<uint4*>(xdst + c * 32);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) d4[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) __stcs(d4 + q, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -414,7 +414,7 @@ __device__ __noinline__ void epilogue_conv_norm_pad(const GemmParams& p, const R
             const uint4* x4 = reinterpret_cast<const uint4*>(xdst + c * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 u = x4[q];
+                const uint4 u = __ldcs(x4 + q);
                 w[4 * q] = u.x; w[4 * q + 1] = u.y; w[4 * q + 2] = u.z; w[4 * q + 3] = u.w;
             }
         } else {
@@ -450,7 +450,7 @@ __device__ __noinline__ void epilogue_conv_norm_pad(const GemmParams& p, const R
         auto put = [&](__nv_bfloat16* d) {
             uint4* d4 = reinterpret_cast<uint4*>(d + c * 32);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) d4[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) __stcs(d4 + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
         };
         put(d_main);
         if (!simple) {
@@ -695,8 +695,15 @@ struct PairCfg {
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
+// The conv variants (MODE 1) run TWO epilogue warpgroups, one per TMEM accumulator stage, on alternating tiles: with one
+// warp per scheduler the epilogue is latency-bound (a 128x128 tile with residual, x store and the fused producer takes
+// ~16 us against an 11 us main loop at C = 128), and two groups give every tile two main loops of time.
+template <int MODE>
+struct PairThreads {
+    static constexpr int value = MODE == 1 ? 384 : kThreads;
+};
 template <int BN, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairThreads<MODE>::value, 1)
 gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ GemmParams p) {
     using PC = PairCfg<BN, MODE>;
@@ -841,7 +848,15 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                (p.N % 32 == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        constexpr int kEpiGroups = PairThreads<MODE>::value == 384 ? 2 : 1;
+        const int epi_group = (warp_idx - 4) >> 2;
+        int it = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            if (kEpiGroups == 2) {  // group g owns accumulator stage g: tiles g, g+2, g+4, ... of this cluster
+                if ((it & 1) != epi_group) continue;
+                acc = epi_group;
+                acc_phase = (it >> 1) & 1;
+            }
             const int m_cta0 = (tile % num_m) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
             const int n0 = (tile / num_m) * kPairBlockN;
             const int m_warp0 = m_cta0 + quad * 32;
@@ -882,7 +897,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     chunk(c + 1, res_b);
                 }
             }
-            if (++acc == 2) {
+            if (kEpiGroups == 1 && ++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
             }
@@ -964,7 +979,7 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
         if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
-        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE>, dim3(2 * clusters), dim3(kThreads), PC::kSmemBytes,
+        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE>, dim3(2 * clusters), dim3(PairThreads<MODE>::value), PC::kSmemBytes,
                                     stream, ta, tb, p);
         if (le != cudaSuccess) return le;
     }

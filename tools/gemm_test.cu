@@ -234,7 +234,67 @@ static int test_conv(int T, int H, int W, int Cin, int Cout, bool timing) {
     return st.bad ? 1 : 0;
 }
 
+// epilogue cost study at one conv shape: which part of the fused producer epilogue outlasts the main loop?
+static void time_conv_variants(int T, int H, int W, int C) {
+    const int Hp = H + 2, Wp = W + 2, plane = Hp * Wp;
+    const size_t rows = (size_t)(T + 2) * plane;
+    __nv_bfloat16 *xp, *pn, *w, *out, *resid;
+    float *bias, *sc;
+    CK(cudaMalloc(&xp, rows * C * 2));
+    CK(cudaMalloc(&pn, rows * C * 2));
+    CK(cudaMalloc(&w, (size_t)C * 27 * C * 2));
+    CK(cudaMalloc(&out, (size_t)T * H * W * C * 2));
+    CK(cudaMalloc(&resid, (size_t)T * H * W * C * 2));
+    CK(cudaMalloc(&bias, C * 4));
+    CK(cudaMalloc(&sc, C * 4));
+    fill_bf16<<<(rows * C + 255) / 256, 256>>>(xp, rows * C, 11, 1.0f);
+    CK(cudaMemset(pn, 0, rows * C * 2));
+    fill_bf16<<<((size_t)C * 27 * C + 255) / 256, 256>>>(w, (size_t)C * 27 * C, 12, 1.0f / sqrtf(27.f * C));
+    fill_bf16<<<((size_t)T * H * W * C + 255) / 256, 256>>>(resid, (size_t)T * H * W * C, 13, 1.0f);
+    fill_f32<<<(C + 255) / 256, 256>>>(bias, C, 14, 0.5f);
+    fill_f32<<<(C + 255) / 256, 256>>>(sc, C, 15, 0.1f);
+    GemmOperands ops{xp, (int64_t)rows, C, w, C, 27 * C};
+    struct V { const char* name; int epi; bool x, res, norm, silu, mod; };
+    const V vs[] = {{"plain, no residual (conv1 unfused)", EPI_CONV_NDHWC, true, false, false, false, false},
+                    {"plain + residual   (conv2 unfused)", EPI_CONV_NDHWC, true, true, false, false, false},
+                    {"fused p only       (conv1 fused)", EPI_CONV_NORM_PAD, false, false, true, true, true},
+                    {"fused x + p + res  (conv2 fused)", EPI_CONV_NORM_PAD, true, true, true, true, true},
+                    {"fused x + p, no residual", EPI_CONV_NORM_PAD, true, false, true, true, true},
+                    {"fused p + res, no x store", EPI_CONV_NORM_PAD, false, true, true, true, true},
+                    {"fused x + p + res, raw (no norm/silu/mod)", EPI_CONV_NORM_PAD, true, true, false, false, false},
+                    {"fused x + p + res, norm only", EPI_CONV_NORM_PAD, true, true, true, false, false}};
+    for (const V& v : vs) {
+        GemmParams p{};
+        p.M = T * plane; p.N = C; p.K = 27 * C; p.num_k_blocks = 27 * (C / 64);
+        p.epi = v.epi; p.ldo = C; p.bias = bias; p.out = v.x ? out : nullptr; p.res_bf16 = v.res ? resid : nullptr;
+        p.conv = 1; p.cin_blocks = C / 64; p.T = T; p.H = H; p.W = W; p.cin = C; p.a_ptr = xp;
+        p.norm_out = pn; p.norm_do = v.norm; p.norm_silu = v.silu; p.norm_tf = 1;
+        p.norm_scale = v.mod ? sc : nullptr; p.norm_shift = v.mod ? sc : nullptr;
+        for (int kt = 0; kt < 3; ++kt)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) p.tap_off[(kt * 3 + kh) * 3 + kw] = kt * plane + (kh - 1) * Wp + (kw - 1);
+        if (p.epi == EPI_CONV_NDHWC && p.out == nullptr) continue;
+        for (int i = 0; i < 2; ++i) CK(launch_gemm_bf16(ops, p, 0, 0));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        const int iters = 5;
+        for (int i = 0; i < iters; ++i) launch_gemm_bf16(ops, p, 0, 0);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        ms /= iters;
+        printf("conv C=%d %dx%dx%d  %-44s %.3f ms  %.0f TFLOP/s\n", C, T, H, W, v.name, ms, 2.0 * C * C * 27.0 * T * H * W / ms * 1e-9);
+    }
+    cudaFree(xp); cudaFree(pn); cudaFree(w); cudaFree(out); cudaFree(resid); cudaFree(bias); cudaFree(sc);
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && atoi(argv[1]) == 4) {
+        time_conv_variants(49, 128, 192, 128);
+        time_conv_variants(49, 64, 96, 256);
+        return 0;
+    }
     bool big = argc > 1 && atoi(argv[1]) > 0;
     int fails = 0;
     if (argc > 1 && atoi(argv[1]) == 3) {  // every kernel variant at the [9984, 2048] x [2048, 2048] projections
