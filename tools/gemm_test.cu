@@ -297,6 +297,18 @@ int main(int argc, char** argv) {
     }
     bool big = argc > 1 && atoi(argv[1]) > 0;
     int fails = 0;
+    if (argc > 1 && atoi(argv[1]) == 5) {  // auto dispatch at the batched-CFG c2 shapes (M = 2S = 9984), incl. a ragged M
+        int f = 0;
+        f += test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, 0, true);
+        f += test_gemm(9984, 2048, 2048, EPI_STORE_BF16, 0, 0, true);
+        f += test_gemm(9984, 2048, 8192, EPI_RESIDUAL_F32, 0, 0, true);
+        f += test_gemm(9984, 6144, 2048, EPI_STORE_BF16, 0, 0, true);
+        f += test_gemm(9984, 8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH, 0, true);
+        f += test_gemm(4992, 2048, 2048, EPI_RESIDUAL_F32, 0, 0, true);
+        f += test_gemm(9900, 2048, 2048, EPI_STORE_F32, 0, 0, true);  // ragged M in the tail rectangle
+        printf("%s\n", f ? "GEMM_TEST_FAIL" : "GEMM_TEST_OK");
+        return f;
+    }
     if (argc > 1 && atoi(argv[1]) == 3) {  // every kernel variant at the [9984, 2048] x [2048, 2048] projections
         for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, bn, true);
         for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_STORE_BF16, 0, bn, true);
