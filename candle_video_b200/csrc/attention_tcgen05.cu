@@ -391,9 +391,6 @@ constexpr int kV3Threads = 384;
 constexpr int kV3Stages = 6;
 constexpr int kV3L2Ahead = 4;  // K/V tiles prefetched into L2 beyond the smem ring
 constexpr int kV3SmemBytes = 2 * kV2QBytes + 2 * kV3Stages * kV2KVBytes + 512;
-#ifndef LTXV_ATTN_PINGPONG
-#define LTXV_ATTN_PINGPONG 0
-#endif
 
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
     uint64_t r;
@@ -782,12 +779,6 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             const uint64_t c2 = pack_f32x2(c, c);
             float m_used = -INFINITY;
             uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
-#if LTXV_ATTN_PINGPONG
-            // ping-pong between the two softmax groups (named barriers 1 + t): the MUFU-heavy exponential phases of
-            // the two query tiles alternate, so each runs at the full 16 exp2/clk/SM while the other group does its
-            // TMEM load / max / waits.
-            if (two && t == 1) named_bar_arrive(1, 256);  // tile 0 goes first
-#endif
 #ifdef LTXV_ATTN_TIMING
             const bool tm_on = (qb == 3 && head == 5 && split == 0 && lane == 0 && (warp_idx == 0 || warp_idx == 4));
             long long tm_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -856,9 +847,6 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 }
                 TMARK(3);
                 const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
-#if LTXV_ATTN_PINGPONG
-                if (two) named_bar_sync(1 + t, 256);  // my turn on the MUFU pipe
-#endif
                 uint32_t pk[32];
                 exp_chunk_v3(s0, c2, negm2, l2a, l2b, pk);
                 exp_chunk_v3(s1, c2, negm2, l2a, l2b, pk + 16);
@@ -876,9 +864,6 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 exp_chunk_v3(s2, c2, negm2, l2a, l2b, pk);
                 exp_chunk_v3(s3, c2, negm2, l2a, l2b, pk + 16);
                 tmem_st_32x32b_x32(tmem_p + 32, pk);     // keys 64..127 -> P columns 32..63
-#if LTXV_ATTN_PINGPONG
-                if (two) named_bar_arrive(1 + (t ^ 1), 256);  // hand the MUFU pipe to the other tile
-#endif
                 TMARK(6);
                 tmem_st_wait();
                 tcgen05_fence_before();
