@@ -202,7 +202,8 @@ void LtxVideoEncoder3d::ensure_workspace(int F, int H, int W) {
 }
 
 void LtxVideoEncoder3d::conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out,
-                             const void* res, int n_cols, int ldo, cudaStream_t s, void* fused_norm_out) {
+                             const void* res, int n_cols, int ldo, cudaStream_t s, void* fused_norm_out, int fused_raw,
+                             int fused_tf) {
     const int Wp = W + 2, plane = (H + 2) * Wp;
     GemmOperands ops{a_padded, static_cast<int64_t>(T + 2) * plane, cw.Cin, cw.w, cw.rows_out, 27ll * cw.Cin};
     GemmParams p{};
@@ -230,22 +231,33 @@ void LtxVideoEncoder3d::conv(const ConvW& cw, const void* a_padded, int T, int H
         // the epilogue is also the producer of the next conv's input: pixel norm + SiLU into the causally padded volume
         p.epi = EPI_CONV_NORM_PAD;
         p.norm_out = fused_norm_out;
-        p.norm_do = p.norm_silu = 1;
-        p.norm_tf = 2;
+        p.norm_do = p.norm_silu = fused_raw ? 0 : 1;  // raw: the downsampler's conv reads the activations as they are
+        p.norm_tf = fused_tf;
     }
     LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
 }
 
-// LtxVideoResnetBlock3d::forward (vae.rs:755-821), in == out, causal, no conditioning
-void LtxVideoEncoder3d::resnet(const ResnetW& rw, int l, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s) {
+// LtxVideoResnetBlock3d::forward (vae.rs:755-821), in == out, causal, no conditioning.
+// `ready`: p_[l] already holds this resnet's conv1 input (written by the previous conv2's epilogue).  next_kind: what
+// consumes the output -- 0 nothing fused, 1 another resnet (pixel norm + SiLU), 2 the downsampler (raw, `next_tf` front
+// frames); on return `ready` says whether p_[l] holds that consumer's input.
+void LtxVideoEncoder3d::resnet(const ResnetW& rw, int l, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s,
+                               bool* ready, int next_kind, int next_tf) {
     const int C = ch_[l], T = T_[l], H = H_[l], W = W_[l];
     static const bool no_fuse = getenv("LTXV_VAE_NO_FUSED_PREP") != nullptr;
-    LTXV_CUDA(launch_vae_prep(x, p_[l].p, nullptr, nullptr, 1, 1, T, H, W, C, s, nullptr, nullptr, 2));
+    static const bool no_conv2 = getenv("LTXV_VAE_NO_FUSE_CONV2") != nullptr;
+    if (!(ready && *ready)) LTXV_CUDA(launch_vae_prep(x, p_[l].p, nullptr, nullptr, 1, 1, T, H, W, C, s, nullptr, nullptr, 2));
+    if (ready) *ready = false;
     if (C <= 256 && !no_fuse) {
         // narrow level: conv1's epilogue writes conv2's input (norm2 + SiLU) straight into the second padded volume;
         // its raw output is never stored (see EPI_CONV_NORM_PAD, gemm.h)
-        conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, nullptr, nullptr, C, C, s, q_[l].p);
-        conv(rw.conv2, q_[l].p, T, H, W, EPI_CONV_NDHWC, x_alt, x, C, C, s);
+        conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, nullptr, nullptr, C, C, s, q_[l].p, 0, 2);
+        // C = 256: conv2's epilogue also produces the next consumer's input into p_[l] (hidden under the longer main
+        // loop there; at C = 128 it is not, see vae.cu)
+        const bool fuse2 = C == 256 && !no_conv2 && next_kind != 0 && ready != nullptr;
+        conv(rw.conv2, q_[l].p, T, H, W, EPI_CONV_NDHWC, x_alt, x, C, C, s, fuse2 ? p_[l].p : nullptr, next_kind == 2,
+             next_kind == 2 ? next_tf : 2);
+        if (fuse2) *ready = true;
     } else {
         conv(rw.conv1, p_[l].p, T, H, W, EPI_CONV_NDHWC, hb_.p, nullptr, C, C, s);
         LTXV_CUDA(launch_vae_prep(hb_.p, p_[l].p, nullptr, nullptr, 1, 1, T, H, W, C, s, nullptr, nullptr, 2));
@@ -271,13 +283,17 @@ void LtxVideoEncoder3d::encode(const void* xin, int x_dtype, int B, int F, int H
         __nv_bfloat16* x_alt = xb_.as<__nv_bfloat16>();
         conv(conv_in_, a_in_.p, T_[0], H_[0], W_[0], EPI_CONV_NDHWC, x, nullptr, ch_[0], ch_[0], s);
         for (int l = 0; l < 5; ++l) {
-            for (size_t i = 0; i < res_[l].size(); ++i) resnet(res_[l][i], l, x, x_alt, s);
+            const int st_l = l < 4 ? stride_[l][0] : 1;
+            bool ready = false;
+            for (size_t i = 0; i < res_[l].size(); ++i)
+                resnet(res_[l][i], l, x, x_alt, s, &ready, i + 1 < res_[l].size() ? 1 : (l < 4 ? 2 : 0), 2 + (st_l - 1));
             if (l == 4) break;
             // LtxVideoDownsampler3d (vae.rs:534-582)
             const int st = stride_[l][0], sh = stride_[l][1], sw = stride_[l][2];
             const int Tp = T_[l] + st - 1;
-            LTXV_CUDA(launch_vae_prep(x, p_[l].p, nullptr, nullptr, 0, 0, T_[l], H_[l], W_[l], ch_[l], s, nullptr, nullptr,
-                                      2 + (st - 1)));
+            if (!ready)
+                LTXV_CUDA(launch_vae_prep(x, p_[l].p, nullptr, nullptr, 0, 0, T_[l], H_[l], W_[l], ch_[l], s, nullptr, nullptr,
+                                          2 + (st - 1)));
             conv(down_[l], p_[l].p, Tp, H_[l], W_[l], EPI_CONV_NDHWC, hb_.p, nullptr, down_[l].Cout, down_[l].Cout, s);
             LTXV_CUDA(launch_vae_unshuffle_add(hb_.p, x, x_alt, T_[l + 1], H_[l + 1], W_[l + 1], st, sh, sw, ch_[l],
                                                down_[l].Cout, s));

@@ -39,8 +39,9 @@ private:
     void add_conv(const std::string& prefix, ConvW& cw, int cin_src, int Cin, int Cout, int rows_out);
     void ensure_workspace(int F, int H, int W);
     void conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out, const void* res, int n_cols,
-              int ldo, cudaStream_t s, void* fused_norm_out = nullptr);
-    void resnet(const ResnetW& rw, int level, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s);
+              int ldo, cudaStream_t s, void* fused_norm_out = nullptr, int fused_raw = 0, int fused_tf = 2);
+    void resnet(const ResnetW& rw, int level, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s, bool* ready = nullptr,
+                int next_kind = 0, int next_tf = 2);
 
     ltxv_vae_encoder_config cfg_;
     int device_;
