@@ -18,6 +18,7 @@ using namespace ltxv;
 struct ltxv_dit {
     LtxVideoTransformer3DModel model;
     DevBuf h_hidden, h_enc, h_t, h_mask, h_coords, h_out;  // device staging for the *_host entry points
+    DevBuf p_lat, p_pe, p_ne, p_pm, p_nm;                   // ... and for ltxv_pipeline_denoise_host
     ltxv_dit(const ltxv_dit_config& c, int dev) : model(c, dev) {}
 };
 struct ltxv_comm {
@@ -27,6 +28,7 @@ struct ltxv_comm {
 struct ltxv_vae {
     AutoencoderKLLtxVideo model;
     DevBuf h_z, h_t, h_out;
+    DevBuf p_lat, p_out, p_u8;  // staging of ltxv_pipeline_decode_host / _host_u8 (per handle: lives on the model's device)
     ltxv_vae(const ltxv_vae_config& c, int dev) : model(c, dev) {}
 };
 
@@ -201,6 +203,7 @@ int ltxv_dit_forward_host(ltxv_dit* m, const void* hidden, int hidden_dtype, con
     const size_t ne = static_cast<size_t>(B) * K * c.caption_channels * dsize(enc_dtype);
     const size_t no = static_cast<size_t>(B) * S * c.out_channels * dsize(out_dtype);
     cudaStream_t s = 0;
+    LTXV_CUDA(cudaSetDevice(m->model.device()));
     m->h_hidden.ensure(nh);
     m->h_enc.ensure(ne);
     m->h_t.ensure(B * 4);
@@ -353,6 +356,7 @@ int ltxv_vae_encode_host(ltxv_vae* m, const void* x, int x_dtype, int B, int F, 
     e.latent_dims(F, H, W, &fl, &hl, &wl);
     const size_t in_bytes = static_cast<size_t>(B) * 3 * F * H * W * dsize(x_dtype);
     const size_t out_bytes = static_cast<size_t>(B) * 2 * e.config().latent_channels * fl * hl * wl * 4;
+    LTXV_CUDA(cudaSetDevice(m->model.device()));
     m->h_z.ensure(in_bytes);
     m->h_out.ensure(out_bytes);
     LTXV_CUDA(cudaMemcpy(m->h_z.p, x, in_bytes, cudaMemcpyHostToDevice));
@@ -382,6 +386,7 @@ int ltxv_vae_decode_host(ltxv_vae* m, const void* z, int z_dtype, const float* t
     const size_t nz = static_cast<size_t>(B) * C * F * H * W * dsize(z_dtype);
     const size_t no = static_cast<size_t>(B) * 3 * (8 * F - 7) * (32 * H) * (32 * W) * dsize(out_dtype);
     cudaStream_t s = 0;
+    LTXV_CUDA(cudaSetDevice(m->model.device()));
     m->h_z.ensure(nz);
     m->h_out.ensure(no);
     LTXV_CUDA(cudaMemcpyAsync(m->h_z.p, z, nz, cudaMemcpyHostToDevice, s));
@@ -431,7 +436,11 @@ int ltxv_guidance_euler_step(const float* cond, const float* uncond, const float
                              float stg_scale, float sigma, float sigma_next, void* stream) {
     LTXV_TRY
     if (cond == nullptr) fail("null argument");
-    static DevBuf scratch;
+    static DevBuf scratch_dev[16];  // one per device: the statistics of the std rescale
+    int dev = 0;
+    LTXV_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) fail("device index %d out of range", dev);
+    DevBuf& scratch = scratch_dev[dev];
     scratch.ensure(64);
     const float dt = sigma_next - sigma;
     for (int b = 0; b < B; ++b)
@@ -592,7 +601,8 @@ int ltxv_pipeline_denoise_host(ltxv_dit* dit, const ltxv_pipeline_params* p, flo
     const size_t nl = static_cast<size_t>(F) * H * W * c.in_channels * 4;
     const size_t ne = static_cast<size_t>(K) * c.caption_channels * dsize(embeds_dtype);
     cudaStream_t s = 0;
-    static DevBuf d_lat, d_pe, d_ne, d_pm, d_nm;
+    LTXV_CUDA(cudaSetDevice(dit->model.device()));
+    DevBuf &d_lat = dit->p_lat, &d_pe = dit->p_pe, &d_ne = dit->p_ne, &d_pm = dit->p_pm, &d_nm = dit->p_nm;
     d_lat.ensure(nl);
     d_pe.ensure(ne);
     LTXV_CUDA(cudaMemcpyAsync(d_lat.p, latents, nl, cudaMemcpyHostToDevice, s));
@@ -627,7 +637,8 @@ int ltxv_pipeline_decode_host(ltxv_vae* vae, const ltxv_pipeline_params* p, cons
     const size_t nl = static_cast<size_t>(F) * H * W * C * 4;
     const size_t no = 3ull * (8 * F - 7) * (32 * H) * (32 * W) * 4;
     cudaStream_t s = 0;
-    static DevBuf d_lat, d_out;
+    LTXV_CUDA(cudaSetDevice(vae->model.device()));
+    DevBuf &d_lat = vae->p_lat, &d_out = vae->p_out;
     d_lat.ensure(nl);
     d_out.ensure(no);
     LTXV_CUDA(cudaMemcpyAsync(d_lat.p, latents, nl, cudaMemcpyHostToDevice, s));
@@ -653,7 +664,8 @@ int ltxv_pipeline_decode_host_u8(ltxv_vae* vae, const ltxv_pipeline_params* p, c
     const size_t nl = static_cast<size_t>(F) * H * W * C * 4;
     const size_t npx = static_cast<size_t>(Fo) * Ho * Wo;
     cudaStream_t s = 0;
-    static DevBuf d_lat, d_out, d_u8;
+    LTXV_CUDA(cudaSetDevice(vae->model.device()));
+    DevBuf &d_lat = vae->p_lat, &d_out = vae->p_out, &d_u8 = vae->p_u8;
     d_lat.ensure(nl);
     d_out.ensure(npx * 3 * 4);
     d_u8.ensure(npx * 3);

@@ -34,6 +34,7 @@ public:
     ~AutoencoderKLLtxVideo();
 
     const ltxv_vae_config& config() const { return cfg_; }
+    int device() const { return device_; }
     void load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape, int rank);
     bool has_key(const std::string& key) const;
     // encoder half (vae_encoder.h); without it `encoder.*` keys are ignored like in a decode-only deployment
