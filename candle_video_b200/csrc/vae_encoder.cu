@@ -69,6 +69,12 @@ LtxVideoEncoder3d::LtxVideoEncoder3d(const ltxv_vae_encoder_config& cfg, int dev
         const int S = stride_[l][0] * stride_[l][1] * stride_[l][2];
         if (ch_[l + 1] % S != 0 || (ch_[l + 1] / S) % 64 != 0 || (ch_[l] * S) % ch_[l + 1] != 0)
             fail("encoder: block %d cannot pixel-unshuffle %d -> %d channels with stride product %d", l, ch_[l], ch_[l + 1], S);
+        // residual group sizes the downsampler-tail kernel is instantiated for (vae_glue.cu): S/2 and S, i.e. the
+        // channel count doubles or stays the same through a block
+        const int G = ch_[l] * S / ch_[l + 1];
+        if (G != S / 2 && G != S)
+            fail("encoder: block %d (%d -> %d channels, stride product %d) needs a residual group of %d; built: %d and %d",
+                 l, ch_[l], ch_[l + 1], S, G, S / 2, S);
     }
     const std::string P = "encoder.";
     add_conv(P + "conv_in", conv_in_, cfg.in_channels * 16, 64, ch_[0], ch_[0]);
