@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = [
     "ltxv_pipeline_decode_noisy",
     "ltxv_vae_encoder_config_default", "ltxv_vae_enable_encoder", "ltxv_vae_encode_dims", "ltxv_vae_encode",
     "ltxv_vae_encode_host", "ltxv_normalize_latents", "ltxv_frames_to_u8", "ltxv_pipeline_decode_host_u8",
+    "ltxv_vae_encode_tiled",
 ]
 
 
@@ -161,6 +162,7 @@ def _load() -> C.CDLL:
     l.ltxv_vae_encode_dims.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     l.ltxv_vae_encode.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     l.ltxv_vae_encode_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    l.ltxv_vae_encode_tiled.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.POINTER(_VaeTilingC), i32, vp, vp]
     l.ltxv_normalize_latents.argtypes = [vp, vp, vp, vp, f32, i32, i32, i64, vp]
     l.ltxv_frames_to_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     l.ltxv_pipeline_decode_host_u8.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp]
@@ -543,6 +545,21 @@ class AutoencoderKLLtxVideo:
         fl, hl, wl = self.encode_dims(F, H, W)
         out = torch.empty((B, 2 * self.config.latent_channels, fl, hl, wl), dtype=torch.float32, device=x.device)
         _check(lib().ltxv_vae_encode(self._h, _ptr(x), _dtype_code(x), B, F, H, W, _ptr(out), _stream()))
+        return out
+
+    def encode_tiled(self, video, tiling: "Optional[VaeTiling]" = None, use_framewise_encoding: bool = False):
+        """encode_z of the reference with its tiling dispatch (vae.rs:2017-2034); tiling=None is the library default
+        (512/384 px tiles; framewise encoding off, vae.rs:1856-1858)."""
+        torch = _torch()
+        x = _dev(video, "video")
+        B, Cin, F, H, W = x.shape
+        if Cin != 3:
+            raise LtxvError("video must have 3 channels")
+        fl, hl, wl = self.encode_dims(F, H, W)
+        out = torch.empty((B, 2 * self.config.latent_channels, fl, hl, wl), dtype=torch.float32, device=x.device)
+        tp = (tiling or VaeTiling()).to_c()
+        _check(lib().ltxv_vae_encode_tiled(self._h, _ptr(x), _dtype_code(x), B, F, H, W, C.byref(tp),
+                                           int(use_framewise_encoding), _ptr(out), _stream()))
         return out
 
     def encode_host(self, video):

@@ -348,6 +348,13 @@ int ltxv_vae_encode(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H
     encoder_of(m).encode(x, x_dtype, B, F, H, W, moments, static_cast<cudaStream_t>(stream));
     LTXV_CATCH
 }
+int ltxv_vae_encode_tiled(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W,
+                          const ltxv_vae_tiling* tiling, int use_framewise_encoding, float* moments, void* stream) {
+    LTXV_TRY
+    if (x == nullptr || moments == nullptr) fail("null argument");
+    encoder_of(m).encode_z(x, x_dtype, B, F, H, W, tiling, use_framewise_encoding, moments, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
 int ltxv_vae_encode_host(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W, float* moments) {
     LTXV_TRY
     if (x == nullptr || moments == nullptr) fail("null argument");

@@ -9,6 +9,7 @@
 #include "vae_encoder.h"
 
 #include <algorithm>
+#include <memory>
 
 #include <math.h>
 #include <stdlib.h>
@@ -310,6 +311,144 @@ void LtxVideoEncoder3d::encode(const void* xin, int x_dtype, int B, int F, int H
         const int ld = L + 32;
         conv(conv_out_, p_[4].p, T_[4], H_[4], W_[4], EPI_STORE_F32, out32_.p, nullptr, ld, ld, s);
         LTXV_CUDA(launch_vae_moments(out32_.as<float>(), moments + static_cast<size_t>(b) * 2 * L * nvox, nvox, L, ld, s));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiled encode (compatibility mode; the reference's library default is use_tiling = true)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct MomTile {  // one encoded tile: f32 [C, T, H, W]
+    DevBuf buf;
+    int T = 0, H = 0, W = 0;
+    float* p() const { return buf.as<float>(); }
+    void shape(int c, int t, int h, int w) {
+        T = t;
+        H = h;
+        W = w;
+        buf.ensure(static_cast<size_t>(c) * t * h * w * 4);
+    }
+};
+}  // namespace
+
+void LtxVideoEncoder3d::tiled_encode(const void* x, int x_dtype, int T, int H, int W, float* dst, const ltxv_vae_tiling& tp,
+                                     cudaStream_t s) {
+    const int sr = 32, C2 = 2 * cfg_.latent_channels;
+    const int esz = x_dtype == LTXV_F32 ? 4 : 2;
+    int Tl, Hl, Wl;
+    latent_dims(T, H, W, &Tl, &Hl, &Wl);
+    const int min_h = tp.tile_sample_min_height / sr, min_w = tp.tile_sample_min_width / sr;
+    const int str_h = tp.tile_sample_stride_height / sr, str_w = tp.tile_sample_stride_width / sr;
+    if (min_h < 1 || min_w < 1 || str_h < 1 || str_w < 1) fail("tile sizes and strides must be at least %d pixels", sr);
+    if (tp.tile_sample_stride_height % sr || tp.tile_sample_stride_width % sr || tp.tile_sample_min_height % sr ||
+        tp.tile_sample_min_width % sr)
+        fail("tiled encode: tile sizes and strides must be multiples of %d pixels", sr);
+    const int blend_h = std::max(min_h - str_h, 0), blend_w = std::max(min_w - str_w, 0);  // latent units (:2171-2172)
+    const int ncols = (W + tp.tile_sample_stride_width - 1) / tp.tile_sample_stride_width;
+    std::unique_ptr<MomTile[]> row_a(new MomTile[ncols]), row_b(new MomTile[ncols]);
+    MomTile* prev = row_a.get();
+    MomTile* cur = row_b.get();
+    int ri = 0;
+    for (int i = 0; i < H; i += tp.tile_sample_stride_height, ++ri) {
+        const int th = std::min(i + tp.tile_sample_min_height, H) - i;
+        int cj = 0;
+        for (int j = 0; j < W; j += tp.tile_sample_stride_width, ++cj) {
+            const int tw = std::min(j + tp.tile_sample_min_width, W) - j;
+            tx_sp_.ensure(3ull * T * th * tw * esz);
+            LTXV_CUDA(launch_copy_box(x, esz, 3, T, H, W, 0, i, j, tx_sp_.p, T, th, tw, 0, 0, 0, T, th, tw, s));
+            int tl, hl, wl;
+            latent_dims(T, th, tw, &tl, &hl, &wl);
+            MomTile& tile = cur[cj];
+            tile.shape(C2, tl, hl, wl);
+            encode(tx_sp_.p, x_dtype, 1, T, th, tw, tile.p(), s);
+            if (ri > 0)  // blend_v with the (already blended) tile above
+                LTXV_CUDA(launch_blend_axis(prev[cj].p(), prev[cj].T, prev[cj].H, prev[cj].W, tile.p(), tile.T, tile.H,
+                                            tile.W, C2, 2, blend_h, s));
+            if (cj > 0)  // blend_h with the (already blended) left neighbour
+                LTXV_CUDA(launch_blend_axis(cur[cj - 1].p(), cur[cj - 1].T, cur[cj - 1].H, cur[cj - 1].W, tile.p(), tile.T,
+                                            tile.H, tile.W, C2, 3, blend_w, s));
+            // keep the first stride rows / columns, cropped to the latent size (:2211-2222)
+            const int y0 = ri * str_h, x0 = cj * str_w;
+            const int hs = std::min(std::min(str_h, tile.H), Hl - y0), ws = std::min(std::min(str_w, tile.W), Wl - x0);
+            if (hs > 0 && ws > 0)
+                LTXV_CUDA(launch_copy_box(tile.p(), 4, C2, tile.T, tile.H, tile.W, 0, 0, 0, dst, Tl, Hl, Wl, 0, y0, x0, Tl,
+                                          hs, ws, s));
+        }
+        std::swap(prev, cur);
+    }
+    LTXV_CUDA(cudaStreamSynchronize(s));  // the tile buffers die with this frame
+}
+
+void LtxVideoEncoder3d::temporal_tiled_encode(const void* x, int x_dtype, int F, int H, int W, float* dst,
+                                              const ltxv_vae_tiling& tp, cudaStream_t s) {
+    const int tr = 8, C2 = 2 * cfg_.latent_channels;
+    const int esz = x_dtype == LTXV_F32 ? 4 : 2;
+    int Fl, Hl, Wl;
+    latent_dims(F, H, W, &Fl, &Hl, &Wl);
+    const int min_t = tp.tile_sample_min_num_frames / tr, str_t = tp.tile_sample_stride_num_frames / tr;
+    if (str_t < 1 || tp.tile_sample_stride_num_frames % tr || tp.tile_sample_min_num_frames % tr)
+        fail("tile_sample_{min,stride}_num_frames must be multiples of %d", tr);
+    const int blend_t = std::max(min_t - str_t, 0);
+    const size_t plane = static_cast<size_t>(Hl) * Wl;
+    int prev_T = 0, fo = 0, idx = 0;
+    for (int i = 0; i < F && fo < Fl; i += tp.tile_sample_stride_num_frames, ++idx) {
+        const int Tt = std::min(i + tp.tile_sample_min_num_frames + 1, F) - i;
+        tx_tm_.ensure(3ull * Tt * H * W * esz);
+        LTXV_CUDA(launch_copy_box(x, esz, 3, F, H, W, i, 0, 0, tx_tm_.p, Tt, H, W, 0, 0, 0, Tt, H, W, s));
+        int tl, hl, wl;
+        latent_dims(Tt, H, W, &tl, &hl, &wl);
+        t_enc_.ensure(static_cast<size_t>(C2) * tl * plane * 4);
+        if (tp.use_tiling && (H > tp.tile_sample_min_height || W > tp.tile_sample_min_width))
+            tiled_encode(tx_tm_.p, x_dtype, Tt, H, W, t_enc_.as<float>(), tp, s);
+        else
+            encode(tx_tm_.p, x_dtype, 1, Tt, H, W, t_enc_.as<float>(), s);
+        // the FIRST tile loses its first latent frame (:2324-2329); compact into t_cur_
+        const int t0 = idx == 0 ? 1 : 0;
+        const int Tc = tl - t0;
+        if (Tc <= 0) fail("temporal tiled encode: the first tile has a single latent frame (clip too short for framewise encoding)");
+        t_cur_.ensure(static_cast<size_t>(C2) * Tc * plane * 4);
+        LTXV_CUDA(launch_copy_box(t_enc_.p, 4, C2, tl, Hl, Wl, t0, 0, 0, t_cur_.p, Tc, Hl, Wl, 0, 0, 0, Tc, Hl, Wl, s));
+        int take;
+        const float* src = t_cur_.as<float>();
+        if (idx > 0) {
+            // blend with the UNBLENDED previous tile (row[idx - 1], :2342), keep the first `stride` latent frames
+            t_work_.ensure(static_cast<size_t>(C2) * Tc * plane * 4);
+            LTXV_CUDA(cudaMemcpyAsync(t_work_.p, t_cur_.p, static_cast<size_t>(C2) * Tc * plane * 4, cudaMemcpyDeviceToDevice, s));
+            LTXV_CUDA(launch_blend_axis(t_prev_.as<float>(), prev_T, Hl, Wl, t_work_.as<float>(), Tc, Hl, Wl, C2, 1, blend_t, s));
+            src = t_work_.as<float>();
+            take = std::min(str_t, Tc);
+        } else {
+            take = std::min(str_t + 1, Tc);
+        }
+        take = std::min(take, Fl - fo);
+        if (take > 0)
+            LTXV_CUDA(launch_copy_box(src, 4, C2, Tc, Hl, Wl, 0, 0, 0, dst, Fl, Hl, Wl, fo, 0, 0, take, Hl, Wl, s));
+        fo += take;
+        std::swap(t_prev_.p, t_cur_.p);
+        std::swap(t_prev_.bytes, t_cur_.bytes);
+        prev_T = Tc;
+    }
+    if (fo < Fl) fail("temporal tiled encode produced %d of %d latent frames", fo, Fl);
+}
+
+void LtxVideoEncoder3d::encode_z(const void* x, int x_dtype, int B, int F, int H, int W, const ltxv_vae_tiling* tiling,
+                                 int use_framewise_encoding, float* moments, cudaStream_t s) {
+    if (tiling == nullptr) return encode(x, x_dtype, B, F, H, W, moments, s);
+    if (x_dtype != LTXV_F32 && x_dtype != LTXV_BF16) fail("unsupported video dtype %d", x_dtype);
+    const ltxv_vae_tiling& tp = *tiling;
+    const bool temporal = use_framewise_encoding && F > tp.tile_sample_min_num_frames;
+    const bool spatial = tp.use_tiling && (H > tp.tile_sample_min_height || W > tp.tile_sample_min_width);
+    if (!temporal && !spatial) return encode(x, x_dtype, B, F, H, W, moments, s);
+    LTXV_CUDA(cudaSetDevice(device_));
+    int Fl, Hl, Wl;
+    latent_dims(F, H, W, &Fl, &Hl, &Wl);
+    const size_t xsz = x_dtype == LTXV_F32 ? 4 : 2;
+    const size_t x_elems = 3ull * F * H * W, m_elems = 2ull * cfg_.latent_channels * Fl * Hl * Wl;
+    for (int b = 0; b < B; ++b) {
+        const char* xb = static_cast<const char*>(x) + b * x_elems * xsz;
+        float* mb = moments + b * m_elems;
+        if (temporal) temporal_tiled_encode(xb, x_dtype, F, H, W, mb, tp, s);
+        else tiled_encode(xb, x_dtype, F, H, W, mb, tp, s);
     }
 }
 

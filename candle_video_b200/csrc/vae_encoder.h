@@ -28,6 +28,13 @@ public:
     void latent_dims(int F, int H, int W, int* Fl, int* Hl, int* Wl) const;
     // x [B, 3, F, H, W] NCDHW (f32 or bf16, device) -> moments [B, 2*latent, F', H', W'] f32: mean | logvar
     void encode(const void* x, int x_dtype, int B, int F, int H, int W, float* moments, cudaStream_t s);
+    // encode_z dispatch of the reference (vae.rs:2017-2034) with its tiling knobs: temporal tiling when
+    // use_framewise_encoding and F > tile_sample_min_num_frames (:2294-2356), else spatial tiling when H or W exceed the
+    // minimum tile (:2158-2223), each tile encoded by encode() and the seams blended linearly in LATENT space
+    // (:1927-2006).  tiling == nullptr or no branch taken -> plain encode().  Compatibility mode: the library default of
+    // the reference is use_tiling = true, so its encode() of anything wider than 512 px is the blended result.
+    void encode_z(const void* x, int x_dtype, int B, int F, int H, int W, const ltxv_vae_tiling* tiling,
+                  int use_framewise_encoding, float* moments, cudaStream_t s);
 
 private:
     struct Slot {
@@ -38,6 +45,9 @@ private:
     };
     void add_conv(const std::string& prefix, ConvW& cw, int cin_src, int Cin, int Cout, int rows_out);
     void ensure_workspace(int F, int H, int W);
+    void tiled_encode(const void* x, int x_dtype, int T, int H, int W, float* dst, const ltxv_vae_tiling& tp, cudaStream_t s);
+    void temporal_tiled_encode(const void* x, int x_dtype, int F, int H, int W, float* dst, const ltxv_vae_tiling& tp,
+                               cudaStream_t s);
     void conv(const ConvW& cw, const void* a_padded, int T, int H, int W, int epi, void* out, const void* res, int n_cols,
               int ldo, cudaStream_t s, void* fused_norm_out = nullptr, int fused_raw = 0, int fused_tf = 2);
     void resnet(const ResnetW& rw, int level, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s, bool* ready = nullptr,
@@ -57,6 +67,7 @@ private:
     int wsF_ = 0, wsH_ = 0, wsW_ = 0;
     int T_[5], H_[5], W_[5];
     DevBuf a_in_, p_[5], q_[5], xa_, xb_, hb_, out32_;
+    DevBuf tx_sp_, tx_tm_, t_enc_, t_prev_, t_cur_, t_work_;  // tiled encode: sub-videos and encoded tiles
 };
 
 }  // namespace ltxv

@@ -204,7 +204,15 @@ int ltxv_vae_encode_dims(const ltxv_vae* m, int F, int H, int W, int32_t* Fl, in
  * [0, latent) are the posterior mean (DiagonalGaussianDistribution::mode, vae.rs:135), [latent, 2*latent) the
  * log-variance.  Untiled (encode_z with use_tiling / use_framewise_encoding off), no quant_conv. */
 int ltxv_vae_encode(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W, float* moments, void* stream);
-/* same with HOST buffers (copies inside) */
+/* encode_z of the reference with its tiling dispatch (vae.rs:2017-2034): temporal tiling when use_framewise_encoding and
+ * F > tile_sample_min_num_frames (:2294-2356), else spatial tiling when H or W exceed the minimum tile (:2158-2223);
+ * tiles are cut in sample space and blended linearly in latent space.  The reference's LIBRARY DEFAULT is
+ * use_tiling = 1, use_framewise_encoding = 0 (vae.rs:1856-1858): pass ltxv_vae_tiling_default() to reproduce what its
+ * encode() returns for inputs wider than 512 px.  tiling == NULL is ltxv_vae_encode.  (`use_framewise_decoding` of the
+ * struct is ignored here.) */
+int ltxv_vae_encode_tiled(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W,
+                          const ltxv_vae_tiling* tiling, int use_framewise_encoding, float* moments, void* stream);
+/* same as ltxv_vae_encode with HOST buffers (copies inside) */
 int ltxv_vae_encode_host(ltxv_vae* m, const void* x, int x_dtype, int B, int F, int H, int W, float* moments);
 
 /* ------------------------------------------------------------- pipeline glue -------------------------------------- */

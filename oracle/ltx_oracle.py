@@ -549,6 +549,77 @@ def vae_encode(w: Dict[str, Tensor], cfg: VaeEncoderConfig, x: Tensor) -> Tensor
     return torch.cat([h, h[:, -1:].repeat(1, ch - 2, 1, 1, 1)], dim=1)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# tiled / temporal-tiled ENCODE (encode_z dispatch, vae.rs:2017-2034; library defaults use_tiling = true,
+# use_framewise_encoding = false, :1856-1858).  Tiles are cut in SAMPLE space, blended in LATENT space.
+# ---------------------------------------------------------------------------------------------------------------
+def vae_tiled_encode(w, ecfg: "VaeEncoderConfig", x: Tensor, tp: VaeTiling, sr: int = 32) -> Tensor:
+    """AutoencoderKLLtxVideo::tiled_encode, vae.rs:2158-2223."""
+    H, W = x.shape[3], x.shape[4]
+    lat_h, lat_w = H // sr, W // sr
+    min_h, min_w = tp.tile_sample_min_height // sr, tp.tile_sample_min_width // sr
+    str_h, str_w = tp.tile_sample_stride_height // sr, tp.tile_sample_stride_width // sr
+    blend_h, blend_w = max(min_h - str_h, 0), max(min_w - str_w, 0)
+    rows = []
+    for i in range(0, H, tp.tile_sample_stride_height):
+        row = []
+        for j in range(0, W, tp.tile_sample_stride_width):
+            tile = x[:, :, :, i:min(i + tp.tile_sample_min_height, H), j:min(j + tp.tile_sample_min_width, W)]
+            row.append(vae_encode(w, ecfg, tile))
+        rows.append(row)
+    result_rows, prev = [], []
+    for ri, row in enumerate(rows):
+        res, cur = [], []
+        for cj, tile in enumerate(row):
+            if ri > 0:
+                tile = _blend(prev[cj], tile, blend_h, 3)
+            if cj > 0:
+                tile = _blend(cur[cj - 1], tile, blend_w, 4)
+            cur.append(tile)
+            res.append(tile[:, :, :, :min(str_h, tile.shape[3]), :min(str_w, tile.shape[4])])
+        result_rows.append(torch.cat(res, dim=4))
+        prev = cur
+    return torch.cat(result_rows, dim=3)[:, :, :, :lat_h, :lat_w]
+
+
+def vae_temporal_tiled_encode(w, ecfg: "VaeEncoderConfig", x: Tensor, tp: VaeTiling, sr: int = 32, tr: int = 8) -> Tensor:
+    """AutoencoderKLLtxVideo::temporal_tiled_encode, vae.rs:2294-2356 (incl. its quirks: the first tile drops its first
+    latent frame, tiles are blended with the UNBLENDED previous tile, the first `stride` latent frames are kept)."""
+    nf = x.shape[2]
+    lat_f = (nf - 1) // tr + 1
+    min_t, str_t = tp.tile_sample_min_num_frames // tr, tp.tile_sample_stride_num_frames // tr
+    blend_t = max(min_t - str_t, 0)
+    row = []
+    for i in range(0, nf, tp.tile_sample_stride_num_frames):
+        tile = x[:, :, i:min(i + tp.tile_sample_min_num_frames + 1, nf)]
+        if tp.use_tiling and (tile.shape[3] > tp.tile_sample_min_height or tile.shape[4] > tp.tile_sample_min_width):
+            t = vae_tiled_encode(w, ecfg, tile, tp, sr)
+        else:
+            t = vae_encode(w, ecfg, tile)
+        if i == 0:
+            t = t[:, :, 1:]
+        row.append(t)
+    res = []
+    for idx, t in enumerate(row):
+        if idx > 0:
+            bl = _blend(row[idx - 1], t, blend_t, 2)
+            res.append(bl[:, :, :min(str_t, bl.shape[2])])
+        else:
+            res.append(t[:, :, :min(str_t + 1, t.shape[2])])
+    return torch.cat(res, dim=2)[:, :, :lat_f]
+
+
+def vae_encode_z(w, ecfg: "VaeEncoderConfig", x: Tensor, tp: Optional[VaeTiling], use_framewise_encoding: bool = False,
+                 sr: int = 32, tr: int = 8) -> Tensor:
+    """encode_z dispatch, vae.rs:2017-2034 (tp = None: plain encoder)."""
+    if tp is not None:
+        if use_framewise_encoding and x.shape[2] > tp.tile_sample_min_num_frames:
+            return vae_temporal_tiled_encode(w, ecfg, x, tp, sr, tr)
+        if tp.use_tiling and (x.shape[3] > tp.tile_sample_min_height or x.shape[4] > tp.tile_sample_min_width):
+            return vae_tiled_encode(w, ecfg, x, tp, sr)
+    return vae_encode(w, ecfg, x)
+
+
 def vae_encoder_weight_shapes(cfg: VaeEncoderConfig) -> Dict[str, Tuple[int, ...]]:
     """Appendix A (encoder half): keys as consumed by VarBuilder at vae.rs:1342-1412, :863-905, :513-524."""
     s: Dict[str, Tuple[int, ...]] = {}

@@ -134,3 +134,45 @@ def test_encode_decode_shapes_compose(cuda):
     assert torch.equal(zn, z)
     out = m.decode(cv.denormalize_latents(zn, mean, std, 1.0), torch.tensor([0.05], device=cuda))
     assert out.shape == x.shape and torch.isfinite(out).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tiled / temporal-tiled encode (ltxv_vae_encode_tiled) vs the oracle restatement of encode_z (vae.rs:2017-2034,
+# :2158-2223, :2294-2356), with small tiles so every seam type occurs on clips the CPU oracle encodes in seconds
+# ---------------------------------------------------------------------------------------------------------------
+SMALL_TILES = dict(tile_sample_min_height=64, tile_sample_min_width=64, tile_sample_stride_height=32,
+                   tile_sample_stride_width=32, tile_sample_min_num_frames=16, tile_sample_stride_num_frames=8)
+
+
+def test_vae_encode_spatial_tiles(cuda):
+    import candle_video_b200 as cv
+    m, w, ocfg = build()
+    x = video(1, 9, 96, 128, seed=21)   # 3 x 4 tiles of 64 px at stride 32: vertical, horizontal and corner seams
+    ref = O.vae_encode_z(w, ocfg, x, O.VaeTiling(**SMALL_TILES))
+    out = m.encode_tiled(x.to(cuda), cv.VaeTiling(**SMALL_TILES)).cpu()
+    check(out, ref, "spatial tiles 3x4")
+    # the tiled result is NOT the untiled one: the compatibility mode is needed to reproduce the reference's default
+    plain = O.vae_encode(w, ocfg, x)
+    assert rel_l2(ref[:, :128], plain[:, :128]) > 10 * rel_l2(out[:, :128], ref[:, :128])
+
+
+def test_vae_encode_temporal_tiles_batch2(cuda):
+    import candle_video_b200 as cv
+    m, w, ocfg = build()
+    x = video(2, 33, 64, 64, seed=22)   # 5 temporal tiles (17,17,17,9,1 frames), no spatial tiling at 64 px
+    ref = O.vae_encode_z(w, ocfg, x, O.VaeTiling(**SMALL_TILES), use_framewise_encoding=True)
+    out = m.encode_tiled(x.to(cuda), cv.VaeTiling(**SMALL_TILES), use_framewise_encoding=True).cpu()
+    assert out.shape == (2, 256, 5, 2, 2)
+    check(out, ref, "temporal tiles, B=2")
+
+
+def test_vae_encode_tiled_no_branch_is_plain(cuda):
+    import candle_video_b200 as cv
+    m, _, _ = build()
+    x = video(1, 9, 64, 96, seed=23).to(cuda)
+    # library defaults: 96 px <= 512 and framewise encoding off -> no branch (vae.rs:2019-2028)
+    assert torch.equal(m.encode_tiled(x), m.encode(x))
+    assert torch.equal(m.encode_tiled(x, cv.VaeTiling(use_tiling=False, **SMALL_TILES)), m.encode(x))
+    with pytest.raises(cv.LtxvError, match="multiples of 32"):
+        m.encode_tiled(x, cv.VaeTiling(tile_sample_min_height=64, tile_sample_min_width=64, tile_sample_stride_height=48,
+                                       tile_sample_stride_width=32))

@@ -331,3 +331,23 @@ def test_frames_to_u8_kat():
     out = O.frames_to_u8(v)
     assert out.shape == (1, 2, 1, 2, 3) and out.dtype == torch.uint8
     assert out[0, 1, 0, 1].tolist() == [12, 255, 0]
+
+
+def test_tiled_encode_dispatch_and_zero_blend_tiles():
+    """encode_z (vae.rs:2017-2034): no branch -> the plain encoder; with min == stride the blends vanish (extent 0) and
+    every latent tile is exactly the encoder applied to its own crop (vae.rs:2175-2189, :2211-2216)."""
+    cfg = O.VaeEncoderConfig(block_out_channels=(64, 64, 128, 128, 256), layers_per_block=(1, 1, 1, 1, 2))
+    w = O.init_vae_encoder_weights(cfg)
+    x = torch.tanh(torch.randn(1, 3, 9, 64, 128, generator=torch.Generator().manual_seed(5)))
+    assert torch.equal(O.vae_encode_z(w, cfg, x, None), O.vae_encode(w, cfg, x))
+    assert torch.equal(O.vae_encode_z(w, cfg, x, O.VaeTiling()), O.vae_encode(w, cfg, x))  # 128 px <= 512: no tiling
+    tp = O.VaeTiling(tile_sample_min_height=64, tile_sample_min_width=64, tile_sample_stride_height=64,
+                     tile_sample_stride_width=64)
+    out = O.vae_encode_z(w, cfg, x, tp)
+    assert out.shape == (1, 256, 2, 2, 4)
+    right = O.vae_encode(w, cfg, x[..., 64:128])
+    assert torch.equal(out[..., 2:4], right)
+    # framewise: 33 frames -> 5 latent frames whatever the tile bookkeeping does (first tile drops a frame, :2324-2329)
+    x2 = torch.tanh(torch.randn(1, 3, 33, 32, 32, generator=torch.Generator().manual_seed(6)))
+    o2 = O.vae_encode_z(w, cfg, x2, O.VaeTiling(), use_framewise_encoding=True)
+    assert o2.shape == (1, 256, 5, 1, 1) and torch.isfinite(o2).all()
