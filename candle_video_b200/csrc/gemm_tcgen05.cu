@@ -1027,7 +1027,15 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
                 block_n = c;
             }
         }
-        if (p.M > 2 * kBlockM && getenv("LTXV_GEMM_NO_PAIR") == nullptr) {
+        // Short-K square-ish projections (the batched-CFG attention out / cross-attention q projections: N = K = 2048,
+        // M = 9984): the rates above were calibrated at K = 8192; at K = 2048 the small tiles are as efficient as the
+        // large ones and the 5.8 waves of 128x192 tiles beat the 4.2 rounds of 256x256 pairs (measured 1244 vs 1196
+        // TFLOP/s with the bf16 store, 890 vs 866 with the f32 residual epilogue, tools/bin/gemm_test 3).
+        static const bool no_short_k_rule = getenv("LTXV_GEMM_NO_SHORT_K_RULE") != nullptr;
+        const bool short_k_192 = !no_short_k_rule && !p.conv && p.K <= 2048 && p.N <= 2048 && p.N % 192 != 0 &&
+                                 p.N > 1024 && p.M >= 8192;
+        if (short_k_192) block_n = 192;
+        if (!short_k_192 && p.M > 2 * kBlockM && getenv("LTXV_GEMM_NO_PAIR") == nullptr) {
             const int num_mp = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
             int pair_bn = 0;
             if (p.N % 256 == 0) {
