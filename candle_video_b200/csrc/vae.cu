@@ -287,6 +287,8 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
     for (int l = 0; l < 4; ++l) cond += static_cast<size_t>(cfg_.decoder_layers_per_block[l]) * 4 * ch_[l];
     cond += 2 * ch_[3];
     cond_.ensure(cond * 4);
+    // the zero fills above ran on the legacy default stream: make them visible to whatever stream decode() is given
+    LTXV_CUDA(cudaDeviceSynchronize());
     wsF_ = F;
     wsH_ = H;
     wsW_ = W;

@@ -203,6 +203,8 @@ void LtxVideoEncoder3d::ensure_workspace(int F, int H, int W) {
     xb_.ensure(max_unpadded);
     hb_.ensure(max_unpadded);
     out32_.ensure(static_cast<size_t>(T_[4]) * H_[4] * W_[4] * (cfg_.latent_channels + 32) * 4);
+    // the zero fills above ran on the legacy default stream: make them visible to whatever stream encode() is given
+    LTXV_CUDA(cudaDeviceSynchronize());
     wsF_ = F;
     wsH_ = H;
     wsW_ = W;
