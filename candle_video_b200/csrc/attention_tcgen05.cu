@@ -1542,12 +1542,13 @@ cudaError_t split_scratch(SplitScratch** out) {
 }
 
 cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    int cfg_dev = 0;
+    if (configured.need(&cfg_dev)) {
         cudaError_t e =
             cudaFuncSetAttribute(flash_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV3SmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark(cfg_dev);
     }
     CUtensorMap tq, tk, tv;
     cudaError_t e = make_tensor_map_3d_bf16(&tq, p.q, p.B, p.Sq, p.ldq, kTileQ, 64, p.ldq, p.ldq * (int64_t)p.Sq);
@@ -1601,12 +1602,13 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
 
 
 cudaError_t launch_attn3_d128_impl(const AttnParams& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    int cfg_dev = 0;
+    if (configured.need(&cfg_dev)) {
         cudaError_t e = cudaFuncSetAttribute(flash_attn3_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kV5SmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark(cfg_dev);
     }
     CUtensorMap tq, tk, tv;
     cudaError_t e = make_tensor_map_3d_bf16(&tq, p.q, p.B, p.Sq, p.ldq, kTileQ, 64, p.ldq, p.ldq * (int64_t)p.Sq);
@@ -1627,15 +1629,16 @@ cudaError_t launch_attn3_d128_impl(const AttnParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_cross_attn_impl(const AttnParams& p, cudaStream_t stream) {
-    static bool configured = false;
+    static PerDeviceOnce configured;
+    int cfg_dev = 0;
     static int num_sms = 148;
-    if (!configured) {
+    if (configured.need(&cfg_dev)) {
         cudaError_t e = cudaFuncSetAttribute(cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        configured.mark(cfg_dev);
     }
     CUtensorMap tq, tk, tv;
     cudaError_t e = make_tensor_map_3d_bf16(&tq, p.q, p.B, p.Sq, p.ldq, kTileQ, 64, p.ldq, p.ldq * (int64_t)p.Sq);
@@ -1661,12 +1664,13 @@ cudaError_t launch_cross_attn_impl(const AttnParams& p, cudaStream_t stream) {
 template <int D>
 cudaError_t launch_attn_impl(const AttnParams& p, cudaStream_t stream) {
     using C = ACfg<D>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    int cfg_dev = 0;
+    if (configured.need(&cfg_dev)) {
         cudaError_t e =
             cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark(cfg_dev);
     }
     CUtensorMap tq, tk, tv;
     cudaError_t e = make_tensor_map_3d_bf16(&tq, p.q, p.B, p.Sq, p.ldq, kTileQ, 64, p.ldq, p.ldq * (int64_t)p.Sq);

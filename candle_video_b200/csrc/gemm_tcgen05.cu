@@ -917,16 +917,17 @@ std::atomic<uint64_t> g_launches{0};
 template <int BLOCK_N>
 cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
     using C = Cfg<BLOCK_N>;
-    static bool configured = false;
+    static PerDeviceOnce configured;
+    int cfg_dev = 0;
     static int num_sms = 0;
-    if (!configured) {
+    if (configured.need(&cfg_dev)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::kSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        configured.mark(cfg_dev);
     }
     CUtensorMap ta, tb;
     cudaError_t e = make_tensor_map_2d_bf16(&ta, ops.a, ops.a_rows, ops.a_cols, kBlockM, kBlockK);
@@ -953,16 +954,17 @@ template <int BN, int MODE>
 cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
     using PC = PairCfg<BN, MODE>;
     constexpr bool KW3 = PC::KW3;
-    static bool configured = false;
+    static PerDeviceOnce configured;
+    int cfg_dev = 0;
     static int num_sms = 0;
-    if (!configured) {
+    if (configured.need(&cfg_dev)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PC::kSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        configured.mark(cfg_dev);
     }
     if (KW3 && (!p.conv || p.num_k_blocks != 27 * p.cin_blocks)) return cudaErrorInvalidValue;
     if (MODE == 2 && p.num_k_blocks % 2 != 0) return cudaErrorInvalidValue;

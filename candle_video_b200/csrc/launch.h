@@ -13,6 +13,21 @@ inline bool pdl_enabled() {
     return on;
 }
 
+// Function attributes (cudaFuncSetAttribute: opt-in shared memory) belong to the device that was current when they
+// were set.  One of these per launcher remembers, per device, whether its kernel has been configured there, so a
+// process may hold models on several GPUs.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    // true if the kernel still has to be configured on the current device (returned in *dev)
+    bool need(int* dev) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+        *dev = d;
+        return !done[d];
+    }
+    void mark(int dev) { done[dev] = true; }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {
