@@ -814,8 +814,16 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 warp_mbar_arrive(&s_free[t], lane);  // S_t may be overwritten by the next QK^T
                 TRACE(warp_idx, j, 2);
                 TMARK(1);
+#ifdef LTXV_ATTN_EXPERIMENT_NO_MAX
+                // timing experiment only (lead a): what the key loop costs without the per-tile row maximum
+                // -- the running maximum of the first tile is kept for all later tiles (wrong for peaky inputs)
+                float mx = j == 0 ? fmaxf(fmaxf(max32_v3<TAIL>(s0, kv0, p.Skv), max32_v3<TAIL>(s1, kv0 + 32, p.Skv)),
+                                          fmaxf(max32_v3<TAIL>(s2, kv0 + 64, p.Skv), max32_v3<TAIL>(s3, kv0 + 96, p.Skv)))
+                                  : m_used / c;
+#else
                 float mx = fmaxf(fmaxf(max32_v3<TAIL>(s0, kv0, p.Skv), max32_v3<TAIL>(s1, kv0 + 32, p.Skv)),
                                  fmaxf(max32_v3<TAIL>(s2, kv0 + 64, p.Skv), max32_v3<TAIL>(s3, kv0 + 96, p.Skv)));
+#endif
                 mx *= c;
                 TMARK(2);
                 bool pv_waited = (j == 0);
