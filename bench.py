@@ -130,11 +130,15 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's CPU path, restated (oracle/ltx_oracle.py), on a bounded sample of the same workload
+# CPU arm: the reference's CPU path, restated (oracle/ltx_oracle.py).  Two measurements:
+#   * cpu_block_sample: ONE transformer block of the 2B DiT at c2's S = 4992 -- the bounded sample of the headline
+#     workload (a full c2 CFG step is 56 such blocks, about a minute of host time);
+#   * cpu_c1_workload: BASELINE configs[0] IN FULL (28-layer DiT forward at S = 384 + full-depth VAE decode of a 4x8x12
+#     latent, f32, best of 3 after one warm-up) -- nothing extrapolated.
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_block_sample(n_iter: int, warm: int):
-    """Time ONE transformer block of the 2B DiT at S=4992 (f32, all host threads) and scale to a CFG step
-    (28 blocks x 2 forwards).  Returns (steps_per_s, cores, seconds per block list)."""
+    """Time ONE transformer block of the 2B DiT at S=4992 (f32, all host threads).  Returns (seconds per block list,
+    cores)."""
     import torch
     from oracle import ltx_oracle as O
     cores = os.cpu_count() or 1
@@ -158,28 +162,100 @@ def cpu_block_sample(n_iter: int, warm: int):
             dt = time.perf_counter() - t0
             if i >= warm:
                 times.append(dt)
-    t_blk = sum(times) / len(times)
-    return 1.0 / (t_blk * 28 * 2), cores, times
+    return times, cores
+
+
+C1 = {"height": 256, "width": 384, "num_frames": 25, "latent": (4, 8, 12), "text_tokens": 128}
+
+
+def c1_oracle_model(seed=1):
+    """Oracle weights of the full 2B DiT (28 layers) and the full-depth VAE decoder for the c1 workload.  The 28
+    blocks are distinct tensors (own storage: realistic host memory traffic) cloned from two seeded blocks -- drawing
+    1.9 G independent values would take longer than the measurement."""
+    import torch
+    from oracle import ltx_oracle as O
+    cfg = O.DitConfig()
+    g = torch.Generator().manual_seed(seed)
+    one = O.DitConfig(num_layers=2)
+    w = {k: O._init_tensor(k, s, g) for k, s in O.dit_weight_shapes(one).items()}
+    for i in range(2, cfg.num_layers):
+        for k in [k for k in w if k.startswith(f"transformer_blocks.{i % 2}.")]:
+            w[k.replace(f"transformer_blocks.{i % 2}.", f"transformer_blocks.{i}.", 1)] = w[k].clone()
+    vcfg = O.VaeConfig()
+    vw = O.init_vae_weights(vcfg, seed + 1)
+    return cfg, w, vcfg, vw
+
+
+def c1_inputs(seed=2):
+    import torch
+    from oracle import ltx_oracle as O
+    F, H, W = C1["latent"]
+    g = torch.Generator().manual_seed(seed)
+    hidden = torch.randn(1, F * H * W, 128, generator=g)
+    enc = torch.randn(1, C1["text_tokens"], 4096, generator=g)
+    mask = torch.ones(1, C1["text_tokens"])
+    mask[:, 48:] = 0
+    coords = O.video_coords(1, F, H, W, FPS)
+    z = torch.randn(1, 128, F, H, W, generator=g)
+    return hidden, enc, mask, coords, torch.tensor([993.0]), z, torch.tensor([0.05])
+
+
+def cpu_c1_workload(repeats=3):
+    """BASELINE configs[0] in full on the host cores (f32 oracle restatement), best of `repeats` after one warm-up.
+    Returns (result dict, oracle outputs for the parity check, model, inputs)."""
+    import torch
+    from oracle import ltx_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, w, vcfg, vw = c1_oracle_model()
+    hidden, enc, mask, coords, t, z, ts = c1_inputs()
+    F, H, W = C1["latent"]
+    t_dit, t_vae = [], []
+    vel = frames = None
+    with torch.no_grad():
+        for i in range(repeats + 1):
+            t0 = time.perf_counter()
+            vel = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, None, coords, timestep_to_bf16=True)
+            t1 = time.perf_counter()
+            frames = O.vae_decode(vw, vcfg, z, ts)
+            t2 = time.perf_counter()
+            if i > 0:
+                t_dit.append(t1 - t0)
+                t_vae.append(t2 - t1)
+    S = F * H * W
+    res = {"workload": "BASELINE configs[0]: 2B DiT forward (28 layers, S=384, K=128) + full VAE decode (latent 4x8x12 -> "
+                       "25x256x384), f32, run in full (nothing extrapolated)",
+           "dit_forward_s": min(t_dit), "vae_decode_s": min(t_vae), "repeats": repeats, "cores": cores,
+           "dit_forwards_per_s": 1.0 / min(t_dit), "vae_frames_per_s": 25.0 / min(t_vae),
+           "dit_gflops": dit_flops(S) / min(t_dit) / 1e9, "vae_gflops": vae_flops(F, H, W) / min(t_vae) / 1e9,
+           "kind": "port"}
+    return res, (vel, frames), (cfg, w, vcfg, vw), (hidden, enc, mask, coords, t, z, ts)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sps, cores, times = cpu_block_sample(args.steps, args.warmup)
-    sample = ("1 of 28 transformer blocks of the 2B DiT at S=4992 (f32 torch-CPU restatement of candle-video's CPU "
-              "path), per bench step; steps/s = 1 / (t_block * 28 blocks * 2 CFG forwards)")
+    times, cores = cpu_block_sample(args.steps, args.warmup)
+    t_blk = sum(times) / len(times)
+    sps = 1.0 / (t_blk * 28 * 2)
+    sample = ("each bench step = 1 of the 56 transformer-block passes of a c2 CFG step (28 blocks x 2 forwards) of the 2B "
+              "DiT at S=4992, f32 torch-CPU restatement of candle-video's CPU path; value = 1 / (mean block time x 56); "
+              "ms_per_step is the MEASURED time of one sample step, not of a full CFG step")
     line = {
         "impl": "reference", "metric": "dit_denoise_steps_per_s", "value": sps, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": 1000.0 * t_blk, "sample_fraction_of_step": 1.0 / 56.0,
+        "extrapolated_ms_per_full_step": 1000.0 * t_blk * 56, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(),
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference binary cannot be built here (no cargo/rustc; Candle not vendored): oracle port timed",
     }
+    if not args.no_c1:
+        line["c1_full"], _, _, _ = cpu_c1_workload(3)
     print(json.dumps(line))
 
 
@@ -492,17 +568,80 @@ def run_ours(args):
                                                                peaks["tf_sustained"])
             line["dit_forward_ms"] = ms_per_step / 2.0
 
-        # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----
+        # ---- CPU baseline + parity (rank 0, N = 1 only) ----
         if world == 1 and not args.no_cpu_baseline:
-            sps, cores, times = cpu_block_sample(3, 1)
+            times, cores = cpu_block_sample(3, 1)
+            t_blk = sum(times) / len(times)
             line["cpu_baseline"] = {
-                "value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                "sample": "1 of 28 transformer blocks of the 2B DiT at S=4992, f32 torch-CPU oracle restatement, "
-                          f"mean of 3 after 1 warm-up ({sum(times) / len(times):.2f} s/block), scaled x28 blocks x2 forwards"}
+                "value": 1.0 / (t_blk * 56), "unit": "steps/s", "cores": cores, "kind": "port",
+                "sample": "1 of the 56 transformer-block passes of a c2 CFG step (2B DiT, S=4992), f32 torch-CPU oracle "
+                          f"restatement, mean of 3 after 1 warm-up ({t_blk:.2f} s/block), scaled x28 blocks x2 forwards"}
+            line["parity"] = parity_block_c2(cv, dev)
+            if not args.no_c1:
+                # BASELINE configs[0] in full on the host, and the same workload on the GPU checked against it
+                c1, (vel_ref, frames_ref), (cfg1, w1, vcfg1, vw1), (hidden, enc, mask, coords, t, z, ts) = cpu_c1_workload(3)
+                line["cpu_baseline"]["c1_full"] = c1
+                d1 = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset("2b"), device=local_rank)
+                d1.load_state_dict(w1)
+                Fc, Hc, Wc = C1["latent"]
+                d1.forward(hidden.to(dev), enc.to(dev), t.to(dev), mask.to(dev), Fc, Hc, Wc, None, coords.to(dev))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                vel = d1.forward(hidden.to(dev), enc.to(dev), t.to(dev), mask.to(dev), Fc, Hc, Wc, None, coords.to(dev))
+                e1.record()
+                torch.cuda.synchronize()
+                c1_dit_ms = e0.elapsed_time(e1)
+                v1 = cv.AutoencoderKLLtxVideo(cv.VaeConfig(), device=local_rank)
+                v1.load_state_dict(vw1)
+                v1.decode(z.to(dev), ts.to(dev))
+                e0.record()
+                fr = v1.decode(z.to(dev), ts.to(dev))
+                e1.record()
+                torch.cuda.synchronize()
+                c1_vae_ms = e0.elapsed_time(e1)
+                dv = (vel.cpu().double() - vel_ref.double())
+                pa = (fr.cpu().double() * 0.5 + 0.5).clamp(0, 1) * 255
+                pb = (frames_ref.double() * 0.5 + 0.5).clamp(0, 1) * 255
+                m255 = float(((pa - pb) ** 2).mean())
+                line["parity"].update({
+                    "c1_dit_28_layers_rel_l2": float(dv.norm() / vel_ref.double().norm()),
+                    "c1_dit_max_abs": float(dv.abs().max()),
+                    "c1_vae_mse": float(((fr.cpu().double() - frames_ref.double()) ** 2).mean()),
+                    "c1_vae_psnr_db": 99.0 if m255 == 0 else 10.0 * __import__("math").log10(255.0 ** 2 / m255),
+                    "c1_gpu_dit_forward_ms": c1_dit_ms, "c1_gpu_vae_decode_ms": c1_vae_ms,
+                    "tolerance": "DiT rel-L2 <= 2e-2, VAE MSE <= 1e-2 on [-1,1] and PSNR >= 35 dB on 0..255 (SURVEY 8c)"})
+                del d1, v1
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_block_c2(cv, dev):
+    """One 2B block at c2's token count on the GPU (sequential forward, M = 4992) against the oracle on identical
+    weights and inputs: the same check as tests/test_gpu_production_shapes.py, repeated inside the bench run."""
+    import torch
+    from oracle import ltx_oracle as O
+    cfg = O.DitConfig(num_layers=1)
+    w = O.init_dit_weights(cfg, 42)
+    m = cv.LtxVideoTransformer3DModel(cv.DitConfig(num_layers=1), device=dev.index or 0)
+    m.load_state_dict(w)
+    F, H, W = (FRAMES - 1) // 8 + 1, HEIGHT // 32, WIDTH // 32
+    g = torch.Generator().manual_seed(5)
+    hidden = torch.randn(1, F * H * W, 128, generator=g)
+    enc = torch.randn(1, K_TEXT, 4096, generator=g)
+    mask = torch.ones(1, K_TEXT)
+    mask[:, 48:] = 0
+    coords = O.video_coords(1, F, H, W, FPS)
+    t = torch.tensor([993.0])
+    with torch.no_grad():
+        ref = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, None, coords, timestep_to_bf16=True)
+    cv.trace_begin()
+    out = m.forward(hidden.to(dev), enc.to(dev), t.to(dev), mask.to(dev), F, H, W, None, coords.to(dev)).cpu()
+    tr = cv.trace_end()
+    d = out.double() - ref.double()
+    return {"dit_block_c2_rel_l2": float(d.norm() / ref.double().norm()), "dit_block_c2_max_abs": float(d.abs().max()),
+            "dit_block_c2_variants": sorted(tr)}
 
 
 def ncu_traffic_bytes():
@@ -522,6 +661,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c1", action="store_true", help="skip the full BASELINE configs[0] host run / GPU parity check")
     ap.add_argument("--no-encode", action="store_true", help="skip the VAE encoder measurement (roofline_all.vae_encode)")
     ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "pairs", "sharded"],
                     help="multi-GPU decomposition of the headline number (auto = replicas, the throughput-optimal one)")

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "ltxv_pack_latents", "ltxv_unpack_latents", "ltxv_video_coords", "ltxv_guidance_euler_step",
     "ltxv_denormalize_latents", "ltxv_postprocess_video", "ltxv_calculate_shift", "ltxv_scheduler_set_timesteps",
     "ltxv_pipeline_denoise", "ltxv_pipeline_decode", "ltxv_pipeline_denoise_host", "ltxv_pipeline_decode_host",
-    "ltxv_profile_begin", "ltxv_profile_end",
+    "ltxv_profile_begin", "ltxv_profile_end", "ltxv_trace_begin", "ltxv_trace_end", "ltxv_causal_conv3d",
     "ltxv_comm_create", "ltxv_comm_destroy", "ltxv_comm_get_handle", "ltxv_comm_open", "ltxv_comm_barrier",
     "ltxv_parallel_plan", "ltxv_pipeline_denoise_parallel", "ltxv_vae_set_comm",
     "ltxv_remap_official_key_raw", "ltxv_remap_official_key", "ltxv_safetensors_list",
@@ -167,6 +167,9 @@ def _load() -> C.CDLL:
     l.ltxv_frames_to_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     l.ltxv_pipeline_decode_host_u8.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp]
     l.ltxv_profile_begin.argtypes = []
+    l.ltxv_trace_begin.argtypes = []
+    l.ltxv_causal_conv3d.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    l.ltxv_trace_end.argtypes = [C.c_char_p, u64]
     l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return l
 
@@ -864,6 +867,37 @@ def profile_end() -> Dict[str, Dict[str, float]]:
     # classes 4-7 are HBM-bound glue kernels: "flops" holds their algorithmic bytes (also exposed as "bytes")
     return {PROFILE_CLASSES[i]: {"launches": int(n[i]), "ms": float(ms[i]), "flops": float(fl[i]), "bytes": float(fl[i])}
             for i in range(8)}
+
+
+def causal_conv3d(x, weight, bias=None, is_causal: bool = False):
+    """LtxVideoCausalConv3d::forward (vae.rs:298-465), 3x3x3 stride 1: x [1,Cin,T,H,W], weight [Cout,Cin,3,3,3] (f32
+    CUDA) -> [1,Cout,T,H,W] f32."""
+    torch = _torch()
+    x = _dev(x, "x").to(torch.float32).contiguous()
+    w = _dev(weight, "weight").to(torch.float32).contiguous()
+    b = None if bias is None else _dev(bias, "bias").to(torch.float32).contiguous()
+    if x.dim() != 5 or x.shape[0] != 1 or w.dim() != 5 or tuple(w.shape[2:]) != (3, 3, 3) or w.shape[1] != x.shape[1]:
+        raise LtxvError("causal_conv3d expects x [1,Cin,T,H,W] and weight [Cout,Cin,3,3,3]")
+    _, Cin, T, H, W = x.shape
+    Cout = w.shape[0]
+    out = torch.empty((1, Cout, T, H, W), dtype=torch.float32, device=x.device)
+    _check(lib().ltxv_causal_conv3d(_ptr(x), _ptr(w), _ptr(b), Cin, Cout, T, H, W, int(is_causal), _ptr(out), _stream()))
+    return out
+
+
+def trace_begin() -> None:
+    _check(lib().ltxv_trace_begin())
+
+
+def trace_end() -> Dict[str, int]:
+    """{kernel variant: launches} recorded since trace_begin (ltxv_trace_*; test hook)."""
+    buf = C.create_string_buffer(1 << 16)
+    _check(lib().ltxv_trace_end(buf, 1 << 16))
+    out = {}
+    for ln in buf.value.decode().splitlines():
+        name, n = ln.rsplit(" ", 1)
+        out[name] = int(n)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------

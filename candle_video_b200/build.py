@@ -34,6 +34,7 @@ LIB_SOURCES = [
     "dit.cu",
     "vae.cu",
     "vae_encoder.cu",
+    "conv3d_op.cu",
     "pipeline.cu",
     "comm.cu",
     "weights.cc",

@@ -1601,6 +1601,7 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     const int n_items = sp.n_units - sp.n_split_units + sp.n_split_units * sp.nsplit;
     {
         ProfScope prof(PROF_ATTN_SELF, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 64, stream);
+        LTXV_TRACE_VARIANT("flash_attn3_kernel nsplit=%d split_units=%d", sp.nsplit, sp.n_split_units);
         cudaError_t le = launch_pdl(flash_attn3_kernel, dim3(n_items), dim3(kV3Threads), kV3SmemBytes, stream, tq, tk, tv, p, sp);
         if (le != cudaSuccess) return le;
     }
@@ -1628,6 +1629,7 @@ cudaError_t launch_attn3_d128_impl(const AttnParams& p, cudaStream_t stream) {
     const int n_qb = (p.Sq + 2 * kTileQ - 1) / (2 * kTileQ);
     {
         ProfScope prof(PROF_ATTN_SELF, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 128, stream);
+        LTXV_TRACE_VARIANT("flash_attn3_d128_kernel");
         cudaError_t le = launch_pdl(flash_attn3_d128_kernel, dim3(p.B * p.H * n_qb), dim3(kV5Threads), kV5SmemBytes, stream,
                                     tq, tk, tv, p, n_qb);
         if (le != cudaSuccess) return le;
@@ -1662,6 +1664,7 @@ cudaError_t launch_cross_attn_impl(const AttnParams& p, cudaStream_t stream) {
     if (cph < 1) cph = 1;
     {
         ProfScope prof(PROF_ATTN_CROSS, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 64, stream);
+        LTXV_TRACE_VARIANT("cross_attn_kernel bias=%d", p.kv_bias != nullptr ? 1 : 0);
         cudaError_t le = launch_pdl(cross_attn_kernel, dim3(p.B * p.H * cph), dim3(kXThreads), kXSmemBytes, stream, tq, tk, tv, p, cph);
         if (le != cudaSuccess) return le;
     }
@@ -1691,6 +1694,7 @@ cudaError_t launch_attn_impl(const AttnParams& p, cudaStream_t stream) {
     {
         ProfScope prof(p.kv_bias != nullptr || p.Skv != p.Sq ? PROF_ATTN_CROSS : PROF_ATTN_SELF,
                        4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * D, stream);
+        LTXV_TRACE_VARIANT("flash_attn_kernel<%d>", D);
         cudaError_t le = launch_pdl(flash_attn_kernel<D>, grid, dim3(kAttnThreads), C::kSmemBytes, stream, tq, tk, tv, p);
         if (le != cudaSuccess) return le;
     }

@@ -3,6 +3,7 @@
 
 #include "attention.h"
 #include "comm.h"
+#include "conv3d_op.h"
 #include "dit.h"
 #include "gemm.h"
 #include "glue.h"
@@ -57,7 +58,7 @@ const char* ltxv_last_error(void) { return last_error_ref().c_str(); }
 const char* ltxv_version(void) { return "ltxv_b200 0.1 (sm_100a: tcgen05 GEMM/conv3d/attention)"; }
 uint64_t ltxv_launch_count(void) {
     return gemm_launch_count() + attention_launch_count() + glue_launch_count() + vae_glue_launch_count() +
-           common_launch_count() + comm_launch_count();
+           common_launch_count() + comm_launch_count() + conv_op_launch_count();
 }
 
 int ltxv_profile_begin(void) {
@@ -68,6 +69,29 @@ int ltxv_profile_end(uint64_t* launches8, double* ms8, double* work8) {
     LTXV_TRY
     if (launches8 == nullptr || ms8 == nullptr || work8 == nullptr) fail("null argument");
     profiling_end(launches8, ms8, work8);
+    LTXV_CATCH
+}
+
+int ltxv_causal_conv3d(const float* x, const float* weight, const float* bias, int in_channels, int out_channels,
+                       int T, int H, int W, int is_causal, float* out, void* stream) {
+    LTXV_TRY
+    if (x == nullptr || weight == nullptr || out == nullptr) fail("null argument");
+    causal_conv3d(x, weight, bias, in_channels, out_channels, T, H, W, is_causal != 0, out,
+                  static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+int ltxv_trace_begin(void) {
+    trace_begin();
+    return 0;
+}
+int ltxv_trace_end(char* out, uint64_t out_cap) {
+    LTXV_TRY
+    if (out == nullptr) fail("null argument");
+    const char* t = trace_end();
+    const size_t n = strlen(t);
+    if (n + 1 > out_cap) fail("output buffer too small for the variant trace (%zu bytes needed)", n + 1);
+    memcpy(out, t, n + 1);
     LTXV_CATCH
 }
 

@@ -942,6 +942,7 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
         double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
         if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;  // unpadded voxels
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
+        LTXV_TRACE_VARIANT("%s<%d> epi=%d", p.conv ? "conv3d:gemm_bf16_tn_kernel" : "gemm_bf16_tn_kernel", BLOCK_N, p.epi);
         cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BLOCK_N>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, ta, tb, p);
         if (le != cudaSuccess) return le;
     }
@@ -981,6 +982,8 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         double flops = 2.0 * p.M * static_cast<double>(p.N) * p.K;
         if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
+        LTXV_TRACE_VARIANT("%s<%d,%d> epi=%d", p.conv ? "conv3d:gemm_pair_bf16_tn_kernel" : "gemm_pair_bf16_tn_kernel", BN, MODE,
+                           p.epi);
         cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE>, dim3(2 * clusters), dim3(PairThreads<MODE>::value), PC::kSmemBytes,
                                     stream, ta, tb, p);
         if (le != cudaSuccess) return le;

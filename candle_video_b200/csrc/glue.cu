@@ -709,6 +709,7 @@ cudaError_t launch_norm_modulate(const float* x, void* out, const float* scale, 
     if (D % 4 != 0 || (scale == nullptr) != (shift == nullptr)) return cudaErrorInvalidValue;
     const int grid = blocks_for(rows, kWarpsPerBlock);
     ProfScope prof(PROF_NORM_MOD, 6.0 * rows * D, s);  // f32 in, bf16 out
+    LTXV_TRACE_VARIANT(kind == NORM_RMS ? (D == 2048 ? "rms_modulate_row_kernel<16>" : D == 4096 ? "rms_modulate_row_kernel<32>" : "norm_modulate_kernel<RMS>") : "norm_modulate_kernel<LAYER>");
     if (kind == NORM_RMS && D == 2048)
         launch_pdl(rms_modulate_row_kernel<16>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, s, x,
                    reinterpret_cast<__nv_bfloat16*>(out), scale, shift, rows, eps);
@@ -728,6 +729,7 @@ cudaError_t launch_qk_norm_rope(void* x, int64_t ld, int col0, int rows, int D, 
                                 const float* cos_t, const float* sin_t, cudaStream_t s) {
     if (D % 8 != 0 || ld % 8 != 0 || col0 % 8 != 0) return cudaErrorInvalidValue;
     ProfScope prof(PROF_QK_ROPE, 4.0 * rows * D + (cos_t ? 2.0 * rows * (D / 2) * 4 : 0.0), s);
+    LTXV_TRACE_VARIANT(cos_t == nullptr && D == 2048 ? "rms_weight_row_kernel<8>" : cos_t == nullptr && D == 4096 ? "rms_weight_row_kernel<16>" : "qk_norm_rope_kernel");
     if (cos_t == nullptr && D == 2048)
         launch_pdl(rms_weight_row_kernel<8>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
                    reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, w, eps);
@@ -747,6 +749,7 @@ cudaError_t launch_qk_pair_norm_rope(void* x, int64_t ld, int rows, int D, const
     // q,k bf16 in+out for every row; the f32 cos/sin rows once per TABLE row on the register-resident path
     const bool share = D == 2048 && rows % table_rows == 0 && rows > table_rows;
     ProfScope prof(PROF_QK_ROPE, 2.0 * rows * D * 4 + 2.0 * (share ? table_rows : rows) * (D / 2) * 4, s);
+    LTXV_TRACE_VARIANT(share ? "qk_pair_norm_rope_row_kernel<8,true>" : D == 2048 ? "qk_pair_norm_rope_row_kernel<8,false>" : D == 4096 ? "qk_pair_norm_rope_row_kernel<16,false>" : "qk_pair_norm_rope_kernel");
     if (share)
         launch_pdl(qk_pair_norm_rope_row_kernel<8, true>, dim3(blocks_for(table_rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
                    reinterpret_cast<__nv_bfloat16*>(x), ld, rows, wq, wk, eps, cos_t, sin_t, table_rows);

@@ -1,6 +1,11 @@
 #include "profile.h"
 
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 namespace ltxv {
@@ -13,7 +18,34 @@ struct Rec {
 bool g_on = false;
 std::vector<Rec> g_recs;
 std::mutex g_mu;
+bool g_trace_on = false;
+std::map<std::string, uint64_t> g_trace;
+std::string g_trace_text;
 }  // namespace
+
+bool tracing_enabled() { return g_trace_on; }
+void trace_begin() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_trace.clear();
+    g_trace_on = true;
+}
+const char* trace_end() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_trace_on = false;
+    g_trace_text.clear();
+    for (auto& kv : g_trace) g_trace_text += kv.first + " " + std::to_string(kv.second) + "\n";
+    g_trace.clear();
+    return g_trace_text.c_str();
+}
+void trace_variant_slow(const char* fmt, ...) {
+    char buf[160];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_trace_on) ++g_trace[buf];
+}
 
 bool profiling_enabled() { return g_on; }
 

@@ -17,6 +17,18 @@ void profiling_begin();
 // returns, per class: launches, total milliseconds, total algorithmic FLOPs
 void profiling_end(uint64_t* launches, double* ms, double* flops);
 
+// Kernel-variant trace (test support): while on, every launcher records the name of the kernel variant it picked
+// (template instance, tile mode, split count ...) so parity tests can assert that the production variants ran.
+void trace_begin();
+// "name count\n" per distinct variant, sorted by name; tracing is switched off
+const char* trace_end();
+bool tracing_enabled();
+void trace_variant_slow(const char* fmt, ...);
+#define LTXV_TRACE_VARIANT(...)                                   \
+    do {                                                          \
+        if (::ltxv::tracing_enabled()) ::ltxv::trace_variant_slow(__VA_ARGS__); \
+    } while (0)
+
 struct ProfScope {
     bool on;
     int cls;

@@ -385,6 +385,7 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
     ProfScope prof(PROF_VAE_PREP, 4.0 * static_cast<double>(nvox) * C, s);  // bf16 in, bf16 out
+    LTXV_TRACE_VARIANT("vae_prep_kernel<%d>", C);
     switch (C) {
         case 128: launch_pdl(vae_prep_kernel<128>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
         case 256: launch_pdl(vae_prep_kernel<256>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;

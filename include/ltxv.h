@@ -56,6 +56,21 @@ uint64_t ltxv_launch_count(void);
 int ltxv_profile_begin(void);
 int ltxv_profile_end(uint64_t* launches8, double* ms8, double* work8);
 
+/* LtxVideoCausalConv3d::forward (vae.rs:298-465; operator-level reference test tests/verify_conv3d_parity.rs:41-43):
+ * 3x3x3, stride 1.  x [1,Cin,T,H,W], weight [Cout,Cin,3,3,3], bias [Cout] or NULL, out [1,Cout,T,H,W]: device f32,
+ * NCDHW.  is_causal: two copies of frame 0 in front (:383-387), else one replicated frame each side (:388-411); H/W
+ * zero padding.  Cin % 64 == 0, Cout % 32 == 0, W <= 352.  bf16 operands, f32 accumulation, one bf16 rounding of
+ * the result (what the decoder's convs do).  Synchronises the stream before returning. */
+int ltxv_causal_conv3d(const float* x, const float* weight, const float* bias, int in_channels, int out_channels,
+                       int T, int H, int W, int is_causal, float* out, void* stream);
+
+/* Test hook: between begin/end every launcher records the kernel variant it selected (template instance, tile mode,
+ * attention key-split count ...).  end() writes "name count\n" lines (sorted) into `out`.  The production-shape parity
+ * tests use it to assert that the variants the benchmark runs are the ones they compared with the oracle.  Not part of
+ * the reference interface. */
+int ltxv_trace_begin(void);
+int ltxv_trace_end(char* out, uint64_t out_cap);
+
 /* --------------------------------------------------------------- weight files ------------------------------------- */
 /* Official single-file checkpoints (e.g. ltx-video-2b-v0.9.5.safetensors) name tensors differently from the diffusers
  * layout the models consume.  ltxv_remap_official_key_raw = KeyRemapper::remap_key (weight_format.rs:55-143);

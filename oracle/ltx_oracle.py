@@ -918,6 +918,24 @@ def calculate_shift(seq_len: int, base_seq_len: int = 256, max_seq_len: int = 40
     return float(f(seq_len) * m + b)
 
 
+def _libm_expf(x: float) -> float:
+    """`f32::exp` of the reference (scheduler.rs:172-176) lowers to the platform libm's `expf`; so does the C++ host
+    code of the product.  numpy's SIMD exp and a double-precision exp rounded to f32 both differ from glibc's expf by
+    one ulp for some arguments (e.g. mu = 0.48341146), which flips `trunc(sigma * 1000)` at integer boundaries -- the
+    oracle therefore calls the same libm function, and the integer timesteps are compared exactly."""
+    import ctypes
+    import ctypes.util
+    global _LIBM
+    if _LIBM is None:
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _LIBM.expf.restype = ctypes.c_float
+        _LIBM.expf.argtypes = [ctypes.c_float]
+    return float(_LIBM.expf(x))
+
+
+_LIBM = None
+
+
 def scheduler_set_timesteps(num_steps: int, mu: float, sigmas: Optional[Sequence[float]] = None,
                             shift_terminal: Optional[float] = 0.1) -> Tuple[List[float], List[int]]:
     """FlowMatchEulerDiscreteScheduler::set_timesteps as driven by LtxPipeline::call
@@ -934,7 +952,7 @@ def scheduler_set_timesteps(num_steps: int, mu: float, sigmas: Optional[Sequence
             s = (f(1.0) + (f(1.0 / f(n)) - f(1.0)) * np.arange(n, dtype=f) / f(n - 1)).astype(f)
     else:
         s = np.asarray(sigmas, dtype=f)
-    emu = np.exp(f(mu)).astype(f)
+    emu = f(_libm_expf(float(f(mu))))
     with np.errstate(divide="ignore"):
         base = (f(1.0) / s - f(1.0)).astype(f)  # sigma exponent 1.0: powf(x, 1) == x
     s = (emu / (emu + base)).astype(f)
