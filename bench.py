@@ -259,14 +259,173 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+CONFIG_NAME = "c2"
+
+
 def workload_config():
     F, H, W = (FRAMES - 1) // 8 + 1, HEIGHT // 32, WIDTH // 32
-    return {"workload": "LTX-Video 2B 0.9.5 arch, CFG denoise step (2 DiT forwards + combine + Euler) + 3D-VAE decode "
-                        "at 512x768x97 (BASELINE configs[1])",
+    fw = 2 if GUIDANCE > 1.0 else 1
+    text = {"c2": "LTX-Video 2B 0.9.5 arch, CFG denoise step (2 DiT forwards + combine + Euler) + 3D-VAE decode at "
+                  "512x768x97 (BASELINE configs[1])"}.get(CONFIG_NAME, "LTX-Video " + CONFIGS[CONFIG_NAME][5])
+    return {"workload": text, "name": CONFIG_NAME,
             "height": HEIGHT, "width": WIDTH, "num_frames": FRAMES, "latent": [F, H, W], "tokens": F * H * W,
-            "text_tokens": K_TEXT, "guidance_scale": GUIDANCE, "forwards_per_step": 2,
-            "cache": "no explicit L2 flush: every step streams 3.8 GB of weights (>> 126 MB L2)"}
+            "text_tokens": K_TEXT, "guidance_scale": GUIDANCE, "forwards_per_step": fw,
+            "cache": "no explicit L2 flush: every step streams the model's bf16 weights (3.8 GB for 2B, >> 126 MB L2)"}
 
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The other BASELINE configurations (configs[2..4]) and the strong-scaling suite of the sharded design
+# ----------------------------------------------------------------------------------------------------------------
+CONFIGS = {
+    # name: (DiT preset, height, width, frames, guidance_scale, what it is)
+    "c2": ("2b", 512, 768, 97, 3.0, "2B 0.9.5, CFG, 512x768x97 (configs[1])"),
+    "c3": ("2b", 704, 1216, 121, 1.0, "2B 0.9.8-distilled, 1 forward/step, 704x1216x121 (configs[2])"),
+    # BASELINE.json says 720x1280: 720 is not a multiple of 32 and the reference rejects it (t2v_pipeline.rs:323-327)
+    "c4": ("13b", 736, 1280, 161, 3.0, "13B 0.9.8, CFG, 736x1280x161 (configs[3]; 720 is not divisible by 32)"),
+    "c5": (None, 704, 1216, 257, 0.0, "VAE decode only, 128-ch latents -> 1216x704x257 (configs[4])"),
+}
+
+
+def config_dims(name):
+    preset, h, w, fr, g, _ = CONFIGS[name]
+    F, H, W = (fr - 1) // 8 + 1, h // 32, w // 32
+    return preset, h, w, fr, g, F, H, W
+
+
+def measure_config(cv, torch, dev, name, dit, vae, n_steps, comm=None, sync=None, maxr=None, compare=True,
+                   nosplit_check=False):
+    """One BASELINE configuration on this rank (comm None) or sharded over all ranks of `comm`.  Returns a compact
+    dict: ms/step (n_steps timed after a 1-step warm-up), ms/decode (best effort: 1 warm-up + 2 timed), and -- when
+    sharded -- how the sharded result compares with the single-GPU one on the same inputs."""
+    preset, h, w, fr, g, F, H, W = config_dims(name)
+    S = F * H * W
+    sync = sync or (lambda: torch.cuda.synchronize())
+    maxr = maxr or (lambda x: x)
+    gen = torch.Generator().manual_seed(1000 + S)
+    lat0 = torch.randn(S, 128, generator=gen)
+    out = {"S": S, "frames": 8 * F - 7}
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    if dit is not None:
+        pe = torch.randn(K_TEXT, 4096, generator=gen).to(dev)
+        ne = torch.randn(K_TEXT, 4096, generator=gen).to(dev)
+        pm = torch.cat([torch.ones(48), torch.zeros(K_TEXT - 48)]).to(dev)
+        nm = torch.cat([torch.ones(8), torch.zeros(K_TEXT - 8)]).to(dev)
+
+        def params(n):
+            return cv.PipelineParams(height=h, width=w, num_frames=fr, frame_rate=FPS, num_inference_steps=n,
+                                     custom_sigmas=[0.9 - 0.1 * i for i in range(n)], guidance_scale=g,
+                                     shift_terminal=None)
+
+        def denoise(lat, n, sharded):
+            if sharded:
+                cv.pipeline_denoise_parallel(dit, comm, params(n), lat, pe, pm, ne if g > 1 else None, nm if g > 1 else None)
+            else:
+                cv.pipeline_denoise(dit, params(n), lat, pe, pm, ne if g > 1 else None, nm if g > 1 else None)
+
+        def timed(sharded):
+            lat = lat0.to(dev).contiguous()
+            denoise(lat, 1, sharded)
+            lat.copy_(lat0)
+            sync()
+            e0, e1 = ev(), ev()
+            e0.record()
+            denoise(lat, n_steps, sharded)
+            e1.record()
+            sync()
+            return maxr(e0.elapsed_time(e1)) / n_steps, lat
+
+        t1, lat1 = timed(False)
+        out["single_ms_per_step"] = round(t1, 3)
+        out["forwards_per_step"] = 2 if g > 1 else 1
+        out["single_tflops"] = round((2 if g > 1 else 1) * dit_flops(S, *DIT_DIMS[preset]) / (t1 * 1e-3) / 1e12, 1)
+        if comm is not None:
+            tn, latn = timed(True)
+            plan = cv.parallel_plan(comm.nranks, comm.rank, S, g > 1.0)
+            out.update({"sharded_ms_per_step": round(tn, 3), "speedup": round(t1 / tn, 3),
+                        "efficiency": round(t1 / tn / comm.nranks, 3),
+                        "plan": f"cfg_groups {plan['cfg_groups']} x ulysses {plan['sp_size']}"})
+            if compare:
+                d = (latn.double() - lat1.double())
+                eq = torch.tensor([int(torch.equal(latn, lat1))], device=dev)
+                rl = torch.tensor([float(d.norm() / lat1.double().norm())], device=dev)
+                if comm.nranks > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+                    dist.all_reduce(rl, op=dist.ReduceOp.MAX)
+                out["sharded_vs_single_rel_l2"] = float(rl)
+                out["sharded_equals_single"] = bool(int(eq))
+            if nosplit_check:
+                # with the attention tail split off both paths run the same instruction sequence per row: bit identity
+                cv.set_option("attn_nosplit", 1)
+                a = lat0.to(dev).contiguous()
+                b = lat0.to(dev).contiguous()
+                denoise(a, 2, False)
+                denoise(b, 2, True)
+                sync()
+                cv.set_option("attn_nosplit", 0)
+                eq = torch.tensor([int(torch.equal(a, b))], device=dev)
+                import torch.distributed as dist
+                dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+                out["sharded_equals_single_tail_split_off"] = bool(int(eq))
+    if vae is not None:
+        frames = 8 * F - 7
+        lat = lat0.to(dev).contiguous()
+        p1 = cv.PipelineParams(height=h, width=w, num_frames=fr, decode_timestep=0.05)
+        vid = torch.empty((3, frames, h, w), dtype=torch.float32, device=dev)
+
+        def decode_timed():
+            cv.pipeline_decode(vae, p1, lat, out=vid)
+            sync()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(2):
+                cv.pipeline_decode(vae, p1, lat, out=vid)
+            e1.record()
+            sync()
+            return maxr(e0.elapsed_time(e1) / 2)
+
+        t1 = decode_timed()
+        out["single_ms_per_decode"] = round(t1, 3)
+        out["single_frames_per_s"] = round(frames * 1000.0 / t1, 1)
+        out["single_vae_tflops"] = round(vae_flops(F, H, W) / (t1 * 1e-3) / 1e12, 1)
+        if comm is not None:
+            ref = vid.clone() if compare else None
+            cv.vae_set_comm(vae, comm)
+            tn = decode_timed()
+            cv.vae_set_comm(vae, None)
+            out.update({"sharded_ms_per_decode": round(tn, 3), "vae_speedup": round(t1 / tn, 3),
+                        "vae_efficiency": round(t1 / tn / comm.nranks, 3), "vae_h_slabs": comm.nranks,
+                        "sharded_frames_per_s": round(frames * 1000.0 / tn, 1)})
+            if compare and comm.rank == 0:
+                out["vae_sharded_equals_single"] = bool(torch.equal(vid, ref))
+            del ref
+        del vid
+    return out
+
+
+def run_vae_only(args, cv, torch, dist, dev, rank, world, local_rank, barrier, max_over_ranks):
+    """--config c5: the decode-only sweep point (configs[4]); headline = decoded frames/s, sharded over all ranks."""
+    vae = cv.AutoencoderKLLtxVideo(cv.VaeConfig(), device=local_rank)
+    vae.init_random(4321)
+    comm = cv.PeerComm(world, rank, local_rank, heap_bytes=20 << 30) if world > 1 else None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    r = measure_config(cv, torch, dev, args.config, None, vae, 0, comm=comm, sync=barrier, maxr=max_over_ranks)
+    clocks = sampler.stop()
+    ms = r.get("sharded_ms_per_decode", r["single_ms_per_decode"])
+    if rank == 0:
+        line = {"metric": "vae_decoded_frames_per_s", "value": r["frames"] * 1000.0 / ms, "unit": "frames/s",
+                "n_gpus": world, "steps": 2, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(), "detail": r, "clocks": clocks, "gpu_launches": int(cv.launch_count())}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+DIT_DIMS = {"2b": (2048, 28, K_TEXT), "13b": (4096, 48, K_TEXT)}
 
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
@@ -300,10 +459,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    F, H, W = (FRAMES - 1) // 8 + 1, HEIGHT // 32, WIDTH // 32
+    global HEIGHT, WIDTH, FRAMES, GUIDANCE, CONFIG_NAME
+    CONFIG_NAME = args.config
+    preset, HEIGHT, WIDTH, FRAMES, GUIDANCE, F, H, W = config_dims(args.config)
+    if preset is None:
+        return run_vae_only(args, cv, torch, dist, dev, rank, world, local_rank, barrier, max_over_ranks)
     S = F * H * W
     frames = 8 * F - 7
-    dit = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset("2b"), device=local_rank)
+    D_, L_, _ = DIT_DIMS[preset]
+    dit = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset(preset), device=local_rank)
     dit.init_random(1234)
     vae = cv.AutoencoderKLLtxVideo(cv.VaeConfig(), device=local_rank)
     vae.init_random(4321)
@@ -342,9 +506,9 @@ def run_ours(args):
             return None, world, 100 + rank
         if mode == "pairs":
             groups = [dist.new_group([2 * i, 2 * i + 1]) for i in range(world // 2)]
-            comm = cv.PeerComm(2, rank % 2, local_rank, heap_bytes=3 << 30, group=groups[rank // 2])
+            comm = cv.PeerComm(2, rank % 2, local_rank, heap_bytes=6 << 30, group=groups[rank // 2])
             return comm, world // 2, 100 + rank // 2
-        comm = cv.PeerComm(world, rank, local_rank, heap_bytes=3 << 30)
+        comm = cv.PeerComm(world, rank, local_rank, heap_bytes=6 << 30)
         return comm, 1, 100
 
     def run_mode(mode, n_steps, count_launches=False):
@@ -433,16 +597,44 @@ def run_ours(args):
                            "H-slabs"}
         line["config"]["parallelism"] = desc[headline_mode]
         line["config"]["mode"] = headline_mode
-        # the other decompositions of the same N GPUs, for the scaling picture (same K steps each)
-        others = {}
-        for m in ("replicas", "pairs", "sharded"):
-            if m == headline_mode or (m == "pairs" and (world % 2 != 0 or world == 2)):
-                continue
-            r, _ = run_mode(m, args.steps)
-            others[m] = r
-        if world == 2 and headline_mode == "pairs":
-            others["sharded"] = dict(head, mode="sharded (= pairs at N=2)")
-        line["modes"] = others
+        # ---- the SHARDED design on the configurations north_star assigns to it: one video over all N
+        # GPUs, strong scaling against the single-GPU time measured in this same process on the same inputs ----
+        names = [c for c in args.scaling_configs.split(",") if c]
+        if args.config not in names:
+            names.insert(0, args.config)
+        if world == 8 and "c4" not in names and not args.no_c4:
+            names.append("c4")
+        comm = cv.PeerComm(world, rank, local_rank, heap_bytes=(20 if world == 2 else 14) << 30)
+        n_sc = max(2, min(args.steps, 4))
+        scal = {}
+        for name in names:
+            pr = config_dims(name)[0]
+            d_ = dit if pr == preset else None
+            own = None
+            if pr is not None and d_ is None:
+                own = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset(pr), device=local_rank)
+                own.init_random(1234)
+                d_ = own
+            r = measure_config(cv, torch, dev, name, d_, vae if name != "c4" else None, n_sc, comm=comm, sync=barrier,
+                               maxr=max_over_ranks, nosplit_check=(name == "c2"))
+            r["what"] = CONFIGS[name][5]
+            scal[name] = r
+            del own, d_
+            torch.cuda.empty_cache()
+        del comm
+        line = dict({"strong_scaling": {"n_gpus": world, "steps_timed": n_sc, "configs": scal,
+                                        "note": "sharded = ONE video over all N GPUs (CFG branch groups x Ulysses token "
+                                                "shards; VAE in N H-slabs with halo rows stored by the producers); "
+                                                "single = the same inputs on one GPU, timed in this process"}}, **line)
+        if args.mode != "auto" or args.all_modes:
+            # the other decompositions of the same N GPUs (same K steps each)
+            others = {}
+            for m in ("replicas", "pairs", "sharded"):
+                if m == headline_mode or (m == "pairs" and (world % 2 != 0 or world == 2)):
+                    continue
+                r, _ = run_mode(m, args.steps)
+                others[m] = r
+            line["modes"] = others
 
     # ---- end to end through the host-buffer C ABI, every rank on its own video: per step H2D latents+embeddings,
     # D2H latents; per decode H2D latents, D2H video ----
@@ -481,6 +673,7 @@ def run_ours(args):
                    "vae_u8_frames_per_s": world * frames / t_vae_u8, "vae_u8_d2h_bytes": int(vid_u8.numel()),
                    "vae_u8_api": "ltxv_pipeline_decode_host_u8 (u8 [F,H,W,3] frames, the example's output hand-off)"}
 
+    FW = 2 if GUIDANCE > 1.0 else 1
     if rank == 0:
         peaks = measured_peaks()
         # ---- instrumented pass: per-kernel-class device time inside a real step (CUDA events on the stream) ----
@@ -533,8 +726,8 @@ def run_ours(args):
             "dit_qk_norm_rope": hbm(prof_dit["qk_norm_rope"], 2),
             "vae_prep": hbm(prof_vae["vae_prep"], 1),
             "single_gpu_ms_per_step": step1,
-            "dit_step_algorithmic_tflops": 2 * dit_flops(S) / (step1 * 1e-3) / 1e12,
-            "dit_step_frac_of_peak": 2 * dit_flops(S) / (step1 * 1e-3) / 1e12 / peaks["tf_sustained"],
+            "dit_step_algorithmic_tflops": FW * dit_flops(S, D_, L_) / (step1 * 1e-3) / 1e12,
+            "dit_step_frac_of_peak": FW * dit_flops(S, D_, L_) / (step1 * 1e-3) / 1e12 / peaks["tf_sustained"],
             "glue_ms_per_step": step1 - (gm["ms"] + attn_ms) / 2,
             "unattributed_ms_per_step": step1 - (gm["ms"] + attn_ms + prof_dit["norm_modulate"]["ms"] +
                                                  prof_dit["qk_norm_rope"]["ms"]) / 2,
@@ -566,7 +759,46 @@ def run_ours(args):
             line["roofline_all"]["vae_decode_algorithmic_tflops"] = vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12
             line["roofline_all"]["vae_decode_frac_of_peak"] = (vae_flops(F, H, W) / (vae_ms * 1e-3) / 1e12 /
                                                                peaks["tf_sustained"])
-            line["dit_forward_ms"] = ms_per_step / 2.0
+            line["dit_forward_ms"] = ms_per_step / FW
+
+        if world == 1 and args.config == "c2":
+            # ---- the 0.9.5 preset step (configs.rs:165-171): guidance 3, STG scale 1 on block 19, rescale 0.7 ->
+            # 3 forwards per step (t2v_pipeline.rs:910-939); the headline above is the same step with stg_scale = 0 ----
+            p_stg = cv.PipelineParams(height=HEIGHT, width=WIDTH, num_frames=FRAMES, frame_rate=FPS,
+                                      num_inference_steps=3, guidance_scale=3.0, guidance_rescale=0.7, stg_scale=1.0,
+                                      skip_block_list=[19], shift_terminal=0.1)
+            lat_s = lat_h.to(dev)
+            cv.pipeline_denoise(dit, p_stg, lat_s, pe_d, pm, ne_d, nm)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cv.pipeline_denoise(dit, p_stg, lat_s, pe_d, pm, ne_d, nm)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_stg = e0.elapsed_time(e1) / 3
+            dit.set_skip_block_list([])
+            line["stg_preset_step"] = {
+                "ms_per_step": ms_stg, "steps_per_s": 1000.0 / ms_stg, "forwards_per_step": 3,
+                "algorithmic_tflops": 3 * dit_flops(S) / (ms_stg * 1e-3) / 1e12,
+                "what": "0.9.5 preset: CFG 3.0 + STG 1.0 (block 19) + rescale 0.7 (configs.rs:165-171)",
+                "outputs_finite": bool(torch.isfinite(lat_s).all().item())}
+            # ---- the other BASELINE configurations on one GPU (configs[2..4]) ----
+            if not args.no_other_configs:
+                oc = {}
+                for name in ("c3", "c5", "c4"):
+                    if name == "c4" and args.no_c4:
+                        continue
+                    pr = config_dims(name)[0]
+                    own = None
+                    if pr == "13b":
+                        own = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset("13b"), device=local_rank)
+                        own.init_random(1234)
+                    d_ = own if own is not None else (dit if pr == "2b" else None)
+                    oc[name] = measure_config(cv, torch, dev, name, d_, vae if name != "c4" else None, 2)
+                    oc[name]["what"] = CONFIGS[name][5]
+                    del own, d_
+                    torch.cuda.empty_cache()
+                line["other_configs"] = oc
 
         # ---- CPU baseline + parity (rank 0, N = 1 only) ----
         if world == 1 and not args.no_cpu_baseline:
@@ -663,6 +895,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c1", action="store_true", help="skip the full BASELINE configs[0] host run / GPU parity check")
     ap.add_argument("--no-encode", action="store_true", help="skip the VAE encoder measurement (roofline_all.vae_encode)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE configuration of the headline number")
+    ap.add_argument("--scaling-configs", default="c2,c3,c5",
+                    help="N > 1: configurations of the strong-scaling suite (c4 = 13B is added at N = 8)")
+    ap.add_argument("--no-c4", action="store_true", help="leave the 13B configuration out of the suites")
+    ap.add_argument("--no-other-configs", action="store_true", help="N = 1: skip the c3 / c4 / c5 measurements")
+    ap.add_argument("--all-modes", action="store_true", help="N > 1: also time the pairs / sharded throughput modes")
     ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "pairs", "sharded"],
                     help="multi-GPU decomposition of the headline number (auto = replicas, the throughput-optimal one)")
     args = ap.parse_args()

@@ -37,9 +37,10 @@ EXPORTED_SYMBOLS = [
     "ltxv_pack_latents", "ltxv_unpack_latents", "ltxv_video_coords", "ltxv_guidance_euler_step",
     "ltxv_denormalize_latents", "ltxv_postprocess_video", "ltxv_calculate_shift", "ltxv_scheduler_set_timesteps",
     "ltxv_pipeline_denoise", "ltxv_pipeline_decode", "ltxv_pipeline_denoise_host", "ltxv_pipeline_decode_host",
-    "ltxv_profile_begin", "ltxv_profile_end", "ltxv_trace_begin", "ltxv_trace_end", "ltxv_causal_conv3d",
+    "ltxv_profile_begin", "ltxv_profile_end", "ltxv_trace_begin", "ltxv_trace_end", "ltxv_causal_conv3d", "ltxv_set_option", "ltxv_get_option",
     "ltxv_comm_create", "ltxv_comm_destroy", "ltxv_comm_get_handle", "ltxv_comm_open", "ltxv_comm_barrier",
-    "ltxv_parallel_plan", "ltxv_pipeline_denoise_parallel", "ltxv_vae_set_comm",
+    "ltxv_parallel_plan", "ltxv_pipeline_denoise_parallel", "ltxv_pipeline_denoise_parallel_stochastic",
+    "ltxv_vae_set_comm",
     "ltxv_remap_official_key_raw", "ltxv_remap_official_key", "ltxv_safetensors_list",
     "ltxv_dit_load_safetensors", "ltxv_vae_load_safetensors",
     "ltxv_vae_tiling_default", "ltxv_vae_decode_tiled",
@@ -145,6 +146,7 @@ def _load() -> C.CDLL:
     l.ltxv_comm_barrier.argtypes = [vp, vp]
     l.ltxv_parallel_plan.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_int32)]
     l.ltxv_pipeline_denoise_parallel.argtypes = [vp, vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32, vp]
+    l.ltxv_pipeline_denoise_parallel_stochastic.argtypes = [vp, vp, C.POINTER(_PipelineParamsC), vp, vp, vp, vp, vp, i32, i32, vp, vp]
     l.ltxv_vae_set_comm.argtypes = [vp, vp]
     l.ltxv_remap_official_key_raw.argtypes = [C.c_char_p, C.c_char_p, u64]
     l.ltxv_remap_official_key.argtypes = [C.c_char_p, C.c_char_p, u64, C.POINTER(C.c_int32)]
@@ -168,6 +170,8 @@ def _load() -> C.CDLL:
     l.ltxv_pipeline_decode_host_u8.argtypes = [vp, C.POINTER(_PipelineParamsC), vp, vp]
     l.ltxv_profile_begin.argtypes = []
     l.ltxv_trace_begin.argtypes = []
+    l.ltxv_set_option.argtypes = [C.c_char_p, i32]
+    l.ltxv_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
     l.ltxv_causal_conv3d.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     l.ltxv_trace_end.argtypes = [C.c_char_p, u64]
     l.ltxv_profile_end.argtypes = [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -885,6 +889,17 @@ def causal_conv3d(x, weight, bias=None, is_causal: bool = False):
     return out
 
 
+def set_option(name: str, value: int) -> None:
+    """Experiment knob override (ltxv_set_option)."""
+    _check(lib().ltxv_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_int32()
+    _check(lib().ltxv_get_option(name.encode(), C.byref(v)))
+    return int(v.value)
+
+
 def trace_begin() -> None:
     _check(lib().ltxv_trace_begin())
 
@@ -983,8 +998,9 @@ class PeerComm:
 
 
 def pipeline_denoise_parallel(dit: LtxVideoTransformer3DModel, comm: PeerComm, params: PipelineParams, latents,
-                              prompt_embeds, prompt_mask, negative_embeds=None, negative_mask=None):
-    """Denoise loop sharded over all ranks of `comm`: CFG branch split x Ulysses sequence parallelism."""
+                              prompt_embeds, prompt_mask, negative_embeds=None, negative_mask=None, step_noise=None):
+    """Denoise loop sharded over all ranks of `comm`: CFG branch split x Ulysses sequence parallelism.  step_noise:
+    optional f32 CUDA [num_inference_steps, S, 128] (stochastic sampling with the caller's noise)."""
     torch = _torch()
     p, keep = params.to_c()
     pe = _dev(prompt_embeds, "prompt_embeds")
@@ -996,6 +1012,14 @@ def pipeline_denoise_parallel(dit: LtxVideoTransformer3DModel, comm: PeerComm, p
     nm = None if negative_mask is None else _dev(negative_mask, "negative_mask").to(torch.float32).reshape(-1).contiguous()
     if latents.dtype != torch.float32 or not latents.is_cuda or not latents.is_contiguous():
         raise LtxvError("latents must be a contiguous float32 CUDA tensor")
+    if step_noise is not None:
+        sn = _dev(step_noise, "step_noise")
+        if sn.dtype != torch.float32 or sn.numel() != params.num_inference_steps * latents.numel():
+            raise LtxvError("step_noise must be a contiguous float32 CUDA tensor [num_inference_steps, S, C]")
+        _check(lib().ltxv_pipeline_denoise_parallel_stochastic(dit._h, comm._h, C.byref(p), _ptr(latents), _ptr(pe),
+                                                               _ptr(pm), _ptr(ne), _ptr(nm), _dtype_code(pe),
+                                                               pe.shape[0], _ptr(sn), _stream()))
+        return latents
     _check(lib().ltxv_pipeline_denoise_parallel(dit._h, comm._h, C.byref(p), _ptr(latents), _ptr(pe), _ptr(pm),
                                                 _ptr(ne), _ptr(nm), _dtype_code(pe), pe.shape[0], _stream()))
     return latents

@@ -42,12 +42,13 @@ LIB_SOURCES = [
     "model_common.cu",
     "tensormap.cc",
     "profile.cc",
+    "options.cc",
 ]
 
 TOOLS = {
-    "gemm_test": (["tools/gemm_test.cu"], ["gemm_tcgen05.cu", "tensormap.cc", "profile.cc"]),
-    "attn_test": (["tools/attn_test.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc"]),
-    "attn_prof": (["tools/attn_prof.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc"]),
+    "gemm_test": (["tools/gemm_test.cu"], ["gemm_tcgen05.cu", "tensormap.cc", "profile.cc", "options.cc"]),
+    "attn_test": (["tools/attn_test.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc", "options.cc"]),
+    "attn_prof": (["tools/attn_prof.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc", "options.cc"]),
 }
 
 

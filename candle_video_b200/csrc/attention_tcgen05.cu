@@ -13,10 +13,14 @@
 #include "launch.h"
 #include "common.cuh"
 #include "tensormap.h"
+#include "options.h"
 #include "profile.h"
 
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <type_traits>
+#include <utility>
 #include <stdlib.h>
 
 namespace ltxv {
@@ -1527,13 +1531,16 @@ struct SplitScratch {
     int* counters = nullptr;
     int n_sm = 0;
 };
-cudaError_t split_scratch(SplitScratch** out) {
-    static SplitScratch per_dev[16];
+// One scratch area per (device, stream): launches on the same stream are ordered, so they may share it; two streams
+// (two models driven by two host threads) must not, or their partial (O, m, l) rows and tickets would interleave.
+cudaError_t split_scratch(SplitScratch** out, cudaStream_t stream) {
+    static std::map<std::pair<int, cudaStream_t>, SplitScratch> per_stream;
+    static std::mutex mu;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
-    SplitScratch& s = per_dev[dev];
+    std::lock_guard<std::mutex> lk(mu);
+    SplitScratch& s = per_stream[std::make_pair(dev, stream)];
     if (s.scratch == nullptr) {
         e = cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -1566,7 +1573,7 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     e = make_tensor_map_3d_bf16(&tv, p.v, p.B, p.Skv, p.ldv, kTileKV, 64, p.ldv, p.ldv * (int64_t)p.Skv);
     if (e != cudaSuccess) return e;
     SplitScratch* ss = nullptr;
-    e = split_scratch(&ss);
+    e = split_scratch(&ss, stream);
     if (e != cudaSuccess) return e;
     SplitPlan sp{};
     sp.n_qb = (p.Sq + 2 * kTileQ - 1) / (2 * kTileQ);
@@ -1577,12 +1584,12 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     sp.counters = ss->counters;
     const int n_tiles = (p.Skv + kTileKV - 1) / kTileKV;
     const int rem = sp.n_units % ss->n_sm;
-    if (rem != 0 && getenv("LTXV_ATTN_NOSPLIT") == nullptr) {
+    if (rem != 0 && !options().attn_nosplit) {
         // key ranges per tail unit: minimise the length of the tail, ceil(rem * ns / SMs) rounds of 1/ns unit each
         // (plus a few percent per extra range for its pipeline fill and the merge), keeping >= 4 key tiles per range
         int max_ns = n_tiles / 4;
         if (max_ns > kMaxSplit) max_ns = kMaxSplit;
-        if (const char* ev = getenv("LTXV_ATTN_NSPLIT")) max_ns = atoi(ev) < max_ns ? atoi(ev) : max_ns;  // experiment knob
+        if (options().attn_nsplit_max > 0 && options().attn_nsplit_max < max_ns) max_ns = options().attn_nsplit_max;  // experiment knob
         int best_ns = 1;
         double best = 1.0;
         for (int ns = 2; ns <= max_ns; ++ns) {
@@ -1714,11 +1721,11 @@ void attention_debug_timing(long long* out32) { cudaMemcpyFromSymbol(out32, g_at
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Skv <= 0) return cudaErrorInvalidValue;
-    if (p.D == 64 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && getenv("LTXV_ATTN_V1") == nullptr)
+    if (p.D == 64 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && !options().attn_v1)
         return launch_attn3_impl(p, stream);
-    if (p.D == 64 && p.Skv <= kTileKV && p.out_rows_per_peer == 0 && getenv("LTXV_ATTN_V1") == nullptr)
+    if (p.D == 64 && p.Skv <= kTileKV && p.out_rows_per_peer == 0 && !options().attn_v1)
         return launch_cross_attn_impl(p, stream);  // one key tile: text cross-attention
-    if (p.D == 128 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && getenv("LTXV_ATTN_V1") == nullptr)
+    if (p.D == 128 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && !options().attn_v1)
         return launch_attn3_d128_impl(p, stream);
     if (p.D == 64) return launch_attn_impl<64>(p, stream);
     if (p.D == 128) return launch_attn_impl<128>(p, stream);

@@ -212,10 +212,18 @@ void LtxVideoTransformer3DModel::ensure_workspace(int S) {
     small_.ensure((256 + 2 * static_cast<size_t>(D) + 6 * D + static_cast<size_t>(L) * 6 * D + 2 * D) * 4);
     if (comm_ != nullptr && S != sp_S_) {
         // a new shard size carves fresh buffers (the symmetric heap is a bump allocator; all ranks of the group take
-        // this branch in the same call, so offsets stay identical across ranks)
-        const size_t Dg = static_cast<size_t>(D) / sp_count_;
-        sp_qkv_off_ = comm_->alloc(static_cast<size_t>(S) * sp_count_ * 3 * Dg * 2);
-        sp_attn_off_ = comm_->alloc(static_cast<size_t>(S) * D * 2);
+        // this branch in the same call, so offsets stay identical across ranks); a (communicator, group size, shard
+        // size) seen before reuses its carve-out, so alternating resolutions do not exhaust the heap
+        const std::vector<int64_t> key = {static_cast<int64_t>(comm_->id()), sp_count_, S};
+        auto it = sp_allocs_.find(key);
+        if (it == sp_allocs_.end()) {
+            const size_t Dg = static_cast<size_t>(D) / sp_count_;
+            const size_t q = comm_->alloc(static_cast<size_t>(S) * sp_count_ * 3 * Dg * 2);
+            const size_t a = comm_->alloc(static_cast<size_t>(S) * D * 2);
+            it = sp_allocs_.emplace(key, std::make_pair(q, a)).first;
+        }
+        sp_qkv_off_ = it->second.first;
+        sp_attn_off_ = it->second.second;
         sp_S_ = S;
     }
 }

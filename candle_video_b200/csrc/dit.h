@@ -44,6 +44,8 @@ public:
 
     const ltxv_dit_config& config() const { return cfg_; }
     int device() const { return device_; }
+    PipeWs& pipe_ws() { return pipe_ws_; }
+    std::map<std::vector<int64_t>, std::vector<size_t>>& pipe_allocs() { return pipe_allocs_; }
     int inner_dim() const { return cfg_.num_attention_heads * cfg_.attention_head_dim; }
 
     void load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape, int rank);
@@ -119,6 +121,9 @@ private:
     int sp_S_ = 0;                       // local token capacity of the symmetric buffers
     uint64_t sp_alloc_comm_ = 0;         // communicator id / group size the symmetric buffers were carved for
     int sp_alloc_count_ = 0;
+    std::map<std::vector<int64_t>, std::pair<size_t, size_t>> sp_allocs_;
+    PipeWs pipe_ws_;
+    std::map<std::vector<int64_t>, std::vector<size_t>> pipe_allocs_;  // pipeline_denoise_parallel exchange buffers  // (comm id, group size, S) -> (qkv, attn) offsets
     size_t sp_qkv_off_ = 0, sp_attn_off_ = 0;  // heap offsets: qkv_full [S_total, 3*D/N], attn_in [S_local, D]
 };
 

@@ -7,6 +7,7 @@
 #include "dit.h"
 #include "gemm.h"
 #include "glue.h"
+#include "options.h"
 #include "pipeline.h"
 #include "profile.h"
 #include "vae.h"
@@ -78,6 +79,19 @@ int ltxv_causal_conv3d(const float* x, const float* weight, const float* bias, i
     if (x == nullptr || weight == nullptr || out == nullptr) fail("null argument");
     causal_conv3d(x, weight, bias, in_channels, out_channels, T, H, W, is_causal != 0, out,
                   static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+
+int ltxv_set_option(const char* name, int value) {
+    LTXV_TRY
+    if (name == nullptr) fail("null argument");
+    if (!set_option(name, value)) fail("unknown option '%s'", name);
+    LTXV_CATCH
+}
+int ltxv_get_option(const char* name, int* value) {
+    LTXV_TRY
+    if (name == nullptr || value == nullptr) fail("null argument");
+    if (!get_option(name, value)) fail("unknown option '%s'", name);
     LTXV_CATCH
 }
 
@@ -613,6 +627,18 @@ int ltxv_pipeline_denoise_parallel(ltxv_dit* dit, ltxv_comm* c, const ltxv_pipel
         fail("null argument");
     pipeline_denoise_parallel(dit->model, c->comm, *p, latents, prompt_embeds, prompt_mask, negative_embeds,
                               negative_mask, embeds_dtype, K, static_cast<cudaStream_t>(stream));
+    LTXV_CATCH
+}
+int ltxv_pipeline_denoise_parallel_stochastic(ltxv_dit* dit, ltxv_comm* c, const ltxv_pipeline_params* p, float* latents,
+                                              const void* prompt_embeds, const float* prompt_mask,
+                                              const void* negative_embeds, const float* negative_mask, int embeds_dtype,
+                                              int K, const float* step_noise, void* stream) {
+    LTXV_TRY
+    if (dit == nullptr || c == nullptr || p == nullptr || latents == nullptr || prompt_embeds == nullptr ||
+        step_noise == nullptr)
+        fail("null argument");
+    pipeline_denoise_parallel(dit->model, c->comm, *p, latents, prompt_embeds, prompt_mask, negative_embeds,
+                              negative_mask, embeds_dtype, K, static_cast<cudaStream_t>(stream), step_noise);
     LTXV_CATCH
 }
 int ltxv_vae_set_comm(ltxv_vae* vae, ltxv_comm* c) {

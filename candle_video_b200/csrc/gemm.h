@@ -57,6 +57,7 @@ struct GemmParams {
     int norm_tf;               // replicated front frames of norm_out: 1 non-causal (+1 behind), 2 causal, 3 causal + dup
     void* norm_halo_up;        // H-slab decode: neighbour buffers receiving this slab's first / last row, or null
     void* norm_halo_dn;
+    int norm_halo_up_h, norm_halo_dn_h;  // slab rows H of those neighbours (ragged slabs); 0 = same as this slab
 };
 
 // A: [rows_a, K_a] bf16 row-major (K contiguous). B: [N, K] bf16 row-major (nn.Linear weight layout).

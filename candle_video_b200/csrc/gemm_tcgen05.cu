@@ -12,6 +12,7 @@
 #include "gemm.h"
 #include "launch.h"
 #include "tensormap.h"
+#include "options.h"
 #include "profile.h"
 
 #include <atomic>
@@ -398,11 +399,16 @@ __device__ __noinline__ void epilogue_conv_norm_pad(const GemmParams& p, const R
     // last frame, and the neighbours' halo rows when it lies in the first / last row of an H-slab
     const int64_t row0 = (static_cast<int64_t>(rc.t + tf) * Hp) * Wp + (rc.w + 1);
     __nv_bfloat16* d_main = reinterpret_cast<__nv_bfloat16*>(p.norm_out) + (row0 + static_cast<int64_t>(rc.h + 1) * Wp) * N;
+    // the neighbours' padded volumes have their own plane stride when the slabs are ragged
+    const int Hu = p.norm_halo_up_h > 0 ? p.norm_halo_up_h : p.H, Hd = p.norm_halo_dn_h > 0 ? p.norm_halo_dn_h : p.H;
+    const int64_t plane_up = static_cast<int64_t>(Hu + 2) * Wp * N, plane_dn = static_cast<int64_t>(Hd + 2) * Wp * N;
     __nv_bfloat16* d_up = (p.norm_halo_up != nullptr && rc.h == 0)
-                              ? reinterpret_cast<__nv_bfloat16*>(p.norm_halo_up) + (row0 + static_cast<int64_t>(p.H + 1) * Wp) * N
+                              ? reinterpret_cast<__nv_bfloat16*>(p.norm_halo_up) + (rc.t + tf) * plane_up +
+                                    (static_cast<int64_t>(Hu + 1) * Wp + (rc.w + 1)) * N
                               : nullptr;
     __nv_bfloat16* d_dn = (p.norm_halo_dn != nullptr && rc.h == p.H - 1)
-                              ? reinterpret_cast<__nv_bfloat16*>(p.norm_halo_dn) + row0 * N
+                              ? reinterpret_cast<__nv_bfloat16*>(p.norm_halo_dn) + (rc.t + tf) * plane_dn +
+                                    static_cast<int64_t>(rc.w + 1) * N
                               : nullptr;
     const int n_front = rc.t == 0 ? tf : 0;
     const bool back = tf == 1 && rc.t == p.T - 1;
@@ -459,9 +465,10 @@ __device__ __noinline__ void epilogue_conv_norm_pad(const GemmParams& p, const R
                 __nv_bfloat16* d = which == 0 ? d_main : (which == 1 ? d_up : d_dn);
                 if (d == nullptr) continue;
                 if (which != 0) put(d);
+                const int64_t pl = which == 0 ? plane_elems : (which == 1 ? plane_up : plane_dn);
 #pragma unroll 1
-                for (int k = 1; k <= n_front; ++k) put(d - k * plane_elems);
-                if (back) put(d + plane_elems);
+                for (int k = 1; k <= n_front; ++k) put(d - k * pl);
+                if (back) put(d + pl);
             }
         }
     }
@@ -1036,11 +1043,11 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         // M = 9984): the rates above were calibrated at K = 8192; at K = 2048 the small tiles are as efficient as the
         // large ones and the 5.8 waves of 128x192 tiles beat the 4.2 rounds of 256x256 pairs (measured 1244 vs 1196
         // TFLOP/s with the bf16 store, 890 vs 866 with the f32 residual epilogue, tools/bin/gemm_test 3).
-        static const bool no_short_k_rule = getenv("LTXV_GEMM_NO_SHORT_K_RULE") != nullptr;
+        const bool no_short_k_rule = options().gemm_no_short_k != 0;
         const bool short_k_192 = !no_short_k_rule && !p.conv && p.K <= 2048 && p.N <= 2048 && p.N % 192 != 0 &&
                                  p.N > 1024 && p.M >= 8192;
         if (short_k_192) block_n = 192;
-        if (!short_k_192 && p.M > 2 * kBlockM && getenv("LTXV_GEMM_NO_PAIR") == nullptr) {
+        if (!short_k_192 && p.M > 2 * kBlockM && !options().gemm_no_pair) {
             const int num_mp = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
             int pair_bn = 0;
             if (p.N % 256 == 0) {
@@ -1057,10 +1064,10 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
                     pair_bn = 128;
                 }
             }
-            const bool kw3 = p.conv && p.num_k_blocks == 27 * p.cin_blocks && getenv("LTXV_CONV_NO_KW3") == nullptr;
+            const bool kw3 = p.conv && p.num_k_blocks == 27 * p.cin_blocks && !options().conv_no_kw3;
             if (norm_pad && !kw3) pair_bn = 0;  // only the KW3 pair kernels carry the fused producer epilogue
             // two k-blocks per stage measured neutral (1341 vs 1353 TFLOP/s on the QKV shape): opt-in only
-            const bool k2 = !p.conv && p.num_k_blocks % 2 == 0 && getenv("LTXV_GEMM_K2") != nullptr;
+            const bool k2 = !p.conv && p.num_k_blocks % 2 == 0 && options().gemm_k2 != 0;
             if (pair_bn == 256)
                 return kw3 ? launch_pair_impl<256, 1>(ops, p, stream)
                            : (k2 ? launch_pair_impl<256, 2>(ops, p, stream) : launch_pair_impl<256, 0>(ops, p, stream));

@@ -6,11 +6,12 @@
 
 #include <utility>
 
+#include "options.h"
+
 namespace ltxv {
 
 inline bool pdl_enabled() {
-    static const bool on = getenv("LTXV_NO_PDL") == nullptr;
-    return on;
+    return !options().no_pdl;
 }
 
 // Function attributes (cudaFuncSetAttribute: opt-in shared memory) belong to the device that was current when they

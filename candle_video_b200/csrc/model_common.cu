@@ -50,7 +50,7 @@ __global__ void convert_kernel(const TS* __restrict__ src, TD* __restrict__ dst,
 }
 inline int grid_for(int64_t n) { return static_cast<int>((n + 255) / 256); }
 
-DevBuf g_stage;  // staging buffer for host -> device ingestion
+DevBuf g_stage[64];  // staging buffer for host -> device ingestion, one per device (a process may hold models on several GPUs)
 std::mutex g_stage_mu;
 }  // namespace
 
@@ -104,9 +104,13 @@ void ingest_tensor(void* dst, bool dst_bf16, const void* src, int src_dtype, int
     std::lock_guard<std::mutex> lk(g_stage_mu);
     const void* dsrc = src;
     if (!on_device) {
-        g_stage.ensure(n * esz);
-        LTXV_CUDA(cudaMemcpy(g_stage.p, src, n * esz, cudaMemcpyHostToDevice));
-        dsrc = g_stage.p;
+        int dev = 0;
+        LTXV_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64) fail("device index %d out of range", dev);
+        DevBuf& stage = g_stage[dev];
+        stage.ensure(n * esz);
+        LTXV_CUDA(cudaMemcpy(stage.p, src, n * esz, cudaMemcpyHostToDevice));
+        dsrc = stage.p;
     }
     if (src_dtype == LTXV_F32 && dst_bf16)
         convert_kernel<float, __nv_bfloat16><<<grid_for(n), 256>>>(static_cast<const float*>(dsrc),

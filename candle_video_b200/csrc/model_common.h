@@ -61,6 +61,43 @@ struct DevBuf {
     }
 };
 
+// Pinned host staging for small per-call parameters (timestep lists, the decode timestep) that are copied to the device
+// asynchronously: the copy must not read a stack buffer after the call returns, and the entry points are enqueue-only
+// (no stream synchronisation).  `fence` is recorded after each copy; the next writer waits for it (already complete in
+// practice) before it overwrites the host side.
+struct PinnedParams {
+    float* h = nullptr;
+    size_t cap = 0;  // floats
+    cudaEvent_t fence = nullptr;
+    PinnedParams() = default;
+    PinnedParams(const PinnedParams&) = delete;
+    PinnedParams& operator=(const PinnedParams&) = delete;
+    ~PinnedParams() {
+        if (h) cudaFreeHost(h);
+        if (fence) cudaEventDestroy(fence);
+    }
+    // host buffer of at least n floats that no pending copy is still reading
+    float* acquire(size_t n) {
+        if (fence == nullptr) LTXV_CUDA(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
+        LTXV_CUDA(cudaEventSynchronize(fence));
+        if (n > cap) {
+            if (h) cudaFreeHost(h);
+            h = nullptr;
+            LTXV_CUDA(cudaMallocHost(&h, n * sizeof(float)));
+            cap = n;
+        }
+        return h;
+    }
+    void copied(cudaStream_t s) { LTXV_CUDA(cudaEventRecord(fence, s)); }
+};
+
+// Workspace of the pipeline entry points (pipeline.cu).  It lives in the model handle it serves -- on that model's
+// device, one per handle -- so two models (on one GPU or on several) never share scratch memory.
+struct PipeWs {
+    DevBuf cond, uncond, pert, comb, pair, coords, ts, scratch, unpacked, denorm, tdec;
+    PinnedParams host;
+};
+
 // Fails loudly when there is no usable CUDA device (no CPU fallback exists).
 void require_cuda_device(int device);
 

@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include "glue.h"
+#include "options.h"
 
 namespace ltxv {
 
@@ -56,28 +57,56 @@ void scheduler_set_timesteps(int n, const float* custom_sigmas, float mu, bool h
 }
 
 namespace {
-struct PipeWs {
-    DevBuf cond, uncond, pert, comb, pair, coords, ts, scratch, unpacked, denorm, tdec;
+// check_inputs (t2v_pipeline.rs:323-327) + the parameter checks shared by the single- and multi-GPU loops
+struct LoopGeom {
+    int F, H, W, S, C;
+    bool do_cfg, do_stg;
 };
-PipeWs& ws() {
-    static PipeWs w;
-    return w;
+LoopGeom check_loop_params(const LtxVideoTransformer3DModel& dit, const ltxv_pipeline_params& p, const void* negative) {
+    if (p.height % 32 != 0 || p.width % 32 != 0)
+        fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
+    if (p.num_frames < 1 || p.frame_rate < 1) fail("num_frames and frame_rate must be positive");
+    if (p.num_inference_steps <= 0) fail("num_inference_steps must be positive");
+    LoopGeom g{};
+    g.F = (p.num_frames - 1) / 8 + 1;  // :743-747
+    g.H = p.height / 32;
+    g.W = p.width / 32;
+    g.S = g.F * g.H * g.W;
+    g.C = dit.config().in_channels;
+    g.do_cfg = p.guidance_scale > 1.0f;  // :308-310
+    g.do_stg = p.stg_scale > 0.0f;       // :304-306
+    if (g.do_cfg && negative == nullptr) fail("negative prompt embeddings are required when guidance_scale > 1");
+    if (p.num_skip_blocks < 0 || (p.num_skip_blocks > 0 && p.skip_block_list == nullptr))
+        fail("skip_block_list is null but num_skip_blocks = %d", p.num_skip_blocks);
+    return g;
+}
+
+// [num_layers] STG mask, 1 = skip (:911-923)
+std::vector<float> make_stg_mask(const LtxVideoTransformer3DModel& dit, const ltxv_pipeline_params& p) {
+    std::vector<float> m(dit.config().num_layers, 0.0f);
+    for (int i = 0; i < p.num_skip_blocks; ++i)
+        if (p.skip_block_list[i] >= 0 && p.skip_block_list[i] < dit.config().num_layers) m[p.skip_block_list[i]] = 1.0f;
+    return m;
+}
+
+// integer-truncated timesteps as f32 (Tensor::full(t as f32), :874) -> device, through the handle's pinned buffer
+void upload_timesteps(PipeWs& w, const std::vector<int64_t>& tsteps, cudaStream_t s) {
+    const int n = static_cast<int>(tsteps.size());
+    w.ts.ensure(static_cast<size_t>(n) * 4);
+    float* h = w.host.acquire(n);
+    for (int i = 0; i < n; ++i) h[i] = static_cast<float>(tsteps[i]);
+    LTXV_CUDA(cudaMemcpyAsync(w.ts.p, h, n * 4, cudaMemcpyHostToDevice, s));
+    w.host.copied(s);
 }
 }  // namespace
 
 void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_params& p, float* latents,
                       const void* prompt, const float* prompt_mask, const void* negative, const float* negative_mask,
                       int embeds_dtype, int K, cudaStream_t s, const float* step_noise) {
-    // check_inputs (t2v_pipeline.rs:323-327)
-    if (p.height % 32 != 0 || p.width % 32 != 0)
-        fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
-    if (p.num_frames < 1 || p.frame_rate < 1) fail("num_frames and frame_rate must be positive");
-    const int F = (p.num_frames - 1) / 8 + 1, H = p.height / 32, W = p.width / 32;  // :743-747
-    const int S = F * H * W;
-    const int C = dit.config().in_channels;
-    const bool do_cfg = p.guidance_scale > 1.0f;  // :308-310
-    const bool do_stg = p.stg_scale > 0.0f;       // :304-306
-    if (do_cfg && negative == nullptr) fail("negative prompt embeddings are required when guidance_scale > 1");
+    const LoopGeom g = check_loop_params(dit, p, negative);
+    const int F = g.F, H = g.H, W = g.W, S = g.S, C = g.C;
+    const bool do_cfg = g.do_cfg, do_stg = g.do_stg;
+    LTXV_CUDA(cudaSetDevice(dit.device()));
 
     // skip-block policy (:691-697)
     if (p.skip_block_list != nullptr) {
@@ -91,19 +120,15 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
     scheduler_set_timesteps(n, p.custom_sigmas, mu, p.has_shift_terminal != 0, p.shift_terminal, sigmas.data(),
                             tsteps.data());
 
-    PipeWs& w = ws();
+    PipeWs& w = dit.pipe_ws();
     const size_t out_bytes = static_cast<size_t>(S) * C * 4;
     w.cond.ensure(out_bytes);
     if (do_cfg) w.uncond.ensure(out_bytes);
     if (do_stg) w.pert.ensure(out_bytes);
     if (step_noise != nullptr) w.comb.ensure(out_bytes);
     w.coords.ensure(static_cast<size_t>(S) * 3 * 4);
-    w.ts.ensure(static_cast<size_t>(n) * 4);
     w.scratch.ensure(64);
-    std::vector<float> ts_f(n);
-    for (int i = 0; i < n; ++i) ts_f[i] = static_cast<float>(tsteps[i]);  // Tensor::full(t as f32) (:874)
-    LTXV_CUDA(cudaMemcpyAsync(w.ts.p, ts_f.data(), n * 4, cudaMemcpyHostToDevice, s));
-    LTXV_CUDA(cudaStreamSynchronize(s));  // ts_f is a stack-lifetime host buffer
+    upload_timesteps(w, tsteps, s);
     LTXV_CUDA(launch_video_coords(w.coords.as<float>(), F, H, W, 8, 32, p.frame_rate, s));  // :798-847
 
     dit.prepare_context(0, prompt, embeds_dtype, prompt_mask, K, s);
@@ -111,7 +136,7 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
     // The reference runs the CFG branches as sequential B = 1 forwards (:878-907).  They share latents, timestep and
     // coordinates, so here they run as ONE forward over 2S tokens (uncond rows first): same per-row arithmetic, better
     // tile occupancy, weights streamed once.  LTXV_NO_CFG_BATCH=1 restores the sequential order.
-    static const bool batch_cfg = getenv("LTXV_NO_CFG_BATCH") == nullptr;
+    const bool batch_cfg = !options().no_cfg_batch;
     const bool pair = do_cfg && batch_cfg;
     float* out_uncond = do_cfg ? w.uncond.as<float>() : nullptr;
     float* out_cond = w.cond.as<float>();
@@ -123,12 +148,7 @@ void pipeline_denoise(LtxVideoTransformer3DModel& dit, const ltxv_pipeline_param
     }
 
     std::vector<float> stg_mask;
-    if (do_stg) {  // :911-923, mask [num_layers, b=1]: 1 = skip
-        stg_mask.assign(dit.config().num_layers, 0.0f);
-        for (int i = 0; i < p.num_skip_blocks; ++i)
-            if (p.skip_block_list[i] >= 0 && p.skip_block_list[i] < dit.config().num_layers)
-                stg_mask[p.skip_block_list[i]] = 1.0f;
-    }
+    if (do_stg) stg_mask = make_stg_mask(dit, p);
     const float* coords = w.coords.as<float>();
     for (int i = 0; i < n; ++i) {
         const float* t_dev = w.ts.as<float>() + i;
@@ -175,15 +195,12 @@ ParallelPlan make_parallel_plan(int nranks, int rank, int S, bool do_cfg) {
 
 void pipeline_denoise_parallel(LtxVideoTransformer3DModel& dit, PeerComm& comm, const ltxv_pipeline_params& p,
                                float* latents, const void* prompt, const float* prompt_mask, const void* negative,
-                               const float* negative_mask, int embeds_dtype, int K, cudaStream_t s) {
-    if (p.height % 32 != 0 || p.width % 32 != 0)
-        fail("`height` and `width` must be divisible by 32, got %d and %d", p.height, p.width);
-    const int F = (p.num_frames - 1) / 8 + 1, H = p.height / 32, W = p.width / 32;
-    const int S = F * H * W;
-    const int C = dit.config().in_channels;
-    const bool do_cfg = p.guidance_scale > 1.0f;
-    const bool do_stg = p.stg_scale > 0.0f;
-    if (do_cfg && negative == nullptr) fail("negative prompt embeddings are required when guidance_scale > 1");
+                               const float* negative_mask, int embeds_dtype, int K, cudaStream_t s,
+                               const float* step_noise) {
+    const LoopGeom g = check_loop_params(dit, p, negative);
+    const int F = g.F, H = g.H, W = g.W, S = g.S, C = g.C;
+    const bool do_cfg = g.do_cfg, do_stg = g.do_stg;
+    LTXV_CUDA(cudaSetDevice(dit.device()));
     const int N = comm.nranks(), rank = comm.rank();
     const ParallelPlan pl = make_parallel_plan(N, rank, S, do_cfg);
     const bool split = pl.cfg_groups == 2;
@@ -199,31 +216,30 @@ void pipeline_denoise_parallel(LtxVideoTransformer3DModel& dit, PeerComm& comm, 
     const float mu = p.custom_sigmas ? 0.0f : calculate_shift(S);
     scheduler_set_timesteps(n, p.custom_sigmas, mu, p.has_shift_terminal != 0, p.shift_terminal, sigmas.data(),
                             tsteps.data());
-    PipeWs& w = ws();
+    PipeWs& w = dit.pipe_ws();
     const size_t loc_elems = static_cast<size_t>(pl.s_local) * C;
     w.coords.ensure(static_cast<size_t>(S) * 3 * 4);
-    w.ts.ensure(static_cast<size_t>(n) * 4);
     w.scratch.ensure(64);
-    // symmetric buffers: branch outputs [3][s_local, C] f32 (uncond, cond, perturbed) and the gathered latents [S, C]
-    static size_t xchg_off = 0, lat_off = 0, stat_off = 0;
-    static uint64_t xchg_comm = 0;
-    static size_t xchg_elems = 0;
-    if (xchg_comm != comm.id() || xchg_elems != loc_elems) {
-        xchg_off = comm.alloc(3 * loc_elems * 4);
-        lat_off = comm.alloc(static_cast<size_t>(S) * C * 4);
-        stat_off = comm.alloc(4 * sizeof(double));
-        xchg_comm = comm.id();
-        xchg_elems = loc_elems;
+    // symmetric buffers: branch outputs [3][s_local, C] f32 (uncond, cond, perturbed), the gathered latents [S, C] and the
+    // std partial sums.  Carved once per (communicator, S, shard count, C): a call with another geometry gets its own
+    // buffers (same loc_elems does not imply the same S: CFG on 2 ranks vs no CFG on 2 ranks).
+    const std::vector<int64_t> key = {static_cast<int64_t>(comm.id()), S, pl.sp, C, N};
+    auto& cache = dit.pipe_allocs();
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::vector<size_t> offs(3);
+        offs[0] = comm.alloc(3 * loc_elems * 4);
+        offs[1] = comm.alloc(static_cast<size_t>(S) * C * 4);
+        offs[2] = comm.alloc(4 * sizeof(double));
+        it = cache.emplace(key, std::move(offs)).first;
     }
+    const size_t xchg_off = it->second[0], lat_off = it->second[1], stat_off = it->second[2];
     float* x_unc = static_cast<float*>(comm.local(xchg_off));
     float* x_cond = x_unc + loc_elems;
     float* x_pert = x_cond + loc_elems;
     float* lat_loc = latents + static_cast<size_t>(pl.token0) * C;  // this rank updates only its token shard
 
-    std::vector<float> ts_f(n);
-    for (int i = 0; i < n; ++i) ts_f[i] = static_cast<float>(tsteps[i]);
-    LTXV_CUDA(cudaMemcpyAsync(w.ts.p, ts_f.data(), n * 4, cudaMemcpyHostToDevice, s));
-    LTXV_CUDA(cudaStreamSynchronize(s));
+    upload_timesteps(w, tsteps, s);
     LTXV_CUDA(launch_video_coords(w.coords.as<float>(), F, H, W, 8, 32, p.frame_rate, s));
     const float* coords_loc = w.coords.as<float>() + static_cast<size_t>(pl.token0) * 3;
 
@@ -233,12 +249,7 @@ void pipeline_denoise_parallel(LtxVideoTransformer3DModel& dit, PeerComm& comm, 
     if (run_cond) dit.prepare_context(0, prompt, embeds_dtype, prompt_mask, K, s);
     if (run_uncond) dit.prepare_context(1, negative, embeds_dtype, negative_mask, K, s);
     std::vector<float> stg_mask;
-    if (do_stg) {
-        stg_mask.assign(dit.config().num_layers, 0.0f);
-        for (int i = 0; i < p.num_skip_blocks; ++i)
-            if (p.skip_block_list[i] >= 0 && p.skip_block_list[i] < dit.config().num_layers)
-                stg_mask[p.skip_block_list[i]] = 1.0f;
-    }
+    if (do_stg) stg_mask = make_stg_mask(dit, p);
     const int partner = split ? (rank + pl.sp) % N : rank;
     const bool rescale = do_cfg && p.guidance_rescale > 0.0f;
     for (int i = 0; i < n; ++i) {
@@ -278,9 +289,21 @@ void pipeline_denoise_parallel(LtxVideoTransformer3DModel& dit, PeerComm& comm, 
             parts.n = pl.sp;
             parts.n_total = static_cast<int64_t>(S) * C;
         }
-        LTXV_CUDA(launch_guidance_euler_parts(x_cond, do_cfg ? x_unc : nullptr, do_stg ? x_pert : nullptr, lat_loc,
-                                              nullptr, static_cast<int64_t>(loc_elems), p.guidance_scale,
-                                              p.guidance_rescale, p.stg_scale, dt, parts, s));
+        if (step_noise == nullptr) {
+            LTXV_CUDA(launch_guidance_euler_parts(x_cond, do_cfg ? x_unc : nullptr, do_stg ? x_pert : nullptr, lat_loc,
+                                                  nullptr, static_cast<int64_t>(loc_elems), p.guidance_scale,
+                                                  p.guidance_rescale, p.stg_scale, dt, parts, s));
+        } else {
+            // stochastic_sampling = true (scheduler.rs:557-575): combined velocity of this token shard, then
+            // x <- (1-s')(x - s v) + s' noise_i on the shard's rows of the caller's [n, S, C] noise tensor
+            w.comb.ensure(loc_elems * 4);
+            LTXV_CUDA(launch_guidance_euler_parts(x_cond, do_cfg ? x_unc : nullptr, do_stg ? x_pert : nullptr, nullptr,
+                                                  w.comb.as<float>(), static_cast<int64_t>(loc_elems), p.guidance_scale,
+                                                  p.guidance_rescale, p.stg_scale, dt, parts, s));
+            LTXV_CUDA(launch_stochastic_step(lat_loc, w.comb.as<float>(),
+                                             step_noise + (static_cast<size_t>(i) * S + pl.token0) * C, sigmas[i],
+                                             sigmas[i + 1], static_cast<int64_t>(loc_elems), s));
+        }
         // partners must not overwrite the exchange buffers / partial sums before they are consumed
         if (split) comm.barrier(s, 0);
         else if (rescale && pl.sp > 1) comm.barrier(s, 1, pl.branch * pl.sp, pl.sp);
@@ -306,7 +329,8 @@ void pipeline_decode(AutoencoderKLLtxVideo& vae, const ltxv_pipeline_params& p, 
     const int F = (p.num_frames - 1) / 8 + 1, H = p.height / 32, W = p.width / 32;
     const int C = vae.config().latent_channels;
     const int64_t n = static_cast<int64_t>(C) * F * H * W;
-    PipeWs& w = ws();
+    LTXV_CUDA(cudaSetDevice(vae.device()));
+    PipeWs& w = vae.pipe_ws();
     w.unpacked.ensure(n * 4);
     w.denorm.ensure(n * 4);
     w.tdec.ensure(4);
@@ -316,14 +340,17 @@ void pipeline_decode(AutoencoderKLLtxVideo& vae, const ltxv_pipeline_params& p, 
                                  inv_sf, C, static_cast<int64_t>(F) * H * W, s));  // :1011-1016
     const float* t_dev = nullptr;
     if (vae.config().timestep_conditioning) {
-        LTXV_CUDA(cudaMemcpyAsync(w.tdec.p, &p.decode_timestep, 4, cudaMemcpyHostToDevice, s));
-        LTXV_CUDA(cudaStreamSynchronize(s));
+        float* h = w.host.acquire(1);
+        h[0] = p.decode_timestep;
+        LTXV_CUDA(cudaMemcpyAsync(w.tdec.p, h, 4, cudaMemcpyHostToDevice, s));
+        w.host.copied(s);
         t_dev = w.tdec.as<float>();
+        // decode-noise blend (:1021-1065): only a timestep-conditioned VAE takes the noise branch in the reference;
+        // the noise tensor is the caller's (the library has no RNG)
+        if (decode_noise != nullptr && decode_noise_scale != 0.0f)
+            LTXV_CUDA(launch_noise_blend(w.denorm.as<float>(), decode_noise, decode_noise_scale,
+                                         static_cast<int64_t>(C) * F * H * W, s));
     }
-    // decode-noise blend (:1049-1062) with the caller's noise tensor; without one, decode_noise_scale = 0
-    if (decode_noise != nullptr && decode_noise_scale != 0.0f)
-        LTXV_CUDA(launch_noise_blend(w.denorm.as<float>(), decode_noise, decode_noise_scale,
-                                     static_cast<int64_t>(C) * F * H * W, s));
     vae.decode(w.denorm.p, LTXV_F32, t_dev, 1, F, H, W, out, LTXV_F32, /*postprocess=*/1, s);  // :1069-1070
 }
 

@@ -23,7 +23,8 @@ struct ParallelPlan {
 ParallelPlan make_parallel_plan(int nranks, int rank, int S, bool do_cfg);
 void pipeline_denoise_parallel(LtxVideoTransformer3DModel& dit, PeerComm& comm, const ltxv_pipeline_params& p,
                                float* latents, const void* prompt, const float* prompt_mask, const void* negative,
-                               const float* negative_mask, int embeds_dtype, int K, cudaStream_t s);
+                               const float* negative_mask, int embeds_dtype, int K, cudaStream_t s,
+                               const float* step_noise = nullptr);
 // step_noise (above): [num_inference_steps, S, C] f32 or null -> stochastic sampling with caller-supplied noise.
 // decode_noise: [C, F, H, W] f32 or null -> latents <- (1 - scale) latents + scale noise before the VAE.
 void pipeline_decode(AutoencoderKLLtxVideo& vae, const ltxv_pipeline_params& p, const float* latents, float* out,

@@ -17,6 +17,7 @@
 
 #include "gemm.h"
 #include "glue.h"
+#include "options.h"
 #include "vae_encoder.h"
 #include "vae_glue.h"
 
@@ -237,10 +238,19 @@ void AutoencoderKLLtxVideo::set_comm(PeerComm* comm) {
 void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
     if (F == wsF_ && H == wsH_ && W == wsW_) return;
     const int N = comm_ ? comm_->nranks() : 1;
-    if (H % N != 0) fail("latent height %d is not divisible by the number of decode ranks %d", H, N);
+    const int r = comm_ ? comm_->rank() : 0;
+    if (H < N) fail("latent height %d is smaller than the number of decode ranks %d (every slab needs a row)", H, N);
+    // ragged H-slabs: H = q N + m; ranks [0, m) own q + 1 rows, the rest q (c3 / c5 latents have H = 22)
+    const int q = H / N, m = H % N;
+    auto rows = [&](int k) { return q + (k < m ? 1 : 0); };
+    auto row0 = [&](int k) { return k * q + (k < m ? k : m); };
+    const int Hmax = q + (m ? 1 : 0);
+    lat_h0_ = row0(r);
+    h_up_ = r > 0 ? rows(r - 1) : 0;
+    h_dn_ = r < N - 1 ? rows(r + 1) : 0;
     T_[0] = F;
     Hfull_[0] = H;
-    H_[0] = H / N;  // local slab rows
+    H_[0] = rows(r);  // local slab rows
     W_[0] = W;
     for (int l = 1; l < 4; ++l) {
         T_[l] = 2 * T_[l - 1] - 1;
@@ -249,6 +259,14 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
         W_[l] = 2 * W_[l - 1];
     }
     size_t max_unpadded = 0;
+    SlabAlloc* sa = nullptr;
+    bool fresh = false;
+    if (comm_ != nullptr) {
+        const std::vector<int64_t> key = {static_cast<int64_t>(comm_->id()), N, F, H, W};
+        auto it = slab_allocs_.find(key);
+        fresh = it == slab_allocs_.end();
+        sa = &slab_allocs_[key];
+    }
     for (int l = 0; l < 4; ++l) {
         const size_t padded = static_cast<size_t>(T_[l] + 2) * (H_[l] + 2) * (W_[l] + 2) * ch_[l] * 2;
         if (comm_ == nullptr) {
@@ -259,9 +277,14 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
             p2_[l].ensure(padded, true);
             pp_[l] = 0;
         } else {
+            // every rank carves the size of the LARGEST slab so that offsets stay identical across ranks
+            const size_t padded_max = static_cast<size_t>(T_[l] + 2) * ((Hmax << l) + 2) * (W_[l] + 2) * ch_[l] * 2;
             for (int k = 0; k < 2; ++k) {
-                p_off_[l][k] = comm_->alloc(padded);
-                LTXV_CUDA(cudaMemset(comm_->local(p_off_[l][k]), 0, padded));
+                if (fresh) {
+                    sa->p_off[l][k] = comm_->alloc(padded_max);
+                    LTXV_CUDA(cudaMemset(comm_->local(sa->p_off[l][k]), 0, padded_max));
+                }
+                p_off_[l][k] = sa->p_off[l][k];
             }
             pp_[l] = 0;
         }
@@ -273,9 +296,16 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
         a0_.release();
         a0_.ensure(a0_bytes, true);
     } else {
-        a0_off_ = comm_->alloc(a0_bytes);
-        LTXV_CUDA(cudaMemset(comm_->local(a0_off_), 0, a0_bytes));
-        video_off_ = comm_->alloc(3ull * T_[3] * (4 * Hfull_[3]) * (4 * W_[3]) * 4);
+        if (fresh) {
+            const size_t a0_max = static_cast<size_t>(F + 2) * (Hmax + 2) * (W + 2) * cfg_.latent_channels * 2;
+            sa->a0_off = comm_->alloc(a0_max);
+            LTXV_CUDA(cudaMemset(comm_->local(sa->a0_off), 0, a0_max));
+            sa->video_off = comm_->alloc(3ull * T_[3] * (4 * Hfull_[3]) * (4 * W_[3]) * 4);
+        }
+        a0_off_ = sa->a0_off;
+        video_off_ = sa->video_off;
+        // (host-synchronous on purpose: a geometry change is rare, and the neighbours' halo stores must not race the
+        // zero fills above)
         LTXV_CUDA(cudaDeviceSynchronize());
         comm_->barrier(0, 0);  // every rank's halo rows are zeroed before any neighbour may write them
         LTXV_CUDA(cudaDeviceSynchronize());
@@ -295,7 +325,7 @@ void AutoencoderKLLtxVideo::ensure_workspace(int F, int H, int W) {
 }
 
 bool AutoencoderKLLtxVideo::fusable(int l) const {
-    static const bool off = getenv("LTXV_VAE_NO_FUSED_PREP") != nullptr;
+    const bool off = options().vae_no_fused_prep != 0;
     return !off && ch_[l] <= 256;
 }
 
@@ -315,7 +345,8 @@ void* AutoencoderKLLtxVideo::prep(const void* x, int l, const float* scale, cons
     const int r = comm_->rank(), N = comm_->nranks();
     void* up = r > 0 ? comm_->peer(r - 1, off) : nullptr;
     void* dn = r < N - 1 ? comm_->peer(r + 1, off) : nullptr;
-    LTXV_CUDA(launch_vae_prep(x, comm_->local(off), scale, shift, do_norm, do_silu, T_[l], H_[l], W_[l], ch_[l], s, up, dn));
+    LTXV_CUDA(launch_vae_prep(x, comm_->local(off), scale, shift, do_norm, do_silu, T_[l], H_[l], W_[l], ch_[l], s, up, dn,
+                              1, h_up_ << l, h_dn_ << l));
     comm_->barrier(s, 0);  // halo rows from both neighbours have landed
     return comm_->local(off);
 }
@@ -362,6 +393,8 @@ void AutoencoderKLLtxVideo::conv(const ConvW& cw, const void* a_padded, int T, i
             const int r = comm_->rank(), N = comm_->nranks();
             p.norm_halo_up = r > 0 ? comm_->peer(r - 1, p_off_[l][pp_[l]]) : nullptr;
             p.norm_halo_dn = r < N - 1 ? comm_->peer(r + 1, p_off_[l][pp_[l]]) : nullptr;
+            p.norm_halo_up_h = h_up_ << l;
+            p.norm_halo_dn_h = h_dn_ << l;
         }
     }
     LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
@@ -393,8 +426,8 @@ void AutoencoderKLLtxVideo::resnet(const ResnetW& rw, int l, const float* ss, __
     // conv2's epilogue can also produce the NEXT consumer's input (store x and the padded copy), but that doubles the
     // epilogue: at C = 128 it then outlasts the 11 us main loop of a tile (ncu: 1.34 -> 1.99 ms per conv for 0.33 ms of
     // saved prep), at C = 256 the main loop is 4x longer and it stays hidden (0.65 -> 0.67 ms for 0.08 ms saved).
-    static const bool no_conv2 = getenv("LTXV_VAE_NO_FUSE_CONV2") != nullptr;
-    static const bool all_conv2 = getenv("LTXV_VAE_FUSE_CONV2") != nullptr;
+    const bool no_conv2 = options().vae_no_fuse_conv2 != 0;
+    const bool all_conv2 = options().vae_fuse_conv2 != 0;
     if (no_conv2 || (C < 256 && !all_conv2)) next = nullptr;
     conv(rw.conv2, a2, T, H, W, EPI_CONV_NDHWC, x_alt, x, 0, s, next ? l : -1, next);
     std::swap(x, x_alt);
@@ -449,7 +482,7 @@ void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* time
         }
         // conv_in (vae.rs:1664)
         void* a0 = comm_ ? comm_->local(a0_off_) : a0_.p;
-        LTXV_CUDA(launch_vae_input(zb, z_dtype == LTXV_BF16, a0, cfg_.latent_channels, F, H, W, prank * H_[0], H_[0], s));
+        LTXV_CUDA(launch_vae_input(zb, z_dtype == LTXV_BF16, a0, cfg_.latent_channels, F, H, W, lat_h0_, H_[0], s));
         __nv_bfloat16* x = xa_.as<__nv_bfloat16>();
         __nv_bfloat16* x_alt = xb_.as<__nv_bfloat16>();
         conv(conv_in_, a0, T_[0], H_[0], W_[0], EPI_CONV_NDHWC, x, nullptr, 0, s);
@@ -490,7 +523,7 @@ void AutoencoderKLLtxVideo::decode(const void* z, int z_dtype, const float* time
             conv(conv_out_, af, T_[3], H_[3], W_[3], EPI_CONV_UNPATCHIFY, o32, nullptr, postprocess, s);
         } else {
             // every rank stores its pixel rows into rank 0's frame buffer; rank 0 hands the assembled video out
-            slab_h0_ = prank * 4 * H_[3];
+            slab_h0_ = 4 * (lat_h0_ << 3);
             slab_hfull_ = Ho;
             conv(conv_out_, af, T_[3], H_[3], W_[3], EPI_CONV_UNPATCHIFY, comm_->peer(0, video_off_), nullptr, postprocess, s);
             slab_h0_ = slab_hfull_ = 0;

@@ -35,6 +35,7 @@ public:
 
     const ltxv_vae_config& config() const { return cfg_; }
     int device() const { return device_; }
+    PipeWs& pipe_ws() { return pipe_ws_; }
     void load_tensor(const std::string& key, const void* data, int dtype, const int64_t* shape, int rank);
     bool has_key(const std::string& key) const;
     // encoder half (vae_encoder.h); without it `encoder.*` keys are ignored like in a decode-only deployment
@@ -99,6 +100,7 @@ private:
 
     ltxv_vae_config cfg_;
     int device_;
+    PipeWs pipe_ws_;
     std::unique_ptr<LtxVideoEncoder3d> enc_;
     bool finalized_ = false;
     std::vector<std::unique_ptr<DevBuf>> storage_;
@@ -125,6 +127,17 @@ private:
     int pp_[4] = {0, 0, 0, 0};
     size_t a0_off_ = 0, video_off_ = 0;
     int slab_h0_ = 0, slab_hfull_ = 0;  // unpatchify row offset / full height of the conv_out being launched
+    // Ragged H-slabs: rank r owns latent rows [slab_row0(r), slab_row0(r) + slab_rows(r)); the first H mod N ranks
+    // take one row more.  h_up_ / h_dn_ = slab rows of the neighbours above / below at level 0 (their padded buffers
+    // have their own plane stride), lat_h0_ = first latent row of this rank.
+    int h_up_ = 0, h_dn_ = 0, lat_h0_ = 0;
+    // symmetric-heap carve-outs per decode geometry (the heap is a bump allocator: a geometry seen before reuses its
+    // buffers -- their zero borders are still intact -- instead of carving again)
+    struct SlabAlloc {
+        size_t p_off[4][2];
+        size_t a0_off, video_off;
+    };
+    std::map<std::vector<int64_t>, SlabAlloc> slab_allocs_;
 };
 
 }  // namespace ltxv

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "gemm.h"
+#include "options.h"
 #include "vae_glue.h"
 
 namespace ltxv {
@@ -253,8 +254,8 @@ void LtxVideoEncoder3d::conv(const ConvW& cw, const void* a_padded, int T, int H
 void LtxVideoEncoder3d::resnet(const ResnetW& rw, int l, __nv_bfloat16*& x, __nv_bfloat16*& x_alt, cudaStream_t s,
                                bool* ready, int next_kind, int next_tf) {
     const int C = ch_[l], T = T_[l], H = H_[l], W = W_[l];
-    static const bool no_fuse = getenv("LTXV_VAE_NO_FUSED_PREP") != nullptr;
-    static const bool no_conv2 = getenv("LTXV_VAE_NO_FUSE_CONV2") != nullptr;
+    const bool no_fuse = options().vae_no_fused_prep != 0;
+    const bool no_conv2 = options().vae_no_fuse_conv2 != 0;
     if (!(ready && *ready)) LTXV_CUDA(launch_vae_prep(x, p_[l].p, nullptr, nullptr, 1, 1, T, H, W, C, s, nullptr, nullptr, 2));
     if (ready) *ready = false;
     if (C <= 256 && !no_fuse) {

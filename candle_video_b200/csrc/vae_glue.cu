@@ -43,7 +43,8 @@ template <int C>
 __global__ void __launch_bounds__(256)
 vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
                 const float* __restrict__ shift, int do_norm, int do_silu, int T, int H, int W, int tf,
-                __nv_bfloat16* __restrict__ halo_up, __nv_bfloat16* __restrict__ halo_dn) {
+                __nv_bfloat16* __restrict__ halo_up, __nv_bfloat16* __restrict__ halo_dn, int H_up, int H_dn) {
+    // H_up / H_dn: slab rows of the neighbours owning halo_up / halo_dn (ragged H-slabs: their plane stride differs)
     // tf = replicated frames in front of the volume: 1 = the decoder's non-causal padding (one more copy of the last
     // frame behind it), 2 = the encoder's causal padding (vae.rs:383-387), 3 = causal padding of a volume whose first
     // frame is duplicated once more by the temporal downsampler (vae.rs:539-544)
@@ -119,7 +120,6 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         const int rem = vox - t * hw;
         const int h = rem / W;
         const int w = rem - h * W;
-        const int64_t plane = static_cast<int64_t>(Hp) * Wp;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
             uint4 o;
@@ -128,16 +128,17 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             o.z = pack_bf16x2(v[k][4], v[k][5]);
             o.w = pack_bf16x2(v[k][6], v[k][7]);
             const int c0 = (k * LPV + l) * 8;
-            auto put = [&](__nv_bfloat16* base, int hp) {
-                const int64_t row = (static_cast<int64_t>(t + tf) * Hp + hp) * Wp + (w + 1);
+            auto put = [&](__nv_bfloat16* base, int hp, int hpad) {
+                const int64_t pl = static_cast<int64_t>(hpad) * Wp;
+                const int64_t row = (static_cast<int64_t>(t + tf) * hpad + hp) * Wp + (w + 1);
                 *reinterpret_cast<uint4*>(base + row * C + c0) = o;
                 if (t == 0)  // replicate frame 0
-                    for (int q = 1; q <= tf; ++q) *reinterpret_cast<uint4*>(base + (row - q * plane) * C + c0) = o;
-                if (tf == 1 && t == T - 1) *reinterpret_cast<uint4*>(base + (row + plane) * C + c0) = o;  // frame T-1
+                    for (int q = 1; q <= tf; ++q) *reinterpret_cast<uint4*>(base + (row - q * pl) * C + c0) = o;
+                if (tf == 1 && t == T - 1) *reinterpret_cast<uint4*>(base + (row + pl) * C + c0) = o;  // frame T-1
             };
-            put(out, h + 1);
-            if (halo_up != nullptr && h == 0) put(halo_up, H + 1);   // my first row = bottom halo of the slab above
-            if (halo_dn != nullptr && h == H - 1) put(halo_dn, 0);   // my last row  = top halo of the slab below
+            put(out, h + 1, Hp);
+            if (halo_up != nullptr && h == 0) put(halo_up, H_up + 1, H_up + 2);  // my first row = bottom halo of the slab above
+            if (halo_dn != nullptr && h == H - 1) put(halo_dn, 0, H_dn + 2);     // my last row  = top halo of the slab below
         }
     };
     const int istride = static_cast<int>(stride);
@@ -373,7 +374,10 @@ cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out, int C, int
 }
 
 cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const float* shift, int do_norm, int do_silu,
-                            int T, int H, int W, int C, cudaStream_t s, void* halo_up, void* halo_dn, int tf) {
+                            int T, int H, int W, int C, cudaStream_t s, void* halo_up, void* halo_dn, int tf, int H_up,
+                            int H_dn) {
+    if (H_up <= 0) H_up = H;
+    if (H_dn <= 0) H_dn = H;
     if (tf < 1 || tf > 3 || (C > 1024 && scale != nullptr)) return cudaErrorInvalidValue;
     __nv_bfloat16* hu = reinterpret_cast<__nv_bfloat16*>(halo_up);
     __nv_bfloat16* hd = reinterpret_cast<__nv_bfloat16*>(halo_dn);
@@ -387,11 +391,11 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
     ProfScope prof(PROF_VAE_PREP, 4.0 * static_cast<double>(nvox) * C, s);  // bf16 in, bf16 out
     LTXV_TRACE_VARIANT("vae_prep_kernel<%d>", C);
     switch (C) {
-        case 128: launch_pdl(vae_prep_kernel<128>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
-        case 256: launch_pdl(vae_prep_kernel<256>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
-        case 512: launch_pdl(vae_prep_kernel<512>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
-        case 1024: launch_pdl(vae_prep_kernel<1024>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
-        case 2048: launch_pdl(vae_prep_kernel<2048>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd); break;
+        case 128: launch_pdl(vae_prep_kernel<128>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 256: launch_pdl(vae_prep_kernel<256>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 512: launch_pdl(vae_prep_kernel<512>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 1024: launch_pdl(vae_prep_kernel<1024>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 2048: launch_pdl(vae_prep_kernel<2048>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
         default: return cudaErrorInvalidValue;
     }
     return done();

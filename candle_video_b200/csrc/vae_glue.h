@@ -22,9 +22,10 @@ cudaError_t launch_vae_input(const void* z, int z_is_bf16, void* out_padded, int
 // 2]; 3 = causal padding of cat(x[:1], x) [(T+3) frames] for the temporal downsamplers (vae.rs:383-387, :539-544).
 // halo_up / halo_dn: the padded buffers of the ranks owning the slab above / below (peer memory) or null: the first /
 // last local row is also stored into their bottom / top halo row (conv halo exchange fused into the producer).
+// H_up / H_dn: slab rows of those neighbours when they differ from H (ragged slabs; 0 = same).
 cudaError_t launch_vae_prep(const void* x, void* out_padded, const float* scale, const float* shift, int do_norm,
                             int do_silu, int T, int H, int W, int C, cudaStream_t s, void* halo_up = nullptr,
-                            void* halo_dn = nullptr, int t_front = 1);
+                            void* halo_dn = nullptr, int t_front = 1, int H_up = 0, int H_dn = 0);
 
 // Conv3d weight [Cout, Cin, 3,3,3] (f32 or bf16, device) -> GEMM B matrix bf16 [rows_out, 27*Cin], k = tap*Cin + c.
 // d2s_perm: output channel co = c'*8 + sub is stored at row sub*(Cout/8) + c' (upsampler, see EPI_CONV_D2S).

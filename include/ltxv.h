@@ -64,6 +64,13 @@ int ltxv_profile_end(uint64_t* launches8, double* ms8, double* work8);
 int ltxv_causal_conv3d(const float* x, const float* weight, const float* bias, int in_channels, int out_channels,
                        int T, int H, int W, int is_causal, float* out, void* stream);
 
+/* Experiment knobs: kernel-variant switches, each initialised once per process from its LTXV_*
+ * environment variable; these calls override them at run time (names: no_cfg_batch, gemm_no_pair, conv_no_kw3,
+ * gemm_k2, gemm_no_short_k, attn_v1, attn_nosplit, attn_nsplit_max, vae_no_fused_prep, vae_no_fuse_conv2,
+ * vae_fuse_conv2, no_pdl, qk_unfused).  Process-wide; not synchronised with in-flight calls of other threads. */
+int ltxv_set_option(const char* name, int value);
+int ltxv_get_option(const char* name, int* value);
+
 /* Test hook: between begin/end every launcher records the kernel variant it selected (template instance, tile mode,
  * attention key-split count ...).  end() writes "name count\n" lines (sorted) into `out`.  The production-shape parity
  * tests use it to assert that the variants the benchmark runs are the ones they compared with the oracle.  Not part of
@@ -323,6 +330,14 @@ int ltxv_parallel_plan(int nranks, int rank, int S, int do_cfg, int32_t* out6);
 int ltxv_pipeline_denoise_parallel(ltxv_dit* dit, ltxv_comm* c, const ltxv_pipeline_params* p, float* latents,
                                    const void* prompt_embeds, const float* prompt_mask, const void* negative_embeds,
                                    const float* negative_mask, int embeds_dtype, int K, void* stream);
+/* ... with stochastic_sampling = true (scheduler.rs:557-575; ltxv_pipeline_denoise_stochastic): step_noise is the same
+ * full [num_inference_steps, S, 128] f32 tensor on every rank, each rank reads its token shard's rows. */
+int ltxv_pipeline_denoise_parallel_stochastic(ltxv_dit* dit, ltxv_comm* c, const ltxv_pipeline_params* p, float* latents,
+                                              const void* prompt_embeds, const float* prompt_mask,
+                                              const void* negative_embeds, const float* negative_mask, int embeds_dtype,
+                                              int K, const float* step_noise, void* stream);
+/* H-slab decode over all ranks: latent heights need not be divisible by the rank count (ragged slabs: the first
+ * H mod nranks ranks take one latent row more; c3 / c5 latents are 22 rows high). */
 /* H-slab decode over all ranks of `c` (NULL restores single-GPU decode): ltxv_vae_decode / ltxv_pipeline_decode then
  * take the full latent on every rank and deliver the video on rank 0 (other ranks' `out` is left untouched). */
 int ltxv_vae_set_comm(ltxv_vae* vae, ltxv_comm* c);
