@@ -391,7 +391,19 @@ __device__ long long g_attn_trace[11][40][8];
 #else
 #define TRACE(role, j, ev) do { } while (0)
 #endif
-constexpr int kV3Threads = 384;
+#ifndef LTXV_ATTN_ISSUERS4
+#define LTXV_ATTN_ISSUERS4 1
+#endif
+// ISSUERS4: the tcgen05.mma issue work is spread over FOUR single-thread issuers, one per SM sub-partition (warps 8..11:
+// query tile 0 even / odd key tiles, query tile 1 even / odd key tiles), and the TMA producer moves to a 13th warp.
+// Measured (clock64 trace of one CTA, tools/attn_prof.cu): a sub-partition that hosts an issuer runs its two softmax
+// warps ~15-20 % slower (descriptor arithmetic on the uniform datapath + UTCHMMA dispatch share its issue port); with
+// one issuer per query tile the four softmax warps of a tile -- one per sub-partition, coupled twice per key tile by
+// the 4-arrival s_free / p_full barriers -- drifted ~1000 cycles apart, and the leaders idled at pv_done / s_full.
+// setmaxnreg is a warpgroup-wide instruction: the fifth control warp needs a full (otherwise idle) warpgroup around it,
+// hence 16 warps; the 8 control warps drop to 32 registers so that 8 x 32 x 224 + 8 x 32 x 32 = 64 K registers.
+constexpr int kV3Threads = LTXV_ATTN_ISSUERS4 ? 512 : 384;
+constexpr int kV3CtrlRegs = LTXV_ATTN_ISSUERS4 ? 32 : 48;
 constexpr int kV3Stages = 6;
 constexpr int kV3L2Ahead = 4;  // K/V tiles prefetched into L2 beyond the smem ring
 constexpr int kV3SmemBytes = 2 * kV2QBytes + 2 * kV3Stages * kV2KVBytes + 512;
@@ -486,6 +498,22 @@ __device__ __forceinline__ void ex2_poly_pair(float x0, float x1, float& e0, flo
     e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(f0) << 23));
     e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(f1) << 23));
 }
+// control-warp roles of flash_attn3_kernel (warps 8..11 live on SM sub-partitions 0..3)
+#ifndef LTXV_ATTN_ROLES
+#define LTXV_ATTN_ROLES 0
+#endif
+#if LTXV_ATTN_ISSUERS4
+constexpr int kV3WarpTma = 12, kV3WarpIss0 = 8, kV3WarpIss1 = 10;
+#elif LTXV_ATTN_ROLES == 0
+constexpr int kV3WarpTma = 8, kV3WarpIss0 = 9, kV3WarpIss1 = 10;
+#elif LTXV_ATTN_ROLES == 1  // experiment: issuers on sub-partitions 0 and 3
+constexpr int kV3WarpTma = 9, kV3WarpIss0 = 8, kV3WarpIss1 = 11;
+#elif LTXV_ATTN_ROLES == 2  // experiment: both issuers on sub-partitions 1 and 1+... (tile 1's issuer on 0)
+constexpr int kV3WarpTma = 10, kV3WarpIss0 = 9, kV3WarpIss1 = 8;
+#endif
+#ifndef LTXV_ATTN_PINGPONG
+#define LTXV_ATTN_PINGPONG 0  // 0 off; 1 hand over at the end of the exp phase, 2 at half, 3 at three quarters
+#endif
 #ifndef LTXV_ATTN_POLY
 #define LTXV_ATTN_POLY 2  // pairs out of every 8 (16 scores) whose exp2 runs on the FMA pipe instead of MUFU: 0..8
 #endif
@@ -575,7 +603,8 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     uint64_t* s_free = s_full + 2;                 // [2]  S_t copied to registers (128 arrivals)
     uint64_t* p_full = s_free + 2;                 // [2]  P_t stored to TMEM (128 arrivals)
     uint64_t* pv_done = p_full + 2;                // [2]  O_t += P_t V retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    uint64_t* turn = pv_done + 2;                  // [2]  exp-phase hand-off between the two softmax groups (ping-pong)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
     volatile uint32_t* split_flag = tmem_slot + 1;  // 1 = this CTA drew the last ticket of its split unit
 
     const int warp_idx = threadIdx.x >> 5;
@@ -627,10 +656,12 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             mbar_init(&s_free[t], 4);  // one arrival per softmax warp
             mbar_init(&p_full[t], 4);
             mbar_init(&pv_done[t], 1);
+            mbar_init(&turn[t], 4);
         }
         fence_barrier_init();
     }
-    if (warp_idx == 11) tmem_alloc<512>(tmem_slot);
+    constexpr int kTmemWarp = LTXV_ATTN_ISSUERS4 ? 12 : 11;
+    if (warp_idx == kTmemWarp) tmem_alloc<512>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -648,8 +679,8 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // owner).  The control warps sit at the HIGH warp ids on purpose: their few instructions win the issue
     // arbitration against the always-ready softmax warps that share their scheduler.
     if (warp_idx >= 8) {
-        setmaxnreg_dec<48>();
-        if (warp_idx == 8) {
+        setmaxnreg_dec<kV3CtrlRegs>();
+        if (warp_idx == kV3WarpTma) {
             // ===================== TMA producer =====================
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, nt * kV2QBytes);
@@ -683,46 +714,53 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     }
                 }
             }
-        } else if (warp_idx == 9 || (warp_idx == 10 && two)) {
-            // ===================== UMMA issuer of query tile t =====================
-            const int t = warp_idx - 9;
+        } else if (LTXV_ATTN_ISSUERS4 ? (warp_idx <= 11 && (warp_idx < 10 || two))
+                                      : (warp_idx == kV3WarpIss0 || (warp_idx == kV3WarpIss1 && two))) {
+            // ===================== UMMA issuer of query tile t (ISSUERS4: of its even / odd key tiles) =====================
+#if LTXV_ATTN_ISSUERS4
+            const int t = (warp_idx - 8) >> 1;
+            const int par = (warp_idx - 8) & 1, jstep = 2;
+#else
+            const int t = warp_idx == kV3WarpIss0 ? 0 : 1;
+            const int par = 0, jstep = 1;
+#endif
             if (elect_one()) {
                 constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, false, false);
                 constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, D, false, true);  // B = V is MN-major
-                const uint32_t qa = smem_u32(sq) + t * kV2QBytes;
                 const uint32_t tmem_s = tmem_base + t * 128;
                 const uint32_t tmem_o = tmem_base + 256 + t * 64;
                 const uint32_t tmem_p = tmem_base + 384 + t * 64;
+                // descriptors differ from tile to tile only in the 14-bit start-address field: build the constant part
+                // once and add (address >> 4) per instruction (all operand addresses stay below 256 KB: no carry)
+                const uint64_t desc_k0 = make_smem_desc_sw128(0, 1024, 0);
+                const uint64_t desc_v0 = make_smem_desc_sw128(0, 1024, kTileKV * 128);
+                const uint64_t desc_q = make_smem_desc_sw128(smem_u32(sq) + t * kV2QBytes, 1024, 0);
+                const uint32_t sk_a = smem_u32(sk) >> 4, sv_a = smem_u32(sv) >> 4;
                 auto issue_s = [&](int stage) {
-                    const uint32_t k_addr = smem_u32(sk + stage * kV2KVBytes);
+                    const uint64_t dk = desc_k0 + (sk_a + stage * (kV2KVBytes >> 4));
 #pragma unroll
                     for (int ks = 0; ks < D / 16; ++ks)
-                        umma_bf16_ss(tmem_s, make_smem_desc_sw128(qa + ks * 32, 1024, 0),
-                                     make_smem_desc_sw128(k_addr + ks * 32, 1024, 0), idesc_s, ks != 0 ? 1u : 0u);
+                        umma_bf16_ss(tmem_s, desc_q + ks * 2, dk + ks * 2, idesc_s, ks != 0 ? 1u : 0u);
                 };
-                mbar_wait_sleep(q_full, 0);
-                mbar_wait_sleep(&k_full[0], 0);
-                tcgen05_fence_after();
-                issue_s(0);
-                umma_commit(&s_full[t]);
-                umma_commit(&k_empty[0]);
+                if (par == 0) {
+                    mbar_wait_sleep(q_full, 0);
+                    mbar_wait_sleep(&k_full[0], 0);
+                    tcgen05_fence_after();
+                    issue_s(0);
+                    umma_commit(&s_full[t]);
+                    umma_commit(&k_empty[0]);
+                }
 #ifdef LTXV_ATTN_TIMING
-                const bool tm_on = (qb == 3 && head == 5 && split == 0);
+                const bool tm_on = (qb == 3 && head == 5 && split == 0 && par == 0);
                 long long tm_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 long long tm_last = clock64();
 #endif
 #ifdef LTXV_ATTN_TRACE
                 const bool tr_on = (qb == 3 && head == 5 && split == 0);
 #endif
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int j = 0; j < n_tiles; ++j) {
-                    int nstage = stage + 1;
-                    uint32_t nphase = phase;
-                    if (nstage == kV3Stages) {
-                        nstage = 0;
-                        nphase ^= 1;
-                    }
+                for (int j = par; j < n_tiles; j += jstep) {
+                    const int stage = j % kV3Stages, nstage = (j + 1) % kV3Stages;
+                    const uint32_t phase = (j / kV3Stages) & 1, nphase = ((j + 1) / kV3Stages) & 1;
                     if (j + 1 < n_tiles) {
 #ifdef LTXV_ATTN_TIMING
                         TMARK(7);
@@ -750,18 +788,14 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     TMARK(4);
                     TRACE(8 + t, j, 4);
                     tcgen05_fence_after();
-                    const uint32_t v_addr = smem_u32(sv + stage * kV2KVBytes);
+                    const uint64_t dv = desc_v0 + (sv_a + stage * (kV2KVBytes >> 4));
 #pragma unroll
                     for (int ks = 0; ks < kTileKV / 16; ++ks)
-                        umma_bf16_ts(tmem_o, tmem_p + ks * 8,
-                                     make_smem_desc_sw128(v_addr + ks * (16 * 128), 1024, kTileKV * 128), idesc_pv,
-                                     (j | ks) != 0 ? 1u : 0u);
+                        umma_bf16_ts(tmem_o, tmem_p + ks * 8, dv + ks * ((16 * 128) >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
                     umma_commit(&pv_done[t]);
                     umma_commit(&v_empty[stage]);
                     TMARK(5);
                     TRACE(8 + t, j, 5);
-                    stage = nstage;
-                    phase = nphase;
                 }
 #ifdef LTXV_ATTN_TIMING
                 if (tm_on)
@@ -860,6 +894,19 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 TMARK(3);
                 const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
                 uint32_t pk[32];
+#if LTXV_ATTN_PINGPONG
+                // The exponentials of the two query tiles alternate on the XU (MUFU) pipe they share: group 0 runs the
+                // exp phase of key tile j, then group 1, then group 0 for j+1 ...; the other group's max / TMEM traffic /
+                // barrier waits fill the gaps.  Without the hand-off both groups enter their exp phases together, halve
+                // each other's MUFU rate and then leave the pipe idle together.
+                if (two) {
+                    if (t == 0) {
+                        if (j > 0) warp_mbar_wait(&turn[0], (j - 1) & 1, lane);
+                    } else {
+                        warp_mbar_wait(&turn[1], j & 1, lane);
+                    }
+                }
+#endif
                 exp_chunk_v3(s0, c2, negm2, l2a, l2b, pk);
                 exp_chunk_v3(s1, c2, negm2, l2a, l2b, pk + 16);
                 TMARK(4);
@@ -873,8 +920,17 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 TMARK(5);
                 TRACE(warp_idx, j, 4);
                 tmem_st_32x32b_x32(tmem_p, pk);          // keys  0..63  -> P columns  0..31
+#if LTXV_ATTN_PINGPONG == 2
+                if (two) warp_mbar_arrive(&turn[1 - t], lane);  // early release: half of this phase still to go
+#endif
                 exp_chunk_v3(s2, c2, negm2, l2a, l2b, pk);
+#if LTXV_ATTN_PINGPONG == 3
+                if (two) warp_mbar_arrive(&turn[1 - t], lane);  // early release: a quarter of this phase still to go
+#endif
                 exp_chunk_v3(s3, c2, negm2, l2a, l2b, pk + 16);
+#if LTXV_ATTN_PINGPONG == 1
+                if (two) warp_mbar_arrive(&turn[1 - t], lane);
+#endif
                 tmem_st_32x32b_x32(tmem_p + 32, pk);     // keys 64..127 -> P columns 32..63
                 TMARK(6);
                 tmem_st_wait();
@@ -1023,7 +1079,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
     if (threadIdx.x == 0 && item == 0) g_attn_trace[9][19][5] = static_cast<long long>(globaltimer_ns());
 #endif
-    if (warp_idx == 11) {
+    if (warp_idx == kTmemWarp) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
     }

@@ -60,7 +60,7 @@ int main(int argc, char** argv) {
                        tr[9][20 + sidx][1] - tr[9][20 + sidx][0], tr[9][20 + sidx][2] - tr[9][20 + sidx][0],
                        tr[9][20 + sidx][3] - tr[9][20 + sidx][0], tr[9][20 + sidx][4] - tr[9][20 + sidx][0], tr[9][20 + sidx][6],
                        tr[9][20 + sidx][5] - tr[9][19][4]);
-        for (int j = 16; j < 17; ++j) {
+        for (int j = 15; j < 18; ++j) {
             for (int w = 0; w < 8; ++w) {
                 printf("j=%d softmax warp %d (tile %d):", j, w, w >> 2);
                 for (int e = 0; e < 6; ++e) printf(" %s=%lld", sm[e], tr[w][j][e] - t0);
