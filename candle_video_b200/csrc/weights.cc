@@ -164,13 +164,20 @@ struct Json {
         ++p;
         return out;
     }
+    // bounded by [p, end): the header is a slice of an mmap'd file and is NOT NUL-terminated (strtoll would run past it)
     int64_t integer() {
         ws();
-        char* e = nullptr;
-        const long long v = strtoll(p, &e, 10);
-        if (e == p) fail("malformed JSON: expected an integer");
-        p = e;
-        return v;
+        bool neg = false;
+        if (p < end && (*p == '-' || *p == '+')) neg = *p++ == '-';
+        if (p >= end || *p < '0' || *p > '9') fail("malformed JSON: expected an integer");
+        int64_t v = 0;
+        while (p < end && *p >= '0' && *p <= '9') {
+            if (__builtin_mul_overflow(v, static_cast<int64_t>(10), &v) ||
+                __builtin_add_overflow(v, static_cast<int64_t>(*p - '0'), &v))
+                fail("malformed JSON: integer out of range");
+            ++p;
+        }
+        return neg ? -v : v;
     }
     void skip_value() {
         ws();
@@ -254,17 +261,26 @@ bool dir_exists(const std::string& p) {
 // SafeTensorsFile
 // ------------------------------------------------------------------------------------------------
 SafeTensorsFile::SafeTensorsFile(const std::string& path) : path_(path) {
+    // a constructor that throws does not run the destructor: release the mapping / descriptor before re-throwing
+    try {
+        parse(path);
+    } catch (...) {
+        if (map_) munmap(const_cast<uint8_t*>(map_), size_);
+        if (fd_ >= 0) close(fd_);
+        map_ = nullptr;
+        fd_ = -1;
+        throw;
+    }
+}
+
+void SafeTensorsFile::parse(const std::string& path) {
     fd_ = open(path.c_str(), O_RDONLY);
     if (fd_ < 0) fail("cannot open safetensors file '%s'", path.c_str());
     struct stat st;
-    if (fstat(fd_, &st) != 0 || st.st_size < 8) {
-        close(fd_);
-        fail("'%s' is too short to be a safetensors file", path.c_str());
-    }
+    if (fstat(fd_, &st) != 0 || st.st_size < 8) fail("'%s' is too short to be a safetensors file", path.c_str());
     size_ = static_cast<size_t>(st.st_size);
     map_ = static_cast<const uint8_t*>(mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0));
     if (map_ == MAP_FAILED) {
-        close(fd_);
         map_ = nullptr;
         fail("mmap of '%s' failed", path.c_str());
     }
@@ -311,9 +327,13 @@ SafeTensorsFile::SafeTensorsFile(const std::string& path) : path_(path) {
                 }
             } while (j.eat(','));
             j.expect('}');
-            int64_t numel = 1;
-            for (auto d : info.shape) numel *= d;
-            if (endo < begin || endo > data_bytes || (endo - begin) != static_cast<uint64_t>(numel) * dtype_size(info.dtype))
+            int64_t numel = 1, nbytes = 0;
+            for (auto d : info.shape)
+                if (d < 0 || __builtin_mul_overflow(numel, d, &numel))
+                    fail("'%s': tensor '%s' has a negative or overflowing shape", path.c_str(), name.c_str());
+            if (__builtin_mul_overflow(numel, static_cast<int64_t>(dtype_size(info.dtype)), &nbytes))
+                fail("'%s': tensor '%s' is too large", path.c_str(), name.c_str());
+            if (endo < begin || endo > data_bytes || (endo - begin) != static_cast<uint64_t>(nbytes))
                 fail("'%s': tensor '%s' has inconsistent offsets [%llu,%llu) for %lld x %s", path.c_str(), name.c_str(),
                      static_cast<unsigned long long>(begin), static_cast<unsigned long long>(endo),
                      static_cast<long long>(numel), info.dtype.c_str());
@@ -323,6 +343,18 @@ SafeTensorsFile::SafeTensorsFile(const std::string& path) : path_(path) {
         } while (j.eat(','));
         j.expect('}');
     }
+    // the format requires the tensors to tile the data section: no overlap, no hole (safetensors README, "Format")
+    std::vector<std::pair<const uint8_t*, size_t>> spans;
+    for (const SafeTensorInfo& t : tensors_) spans.emplace_back(t.data, t.bytes);
+    std::sort(spans.begin(), spans.end());
+    const uint8_t* cursor = data_;
+    for (const auto& sp : spans) {
+        if (sp.first != cursor)
+            fail("'%s': tensor data ranges %s", path.c_str(), sp.first < cursor ? "overlap" : "leave a hole in the data section");
+        cursor = sp.first + sp.second;
+    }
+    if (cursor != data_ + data_bytes) fail("'%s': %zu trailing bytes after the last tensor", path.c_str(),
+                                           static_cast<size_t>(data_ + data_bytes - cursor));
     std::sort(tensors_.begin(), tensors_.end(),
               [](const SafeTensorInfo& a, const SafeTensorInfo& b) { return a.name < b.name; });
 }

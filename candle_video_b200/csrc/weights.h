@@ -33,6 +33,7 @@ public:
     const std::vector<SafeTensorInfo>& tensors() const { return tensors_; }  // sorted by name
 
 private:
+    void parse(const std::string& path);
     std::string path_;
     int fd_ = -1;
     const uint8_t* map_ = nullptr;

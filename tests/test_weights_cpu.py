@@ -140,3 +140,34 @@ def test_official_names_round_trip_through_the_remap():
     assert len(off) == len(w)
     assert {cv.remap_official_key(k)[0] for k in off} == set(w)
     assert all(cv.remap_official_key(k)[1] == "vae" for k in off)
+
+
+def _raw_safetensors(tmp_path, header: dict, data: bytes, name="bad.safetensors"):
+    import json
+    import struct
+    h = json.dumps(header, separators=(",", ":")).encode()
+    p = tmp_path / name
+    p.write_bytes(struct.pack("<Q", len(h)) + h + data)
+    return p
+
+
+def test_safetensors_parser_rejects_malformed_headers(tmp_path):
+    """Untrusted-file hygiene of the header parser (csrc/weights.cc): negative / overflowing dims, overlapping or
+    non-covering data ranges and out-of-range integers fail loudly instead of wrapping around."""
+    import candle_video_b200 as cv
+    ok = _raw_safetensors(tmp_path, {"a": {"dtype": "F32", "shape": [2, 2], "data_offsets": [0, 16]}}, b"\0" * 16, "ok.safetensors")
+    assert cv.safetensors_list(ok) == [("a", "F32", [2, 2], 16)]
+    cases = {
+        "negative": ({"a": {"dtype": "F32", "shape": [-2, -2], "data_offsets": [0, 16]}}, b"\0" * 16),
+        "overflow": ({"a": {"dtype": "F32", "shape": [1 << 62, 8], "data_offsets": [0, 16]}}, b"\0" * 16),
+        "overlap": ({"a": {"dtype": "F32", "shape": [4], "data_offsets": [0, 16]},
+                     "b": {"dtype": "F32", "shape": [4], "data_offsets": [8, 24]}}, b"\0" * 24),
+        "hole": ({"a": {"dtype": "F32", "shape": [2], "data_offsets": [0, 8]},
+                  "b": {"dtype": "F32", "shape": [2], "data_offsets": [16, 24]}}, b"\0" * 24),
+        "trailing": ({"a": {"dtype": "F32", "shape": [2], "data_offsets": [0, 8]}}, b"\0" * 12),
+        "huge_int": ({"a": {"dtype": "F32", "shape": [99999999999999999999999], "data_offsets": [0, 8]}}, b"\0" * 8),
+    }
+    for tag, (hdr, data) in cases.items():
+        p = _raw_safetensors(tmp_path, hdr, data, f"{tag}.safetensors")
+        with pytest.raises(cv.LtxvError):
+            cv.safetensors_list(p)
