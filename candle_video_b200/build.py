@@ -49,6 +49,7 @@ TOOLS = {
     "gemm_test": (["tools/gemm_test.cu"], ["gemm_tcgen05.cu", "tensormap.cc", "profile.cc", "options.cc"]),
     "attn_test": (["tools/attn_test.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc", "options.cc"]),
     "attn_prof": (["tools/attn_prof.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc", "options.cc"]),
+    "attn_bench": (["tools/attn_bench.cu"], ["attention_tcgen05.cu", "tensormap.cc", "profile.cc", "options.cc"]),
 }
 
 

@@ -391,19 +391,7 @@ __device__ long long g_attn_trace[11][40][8];
 #else
 #define TRACE(role, j, ev) do { } while (0)
 #endif
-#ifndef LTXV_ATTN_ISSUERS4
-#define LTXV_ATTN_ISSUERS4 1
-#endif
-// ISSUERS4: the tcgen05.mma issue work is spread over FOUR single-thread issuers, one per SM sub-partition (warps 8..11:
-// query tile 0 even / odd key tiles, query tile 1 even / odd key tiles), and the TMA producer moves to a 13th warp.
-// Measured (clock64 trace of one CTA, tools/attn_prof.cu): a sub-partition that hosts an issuer runs its two softmax
-// warps ~15-20 % slower (descriptor arithmetic on the uniform datapath + UTCHMMA dispatch share its issue port); with
-// one issuer per query tile the four softmax warps of a tile -- one per sub-partition, coupled twice per key tile by
-// the 4-arrival s_free / p_full barriers -- drifted ~1000 cycles apart, and the leaders idled at pv_done / s_full.
-// setmaxnreg is a warpgroup-wide instruction: the fifth control warp needs a full (otherwise idle) warpgroup around it,
-// hence 16 warps; the 8 control warps drop to 32 registers so that 8 x 32 x 224 + 8 x 32 x 32 = 64 K registers.
-constexpr int kV3Threads = LTXV_ATTN_ISSUERS4 ? 512 : 384;
-constexpr int kV3CtrlRegs = LTXV_ATTN_ISSUERS4 ? 32 : 48;
+constexpr int kV3Threads = 384;
 constexpr int kV3Stages = 6;
 constexpr int kV3L2Ahead = 4;  // K/V tiles prefetched into L2 beyond the smem ring
 constexpr int kV3SmemBytes = 2 * kV2QBytes + 2 * kV3Stages * kV2KVBytes + 512;
@@ -498,22 +486,12 @@ __device__ __forceinline__ void ex2_poly_pair(float x0, float x1, float& e0, flo
     e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(f0) << 23));
     e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(f1) << 23));
 }
-// control-warp roles of flash_attn3_kernel (warps 8..11 live on SM sub-partitions 0..3)
-#ifndef LTXV_ATTN_ROLES
-#define LTXV_ATTN_ROLES 0
-#endif
-#if LTXV_ATTN_ISSUERS4
-constexpr int kV3WarpTma = 12, kV3WarpIss0 = 8, kV3WarpIss1 = 10;
-#elif LTXV_ATTN_ROLES == 0
-constexpr int kV3WarpTma = 8, kV3WarpIss0 = 9, kV3WarpIss1 = 10;
-#elif LTXV_ATTN_ROLES == 1  // experiment: issuers on sub-partitions 0 and 3
-constexpr int kV3WarpTma = 9, kV3WarpIss0 = 8, kV3WarpIss1 = 11;
-#elif LTXV_ATTN_ROLES == 2  // experiment: both issuers on sub-partitions 1 and 1+... (tile 1's issuer on 0)
-constexpr int kV3WarpTma = 10, kV3WarpIss0 = 9, kV3WarpIss1 = 8;
-#endif
-#ifndef LTXV_ATTN_PINGPONG
-#define LTXV_ATTN_PINGPONG 0  // 0 off; 1 hand over at the end of the exp phase, 2 at half, 3 at three quarters
-#endif
+// Early probes: the softmax warps test s_full(j+1) / pv_done(j-1) with a non-blocking mbarrier.test_wait issued in the
+// middle of the exponentials and only fall back to the blocking wait when the probe failed.  A blocking wait on an
+// already completed phase still costs ~230 cycles per warp (TRYWAIT round trip + warp re-convergence; clock64 trace of
+// tools/attn_prof.cu), twice per key tile; P is stored in one piece at the end of the tile so that the pv_done check
+// moves from the middle of the exponentials (where P V(j-1) is often still in flight) to their end.  +2.5 % at c2,
+// +5 % at c3 (800 -> 820, 869 -> 911 TFLOP/s isolated).
 #ifndef LTXV_ATTN_POLY
 #define LTXV_ATTN_POLY 2  // pairs out of every 8 (16 scores) whose exp2 runs on the FMA pipe instead of MUFU: 0..8
 #endif
@@ -603,8 +581,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     uint64_t* s_free = s_full + 2;                 // [2]  S_t copied to registers (128 arrivals)
     uint64_t* p_full = s_free + 2;                 // [2]  P_t stored to TMEM (128 arrivals)
     uint64_t* pv_done = p_full + 2;                // [2]  O_t += P_t V retired
-    uint64_t* turn = pv_done + 2;                  // [2]  exp-phase hand-off between the two softmax groups (ping-pong)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
     volatile uint32_t* split_flag = tmem_slot + 1;  // 1 = this CTA drew the last ticket of its split unit
 
     const int warp_idx = threadIdx.x >> 5;
@@ -656,12 +633,10 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             mbar_init(&s_free[t], 4);  // one arrival per softmax warp
             mbar_init(&p_full[t], 4);
             mbar_init(&pv_done[t], 1);
-            mbar_init(&turn[t], 4);
         }
         fence_barrier_init();
     }
-    constexpr int kTmemWarp = LTXV_ATTN_ISSUERS4 ? 12 : 11;
-    if (warp_idx == kTmemWarp) tmem_alloc<512>(tmem_slot);
+    if (warp_idx == 11) tmem_alloc<512>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -679,8 +654,8 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // owner).  The control warps sit at the HIGH warp ids on purpose: their few instructions win the issue
     // arbitration against the always-ready softmax warps that share their scheduler.
     if (warp_idx >= 8) {
-        setmaxnreg_dec<kV3CtrlRegs>();
-        if (warp_idx == kV3WarpTma) {
+        setmaxnreg_dec<48>();
+        if (warp_idx == 8) {
             // ===================== TMA producer =====================
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, nt * kV2QBytes);
@@ -714,16 +689,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     }
                 }
             }
-        } else if (LTXV_ATTN_ISSUERS4 ? (warp_idx <= 11 && (warp_idx < 10 || two))
-                                      : (warp_idx == kV3WarpIss0 || (warp_idx == kV3WarpIss1 && two))) {
-            // ===================== UMMA issuer of query tile t (ISSUERS4: of its even / odd key tiles) =====================
-#if LTXV_ATTN_ISSUERS4
-            const int t = (warp_idx - 8) >> 1;
-            const int par = (warp_idx - 8) & 1, jstep = 2;
-#else
-            const int t = warp_idx == kV3WarpIss0 ? 0 : 1;
-            const int par = 0, jstep = 1;
-#endif
+        } else if (warp_idx == 9 || (warp_idx == 10 && two)) {
+            // ===================== UMMA issuer of query tile t =====================
+            const int t = warp_idx - 9;
             if (elect_one()) {
                 constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, false, false);
                 constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, D, false, true);  // B = V is MN-major
@@ -739,26 +707,25 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 auto issue_s = [&](int stage) {
                     const uint64_t dk = desc_k0 + (sk_a + stage * (kV2KVBytes >> 4));
 #pragma unroll
-                    for (int ks = 0; ks < D / 16; ++ks)
+                    for (int ks = 0; ks < D / 16; ++ks) {
                         umma_bf16_ss(tmem_s, desc_q + ks * 2, dk + ks * 2, idesc_s, ks != 0 ? 1u : 0u);
+                    }
                 };
-                if (par == 0) {
-                    mbar_wait_sleep(q_full, 0);
-                    mbar_wait_sleep(&k_full[0], 0);
-                    tcgen05_fence_after();
-                    issue_s(0);
-                    umma_commit(&s_full[t]);
-                    umma_commit(&k_empty[0]);
-                }
+                mbar_wait_sleep(q_full, 0);
+                mbar_wait_sleep(&k_full[0], 0);
+                tcgen05_fence_after();
+                issue_s(0);
+                umma_commit(&s_full[t]);
+                umma_commit(&k_empty[0]);
 #ifdef LTXV_ATTN_TIMING
-                const bool tm_on = (qb == 3 && head == 5 && split == 0 && par == 0);
+                const bool tm_on = (qb == 3 && head == 5 && split == 0);
                 long long tm_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 long long tm_last = clock64();
 #endif
 #ifdef LTXV_ATTN_TRACE
                 const bool tr_on = (qb == 3 && head == 5 && split == 0);
 #endif
-                for (int j = par; j < n_tiles; j += jstep) {
+                for (int j = 0; j < n_tiles; ++j) {
                     const int stage = j % kV3Stages, nstage = (j + 1) % kV3Stages;
                     const uint32_t phase = (j / kV3Stages) & 1, nphase = ((j + 1) / kV3Stages) & 1;
                     if (j + 1 < n_tiles) {
@@ -790,8 +757,9 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                     tcgen05_fence_after();
                     const uint64_t dv = desc_v0 + (sv_a + stage * (kV2KVBytes >> 4));
 #pragma unroll
-                    for (int ks = 0; ks < kTileKV / 16; ++ks)
+                    for (int ks = 0; ks < kTileKV / 16; ++ks) {
                         umma_bf16_ts(tmem_o, tmem_p + ks * 8, dv + ks * ((16 * 128) >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                    }
                     umma_commit(&pv_done[t]);
                     umma_commit(&v_empty[stage]);
                     TMARK(5);
@@ -817,6 +785,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             const uint64_t c2 = pack_f32x2(c, c);
             float m_used = -INFINITY;
             uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+            uint32_t sfull_probe = 0;  // lane 0: result of the early test of s_full(j) issued during tile j-1
 #ifdef LTXV_ATTN_TIMING
             const bool tm_on = (qb == 3 && head == 5 && split == 0 && lane == 0 && (warp_idx == 0 || warp_idx == 4));
             long long tm_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -830,7 +799,8 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 const int kv0 = (jt0 + j) * kTileKV;
                 uint32_t s0[32], s1[32], s2[32], s3[32];
                 TRACE(warp_idx, j, 0);
-                warp_mbar_wait(&s_full[t], j & 1, lane);
+                if (!__shfl_sync(0xffffffffu, sfull_probe, 0)) warp_mbar_wait(&s_full[t], j & 1, lane);
+                sfull_probe = 0;
                 TRACE(warp_idx, j, 1);
                 TMARK(0);
                 tcgen05_fence_after();
@@ -894,44 +864,25 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 TMARK(3);
                 const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
                 uint32_t pk[32];
-#if LTXV_ATTN_PINGPONG
-                // The exponentials of the two query tiles alternate on the XU (MUFU) pipe they share: group 0 runs the
-                // exp phase of key tile j, then group 1, then group 0 for j+1 ...; the other group's max / TMEM traffic /
-                // barrier waits fill the gaps.  Without the hand-off both groups enter their exp phases together, halve
-                // each other's MUFU rate and then leave the pipe idle together.
-                if (two) {
-                    if (t == 0) {
-                        if (j > 0) warp_mbar_wait(&turn[0], (j - 1) & 1, lane);
-                    } else {
-                        warp_mbar_wait(&turn[1], j & 1, lane);
-                    }
-                }
-#endif
                 exp_chunk_v3(s0, c2, negm2, l2a, l2b, pk);
                 exp_chunk_v3(s1, c2, negm2, l2a, l2b, pk + 16);
                 TMARK(4);
                 TRACE(warp_idx, j, 3);
+                uint32_t pk2[32];
+                uint32_t pv_probe = 0;
+                exp_chunk_v3(s2, c2, negm2, l2a, l2b, pk2);
+                if (!pv_waited && lane == 0) pv_probe = mbar_test_wait(&pv_done[t], (j - 1) & 1);
+                if (j + 1 < n_tiles && lane == 0) sfull_probe = mbar_test_wait(&s_full[t], (j + 1) & 1);
+                exp_chunk_v3(s3, c2, negm2, l2a, l2b, pk2 + 16);
+                TMARK(5);
                 if (!pv_waited) {
-                    // P_t is single-buffered: the previous P_t V must have read it before it is overwritten.  The wait
-                    // sits here, after half of the exponentials, so the PV MMA latency hides behind them.
-                    warp_mbar_wait(&pv_done[t], (j - 1) & 1, lane);
+                    // P_t is single-buffered: P_t V(j-1) must have read it before it is overwritten
+                    if (!__shfl_sync(0xffffffffu, pv_probe, 0)) warp_mbar_wait(&pv_done[t], (j - 1) & 1, lane);
                     tcgen05_fence_after();
                 }
-                TMARK(5);
                 TRACE(warp_idx, j, 4);
                 tmem_st_32x32b_x32(tmem_p, pk);          // keys  0..63  -> P columns  0..31
-#if LTXV_ATTN_PINGPONG == 2
-                if (two) warp_mbar_arrive(&turn[1 - t], lane);  // early release: half of this phase still to go
-#endif
-                exp_chunk_v3(s2, c2, negm2, l2a, l2b, pk);
-#if LTXV_ATTN_PINGPONG == 3
-                if (two) warp_mbar_arrive(&turn[1 - t], lane);  // early release: a quarter of this phase still to go
-#endif
-                exp_chunk_v3(s3, c2, negm2, l2a, l2b, pk + 16);
-#if LTXV_ATTN_PINGPONG == 1
-                if (two) warp_mbar_arrive(&turn[1 - t], lane);
-#endif
-                tmem_st_32x32b_x32(tmem_p + 32, pk);     // keys 64..127 -> P columns 32..63
+                tmem_st_32x32b_x32(tmem_p + 32, pk2);    // keys 64..127 -> P columns 32..63
                 TMARK(6);
                 tmem_st_wait();
                 tcgen05_fence_before();
@@ -1079,12 +1030,423 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
     if (threadIdx.x == 0 && item == 0) g_attn_trace[9][19][5] = static_cast<long long>(globaltimer_ns());
 #endif
-    if (warp_idx == kTmemWarp) {
+    if (warp_idx == 11) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
 }
 
+
+// ================================================================================================
+// v4 (head_dim 64, long key sequences): the v3 organisation with HALF a score row per softmax thread.  OPT-IN
+// (LTXV_ATTN_V4 / option attn_v4): correct (tools/attn_test passes on it) but measured SLOWER than v3 -- 744 vs 820
+// TFLOP/s at the batched c2 launch, 828 vs 911 at c3 -- so it documents a negative result rather than a fast path: four
+// softmax warps per sub-partition do not raise the issue rate; the extra per-warp barrier / exchange instructions
+// cost more than the added interleaving buys (fewer polynomial exponentials help it, more hurt it: issue-bound).
+//
+// clock64 traces of v3 (tools/attn_prof.cu) show that a softmax warp needs ~2200 cycles for the ~700 instructions of a
+// key tile even when it never waits: with only two softmax warps per SM sub-partition the dependent MUFU / FMA / F2FP
+// chains leave the issue port idle half of the time (ncu: issue 51 %, XU 56 %, tensor 37 %).  Here every 128-row query
+// tile is served by EIGHT warps instead of four -- warps q and q + 4 of a tile share TMEM lane quadrant q and take key
+// columns [0, 64) and [64, 128) of the same rows -- so each sub-partition interleaves four softmax warps.  The two halves
+// of a row exchange their partial row maximum through shared memory (one 64-thread named barrier per key tile) and keep
+// private partial row sums that are combined once at the end; everything else (P in TMEM, TS-form P V, lazy O rescale,
+// tail splitting) is as in v3.
+//   warps  0..15  softmax: tile t = w >> 3, half h = (w >> 2) & 1, quadrant = w & 3   (112 registers)
+//   warp   16     TMA producer;  17, 18  UMMA issuers of tile 0 / 1;  19  TMEM owner   (32 registers)
+// ================================================================================================
+constexpr int kV4Threads = 640;
+constexpr int kV4Stages = 5;  // 227 KB of shared memory: 5 K/V stages + the 6 KB of row-max / row-sum exchange buffers
+constexpr int kV4RingBytes = 2 * kV2QBytes + 2 * kV4Stages * kV2KVBytes + 512;
+constexpr int kV4SmemBytes = kV4RingBytes + 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4;  // + xmax[2][2][2][128] + xsum[2][2][128]
+
+// 32 scores -> exp2(s*c - m) -> row-sum (packed) -> 16 bf16x2 words; a polynomial share of LTXV_ATTN_POLY4 pairs per 8
+#ifndef LTXV_ATTN_POLY4
+#define LTXV_ATTN_POLY4 2
+#endif
+__device__ __forceinline__ void exp_chunk_v4(const uint32_t (&r)[32], uint64_t c2, uint64_t negm2, uint64_t& l2a,
+                                             uint64_t& l2b, uint32_t* out16) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        float x0, x1, x2, x3;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, negm2), x0, x1);
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, negm2), x2, x3);
+        float e0, e1, e2, e3;
+        constexpr int kOrder[8] = {7, 3, 5, 1, 6, 2, 4, 0};
+        bool poly_a = false, poly_b = false;
+#pragma unroll
+        for (int q = 0; q < LTXV_ATTN_POLY4; ++q) {
+            poly_a = poly_a || (kOrder[q] == ((i >> 1) & 7));
+            poly_b = poly_b || (kOrder[q] == (((i >> 1) + 1) & 7));
+        }
+        if (poly_a) {
+            ex2_poly_pair(x0, x1, e0, e1);
+        } else {
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+        }
+        if (poly_b) {
+            ex2_poly_pair(x2, x3, e2, e3);
+        } else {
+            e2 = ex2_approx(x2);
+            e3 = ex2_approx(x3);
+        }
+        l2a = add_f32x2(l2a, pack_f32x2(e0, e1));
+        l2b = add_f32x2(l2b, pack_f32x2(e2, e3));
+        out16[i / 2] = pack_bf16x2(e0, e1);
+        out16[i / 2 + 1] = pack_bf16x2(e2, e3);
+    }
+}
+
+__global__ void __launch_bounds__(kV4Threads, 1)
+flash_attn4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ AttnParams p,
+                   const SplitPlan sp) {
+    constexpr int D = 64;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sq = smem;
+    uint8_t* sk = sq + 2 * kV2QBytes;
+    uint8_t* sv = sk + kV4Stages * kV2KVBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sv + kV4Stages * kV2KVBytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;                   // [St]
+    uint64_t* k_empty = bars + 1 + kV4Stages;      // [St]  one arrival per active query tile
+    uint64_t* v_full = bars + 1 + 2 * kV4Stages;   // [St]
+    uint64_t* v_empty = bars + 1 + 3 * kV4Stages;  // [St]  one arrival per active query tile
+    uint64_t* s_full = bars + 1 + 4 * kV4Stages;   // [2]  S_t landed in TMEM
+    uint64_t* s_free = s_full + 2;                 // [2]  S_t copied to registers (8 warp arrivals)
+    uint64_t* p_full = s_free + 2;                 // [2]  P_t stored to TMEM (8 warp arrivals)
+    uint64_t* pv_done = p_full + 2;                // [2]  O_t += P_t V retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    volatile uint32_t* split_flag = tmem_slot + 1;  // 1 = this CTA drew the last ticket of its split unit
+    float* xmax = reinterpret_cast<float*>(smem + kV4RingBytes);  // [slot 2][tile 2][half 2][row 128]
+    float* xsum = xmax + 2 * 2 * 2 * 128;                         // [tile 2][half 2][row 128]
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x;
+    const int first_split = sp.n_units - sp.n_split_units;
+    int unit = item, split = 0;
+    const bool is_split = item >= first_split;
+    if (is_split) {
+        unit = first_split + (item - first_split) / sp.nsplit;
+        split = (item - first_split) % sp.nsplit;
+    }
+    const int qb = unit % sp.n_qb;
+    const int head = (unit / sp.n_qb) % p.H;
+    const int batch = unit / (sp.n_qb * p.H);
+    const int q0 = qb * (2 * kTileQ);
+    const int n_tiles_all = (p.Skv + kTileKV - 1) / kTileKV;
+    const int jt0 = is_split ? (split * n_tiles_all) / sp.nsplit : 0;
+    const int jt1 = is_split ? ((split + 1) * n_tiles_all) / sp.nsplit : n_tiles_all;
+    const int n_tiles = jt1 - jt0;
+    const bool two = (q0 + kTileQ) < p.Sq;
+    const int nt = two ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {
+            printf("ltxv attention v4: dynamic smem base not 1024B aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < kV4Stages; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], nt);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], nt);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&s_free[t], 8);  // one arrival per softmax warp of the tile
+            mbar_init(&p_full[t], 8);
+            mbar_init(&pv_done[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 19) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();
+
+    if (warp_idx >= 16) {
+        // setmaxnreg.inc can only take registers that other warps of the CTA released: the launch allocates 640 x 96, the
+        // control warpgroup gives back 128 x (96 - 32) = 8192 = the 512 x (112 - 96) the softmax warps ask for
+        setmaxnreg_dec<32>();
+        if (warp_idx == 16) {
+            // ===================== TMA producer =====================
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, nt * kV2QBytes);
+                tma_load_3d(sq, &tm_q, q_full, p.q_col0 + head * D, q0, batch);
+                if (two) tma_load_3d(sq + kV2QBytes, &tm_q, q_full, p.q_col0 + head * D, q0 + kTileQ, batch);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_tiles; ++j) {
+                    const int kv0 = (jt0 + j) * kTileKV;
+                    if (j + kV4Stages + kV3L2Ahead - 1 < n_tiles) {
+                        const int kvp = kv0 + (kV4Stages + kV3L2Ahead - 1) * kTileKV;
+                        tma_prefetch_3d(&tm_k, p.k_col0 + head * D, kvp, batch);
+                        tma_prefetch_3d(&tm_v, p.v_col0 + head * D, kvp, batch);
+                    }
+                    mbar_wait_sleep(&k_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&k_full[stage], kV2KVBytes);
+                    tma_load_3d(sk + stage * kV2KVBytes, &tm_k, &k_full[stage], p.k_col0 + head * D, kv0, batch);
+                    mbar_wait_sleep(&v_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&v_full[stage], kV2KVBytes);
+                    tma_load_3d(sv + stage * kV2KVBytes, &tm_v, &v_full[stage], p.v_col0 + head * D, kv0, batch);
+                    if (++stage == kV4Stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        } else if (warp_idx == 17 || (warp_idx == 18 && two)) {
+            // ===================== UMMA issuer of query tile t =====================
+            const int t = warp_idx - 17;
+            if (elect_one()) {
+                constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV, false, false);
+                constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, D, false, true);  // B = V is MN-major
+                const uint32_t tmem_s = tmem_base + t * 128;
+                const uint32_t tmem_o = tmem_base + 256 + t * 64;
+                const uint32_t tmem_p = tmem_base + 384 + t * 64;
+                const uint64_t desc_k0 = make_smem_desc_sw128(0, 1024, 0);
+                const uint64_t desc_v0 = make_smem_desc_sw128(0, 1024, kTileKV * 128);
+                const uint64_t desc_q = make_smem_desc_sw128(smem_u32(sq) + t * kV2QBytes, 1024, 0);
+                const uint32_t sk_a = smem_u32(sk) >> 4, sv_a = smem_u32(sv) >> 4;
+                auto issue_s = [&](int stage) {
+                    const uint64_t dk = desc_k0 + (sk_a + stage * (kV2KVBytes >> 4));
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_bf16_ss(tmem_s, desc_q + ks * 2, dk + ks * 2, idesc_s, ks != 0 ? 1u : 0u);
+                };
+                mbar_wait_sleep(q_full, 0);
+                mbar_wait_sleep(&k_full[0], 0);
+                tcgen05_fence_after();
+                issue_s(0);
+                umma_commit(&s_full[t]);
+                umma_commit(&k_empty[0]);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_tiles; ++j) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == kV4Stages) {
+                        nstage = 0;
+                        nphase ^= 1;
+                    }
+                    if (j + 1 < n_tiles) {
+                        mbar_wait_sleep(&k_full[nstage], nphase);
+                        mbar_wait_sleep(&s_free[t], j & 1);
+                        tcgen05_fence_after();
+                        issue_s(nstage);
+                        umma_commit(&s_full[t]);
+                        umma_commit(&k_empty[nstage]);
+                    }
+                    mbar_wait_sleep(&v_full[stage], phase);
+                    mbar_wait_sleep(&p_full[t], j & 1);
+                    tcgen05_fence_after();
+                    const uint64_t dv = desc_v0 + (sv_a + stage * (kV2KVBytes >> 4));
+#pragma unroll
+                    for (int ks = 0; ks < kTileKV / 16; ++ks)
+                        umma_bf16_ts(tmem_o, tmem_p + ks * 8, dv + ks * ((16 * 128) >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                    umma_commit(&pv_done[t]);
+                    umma_commit(&v_empty[stage]);
+                    stage = nstage;
+                    phase = nphase;
+                }
+            }
+        }
+    } else {
+        setmaxnreg_inc<112>();
+        const int t = warp_idx >> 3;         // query tile
+        const int half = (warp_idx >> 2) & 1;  // key columns [64 half, 64 half + 64) of every tile
+        if (t == 0 || two) {
+            const int quad = warp_idx & 3;
+            const int row = quad * 32 + lane;
+            const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+            const uint32_t tmem_s = lane_base + t * 128 + half * 64;
+            const uint32_t tmem_o = lane_base + 256 + t * 64 + half * 32;   // this thread's 32 of the 64 O columns
+            const uint32_t tmem_p = lane_base + 384 + t * 64 + half * 32;   // 64 keys -> 32 packed columns
+            const int pair_bar = 1 + t * 4 + quad;                          // named barrier of the two half-row warps
+            float* my_max = xmax + (t * 2 + half) * 128 + row;              // + slot * 512
+            const float* other_max = xmax + (t * 2 + (half ^ 1)) * 128 + row;
+            const float c = p.scale * kLog2e;
+            const uint64_t c2 = pack_f32x2(c, c);
+            float m_used = -INFINITY;
+            uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+            uint32_t sfull_probe = 0;
+            auto tile = [&](int j, auto tail_tag) {
+                constexpr bool TAIL = decltype(tail_tag)::value;
+                const int kv0 = (jt0 + j) * kTileKV + half * 64;
+                uint32_t s0[32], s1[32];
+                if (!__shfl_sync(0xffffffffu, sfull_probe, 0)) warp_mbar_wait(&s_full[t], j & 1, lane);
+                sfull_probe = 0;
+                tcgen05_fence_after();
+                tmem_ld_32x32b_x32(tmem_s + 0, s0);
+                tmem_ld_32x32b_x32(tmem_s + 32, s1);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                warp_mbar_arrive(&s_free[t], lane);  // S_t may be overwritten by the next QK^T
+                float mx = fmaxf(max32_v3<TAIL>(s0, kv0, p.Skv), max32_v3<TAIL>(s1, kv0 + 32, p.Skv));
+                // the other half of the row lives in warp (w ^ 4): exchange the partial maxima (double-buffered slot)
+                my_max[(j & 1) * 512] = mx;
+                named_bar_sync(pair_bar, 64);
+                mx = fmaxf(mx, other_max[(j & 1) * 512]) * c;
+                bool pv_waited = (j == 0);
+                if (j == 0) {
+                    m_used = mx;
+                } else {
+                    const float m_new = fmaxf(m_used, mx);
+                    // both halves see the same maxima and the same m_used: the decision is identical in both warps
+                    if (__any_sync(0xffffffffu, (m_new - m_used) > kRescaleThreshold)) {
+                        warp_mbar_wait(&pv_done[t], (j - 1) & 1, lane);
+                        pv_waited = true;
+                        tcgen05_fence_after();
+                        const float alpha = ex2_approx(m_used - m_new);
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tmem_o, r);  // this half rescales its own 32 O columns
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st_32x32b_x32(tmem_o, r);
+                        tmem_st_wait();
+                        const uint64_t a2 = pack_f32x2(alpha, alpha), z2 = pack_f32x2(0.f, 0.f);
+                        l2a = fma_f32x2(l2a, a2, z2);
+                        l2b = fma_f32x2(l2b, a2, z2);
+                        m_used = m_new;
+                    }
+                }
+                const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
+                uint32_t pk[32];
+                uint32_t pv_probe = 0;
+                exp_chunk_v4(s0, c2, negm2, l2a, l2b, pk);
+                if (!pv_waited && lane == 0) pv_probe = mbar_test_wait(&pv_done[t], (j - 1) & 1);
+                if (j + 1 < n_tiles && lane == 0) sfull_probe = mbar_test_wait(&s_full[t], (j + 1) & 1);
+                exp_chunk_v4(s1, c2, negm2, l2a, l2b, pk + 16);
+                if (!pv_waited) {
+                    // P_t is single-buffered: P_t V(j-1) must have read it before it is overwritten
+                    if (!__shfl_sync(0xffffffffu, pv_probe, 0)) warp_mbar_wait(&pv_done[t], (j - 1) & 1, lane);
+                    tcgen05_fence_after();
+                }
+                tmem_st_32x32b_x32(tmem_p, pk);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                warp_mbar_arrive(&p_full[t], lane);
+            };
+            const bool ragged = (jt1 == n_tiles_all) && (p.Skv % kTileKV != 0);
+            const int n_full = n_tiles - (ragged ? 1 : 0);
+            for (int j = 0; j < n_full; ++j) tile(j, std::false_type{});
+            if (ragged) tile(n_full, std::true_type{});
+            // row sum: this half's partial + the other half's
+            float la, lb, lc, ld;
+            unpack_f32x2(l2a, la, lb);
+            unpack_f32x2(l2b, lc, ld);
+            float l_row = (la + lb) + (lc + ld);
+            xsum[(t * 2 + half) * 128 + row] = l_row;
+            named_bar_sync(pair_bar, 64);
+            {
+                // add in a fixed order (half 0 first) so that both halves hold the same bits
+                const float l0 = xsum[(t * 2 + 0) * 128 + row], l1 = xsum[(t * 2 + 1) * 128 + row];
+                l_row = l0 + l1;
+            }
+            warp_mbar_wait(&pv_done[t], (n_tiles - 1) & 1, lane);
+            tcgen05_fence_after();
+            const int qrow = q0 + t * kTileQ + row;
+            __nv_bfloat16* orow = attn_out_row(p, batch, qrow < p.Sq ? qrow : 0, head, D) + half * 32;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_o, r);
+            tmem_ld_wait();
+            if (!is_split) {
+                const float inv_l = 1.0f / l_row;
+                if (qrow < p.Sq) store_row_bf16(orow, r, inv_l);
+            } else {
+                // ---- split unit: publish (O unnormalised, m, l) of this key range; the LAST of the nsplit CTAs of the
+                // unit (ticket counter) merges all partials and writes the output rows ----
+                const int su = unit - first_split;
+                const int r256 = t * kTileQ + row;
+                float4* mine = reinterpret_cast<float4*>(sp.scratch) +
+                               static_cast<int64_t>(su * sp.nsplit + split) * (kSplitCols4 * 256) + r256;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    mine[(half * 8 + q) * 256] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                if (half == 0) mine[16 * 256] = make_float4(m_used, l_row, 0.f, 0.f);
+                __threadfence();
+                named_bar_sync(9, 256 * nt);  // all softmax threads of the CTA have published
+                if (threadIdx.x == 0) {
+                    const int ticket = atomicAdd(sp.counters + su, 1);
+                    *split_flag = (ticket == sp.nsplit - 1) ? 1 : 0;
+                    if (ticket == sp.nsplit - 1) sp.counters[su] = 0;  // re-arm for the next launch on this stream
+                    __threadfence();
+                }
+                named_bar_sync(9, 256 * nt);
+                if (*split_flag != 0) {
+                    const float4* base = reinterpret_cast<const float4*>(sp.scratch) +
+                                         static_cast<int64_t>(su * sp.nsplit) * (kSplitCols4 * 256) + r256;
+                    constexpr int64_t stride = kSplitCols4 * 256;
+                    float4 ml[kMaxSplit];
+#pragma unroll
+                    for (int i = 0; i < kMaxSplit; ++i)
+                        ml[i] = i < sp.nsplit ? __ldcg(base + i * stride + 16 * 256) : make_float4(-INFINITY, 0.f, 0.f, 0.f);
+                    float m_all = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < kMaxSplit; ++i) m_all = fmaxf(m_all, ml[i].x);
+                    float wgt[kMaxSplit];
+                    float l_all = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kMaxSplit; ++i) {
+                        wgt[i] = i < sp.nsplit ? ex2_approx(ml[i].x - m_all) : 0.f;
+                        l_all = fmaf(ml[i].y, wgt[i], l_all);
+                    }
+                    const float inv_l = 1.0f / l_all;
+#pragma unroll 1
+                    for (int dc = 0; dc < 2; ++dc) {  // this half's 32 output columns, 16 at a time
+                        float acc[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < kMaxSplit; ++i) {
+                            if (i < sp.nsplit) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 v = __ldcg(base + i * stride + (half * 8 + dc * 4 + q) * 256);
+                                    acc[4 * q + 0] = fmaf(v.x, wgt[i], acc[4 * q + 0]);
+                                    acc[4 * q + 1] = fmaf(v.y, wgt[i], acc[4 * q + 1]);
+                                    acc[4 * q + 2] = fmaf(v.z, wgt[i], acc[4 * q + 2]);
+                                    acc[4 * q + 3] = fmaf(v.w, wgt[i], acc[4 * q + 3]);
+                                }
+                            }
+                        }
+                        if (qrow < p.Sq) {
+                            uint4* d4 = reinterpret_cast<uint4*>(orow + dc * 16);
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                uint4 u;
+                                u.x = pack_bf16x2(acc[8 * q + 0] * inv_l, acc[8 * q + 1] * inv_l);
+                                u.y = pack_bf16x2(acc[8 * q + 2] * inv_l, acc[8 * q + 3] * inv_l);
+                                u.z = pack_bf16x2(acc[8 * q + 4] * inv_l, acc[8 * q + 5] * inv_l);
+                                u.w = pack_bf16x2(acc[8 * q + 6] * inv_l, acc[8 * q + 7] * inv_l);
+                                d4[q] = u;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 19) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
 
 // ================================================================================================
 // Self-attention, head_dim 128 (the 13B preset: 32 heads x 128).  Same organisation as flash_attn3_kernel (two query
@@ -1619,6 +1981,8 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
         cudaError_t e =
             cudaFuncSetAttribute(flash_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV3SmemBytes);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(flash_attn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV4SmemBytes);
+        if (e != cudaSuccess) return e;
         configured.mark(cfg_dev);
     }
     CUtensorMap tq, tk, tv;
@@ -1664,8 +2028,14 @@ cudaError_t launch_attn3_impl(const AttnParams& p, cudaStream_t stream) {
     const int n_items = sp.n_units - sp.n_split_units + sp.n_split_units * sp.nsplit;
     {
         ProfScope prof(PROF_ATTN_SELF, 4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * 64, stream);
-        LTXV_TRACE_VARIANT("flash_attn3_kernel nsplit=%d split_units=%d", sp.nsplit, sp.n_split_units);
-        cudaError_t le = launch_pdl(flash_attn3_kernel, dim3(n_items), dim3(kV3Threads), kV3SmemBytes, stream, tq, tk, tv, p, sp);
+        cudaError_t le;
+        if (!options().attn_v4) {
+            LTXV_TRACE_VARIANT("flash_attn3_kernel nsplit=%d split_units=%d", sp.nsplit, sp.n_split_units);
+            le = launch_pdl(flash_attn3_kernel, dim3(n_items), dim3(kV3Threads), kV3SmemBytes, stream, tq, tk, tv, p, sp);
+        } else {
+            LTXV_TRACE_VARIANT("flash_attn4_kernel nsplit=%d split_units=%d", sp.nsplit, sp.n_split_units);
+            le = launch_pdl(flash_attn4_kernel, dim3(n_items), dim3(kV4Threads), kV4SmemBytes, stream, tq, tk, tv, p, sp);
+        }
         if (le != cudaSuccess) return le;
     }
     g_attn_launches.fetch_add(1, std::memory_order_relaxed);

@@ -76,6 +76,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking phase test (never suspends).  The result predicate is produced asynchronously by the SYNCS unit: issued
+// early and consumed later, its ~150-cycle latency hides behind whatever the thread does in between.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
 // try_wait with an explicit suspend-time hint (ns): the thread sleeps IN HARDWARE until the phase completes or the hint
 // expires, instead of returning after the (very short) default slice.  A control warp that spins on plain try_wait
 // issues TRYWAIT+BRA back to back and steals issue slots from the compute warps on its scheduler.
@@ -99,7 +114,14 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait_hint(bar, parity, LTXV_MBAR_HINT_NS)) {
+#ifdef LTXV_MBAR_DEBUG
+        if (++spins > 20000u) {
+            printf("ltxv: mbarrier timeout block=%d thread=%d bar@%u parity=%u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+#else
         if (++spins > 400000u) __trap();  // >= several seconds with a 20 us slice
+#endif
     }
 }
 

@@ -18,6 +18,7 @@ const Entry kEntries[] = {
     {"gemm_k2", "LTXV_GEMM_K2", &Options::gemm_k2, false},
     {"gemm_no_short_k", "LTXV_GEMM_NO_SHORT_K_RULE", &Options::gemm_no_short_k, false},
     {"attn_v1", "LTXV_ATTN_V1", &Options::attn_v1, false},
+    {"attn_v4", "LTXV_ATTN_V4", &Options::attn_v4, false},
     {"attn_nosplit", "LTXV_ATTN_NOSPLIT", &Options::attn_nosplit, false},
     {"attn_nsplit_max", "LTXV_ATTN_NSPLIT", &Options::attn_nsplit_max, true},
     {"vae_no_fused_prep", "LTXV_VAE_NO_FUSED_PREP", &Options::vae_no_fused_prep, false},

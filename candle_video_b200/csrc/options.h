@@ -12,6 +12,7 @@ struct Options {
     int gemm_k2;             // LTXV_GEMM_K2: two k-blocks per stage (opt-in)
     int gemm_no_short_k;     // LTXV_GEMM_NO_SHORT_K_RULE: no 128x192 preference for the short-K N = K = 2048 projections
     int attn_v1;             // LTXV_ATTN_V1: general attention kernel everywhere
+    int attn_v4;             // LTXV_ATTN_V4: half a score row per softmax thread (flash_attn4_kernel; measured slower)
     int attn_nosplit;        // LTXV_ATTN_NOSPLIT: no key-range tail splitting
     int attn_nsplit_max;     // LTXV_ATTN_NSPLIT=n: cap on key ranges per tail unit (0 = no cap)
     int vae_no_fused_prep;   // LTXV_VAE_NO_FUSED_PREP: no fused producer epilogue at all
