@@ -21,6 +21,14 @@ enum EpiMode : int {
     // x = bf16(acc + bias (+ residual)) is stored to `out` if non-null, then pixel-norm / (1+scale)x+shift / SiLU of x
     // goes to the zero-bordered, T-replicated padded volume `norm_out` (what vae_prep_kernel would have produced).
     EPI_CONV_NORM_PAD = 6,
+    // Linear + the weight / rotation half of the q,k RMS-norm + RoPE (ltx_transformer.rs:671-678, :314-339): for the
+    // leading `qk_cols` columns (q, or q|k of the fused QKV projection, each `qk_dim` wide)
+    //   v = acc + bias;  ss[row] += v^2;  y = v * w[col];  (y0, y1) <- (y0 cos - y1 sin, y1 cos + y0 sin)
+    // is stored as bf16; the per-row scalar rsqrt(mean(v^2) + eps) commutes with both steps and is applied by the
+    // consumer (attention: folded into the softmax scale of the row for q; one pass over k for k).  The remaining
+    // columns (v of the QKV projection) are a plain bf16 store.  ss goes to qk_ss[row, first 64-column group of the
+    // tile] (the other groups of the tile are written as 0): consumers add the qk_dim / 64 entries of a row in order.
+    EPI_QKV_ROPE = 7,
 };
 
 enum ActMode : int { ACT_NONE = 0, ACT_GELU_TANH = 1 };
@@ -58,6 +66,15 @@ struct GemmParams {
     void* norm_halo_up;        // H-slab decode: neighbour buffers receiving this slab's first / last row, or null
     void* norm_halo_dn;
     int norm_halo_up_h, norm_halo_dn_h;  // slab rows H of those neighbours (ragged slabs); 0 = same as this slab
+
+    // ---- EPI_QKV_ROPE ----
+    int qk_cols, qk_dim;        // treated columns (qk_dim or 2 qk_dim) and the width of q (= of k): multiples of 64
+    const float* qk_w[2];       // f32 [qk_dim] norm weights of q and of k
+    const float* rope_cos;      // f32 [rope_rows, qk_dim / 2] or null (no rotation: cross-attention queries)
+    const float* rope_sin;
+    int rope_rows;              // table row of output row m is m % rope_rows (batched CFG: both halves share the table)
+    int rope_row0;              // ... + rope_row0 (sequence-parallel shard: first token of this rank)
+    float* qk_ss;               // f32 [M, qk_cols / 64] sums of squares per 64-column group (see EPI_QKV_ROPE)
 };
 
 // A: [rows_a, K_a] bf16 row-major (K contiguous). B: [N, K] bf16 row-major (nn.Linear weight layout).

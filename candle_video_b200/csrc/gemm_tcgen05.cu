@@ -246,7 +246,8 @@ __device__ __forceinline__ void epilogue_load_residual(const GemmParams& p, int 
 }
 
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, int m_warp0, int col0, int lane,
-                                                         float (&v)[32], float* stage, const float4 (&res)[8]) {
+                                                         float (&v)[32], float* stage, const float4 (&res)[8],
+                                                         float (&ss)[8]) {
     float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiRowFloats);
 #pragma unroll
     for (int i = 0; i < 8; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -271,7 +272,31 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
         v4.z += b.z;
         v4.w += b.w;
         if (m >= p.M) continue;
-        if (p.epi == EPI_STORE_BF16) {
+        if (p.epi == EPI_QKV_ROPE) {
+            if (col < p.qk_cols) {
+                ss[i] += (v4.x * v4.x + v4.y * v4.y) + (v4.z * v4.z + v4.w * v4.w);
+                const int which = col >= p.qk_dim ? 1 : 0;
+                const int cc = col - which * p.qk_dim;
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.qk_w[which] + cc));
+                v4.x *= w4.x;
+                v4.y *= w4.y;
+                v4.z *= w4.z;
+                v4.w *= w4.w;
+                if (p.rope_cos != nullptr) {
+                    // interleaved pairs: rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]; f32 math (ltx_transformer.rs:314-339)
+                    const int64_t tr = (static_cast<int64_t>(m % p.rope_rows) + p.rope_row0) * (p.qk_dim >> 1) + (cc >> 1);
+                    const float2 cs = __ldg(reinterpret_cast<const float2*>(p.rope_cos + tr));
+                    const float2 sn = __ldg(reinterpret_cast<const float2*>(p.rope_sin + tr));
+                    const float x0 = v4.x, x1 = v4.y, x2 = v4.z, x3 = v4.w;
+                    v4.x = x0 * cs.x - x1 * sn.x;
+                    v4.y = x1 * cs.x + x0 * sn.x;
+                    v4.z = x2 * cs.y - x3 * sn.y;
+                    v4.w = x3 * cs.y + x2 * sn.y;
+                }
+            }
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col) =
+                make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+        } else if (p.epi == EPI_STORE_BF16) {
             if (p.act == ACT_GELU_TANH) {
                 v4.x = gelu_tanh_f32(v4.x);
                 v4.y = gelu_tanh_f32(v4.y);
@@ -294,6 +319,26 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
         }
     }
     __syncwarp();  // the tile is rewritten by the next chunk
+}
+
+// EPI_QKV_ROPE: per-row sums of squares of one tile (lane owns 4 columns of rows 4i + lane/8): add the 8 lanes of a row
+// group and store the total at the tile's first 64-column group; the tile's other groups get 0.
+__device__ __forceinline__ void epilogue_store_row_ss(const GemmParams& p, int m_warp0, int n0, int tile_n, int lane,
+                                                      float (&ss)[8]) {
+    if (n0 >= p.qk_cols) return;
+    const int groups_total = p.qk_cols >> 6;
+    const int g0 = n0 >> 6, g = lane & 7, rsub = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float t = ss[i];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        const int64_t m = m_warp0 + 4 * i + rsub;
+        if (m < p.M && g < (tile_n >> 6) && g0 + g < groups_total)
+            p.qk_ss[m * groups_total + g0 + g] = g == 0 ? t : 0.f;
+        ss[i] = 0.f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -603,10 +648,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== epilogue =====================
         const int quad = warp_idx & 3;
         float* stage = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256) + quad * (32 * kEpiRowFloats);
-        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32) &&
+        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32 ||
+                                           p.epi == EPI_QKV_ROPE) &&
                                (p.N % 32 == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
+        float row_ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // EPI_QKV_ROPE: sums of squares of this tile's rows
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const Tile t = tile_coords(tile, num_m);
             const int n0 = t.n0 * BLOCK_N;
@@ -635,7 +682,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage, res);
+                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage, res, row_ss);
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
@@ -649,6 +696,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (prefetch_res && c + 2 < BLOCK_N / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
                     chunk(c + 1, res_b);
                 }
+                if (p.epi == EPI_QKV_ROPE) epilogue_store_row_ss(p, m_warp0, n0, BLOCK_N, lane, row_ss);
             }
             if (++acc == 2) {
                 acc = 0;
@@ -851,13 +899,15 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ===================== epilogue (both CTAs: this CTA's 128 rows of the tile) =====================
         const int quad = warp_idx & 3;
         float* stage_buf = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + 256) + quad * (32 * kEpiRowFloats);
-        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32) &&
+        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32 ||
+                                           p.epi == EPI_QKV_ROPE) &&
                                (p.N % 32 == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr int kEpiGroups = PairThreads<MODE>::value == 384 ? 2 : 1;
         const int epi_group = (warp_idx - 4) >> 2;
         int it = 0;
+        float row_ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // EPI_QKV_ROPE: sums of squares of this tile's rows
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             if (kEpiGroups == 2) {  // group g owns accumulator stage g: tiles g, g+2, g+4, ... of this cluster
                 if ((it & 1) != epi_group) continue;
@@ -889,7 +939,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage_buf, res);
+                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage_buf, res, row_ss);
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
@@ -903,6 +953,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (prefetch_res && c + 2 < kPairBlockN / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
                     chunk(c + 1, res_b);
                 }
+                if (p.epi == EPI_QKV_ROPE) epilogue_store_row_ss(p, m_warp0, n0, kPairBlockN, lane, row_ss);
             }
             if (kEpiGroups == 1 && ++acc == 2) {
                 acc = 0;
@@ -1010,6 +1061,14 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
                      p.norm_out == p.a_ptr || p.norm_tf < 1 || p.norm_tf > 3 ||
                      (p.norm_scale == nullptr) != (p.norm_shift == nullptr)))
         return cudaErrorInvalidValue;
+    if (p.epi == EPI_QKV_ROPE) {
+        if (p.conv || p.N % 64 != 0 || p.qk_dim <= 0 || p.qk_dim % 64 != 0 || (p.qk_cols != p.qk_dim && p.qk_cols != 2 * p.qk_dim) ||
+            p.qk_cols > p.N || p.qk_w[0] == nullptr || (p.qk_cols > p.qk_dim && p.qk_w[1] == nullptr) || p.qk_ss == nullptr ||
+            (p.rope_cos == nullptr) != (p.rope_sin == nullptr) || (p.rope_cos != nullptr && p.rope_rows <= 0))
+            return cudaErrorInvalidValue;
+    }
+    // a tile of the fused QKV projection must not straddle the q | k | v boundaries (one sum of squares per tile)
+    const bool qk_tiles = p.epi == EPI_QKV_ROPE && p.qk_cols > p.qk_dim;
     if (block_n == -2) return launch_pair_impl<256, 0>(ops, p, stream);
     if (block_n == -3) return launch_pair_impl<128, 0>(ops, p, stream);
     if (block_n == -4) return launch_pair_impl<256, 1>(ops, p, stream);   // conv3d, three kw taps per step
@@ -1031,6 +1090,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             const int c = cands[i];
             if (c > 64 && p.N <= c / 2) continue;
             if (norm_pad && (c < p.N || (c != 128 && c != 256))) continue;
+            if (qk_tiles && p.qk_dim % c != 0) continue;
             const int tiles = num_m * ((p.N + c - 1) / c);
             const int rounds = (tiles + sms - 1) / sms;
             const double cost = rounds * static_cast<double>(c) / rate[i];
@@ -1045,19 +1105,19 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         // TFLOP/s with the bf16 store, 890 vs 866 with the f32 residual epilogue, tools/bin/gemm_test 3).
         const bool no_short_k_rule = options().gemm_no_short_k != 0;
         const bool short_k_192 = !no_short_k_rule && !p.conv && p.K <= 2048 && p.N <= 2048 && p.N % 192 != 0 &&
-                                 p.N > 1024 && p.M >= 8192;
+                                 p.N > 1024 && p.M >= 8192 && !qk_tiles;
         if (short_k_192) block_n = 192;
         if (!short_k_192 && p.M > 2 * kBlockM && !options().gemm_no_pair) {
             const int num_mp = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
             int pair_bn = 0;
-            if (p.N % 256 == 0) {
+            if (p.N % 256 == 0 && !(qk_tiles && p.qk_dim % 256 != 0)) {
                 const int rounds = (num_mp * (p.N / 256) + sms / 2 - 1) / (sms / 2);
                 if (rounds * 256.0 / 1.00 <= best) {
                     best = rounds * 256.0;
                     pair_bn = 256;
                 }
             }
-            if (p.N % 128 == 0 && !(norm_pad && p.N > 128)) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
+            if (p.N % 128 == 0 && !(norm_pad && p.N > 128) && !(qk_tiles && p.qk_dim % 128 != 0)) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
                 const int rounds = (num_mp * (p.N / 128) + sms / 2 - 1) / (sms / 2);
                 if (rounds * 128.0 / 0.80 < best) {
                     best = rounds * 128.0 / 0.80;
