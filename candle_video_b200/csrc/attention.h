@@ -26,6 +26,10 @@ struct AttnParams {
     void* out_peer[8];
     int out_rows_per_peer;
     int out_col0;
+    // Deferred RMS-norm of the queries (producer: GEMM epilogue EPI_QKV_ROPE, gemm.h): q holds w * q (rotated) WITHOUT the
+    // per-row factor rsqrt(mean(q^2) + eps); q_rscale != null -> f32 [B * Sq] factors, the scores of query row r of batch
+    // b are scaled by q_rscale[b Sq + r].  The factor commutes with q k^T, so it is folded into the row's softmax scale.
+    const float* q_rscale;
 };
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);

@@ -47,6 +47,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 
+// per-row factor of the deferred q RMS-norm (AttnParams::q_rscale); 1 when the queries arrive normalised
+__device__ __forceinline__ float q_row_scale(const AttnParams& p, int batch, int qrow) {
+    if (p.q_rscale == nullptr) return 1.0f;
+    if (qrow >= p.Sq) qrow = p.Sq - 1;  // rows of a ragged last tile: any finite value
+    return __ldg(p.q_rscale + static_cast<int64_t>(batch) * p.Sq + qrow);
+}
+
 __device__ __forceinline__ __nv_bfloat16* attn_out_row(const AttnParams& p, int batch, int qrow, int head, int D) {
     if (p.out_rows_per_peer > 0) {
         const int owner = qrow / p.out_rows_per_peer;
@@ -218,7 +225,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
         const uint32_t tmem_s = lane_base;
         const uint32_t tmem_o = lane_base + kOCol;
-        const float c = p.scale * kLog2e;
+        const float c = p.scale * kLog2e * q_row_scale(p, batch, q0 + row);
+        const float inv_c = kLog2e / c;  // bias is added to the UNSCALED scores below, in units of 1 / (scale of this row)
         const float* bias = (p.kv_bias != nullptr) ? p.kv_bias + static_cast<int64_t>(batch) * p.Skv : nullptr;
         uint8_t* prow = sp + row * 128;
         const int sw = row & 7;
@@ -245,7 +253,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     for (int i = 0; i < 32; ++i) {
                         const int col = kv0 + cc * 32 + i;
                         float x = __uint_as_float(r[i]);
-                        if (bias != nullptr && col < p.Skv) x += __ldg(bias + col) * (1.0f / p.scale);
+                        if (bias != nullptr && col < p.Skv) x += __ldg(bias + col) * inv_c;
                         if (col >= p.Skv) x = -INFINITY;
                         mx = fmaxf(mx, x);
                     }
@@ -781,7 +789,7 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             const uint32_t tmem_s = lane_base + t * 128;
             const uint32_t tmem_o = lane_base + 256 + t * 64;
             const uint32_t tmem_p = lane_base + 384 + t * 64;
-            const float c = p.scale * kLog2e;
+            const float c = p.scale * kLog2e * q_row_scale(p, batch, q0 + t * kTileQ + row);
             const uint64_t c2 = pack_f32x2(c, c);
             float m_used = -INFINITY;
             uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
@@ -1275,7 +1283,7 @@ flash_attn4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             const int pair_bar = 1 + t * 4 + quad;                          // named barrier of the two half-row warps
             float* my_max = xmax + (t * 2 + half) * 128 + row;              // + slot * 512
             const float* other_max = xmax + (t * 2 + (half ^ 1)) * 128 + row;
-            const float c = p.scale * kLog2e;
+            const float c = p.scale * kLog2e * q_row_scale(p, batch, q0 + t * kTileQ + row);
             const uint64_t c2 = pack_f32x2(c, c);
             float m_used = -INFINITY;
             uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
@@ -1635,7 +1643,7 @@ flash_attn3_d128_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             const uint32_t tmem_s = lane_base + t * 128;
             const uint32_t tmem_o = lane_base + 256 + t * 128;
             const uint32_t tmem_p = tmem_s;
-            const float c = p.scale * kLog2e;
+            const float c = p.scale * kLog2e * q_row_scale(p, batch, q0 + t * kTileQ + row);
             const uint64_t c2 = pack_f32x2(c, c);
             float m_used = -INFINITY;
             uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
@@ -1865,10 +1873,10 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         const uint32_t tmem_s = lane_base + g * 128;
         const uint32_t tmem_o = lane_base + 256 + g * 64;
         const uint32_t tmem_p = lane_base + 384 + g * 64;
-        const float c = p.scale * kLog2e;
-        const uint64_t c2 = pack_f32x2(c, c);
         const uint64_t one2 = pack_f32x2(1.0f, 1.0f);
         for (int j = 0; j < n; ++j) {
+            const float c = p.scale * kLog2e * q_row_scale(p, batch, (qt0 + 2 * j + g) * kTileQ + row);
+            const uint64_t c2 = pack_f32x2(c, c);
             uint32_t s0[32], s1[32], s2[32], s3[32];
             warp_mbar_wait(&s_full[g], j & 1, lane);
             tcgen05_fence_after();

@@ -17,6 +17,7 @@
 #include "attention.h"
 #include "gemm.h"
 #include "glue.h"
+#include "options.h"
 
 namespace ltxv {
 
@@ -207,6 +208,10 @@ void LtxVideoTransformer3DModel::ensure_workspace(int S) {
         cos_.ensure(sd / 2 * 4);
         sin_.ensure(sd / 2 * 4);
         out_f32_.ensure(static_cast<size_t>(S) * cfg_.out_channels * 4);
+        qk_ss_.ensure(static_cast<size_t>(S) * (2 * D / 64) * 4);  // sums of squares of q | k per 64-column group
+        q2_ss_.ensure(static_cast<size_t>(S) * (D / 64) * 4);
+        q_rs_.ensure(static_cast<size_t>(S) * 4);  // per-row factors of the deferred q norms (self / cross)
+        q2_rs_.ensure(static_cast<size_t>(S) * 4);
         ws_S_ = S;
     }
     small_.ensure((256 + 2 * static_cast<size_t>(D) + 6 * D + static_cast<size_t>(L) * 6 * D + 2 * D) * 4);
@@ -220,10 +225,12 @@ void LtxVideoTransformer3DModel::ensure_workspace(int S) {
             const size_t Dg = static_cast<size_t>(D) / sp_count_;
             const size_t q = comm_->alloc(static_cast<size_t>(S) * sp_count_ * 3 * Dg * 2);
             const size_t a = comm_->alloc(static_cast<size_t>(S) * D * 2);
-            it = sp_allocs_.emplace(key, std::make_pair(q, a)).first;
+            const size_t r = comm_->alloc(static_cast<size_t>(S) * sp_count_ * 4);  // q row sums of ALL tokens
+            it = sp_allocs_.emplace(key, std::vector<size_t>{q, a, r}).first;
         }
-        sp_qkv_off_ = it->second.first;
-        sp_attn_off_ = it->second.second;
+        sp_qkv_off_ = it->second[0];
+        sp_attn_off_ = it->second[1];
+        sp_qss_off_ = it->second[2];
         sp_S_ = S;
     }
 }
@@ -243,6 +250,33 @@ void LtxVideoTransformer3DModel::gemm(const void* a, int64_t a_rows, const Linea
     p.gate = gate;
     p.out = out;
     p.res_f32 = res;
+    LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
+}
+
+// Linear whose epilogue also applies the norm weight (and RoPE) of the q / k RMS-norm and emits the rows' sums of
+// squares (EPI_QKV_ROPE, gemm.h); the per-row rsqrt is applied by the consumers.
+void LtxVideoTransformer3DModel::gemm_qk(const void* a, const LinearW& lin, int M, int qk_cols, const float* wq,
+                                         const float* wk, const float* cos_t, const float* sin_t, int rope_rows,
+                                         int rope_row0, void* out, float* ss, cudaStream_t s) {
+    GemmOperands ops{a, M, lin.K, lin.w, lin.N, lin.K};
+    GemmParams p{};
+    p.M = M;
+    p.N = lin.N;
+    p.K = lin.K;
+    p.num_k_blocks = (lin.K + 63) / 64;
+    p.epi = EPI_QKV_ROPE;
+    p.ldo = lin.N;
+    p.bias = lin.b;
+    p.out = out;
+    p.qk_cols = qk_cols;
+    p.qk_dim = inner_dim();
+    p.qk_w[0] = wq;
+    p.qk_w[1] = wk;
+    p.rope_cos = cos_t;
+    p.rope_sin = sin_t;
+    p.rope_rows = rope_rows;
+    p.rope_row0 = rope_row0;
+    p.qk_ss = ss;
     LTXV_CUDA(launch_gemm_bf16(ops, p, 0, s));
 }
 
@@ -417,11 +451,23 @@ void LtxVideoTransformer3DModel::forward_impl(const DitContext* ctx1, int nb, co
 
         // --- self-attention ---
         LTXV_CUDA(launch_norm_modulate(x, h_.p, a6 + 1 * D, a6 + 0 * D, M, D, cfg_.norm_eps, NORM_RMS, s));
-        gemm(h_.p, M, b.qkv1, M, EPI_STORE_BF16, ACT_NONE, qkv_.p, nullptr, nullptr, s);
+        // fused path: the QKV epilogue applies norm weight + RoPE and emits sum(q^2), sum(k^2) per row; the row factors
+        // are applied by one pass over k and inside the attention kernel for q (ltx_transformer.rs:671-678)
+        const bool fused_qk = !options().qk_unfused && D % 64 == 0 && D / 64 <= 64;
+        const int ssn = D / 64;  // 64-column groups of q (= of k)
+        if (fused_qk)
+            gemm_qk(h_.p, b.qkv1, M, 2 * D, b.norm_q1, b.norm_k1, cos_.as<float>(), sin_.as<float>(), S, 0, qkv_.p,
+                    qk_ss_.as<float>(), s);
+        else
+            gemm(h_.p, M, b.qkv1, M, EPI_STORE_BF16, ACT_NONE, qkv_.p, nullptr, nullptr, s);
         const void* attn1_out = attn_.p;
         if (!sp) {
-            LTXV_CUDA(launch_qk_pair_norm_rope(qkv_.p, 3 * D, M, D, b.norm_q1, b.norm_k1, 1e-5f, cos_.as<float>(),
-                                               sin_.as<float>(), s, S));
+            if (fused_qk)
+                LTXV_CUDA(launch_k_rms_scale(qkv_.p, 3 * D, D, M, D, qk_ss_.as<float>(), 2 * ssn, ssn, 1e-5f,
+                                             q_rs_.as<float>(), s));
+            else
+                LTXV_CUDA(launch_qk_pair_norm_rope(qkv_.p, 3 * D, M, D, b.norm_q1, b.norm_k1, 1e-5f, cos_.as<float>(),
+                                                   sin_.as<float>(), s, S));
             AttnParams ap{};
             ap.q = ap.k = ap.v = qkv_.p;
             ap.ldq = ap.ldk = ap.ldv = 3 * D;
@@ -437,15 +483,24 @@ void LtxVideoTransformer3DModel::forward_impl(const DitContext* ctx1, int nb, co
             ap.Skv = S;
             ap.D = hd;
             ap.scale = attn_scale;
+            if (fused_qk) ap.q_rscale = q_rs_.as<float>();
             LTXV_CUDA(launch_attention(ap, s));
         } else {
-            // Ulysses: tokens -> heads.  The norm+RoPE kernel stores each head group straight into the rank that owns
-            // those heads; the attention epilogue stores each query block straight into the rank that owns those tokens.
+            // Ulysses: tokens -> heads.  The norm+RoPE (or, on the fused path, the k-scale) kernel stores each head group
+            // straight into the rank that owns those heads; the attention epilogue stores each query block straight into
+            // the rank that owns those tokens.
             const int Dg = D / spn;
             ScatterDst dst{};
             for (int g = 0; g < spn; ++g) dst.p[g] = comm_->peer(sp_first_ + g, sp_qkv_off_);
-            LTXV_CUDA(launch_qkv_norm_rope_scatter(qkv_.p, S, D, spn, spr * S, b.norm_q1, b.norm_k1, 1e-5f,
-                                                   cos_.as<float>(), sin_.as<float>(), dst, s));
+            if (fused_qk) {
+                ScatterDst qdst{};
+                for (int g = 0; g < spn; ++g) qdst.p[g] = comm_->peer(sp_first_ + g, sp_qss_off_);
+                LTXV_CUDA(launch_qkv_scatter_scaled(qkv_.p, S, D, spn, spr * S, qk_ss_.as<float>(), 2 * ssn, ssn, 1e-5f, dst,
+                                                    qdst, s));
+            } else {
+                LTXV_CUDA(launch_qkv_norm_rope_scatter(qkv_.p, S, D, spn, spr * S, b.norm_q1, b.norm_k1, 1e-5f,
+                                                       cos_.as<float>(), sin_.as<float>(), dst, s));
+            }
             comm_->barrier(s, 1, sp_first_, spn);
             AttnParams ap{};
             ap.q = ap.k = ap.v = comm_->local(sp_qkv_off_);
@@ -462,6 +517,7 @@ void LtxVideoTransformer3DModel::forward_impl(const DitContext* ctx1, int nb, co
             ap.Skv = S * spn;
             ap.D = hd;
             ap.scale = attn_scale;
+            if (fused_qk) ap.q_rscale = static_cast<const float*>(comm_->local(sp_qss_off_));
             for (int g = 0; g < spn; ++g) ap.out_peer[g] = comm_->peer(sp_first_ + g, sp_attn_off_);
             ap.out_rows_per_peer = S;
             ap.out_col0 = spr * Dg;
@@ -472,8 +528,13 @@ void LtxVideoTransformer3DModel::forward_impl(const DitContext* ctx1, int nb, co
         gemm(attn1_out, M, b.out1, M, EPI_RESIDUAL_F32, ACT_NONE, xb_.p, x, a6 + 2 * D, s);  // x += gate_msa * attn1
 
         // --- cross-attention (no norm, no gate, no RoPE; :903-909) ---
-        gemm(xb_.p, M, b.q2, M, EPI_STORE_BF16, ACT_NONE, q2_.p, nullptr, nullptr, s);
-        LTXV_CUDA(launch_qk_norm_rope(q2_.p, D, 0, M, D, b.norm_q2, 1e-5f, nullptr, nullptr, s));
+        if (fused_qk) {
+            gemm_qk(xb_.p, b.q2, M, D, b.norm_q2, nullptr, nullptr, nullptr, 0, 0, q2_.p, q2_ss_.as<float>(), s);
+            LTXV_CUDA(launch_row_rscale(q2_ss_.as<float>(), ssn, ssn, M, D, 1e-5f, q2_rs_.as<float>(), s));
+        } else {
+            gemm(xb_.p, M, b.q2, M, EPI_STORE_BF16, ACT_NONE, q2_.p, nullptr, nullptr, s);
+            LTXV_CUDA(launch_qk_norm_rope(q2_.p, D, 0, M, D, b.norm_q2, 1e-5f, nullptr, nullptr, s));
+        }
         {
             const __nv_bfloat16* kv =
                 nb == 1 ? ctx1->kv.as<__nv_bfloat16>() + static_cast<size_t>(l) * ctxK * 2 * D
@@ -496,6 +557,7 @@ void LtxVideoTransformer3DModel::forward_impl(const DitContext* ctx1, int nb, co
             ap.Skv = ctxK;
             ap.D = hd;
             ap.scale = attn_scale;
+            if (fused_qk) ap.q_rscale = q2_rs_.as<float>();
             LTXV_CUDA(launch_attention(ap, s));
         }
         gemm(attn_.p, M, b.out2, M, EPI_RESIDUAL_F32, ACT_NONE, nullptr, x, nullptr, s);  // x += attn2

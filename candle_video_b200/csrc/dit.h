@@ -87,6 +87,8 @@ private:
     void ensure_workspace(int S);
     void gemm(const void* a, int64_t a_rows, const LinearW& lin, int M, int epi, int act, void* out, float* res,
               const float* gate, cudaStream_t s);
+    void gemm_qk(const void* a, const LinearW& lin, int M, int qk_cols, const float* wq, const float* wk, const float* cos_t,
+                 const float* sin_t, int rope_rows, int rope_row0, void* out, float* ss, cudaStream_t s);
 
     ltxv_dit_config cfg_;
     int device_;
@@ -111,7 +113,7 @@ private:
 
     // workspace
     int ws_S_ = 0;
-    DevBuf x_, xb_, h_, qkv_, attn_, q2_, ff_, a_in_, cos_, sin_, out_f32_, orig_;
+    DevBuf x_, xb_, h_, qkv_, attn_, q2_, ff_, a_in_, cos_, sin_, out_f32_, orig_, qk_ss_, q2_ss_, q_rs_, q2_rs_;
     DevBuf small_;  // tp[256] | t1[D] | e[D] | temb[6D] | ada[L*6D] | fin[2D]
     DevBuf enc_bf16_, cap_mid_, enc_proj_;
 
@@ -121,7 +123,8 @@ private:
     int sp_S_ = 0;                       // local token capacity of the symmetric buffers
     uint64_t sp_alloc_comm_ = 0;         // communicator id / group size the symmetric buffers were carved for
     int sp_alloc_count_ = 0;
-    std::map<std::vector<int64_t>, std::pair<size_t, size_t>> sp_allocs_;
+    std::map<std::vector<int64_t>, std::vector<size_t>> sp_allocs_;  // (comm id, group size, S) -> (qkv, attn, q row sums) offsets
+    size_t sp_qss_off_ = 0;  // heap offset of the gathered q row sums [S_total] (fused q/k epilogue path)
     PipeWs pipe_ws_;
     std::map<std::vector<int64_t>, std::vector<size_t>> pipe_allocs_;  // pipeline_denoise_parallel exchange buffers  // (comm id, group size, S) -> (qkv, attn) offsets
     size_t sp_qkv_off_ = 0, sp_attn_off_ = 0;  // heap offsets: qkv_full [S_total, 3*D/N], attn_in [S_local, D]

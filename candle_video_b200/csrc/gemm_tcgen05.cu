@@ -245,6 +245,7 @@ __device__ __forceinline__ void epilogue_load_residual(const GemmParams& p, int 
     }
 }
 
+template <bool QK>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, int m_warp0, int col0, int lane,
                                                          float (&v)[32], float* stage, const float4 (&res)[8],
                                                          float (&ss)[8]) {
@@ -272,30 +273,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
         v4.z += b.z;
         v4.w += b.w;
         if (m >= p.M) continue;
-        if (p.epi == EPI_QKV_ROPE) {
-            if (col < p.qk_cols) {
-                ss[i] += (v4.x * v4.x + v4.y * v4.y) + (v4.z * v4.z + v4.w * v4.w);
-                const int which = col >= p.qk_dim ? 1 : 0;
-                const int cc = col - which * p.qk_dim;
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.qk_w[which] + cc));
-                v4.x *= w4.x;
-                v4.y *= w4.y;
-                v4.z *= w4.z;
-                v4.w *= w4.w;
-                if (p.rope_cos != nullptr) {
-                    // interleaved pairs: rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]; f32 math (ltx_transformer.rs:314-339)
-                    const int64_t tr = (static_cast<int64_t>(m % p.rope_rows) + p.rope_row0) * (p.qk_dim >> 1) + (cc >> 1);
-                    const float2 cs = __ldg(reinterpret_cast<const float2*>(p.rope_cos + tr));
-                    const float2 sn = __ldg(reinterpret_cast<const float2*>(p.rope_sin + tr));
-                    const float x0 = v4.x, x1 = v4.y, x2 = v4.z, x3 = v4.w;
-                    v4.x = x0 * cs.x - x1 * sn.x;
-                    v4.y = x1 * cs.x + x0 * sn.x;
-                    v4.z = x2 * cs.y - x3 * sn.y;
-                    v4.w = x3 * cs.y + x2 * sn.y;
-                }
-            }
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col) =
-                make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+        if (QK) {
+            continue;  // handled below (all table loads of the chunk are issued before the first use)
         } else if (p.epi == EPI_STORE_BF16) {
             if (p.act == ACT_GELU_TANH) {
                 v4.x = gelu_tanh_f32(v4.x);
@@ -316,6 +295,53 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
             if (p.out != nullptr)
                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col) =
                     make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+        }
+    }
+    if constexpr (QK) {
+        // EPI_QKV_ROPE (see gemm.h).  x[] holds acc (bias not yet added); rows 4i + rsub, columns col .. col + 3.
+        const bool treat = col < p.qk_cols;
+        const int which = col >= p.qk_dim ? 1 : 0;
+        const int cc = col - which * p.qk_dim;
+        float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        float2 cs[8], sn[8];
+        const bool rot = treat && p.rope_cos != nullptr;
+        if (treat) w4 = __ldg(reinterpret_cast<const float4*>(p.qk_w[which] + cc));
+        if (rot) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int64_t m = m_warp0 + 4 * i + rsub;
+                if (m >= p.M) m = p.M - 1;
+                const int64_t tr = (static_cast<int64_t>(m % p.rope_rows) + p.rope_row0) * (p.qk_dim >> 1) + (cc >> 1);
+                cs[i] = __ldg(reinterpret_cast<const float2*>(p.rope_cos + tr));
+                sn[i] = __ldg(reinterpret_cast<const float2*>(p.rope_sin + tr));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t m = m_warp0 + 4 * i + rsub;
+            float4 v4 = x[i];
+            v4.x += b.x;
+            v4.y += b.y;
+            v4.z += b.z;
+            v4.w += b.w;
+            if (m >= p.M) continue;
+            if (treat) {
+                ss[i] += (v4.x * v4.x + v4.y * v4.y) + (v4.z * v4.z + v4.w * v4.w);
+                v4.x *= w4.x;
+                v4.y *= w4.y;
+                v4.z *= w4.z;
+                v4.w *= w4.w;
+                if (rot) {
+                    // interleaved pairs: rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]; f32 math (ltx_transformer.rs:314-339)
+                    const float x0 = v4.x, x1 = v4.y, x2 = v4.z, x3 = v4.w;
+                    v4.x = x0 * cs[i].x - x1 * sn[i].x;
+                    v4.y = x1 * cs[i].x + x0 * sn[i].x;
+                    v4.z = x2 * cs[i].y - x3 * sn[i].y;
+                    v4.w = x3 * cs[i].y + x2 * sn[i].y;
+                }
+            }
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col) =
+                make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
         }
     }
     __syncwarp();  // the tile is rewritten by the next chunk
@@ -536,7 +562,7 @@ __device__ __forceinline__ void conv_kblock(const GemmParams& p, int kb, int& a_
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, bool QK = false>  // QK: the EPI_QKV_ROPE epilogue (its own instances: the others carry none of its code)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ GemmParams p) {
@@ -648,8 +674,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== epilogue =====================
         const int quad = warp_idx & 3;
         float* stage = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256) + quad * (32 * kEpiRowFloats);
-        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32 ||
-                                           p.epi == EPI_QKV_ROPE) &&
+        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32 || QK) &&
                                (p.N % 32 == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -682,7 +707,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage, res, row_ss);
+                    if (coalesced) epilogue_chunk_coalesced<QK>(p, m_warp0, col0, lane, v, stage, res, row_ss);
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
@@ -696,7 +721,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (prefetch_res && c + 2 < BLOCK_N / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
                     chunk(c + 1, res_b);
                 }
-                if (p.epi == EPI_QKV_ROPE) epilogue_store_row_ss(p, m_warp0, n0, BLOCK_N, lane, row_ss);
+                if constexpr (QK) epilogue_store_row_ss(p, m_warp0, n0, BLOCK_N, lane, row_ss);
             }
             if (++acc == 2) {
                 acc = 0;
@@ -734,7 +759,9 @@ constexpr int kABoxBytes3 = kBoxRows3 * kBlockK * 2;   // bytes one KW3 A box tr
 
 // MODE 0: one 64-wide k-block per pipeline stage; MODE 1: KW3 (above); MODE 2: TWO k-blocks per stage (8 MMAs per
 // full/empty barrier round trip instead of 4 -- the plain GEMMs ran at 71 % tensor-pipe activity against 99 % for KW3).
-template <int BN, int MODE>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
+// QK (EPI_QKV_ROPE instances): TWO epilogue warpgroups like the conv variants -- its epilogue (norm weight, RoPE table
+// reads, sums of squares) outlasts the K = 2048 main loop with one -- each with its own transpose tiles; one stage less.
+template <int BN, int MODE, bool QK = false>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
 struct PairCfg {
     static constexpr bool KW3 = MODE == 1;
     static constexpr int kKbPerStage = MODE == 2 ? 2 : 1;
@@ -743,9 +770,9 @@ struct PairCfg {
     static constexpr int kBStage = KW3 ? 3 * kBBytes : kKbPerStage * kBBytes;
     static constexpr int kStageBytes = kAStage + kBStage;
     static constexpr int kTxBytes = (KW3 ? kABoxBytes3 : kKbPerStage * kABytes) + kBStage;  // bytes ONE CTA credits per stage
-    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 6 : 8) / kKbPerStage;
+    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : ((BN == 256 ? 6 : 8) - (QK ? 1 : 0)) / kKbPerStage;
     static constexpr int kTmemCols = 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiStageBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + (QK ? 2 : 1) * kEpiStageBytes;
     static_assert(BN == 256 || BN == 128, "pair tile width");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -753,15 +780,15 @@ struct PairCfg {
 // The conv variants (MODE 1) run TWO epilogue warpgroups, one per TMEM accumulator stage, on alternating tiles: with one
 // warp per scheduler the epilogue is latency-bound (a 128x128 tile with residual, x store and the fused producer takes
 // ~16 us against an 11 us main loop at C = 128), and two groups give every tile two main loops of time.
-template <int MODE>
+template <int MODE, bool QK = false>
 struct PairThreads {
-    static constexpr int value = MODE == 1 ? 384 : kThreads;
+    static constexpr int value = (MODE == 1 || QK) ? 384 : kThreads;
 };
-template <int BN, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairThreads<MODE>::value, 1)
+template <int BN, int MODE, bool QK = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairThreads<MODE, QK>::value, 1)
 gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ GemmParams p) {
-    using PC = PairCfg<BN, MODE>;
+    using PC = PairCfg<BN, MODE, QK>;
     constexpr bool KW3 = PC::KW3;
     constexpr int kKbPerStage = PC::kKbPerStage;
     constexpr int kPairBlockN = BN;
@@ -898,13 +925,14 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp_idx >= 4) {
         // ===================== epilogue (both CTAs: this CTA's 128 rows of the tile) =====================
         const int quad = warp_idx & 3;
-        float* stage_buf = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + 256) + quad * (32 * kEpiRowFloats);
-        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32 ||
-                                           p.epi == EPI_QKV_ROPE) &&
+        // one transpose tile per epilogue WARP (two warpgroups in the QK instances)
+        float* stage_buf = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + 256) +
+                           (QK ? warp_idx - 4 : quad) * (32 * kEpiRowFloats);
+        const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32 || QK) &&
                                (p.N % 32 == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        constexpr int kEpiGroups = PairThreads<MODE>::value == 384 ? 2 : 1;
+        constexpr int kEpiGroups = PairThreads<MODE, QK>::value == 384 ? 2 : 1;
         const int epi_group = (warp_idx - 4) >> 2;
         int it = 0;
         float row_ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // EPI_QKV_ROPE: sums of squares of this tile's rows
@@ -939,7 +967,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (coalesced) epilogue_chunk_coalesced(p, m_warp0, col0, lane, v, stage_buf, res, row_ss);
+                    if (coalesced) epilogue_chunk_coalesced<QK>(p, m_warp0, col0, lane, v, stage_buf, res, row_ss);
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
@@ -953,7 +981,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (prefetch_res && c + 2 < kPairBlockN / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
                     chunk(c + 1, res_b);
                 }
-                if (p.epi == EPI_QKV_ROPE) epilogue_store_row_ss(p, m_warp0, n0, kPairBlockN, lane, row_ss);
+                if constexpr (QK) epilogue_store_row_ss(p, m_warp0, n0, kPairBlockN, lane, row_ss);
             }
             if (kEpiGroups == 1 && ++acc == 2) {
                 acc = 0;
@@ -972,14 +1000,14 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
 std::atomic<uint64_t> g_launches{0};
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool QK = false>
 cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
     using C = Cfg<BLOCK_N>;
     static PerDeviceOnce configured;
     int cfg_dev = 0;
     static int num_sms = 0;
     if (configured.need(&cfg_dev)) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::kSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -1001,7 +1029,7 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
         if (p.conv) flops = 2.0 * p.T * static_cast<double>(p.H) * p.W * static_cast<double>(p.N) * p.K;  // unpadded voxels
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
         LTXV_TRACE_VARIANT("%s<%d> epi=%d", p.conv ? "conv3d:gemm_bf16_tn_kernel" : "gemm_bf16_tn_kernel", BLOCK_N, p.epi);
-        cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BLOCK_N>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, ta, tb, p);
+        cudaError_t le = launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, QK>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, ta, tb, p);
         if (le != cudaSuccess) return le;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1009,15 +1037,15 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
 }
 
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool QK = false>
 cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
-    using PC = PairCfg<BN, MODE>;
+    using PC = PairCfg<BN, MODE, QK>;
     constexpr bool KW3 = PC::KW3;
     static PerDeviceOnce configured;
     int cfg_dev = 0;
     static int num_sms = 0;
     if (configured.need(&cfg_dev)) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, MODE, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PC::kSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -1042,7 +1070,7 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
         LTXV_TRACE_VARIANT("%s<%d,%d> epi=%d", p.conv ? "conv3d:gemm_pair_bf16_tn_kernel" : "gemm_pair_bf16_tn_kernel", BN, MODE,
                            p.epi);
-        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE>, dim3(2 * clusters), dim3(PairThreads<MODE>::value), PC::kSmemBytes,
+        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE, QK>, dim3(2 * clusters), dim3(PairThreads<MODE, QK>::value), PC::kSmemBytes,
                                     stream, ta, tb, p);
         if (le != cudaSuccess) return le;
     }
@@ -1069,6 +1097,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
     }
     // a tile of the fused QKV projection must not straddle the q | k | v boundaries (one sum of squares per tile)
     const bool qk_tiles = p.epi == EPI_QKV_ROPE && p.qk_cols > p.qk_dim;
+    if (p.epi == EPI_QKV_ROPE && block_n != 0) return cudaErrorInvalidValue;  // tile width is chosen here
     if (block_n == -2) return launch_pair_impl<256, 0>(ops, p, stream);
     if (block_n == -3) return launch_pair_impl<128, 0>(ops, p, stream);
     if (block_n == -4) return launch_pair_impl<256, 1>(ops, p, stream);   // conv3d, three kw taps per step
@@ -1128,10 +1157,21 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             if (norm_pad && !kw3) pair_bn = 0;  // only the KW3 pair kernels carry the fused producer epilogue
             // two k-blocks per stage measured neutral (1341 vs 1353 TFLOP/s on the QKV shape): opt-in only
             const bool k2 = !p.conv && p.num_k_blocks % 2 == 0 && options().gemm_k2 != 0;
+            if (p.epi == EPI_QKV_ROPE && pair_bn == 256) return launch_pair_impl<256, 0, true>(ops, p, stream);
+            if (p.epi == EPI_QKV_ROPE && pair_bn == 128) return launch_pair_impl<128, 0, true>(ops, p, stream);
             if (pair_bn == 256)
                 return kw3 ? launch_pair_impl<256, 1>(ops, p, stream)
                            : (k2 ? launch_pair_impl<256, 2>(ops, p, stream) : launch_pair_impl<256, 0>(ops, p, stream));
             if (pair_bn == 128) return kw3 ? launch_pair_impl<128, 1>(ops, p, stream) : launch_pair_impl<128, 0>(ops, p, stream);
+        }
+    }
+    if (p.epi == EPI_QKV_ROPE) {
+        switch (block_n) {
+            case 256: return launch_impl<256, true>(ops, p, stream);
+            case 192: return launch_impl<192, true>(ops, p, stream);
+            case 128: return launch_impl<128, true>(ops, p, stream);
+            case 64: return launch_impl<64, true>(ops, p, stream);
+            default: return cudaErrorInvalidValue;
         }
     }
     switch (block_n) {

@@ -435,6 +435,95 @@ qkv_norm_rope_scatter_kernel(const __nv_bfloat16* __restrict__ x, int rows, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Deferred k RMS-norm (EPI_QKV_ROPE producers, gemm.h): k arrives as w * k (rotated) without its per-row factor; one
+// in-place pass multiplies every k row by rsqrt(mean(k^2) + eps), the mean taken from the epilogue's sums of squares.
+// 4 B / element (the pass it replaces moved 8 B / element of q and k plus the f32 RoPE table).
+// ------------------------------------------------------------------------------------------------
+// sum of the n <= 64 group sums of a row, by a whole warp: lane l takes entries l and l + 32, then a xor-shuffle tree.
+// Every kernel that needs a row factor goes through this one function, so a row's factor has the same bits everywhere.
+__device__ __forceinline__ float warp_row_sumsq(const float* __restrict__ ss, int n, int lane) {
+    float t = lane < n ? __ldg(ss + lane) : 0.f;
+    if (lane + 32 < n) t += __ldg(ss + lane + 32);
+    return warp_sum(t);
+}
+__device__ __forceinline__ uint4 scale_bf16x8(uint4 u, float r) {
+    u.x = pack_bf16x2(bf16_lo(u.x) * r, bf16_hi(u.x) * r);
+    u.y = pack_bf16x2(bf16_lo(u.y) * r, bf16_hi(u.y) * r);
+    u.z = pack_bf16x2(bf16_lo(u.z) * r, bf16_hi(u.z) * r);
+    u.w = pack_bf16x2(bf16_lo(u.w) * r, bf16_hi(u.w) * r);
+    return u;
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_rms_scale_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int rows, int D, const float* __restrict__ ss,
+                   int ss_ld, int ss_n, float eps, float* __restrict__ q_rscale) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* srow = ss + static_cast<int64_t>(row) * ss_ld;  // ss_n groups of q, then ss_n groups of k
+    const float invD = 1.0f / static_cast<float>(D);
+    const float rq = rsqrtf(warp_row_sumsq(srow, ss_n, lane) * invD + eps);
+    const float r = rsqrtf(warp_row_sumsq(srow + ss_n, ss_n, lane) * invD + eps);
+    if (lane == 0) q_rscale[row] = rq;
+    uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + col0);
+    const int nv = D >> 3;
+    // all loads of the row in flight before the first store (D = 2048: 8 x 16 B per lane)
+    for (int i0 = lane; i0 < nv; i0 += 8 * 32) {
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k * 32 < nv) u[k] = xr[i0 + k * 32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k * 32 < nv) xr[i0 + k * 32] = scale_bf16x8(u[k], r);
+    }
+}
+
+// factor of rows whose tensor needs no pass of its own (cross-attention queries): out[row] = rsqrt(sum / D + eps)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+row_rscale_kernel(const float* __restrict__ ss, int ss_ld, int ss_n, int rows, int D, float eps, float* __restrict__ out) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float r = rsqrtf(warp_row_sumsq(ss + static_cast<int64_t>(row) * ss_ld, ss_n, lane) / static_cast<float>(D) + eps);
+    if (lane == 0) out[row] = r;
+}
+
+// Ulysses scatter of the fused-epilogue layout: q (as is), k (times its row factor, same arithmetic as
+// k_rms_scale_kernel) and v are copied head-group-wise into the peers' [S_total, 3 D / nranks] buffers; the row's q
+// factor goes to EVERY peer's q_rscale[S_total] (the attention of each head group needs the factor of all its queries).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+qkv_scatter_scaled_kernel(const __nv_bfloat16* __restrict__ x, int rows, int D, int nranks, int row0,
+                          const float* __restrict__ ss, int ss_ld, int ss_n, float eps, ScatterDst dst, ScatterDst q_rs_dst) {
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = D >> 3;
+    const int Dg = D / nranks;
+    const int64_t drow = static_cast<int64_t>(row0 + row) * 3 * Dg;
+    const float* srow = ss + static_cast<int64_t>(row) * ss_ld;
+    const float invD = 1.0f / static_cast<float>(D);
+    const float rq = rsqrtf(warp_row_sumsq(srow, ss_n, lane) * invD + eps);
+    const float rk = rsqrtf(warp_row_sumsq(srow + ss_n, ss_n, lane) * invD + eps);
+    if (lane < nranks) reinterpret_cast<float*>(q_rs_dst.p[lane])[row0 + row] = rq;
+#pragma unroll 1
+    for (int which = 0; which < 3; ++which) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * 3 * D + which * D);
+        for (int i = lane; i < nv; i += 32) {
+            uint4 u = xr[i];
+            if (which == 1) u = scale_bf16x8(u, rk);
+            const int col = i * 8;
+            const int g = col / Dg;
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst.p[g]) + drow + which * Dg + (col - g * Dg);
+            *reinterpret_cast<uint4*>(d) = u;  // NVLink peer store (or local when g == rank)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // RoPE table
 // ------------------------------------------------------------------------------------------------
 __global__ void rope_table_kernel(const float* __restrict__ coords, int F, int H, int W, float m0, float m1, float m2,
@@ -771,6 +860,37 @@ cudaError_t launch_qkv_norm_rope_scatter(const void* x, int rows, int D, int nra
     if (D % (8 * nranks) != 0 || cos_t == nullptr || sin_t == nullptr) return cudaErrorInvalidValue;
     qkv_norm_rope_scatter_kernel<<<blocks_for(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), rows, D, nranks, row0, wq, wk, eps, cos_t, sin_t, dst);
+    return done();
+}
+
+cudaError_t launch_k_rms_scale(void* x, int64_t ld, int col0, int rows, int D, const float* ss, int ss_ld, int ss_n,
+                               float eps, float* q_rscale, cudaStream_t s) {
+    if (D % 8 != 0 || ld % 8 != 0 || col0 % 8 != 0 || ss == nullptr || q_rscale == nullptr || ss_n <= 0 || ss_n > 64)
+        return cudaErrorInvalidValue;
+    ProfScope prof(PROF_QK_ROPE, 4.0 * rows * D, s);  // bf16 in + out
+    LTXV_TRACE_VARIANT("k_rms_scale_kernel");
+    launch_pdl(k_rms_scale_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
+               reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, D, ss, ss_ld, ss_n, eps, q_rscale);
+    return done();
+}
+
+cudaError_t launch_row_rscale(const float* ss, int ss_ld, int ss_n, int rows, int D, float eps, float* out,
+                              cudaStream_t s) {
+    if (ss == nullptr || out == nullptr || ss_n <= 0 || ss_n > 64) return cudaErrorInvalidValue;
+    ProfScope prof(PROF_QK_ROPE, 4.0 * rows * (ss_n + 1), s);
+    LTXV_TRACE_VARIANT("row_rscale_kernel");
+    launch_pdl(row_rscale_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s, ss, ss_ld, ss_n,
+               rows, D, eps, out);
+    return done();
+}
+
+cudaError_t launch_qkv_scatter_scaled(const void* x, int rows, int D, int nranks, int row0, const float* ss, int ss_ld,
+                                      int ss_n, float eps, const ScatterDst& dst, const ScatterDst& q_rs_dst,
+                                      cudaStream_t s) {
+    if (D % (8 * nranks) != 0 || ss == nullptr || nranks > 8 || ss_n <= 0 || ss_n > 64) return cudaErrorInvalidValue;
+    LTXV_TRACE_VARIANT("qkv_scatter_scaled_kernel");
+    qkv_scatter_scaled_kernel<<<blocks_for(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), rows, D, nranks, row0, ss, ss_ld, ss_n, eps, dst, q_rs_dst);
     return done();
 }
 

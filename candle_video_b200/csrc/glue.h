@@ -41,6 +41,20 @@ cudaError_t launch_qkv_norm_rope_scatter(const void* x_bf16, int rows, int D, in
                                          const float* wk, float eps, const float* cos_t, const float* sin_t,
                                          const ScatterDst& dst, cudaStream_t s);
 
+// Deferred q/k RMS-norm of the fused QKV epilogue (EPI_QKV_ROPE, gemm.h).  ss [rows, ss_ld] holds ss_n <= 64 group sums
+// of squares of q followed by ss_n of k.  k: x[row, col0 .. col0+D) *= rsqrt(sum_k / D + eps), in place, bf16;
+// q: the factor itself goes to q_rscale[row] (the attention kernels fold it into the softmax scale).
+cudaError_t launch_k_rms_scale(void* x_bf16, int64_t ld, int col0, int rows, int D, const float* ss, int ss_ld, int ss_n,
+                               float eps, float* q_rscale, cudaStream_t s);
+// out[row] = rsqrt(sum of ss[row, 0 .. ss_n) / D + eps)   (cross-attention queries: no pass over the tensor at all)
+cudaError_t launch_row_rscale(const float* ss, int ss_ld, int ss_n, int rows, int D, float eps, float* out, cudaStream_t s);
+// Ulysses scatter for that layout: x [rows, 3D] holds q (unscaled), k (unscaled), v.  q and v are copied, k is scaled
+// like launch_k_rms_scale, all head-group-wise into dst[g] (layout as above); the q factors go to
+// q_rscale_dst[every rank][row0 + r].
+cudaError_t launch_qkv_scatter_scaled(const void* x_bf16, int rows, int D, int nranks, int row0, const float* ss,
+                                      int ss_ld, int ss_n, float eps, const ScatterDst& dst,
+                                      const ScatterDst& q_rscale_dst, cudaStream_t s);
+
 // y[n] = act_out( sum_k act_in(x[k]) * W[n,k] + b[n] ),  W bf16 [N,K], x/y f32; batch rows handled by the caller.
 enum GemvAct : int { GEMV_NONE = 0, GEMV_SILU = 1 };
 cudaError_t launch_gemv(const float* x, const void* w_bf16, const float* bias, float* y, int N, int K, int act_in,

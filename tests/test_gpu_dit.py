@@ -158,3 +158,32 @@ def test_dit_error_paths(cuda):
     with pytest.raises(cv.LtxvError, match="head_dim"):
         cv.LtxVideoTransformer3DModel(cv.DitConfig(num_attention_heads=2, attention_head_dim=16,
                                                    cross_attention_dim=32, num_layers=1, caption_channels=32))
+
+
+def test_fused_qk_epilogue_matches_separate_pass(cuda):
+    """q/k RMS-norm + RoPE: the default path folds the norm weight and the rotation into the QKV / to_q GEMM epilogues
+    (EPI_QKV_ROPE) and applies the per-row rsqrt in the consumers; option qk_unfused runs the reference's order as a
+    separate pass (ltx_transformer.rs:671-678).  Both must agree with the oracle, and with each other to bf16 rounding."""
+    import candle_video_b200 as cv
+    cfg = small_cfg()
+    m, w = build(cfg)
+    F, H, W, K = 3, 8, 12, 64
+    hidden, enc, mask, coords = inputs(cfg, 1, F, H, W, K, n_keep=40)
+    t = torch.tensor([993.0])
+    ref = O.dit_forward(w, cfg, hidden, enc, t, mask, F, H, W, None, coords, timestep_to_bf16=True)
+    args = (hidden.to(cuda), enc.to(cuda), t.to(cuda), mask.to(cuda), F, H, W, None, coords.to(cuda))
+    try:
+        cv.set_option("qk_unfused", 0)
+        cv.trace_begin()
+        fused = m.forward(*args)
+        tr_f = cv.trace_end()
+        cv.set_option("qk_unfused", 1)
+        cv.trace_begin()
+        unfused = m.forward(*args)
+        tr_u = cv.trace_end()
+    finally:
+        cv.set_option("qk_unfused", 0)
+    assert any("epi=7" in k for k in tr_f) and "k_rms_scale_kernel" in tr_f and "row_rscale_kernel" in tr_f
+    assert not any("epi=7" in k for k in tr_u) and "k_rms_scale_kernel" not in tr_u
+    assert rel_l2(fused, ref) <= REL_L2_TOL and rel_l2(unfused, ref) <= REL_L2_TOL
+    assert rel_l2(fused, unfused) <= 5e-3
