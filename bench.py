@@ -294,7 +294,7 @@ def config_dims(name):
 
 
 def measure_config(cv, torch, dev, name, dit, vae, n_steps, comm=None, sync=None, maxr=None, compare=True,
-                   nosplit_check=False):
+                   nosplit_check=False, breakdown=False):
     """One BASELINE configuration on this rank (comm None) or sharded over all ranks of `comm`.  Returns a compact
     dict: ms/step (n_steps timed after a 1-step warm-up), ms/decode (best effort: 1 warm-up + 2 timed), and -- when
     sharded -- how the sharded result compares with the single-GPU one on the same inputs."""
@@ -355,6 +355,16 @@ def measure_config(cv, torch, dev, name, dit, vae, n_steps, comm=None, sync=None
                     dist.all_reduce(rl, op=dist.ReduceOp.MAX)
                 out["sharded_vs_single_rel_l2"] = float(rl)
                 out["sharded_equals_single"] = bool(int(eq))
+            if breakdown:
+                # where the sharded step spends its time on this rank (CUDA events per kernel class; class "other" =
+                # the NVLink flag-barrier kernels: flag round trip + waiting for the slowest partner)
+                lat_b = lat0.to(dev).contiguous()
+                cv.profile_begin()
+                denoise(lat_b, 2, True)
+                prof = cv.profile_end()
+                if comm.rank == 0:
+                    out["sharded_breakdown_ms_per_step"] = {k: round(v["ms"] / 2, 3) for k, v in prof.items() if v["launches"]}
+                    out["sharded_breakdown_launches_per_step"] = {k: v["launches"] // 2 for k, v in prof.items() if v["launches"]}
             if nosplit_check:
                 # with the attention tail split off both paths run the same instruction sequence per row: bit identity
                 cv.set_option("attn_nosplit", 1)
@@ -616,7 +626,7 @@ def run_ours(args):
                 own.init_random(1234)
                 d_ = own
             r = measure_config(cv, torch, dev, name, d_, vae if name != "c4" else None, n_sc, comm=comm, sync=barrier,
-                               maxr=max_over_ranks, nosplit_check=(name == "c2"))
+                               maxr=max_over_ranks, nosplit_check=(name == "c2"), breakdown=name in ("c2", "c3"))
             r["what"] = CONFIGS[name][5]
             scal[name] = r
             del own, d_

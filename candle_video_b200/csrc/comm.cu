@@ -1,5 +1,7 @@
 #include "comm.h"
 
+#include "profile.h"
+
 #include <atomic>
 #include <string.h>
 
@@ -108,7 +110,12 @@ void PeerComm::barrier(cudaStream_t s, int domain, int first, int count) {
     }
     for (int r = first; r < first + count; ++r)
         if (r != rank_) f.epoch[r] = ++epoch_[domain][r];
-    barrier_kernel<<<1, 32, 0, s>>>(f, static_cast<uint32_t*>(heap_) + domain * kMaxRanks, first, count, rank_);
+    {
+        // class 7 of ltxv_profile_*: the barrier kernel's duration = flag round trip over NVLink + waiting for the slowest
+        // partner (load imbalance); "work" counts the partners
+        ProfScope prof(PROF_OTHER, static_cast<double>(count - 1), s);
+        barrier_kernel<<<1, 32, 0, s>>>(f, static_cast<uint32_t*>(heap_) + domain * kMaxRanks, first, count, rank_);
+    }
     ++launches_;
     g_comm_launches.fetch_add(1, std::memory_order_relaxed);
     LTXV_CUDA(cudaGetLastError());

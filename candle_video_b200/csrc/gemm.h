@@ -67,6 +67,8 @@ struct GemmParams {
     void* norm_halo_dn;
     int norm_halo_up_h, norm_halo_dn_h;  // slab rows H of those neighbours (ragged slabs); 0 = same as this slab
 
+    int raster_g;       // tile raster group (row tiles per group, see tile_mn); set by launch_gemm_bf16
+
     // ---- EPI_QKV_ROPE ----
     int qk_cols, qk_dim;        // treated columns (qk_dim or 2 qk_dim) and the width of q (= of k): multiples of 64
     const float* qk_w[2];       // f32 [qk_dim] norm weights of q and of k
