@@ -625,8 +625,11 @@ def run_ours(args):
                 own = cv.LtxVideoTransformer3DModel(cv.DitConfig.preset(pr), device=local_rank)
                 own.init_random(1234)
                 d_ = own
-            r = measure_config(cv, torch, dev, name, d_, vae if name != "c4" else None, n_sc, comm=comm, sync=barrier,
-                               maxr=max_over_ranks, nosplit_check=(name == "c2"), breakdown=name in ("c2", "c3"))
+            try:
+                r = measure_config(cv, torch, dev, name, d_, vae if name != "c4" else None, n_sc, comm=comm, sync=barrier,
+                                   maxr=max_over_ranks, nosplit_check=(name == "c2"), breakdown=name in ("c2", "c3"))
+            except cv.LtxvError as e:  # raised symmetrically on every rank (same arguments): report, keep the run
+                r = {"error": str(e)[:300]}
             r["what"] = CONFIGS[name][5]
             scal[name] = r
             del own, d_
@@ -887,9 +890,11 @@ def parity_block_c2(cv, dev):
 
 
 def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set
-    full` capture (profiles/r01_ncu_full_gemm.csv; ncu cannot run inside the timed bench)."""
-    p = ROOT / "profiles" / "r01_gemm_traffic.json"
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class (the DiT GEMMs), mean over
+    the 231 GEMM launches of ONE batched-CFG step at the timed shape (M = 9984), from the committed ncu launch list of
+    tools/profile_step2.py (profiles/r02_launches_step_plus_decode.csv -> profiles/r02_gemm_traffic.json; ncu cannot
+    run inside the timed bench, and it flushes the caches before every launch: cold-cache upper bound)."""
+    p = ROOT / "profiles" / "r02_gemm_traffic.json"
     try:
         return json.loads(p.read_text())["bytes_per_launch_mean"]
     except Exception:
