@@ -1949,6 +1949,87 @@ cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
 }
 
+// ================================================================================================
+// CUDA-core fallback for SMALL head dims (8 .. 32, multiples of 8): the reference's own golden DiT geometries are
+// 2 x 16 and 4 x 16 heads (scripts/gen_dit_ref.py:12-38, tests/verify_rope_parity.rs:537-567), which the tcgen05
+// kernels (UMMA K = 16 per instruction over 64- / 128-wide swizzled rows) do not serve.  One thread per query row,
+// 64-key tiles staged in shared memory, two passes per tile (scores + max, then exp and P V), f32 throughout.  Not a
+// performance path: it exists so that fixtures generated for the reference's tests can be loaded and compared.
+// ================================================================================================
+constexpr int kSimtKeys = 64;
+template <int DMAX>
+__global__ void __launch_bounds__(128)
+flash_attn_simt_kernel(const AttnParams p) {
+    __shared__ __align__(16) __nv_bfloat16 sk[kSimtKeys * DMAX];
+    __shared__ __align__(16) __nv_bfloat16 sv[kSimtKeys * DMAX];
+    __shared__ float sbias[kSimtKeys];
+    const int D = p.D;
+    const int head = blockIdx.y, batch = blockIdx.z;
+    const int qrow = blockIdx.x * 128 + threadIdx.x;
+    const bool valid = qrow < p.Sq;
+    const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(p.q) +
+                              (static_cast<int64_t>(batch) * p.Sq + (valid ? qrow : 0)) * p.ldq + p.q_col0 + head * D;
+    float q[DMAX], o[DMAX];
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) {
+        q[i] = i < D ? __bfloat162float(qp[i]) : 0.f;
+        o[i] = 0.f;
+    }
+    const float c = p.scale * kLog2e * q_row_scale(p, batch, valid ? qrow : 0);
+    float m = -INFINITY, l = 0.f;
+    const int vec_per_row = D >> 3;  // 16-byte pieces per key row
+    for (int kv0 = 0; kv0 < p.Skv; kv0 += kSimtKeys) {
+        const int nk = min(kSimtKeys, p.Skv - kv0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kSimtKeys * vec_per_row; i += 128) {
+            const int r = i / vec_per_row, cpos = (i - r * vec_per_row) * 8;
+            uint4 ku = make_uint4(0u, 0u, 0u, 0u), vu = ku;
+            if (r < nk) {
+                const int64_t row = static_cast<int64_t>(batch) * p.Skv + kv0 + r;
+                ku = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.k) + row * p.ldk + p.k_col0 + head * D + cpos);
+                vu = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.v) + row * p.ldv + p.v_col0 + head * D + cpos);
+            }
+            *reinterpret_cast<uint4*>(sk + r * DMAX + cpos) = ku;
+            *reinterpret_cast<uint4*>(sv + r * DMAX + cpos) = vu;
+        }
+        if (threadIdx.x < kSimtKeys)
+            sbias[threadIdx.x] = (p.kv_bias != nullptr && threadIdx.x < nk)
+                                     ? p.kv_bias[static_cast<int64_t>(batch) * p.Skv + kv0 + threadIdx.x] * kLog2e : 0.f;
+        __syncthreads();
+        float sc[kSimtKeys];
+        float mx = -INFINITY;
+#pragma unroll 4
+        for (int r = 0; r < kSimtKeys; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < DMAX; ++i)
+                if (i < D) a = fmaf(q[i], __bfloat162float(sk[r * DMAX + i]), a);
+            a = r < nk ? fmaf(a, c, sbias[r]) : -INFINITY;
+            sc[r] = a;
+            mx = fmaxf(mx, a);
+        }
+        const float m_new = fmaxf(m, mx);
+        const float alpha = m == -INFINITY ? 0.f : ex2_approx(m - m_new);
+        l *= alpha;
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i) o[i] *= alpha;
+#pragma unroll 4
+        for (int r = 0; r < kSimtKeys; ++r) {
+            const float pr = ex2_approx(sc[r] - m_new);  // exp2(-inf) = 0 for the masked tail
+            l += pr;
+#pragma unroll
+            for (int i = 0; i < DMAX; ++i)
+                if (i < D) o[i] = fmaf(pr, __bfloat162float(sv[r * DMAX + i]), o[i]);
+        }
+        m = m_new;
+    }
+    if (!valid) return;
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (static_cast<int64_t>(batch) * p.Sq + qrow) * p.ldo + head * D;
+    for (int i = 0; i < D; i += 2)
+        *reinterpret_cast<uint32_t*>(op + i) = pack_bf16x2(o[i] * inv_l, o[i + 1] * inv_l);
+}
+
 std::atomic<uint64_t> g_attn_launches{0};
 
 // per-device scratch for the tail split + ticket counters
@@ -2155,6 +2236,18 @@ void attention_debug_timing(long long* out32) { cudaMemcpyFromSymbol(out32, g_at
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Skv <= 0) return cudaErrorInvalidValue;
+    if (p.D >= 8 && p.D <= 32 && p.D % 8 == 0) {
+        // small head dims (the reference's golden test geometries): CUDA-core fallback
+        if (p.out_rows_per_peer != 0 || p.ldq % 8 != 0 || p.ldk % 8 != 0 || p.ldv % 8 != 0 || p.ldo % 2 != 0 || p.q_col0 % 8 != 0 ||
+            p.k_col0 % 8 != 0 || p.v_col0 % 8 != 0)
+            return cudaErrorInvalidValue;
+        ProfScope prof(p.kv_bias != nullptr || p.Skv != p.Sq ? PROF_ATTN_CROSS : PROF_ATTN_SELF,
+                       4.0 * p.B * p.H * static_cast<double>(p.Sq) * p.Skv * p.D, stream);
+        LTXV_TRACE_VARIANT("flash_attn_simt_kernel<32> D=%d", p.D);
+        flash_attn_simt_kernel<32><<<dim3((p.Sq + 127) / 128, p.H, p.B), 128, 0, stream>>>(p);
+        g_attn_launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError();
+    }
     if (p.D == 64 && p.kv_bias == nullptr && p.Skv > 2 * kTileKV && p.Sq > kTileQ && !options().attn_v1)
         return launch_attn3_impl(p, stream);
     if (p.D == 64 && p.Skv <= kTileKV && p.out_rows_per_peer == 0 && !options().attn_v1)

@@ -26,8 +26,11 @@ LtxVideoTransformer3DModel::LtxVideoTransformer3DModel(const ltxv_dit_config& cf
     require_cuda_device(device);
     const int D = inner_dim();
     const int hd = cfg.attention_head_dim;
-    if (hd != 64 && hd != 128) fail("attention_head_dim must be 64 or 128 (got %d)", hd);
-    if (D % 64 != 0) fail("inner dim %d must be a multiple of 64", D);
+    // 64 / 128: the tcgen05 kernels (LTX-Video 2B / 13B); 8..32 (multiples of 8): CUDA-core fallback, there for the
+    // reference's golden test geometries (2 x 16, 4 x 16 heads)
+    if (hd != 64 && hd != 128 && !(hd >= 8 && hd <= 32 && hd % 8 == 0))
+        fail("attention_head_dim must be 64, 128 or a multiple of 8 up to 32 (got %d)", hd);
+    if (D % 32 != 0) fail("inner dim %d must be a multiple of 32", D);
     if (cfg.in_channels % 8 != 0 || cfg.out_channels % 32 != 0 || cfg.caption_channels % 8 != 0 ||
         cfg.cross_attention_dim % 8 != 0)
         fail("channel counts must be multiples of 8 (out_channels of 32)");

@@ -26,8 +26,8 @@ enum EpiMode : int {
     //   v = acc + bias;  ss[row] += v^2;  y = v * w[col];  (y0, y1) <- (y0 cos - y1 sin, y1 cos + y0 sin)
     // is stored as bf16; the per-row scalar rsqrt(mean(v^2) + eps) commutes with both steps and is applied by the
     // consumer (attention: folded into the softmax scale of the row for q; one pass over k for k).  The remaining
-    // columns (v of the QKV projection) are a plain bf16 store.  ss goes to qk_ss[row, first 64-column group of the
-    // tile] (the other groups of the tile are written as 0): consumers add the qk_dim / 64 entries of a row in order.
+    // columns (v of the QKV projection) are a plain bf16 store.  ss goes to qk_ss[row, 64-column group]: consumers add
+    // the qk_dim / 64 entries of a row in a fixed order (independent of the tile width the launcher picked).
     EPI_QKV_ROPE = 7,
 };
 

@@ -368,13 +368,13 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
     __syncwarp();  // the tile is rewritten by the next chunk
 }
 
-// EPI_QKV_ROPE: per-row sums of squares of one tile (lane owns 4 columns of rows 4i + lane/8): add the 8 lanes of a row
-// group and store the total at the tile's first 64-column group; the tile's other groups get 0.
-__device__ __forceinline__ void epilogue_store_row_ss(const GemmParams& p, int m_warp0, int n0, int tile_n, int lane,
-                                                      float (&ss)[8]) {
-    if (n0 >= p.qk_cols) return;
+// EPI_QKV_ROPE: per-row sums of squares of ONE 64-column group (two 32-column chunks; a lane owns 4 columns of rows
+// 4i + lane/8): add the 8 lanes of a row group and store the total at group (n0 / 64).  The grouping is by absolute
+// column, not by tile, so the bits of a row's sums do not depend on the tile width the heuristic picked (single GPU and
+// token shards pick different widths and must still agree bit for bit).
+__device__ __forceinline__ void epilogue_store_row_ss(const GemmParams& p, int m_warp0, int n0, int lane, float (&ss)[8]) {
     const int groups_total = p.qk_cols >> 6;
-    const int g0 = n0 >> 6, g = lane & 7, rsub = lane >> 3;
+    const int g0 = n0 >> 6, rsub = lane >> 3;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float t = ss[i];
@@ -382,8 +382,7 @@ __device__ __forceinline__ void epilogue_store_row_ss(const GemmParams& p, int m
         t += __shfl_xor_sync(0xffffffffu, t, 2);
         t += __shfl_xor_sync(0xffffffffu, t, 4);
         const int64_t m = m_warp0 + 4 * i + rsub;
-        if (m < p.M && g < (tile_n >> 6) && g0 + g < groups_total)
-            p.qk_ss[m * groups_total + g0 + g] = g == 0 ? t : 0.f;
+        if ((lane & 7) == 0 && m < p.M && n0 < p.qk_cols) p.qk_ss[m * groups_total + g0] = t;
         ss[i] = 0.f;
     }
 }
@@ -741,8 +740,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     chunk(c, res_a);
                     if (prefetch_res && c + 2 < BLOCK_N / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
                     chunk(c + 1, res_b);
+                    if constexpr (QK) epilogue_store_row_ss(p, m_warp0, n0 + c * 32, lane, row_ss);
                 }
-                if constexpr (QK) epilogue_store_row_ss(p, m_warp0, n0, BLOCK_N, lane, row_ss);
             }
             if (++acc == 2) {
                 acc = 0;
@@ -1005,8 +1004,8 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     chunk(c, res_a);
                     if (prefetch_res && c + 2 < kPairBlockN / 32) epilogue_load_residual(p, m_warp0, n0 + (c + 2) * 32, lane, res_a);
                     chunk(c + 1, res_b);
+                    if constexpr (QK) epilogue_store_row_ss(p, m_warp0, n0 + c * 32, lane, row_ss);
                 }
-                if constexpr (QK) epilogue_store_row_ss(p, m_warp0, n0, kPairBlockN, lane, row_ss);
             }
             if (kEpiGroups == 1 && ++acc == 2) {
                 acc = 0;
@@ -1133,8 +1132,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             (p.rope_cos == nullptr) != (p.rope_sin == nullptr) || (p.rope_cos != nullptr && p.rope_rows <= 0))
             return cudaErrorInvalidValue;
     }
-    // a tile of the fused QKV projection must not straddle the q | k | v boundaries (one sum of squares per tile)
-    const bool qk_tiles = p.epi == EPI_QKV_ROPE && p.qk_cols > p.qk_dim;
+    // (sums of squares are kept per absolute 64-column group, so any tile width works for EPI_QKV_ROPE)
     if (p.epi == EPI_QKV_ROPE && block_n != 0) return cudaErrorInvalidValue;  // tile width is chosen here
     if (block_n == -2) return launch_pair_impl<256, 0>(ops, p, stream);
     if (block_n == -3) return launch_pair_impl<128, 0>(ops, p, stream);
@@ -1157,7 +1155,6 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             const int c = cands[i];
             if (c > 64 && p.N <= c / 2) continue;
             if (norm_pad && (c < p.N || (c != 128 && c != 256))) continue;
-            if (qk_tiles && p.qk_dim % c != 0) continue;
             const int tiles = num_m * ((p.N + c - 1) / c);
             const int rounds = (tiles + sms - 1) / sms;
             const double cost = rounds * static_cast<double>(c) / rate[i];
@@ -1172,19 +1169,19 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         // TFLOP/s with the bf16 store, 890 vs 866 with the f32 residual epilogue, tools/bin/gemm_test 3).
         const bool no_short_k_rule = options().gemm_no_short_k != 0;
         const bool short_k_192 = !no_short_k_rule && !p.conv && p.K <= 2048 && p.N <= 2048 && p.N % 192 != 0 &&
-                                 p.N > 1024 && p.M >= 8192 && !qk_tiles;
+                                 p.N > 1024 && p.M >= 8192;
         if (short_k_192) block_n = 192;
         if (!short_k_192 && p.M > 2 * kBlockM && !options().gemm_no_pair) {
             const int num_mp = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
             int pair_bn = 0;
-            if (p.N % 256 == 0 && !(qk_tiles && p.qk_dim % 256 != 0)) {
+            if (p.N % 256 == 0) {
                 const int rounds = (num_mp * (p.N / 256) + sms / 2 - 1) / (sms / 2);
                 if (rounds * 256.0 / 1.00 <= best) {
                     best = rounds * 256.0;
                     pair_bn = 256;
                 }
             }
-            if (p.N % 128 == 0 && !(norm_pad && p.N > 128) && !(qk_tiles && p.qk_dim % 128 != 0)) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
+            if (p.N % 128 == 0 && !(norm_pad && p.N > 128)) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
                 const int rounds = (num_mp * (p.N / 128) + sms / 2 - 1) / (sms / 2);
                 if (rounds * 128.0 / 0.80 < best) {
                     best = rounds * 128.0 / 0.80;
