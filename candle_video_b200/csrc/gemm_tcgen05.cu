@@ -779,9 +779,10 @@ constexpr int kABoxBytes3 = kBoxRows3 * kBlockK * 2;   // bytes one KW3 A box tr
 
 // MODE 0: one 64-wide k-block per pipeline stage; MODE 1: KW3 (above); MODE 2: TWO k-blocks per stage (8 MMAs per
 // full/empty barrier round trip instead of 4 -- the plain GEMMs ran at 71 % tensor-pipe activity against 99 % for KW3).
-// QK (EPI_QKV_ROPE instances): TWO epilogue warpgroups like the conv variants -- its epilogue (norm weight, RoPE table
-// reads, sums of squares) outlasts the K = 2048 main loop with one -- each with its own transpose tiles; one stage less.
-template <int BN, int MODE, bool QK = false>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
+// TWO: two epilogue warpgroups like the conv variants, each with its own transpose tiles, one pipeline stage less.  Used
+// where the epilogue outlasts a K = 2048 main loop with one group: EPI_QKV_ROPE (norm weight, RoPE table reads, sums of
+// squares) and the f32 residual read-modify-write of the attention out-projections.
+template <int BN, int MODE, bool TWO = false>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
 struct PairCfg {
     static constexpr bool KW3 = MODE == 1;
     static constexpr int kKbPerStage = MODE == 2 ? 2 : 1;
@@ -790,9 +791,9 @@ struct PairCfg {
     static constexpr int kBStage = KW3 ? 3 * kBBytes : kKbPerStage * kBBytes;
     static constexpr int kStageBytes = kAStage + kBStage;
     static constexpr int kTxBytes = (KW3 ? kABoxBytes3 : kKbPerStage * kABytes) + kBStage;  // bytes ONE CTA credits per stage
-    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : ((BN == 256 ? 6 : 8) - (QK ? 1 : 0)) / kKbPerStage;
+    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : ((BN == 256 ? 6 : 8) - (TWO ? 1 : 0)) / kKbPerStage;
     static constexpr int kTmemCols = 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + (QK ? 2 : 1) * kEpiStageBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + (TWO ? 2 : 1) * kEpiStageBytes;
     static_assert(BN == 256 || BN == 128, "pair tile width");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -800,15 +801,18 @@ struct PairCfg {
 // The conv variants (MODE 1) run TWO epilogue warpgroups, one per TMEM accumulator stage, on alternating tiles: with one
 // warp per scheduler the epilogue is latency-bound (a 128x128 tile with residual, x store and the fused producer takes
 // ~16 us against an 11 us main loop at C = 128), and two groups give every tile two main loops of time.
-template <int MODE, bool QK = false>
+template <int MODE, bool TWO = false>
 struct PairThreads {
-    static constexpr int value = (MODE == 1 || QK) ? 384 : kThreads;
+    static constexpr int value = (MODE == 1 || TWO) ? 384 : kThreads;
 };
-template <int BN, int MODE, bool QK = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairThreads<MODE, QK>::value, 1)
+// E2: 0 = one epilogue warpgroup; 1 = two + the EPI_QKV_ROPE epilogue code; 2 = two, plain epilogues
+template <int BN, int MODE, int E2 = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairThreads<MODE, E2 != 0>::value, 1)
 gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ GemmParams p) {
-    using PC = PairCfg<BN, MODE, QK>;
+    constexpr bool QK = E2 == 1;
+    constexpr bool TWO = E2 != 0;
+    using PC = PairCfg<BN, MODE, TWO>;
     constexpr bool KW3 = PC::KW3;
     constexpr int kKbPerStage = PC::kKbPerStage;
     constexpr int kPairBlockN = BN;
@@ -949,12 +953,12 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int quad = warp_idx & 3;
         // one transpose tile per epilogue WARP (two warpgroups in the QK instances)
         float* stage_buf = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + 256) +
-                           (QK ? warp_idx - 4 : quad) * (32 * kEpiRowFloats);
+                           (TWO ? warp_idx - 4 : quad) * (32 * kEpiRowFloats);
         const bool coalesced = !p.conv && (p.epi == EPI_STORE_BF16 || p.epi == EPI_STORE_F32 || p.epi == EPI_RESIDUAL_F32 || QK) &&
                                (p.N % 32 == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        constexpr int kEpiGroups = PairThreads<MODE, QK>::value == 384 ? 2 : 1;
+        constexpr int kEpiGroups = PairThreads<MODE, TWO>::value == 384 ? 2 : 1;
         const int epi_group = (warp_idx - 4) >> 2;
         int it = 0;
         float row_ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // EPI_QKV_ROPE: sums of squares of this tile's rows
@@ -1072,15 +1076,15 @@ cudaError_t launch_impl(const GemmOperands& ops, const GemmParams& p, cudaStream
 }
 
 
-template <int BN, int MODE, bool QK = false>
+template <int BN, int MODE, int E2 = 0>
 cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaStream_t stream) {
-    using PC = PairCfg<BN, MODE, QK>;
+    using PC = PairCfg<BN, MODE, E2 != 0>;
     constexpr bool KW3 = PC::KW3;
     static PerDeviceOnce configured;
     int cfg_dev = 0;
     static int num_sms = 0;
     if (configured.need(&cfg_dev)) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, MODE, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_tn_kernel<BN, MODE, E2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PC::kSmemBytes);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -1107,7 +1111,7 @@ cudaError_t launch_pair_impl(const GemmOperands& ops, const GemmParams& p, cudaS
         ProfScope prof(p.conv ? PROF_CONV : PROF_GEMM, flops, stream);
         LTXV_TRACE_VARIANT("%s<%d,%d> epi=%d", p.conv ? "conv3d:gemm_pair_bf16_tn_kernel" : "gemm_pair_bf16_tn_kernel", BN, MODE,
                            p.epi);
-        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE, QK>, dim3(2 * clusters), dim3(PairThreads<MODE, QK>::value), PC::kSmemBytes,
+        cudaError_t le = launch_pdl(gemm_pair_bf16_tn_kernel<BN, MODE, E2>, dim3(2 * clusters), dim3(PairThreads<MODE, E2 != 0>::value), PC::kSmemBytes,
                                     stream, ta, tb, pr);
         if (le != cudaSuccess) return le;
     }
@@ -1168,8 +1172,9 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         // large ones and the 5.8 waves of 128x192 tiles beat the 4.2 rounds of 256x256 pairs (measured 1244 vs 1196
         // TFLOP/s with the bf16 store, 890 vs 866 with the f32 residual epilogue, tools/bin/gemm_test 3).
         const bool no_short_k_rule = options().gemm_no_short_k != 0;
+        // ... except for the f32 residual epilogue, which runs on the pair kernel with two epilogue warpgroups (E2 = 2)
         const bool short_k_192 = !no_short_k_rule && !p.conv && p.K <= 2048 && p.N <= 2048 && p.N % 192 != 0 &&
-                                 p.N > 1024 && p.M >= 8192;
+                                 p.N > 1024 && p.M >= 8192 && !(p.epi == EPI_RESIDUAL_F32 && !options().gemm_no_epi2);
         if (short_k_192) block_n = 192;
         if (!short_k_192 && p.M > 2 * kBlockM && !options().gemm_no_pair) {
             const int num_mp = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
@@ -1192,8 +1197,12 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             if (norm_pad && !kw3) pair_bn = 0;  // only the KW3 pair kernels carry the fused producer epilogue
             // two k-blocks per stage measured neutral (1341 vs 1353 TFLOP/s on the QKV shape): opt-in only
             const bool k2 = !p.conv && p.num_k_blocks % 2 == 0 && options().gemm_k2 != 0;
-            if (p.epi == EPI_QKV_ROPE && pair_bn == 256) return launch_pair_impl<256, 0, true>(ops, p, stream);
-            if (p.epi == EPI_QKV_ROPE && pair_bn == 128) return launch_pair_impl<128, 0, true>(ops, p, stream);
+            if (p.epi == EPI_QKV_ROPE && pair_bn == 256) return launch_pair_impl<256, 0, 1>(ops, p, stream);
+            if (p.epi == EPI_QKV_ROPE && pair_bn == 128) return launch_pair_impl<128, 0, 1>(ops, p, stream);
+            // f32 residual read-modify-write behind a SHORT main loop (attention out-projections, K <= 2048): two
+            // epilogue warpgroups
+            if (p.epi == EPI_RESIDUAL_F32 && p.K <= 2048 && pair_bn == 256 && !kw3 && !options().gemm_no_epi2)
+                return launch_pair_impl<256, 0, 2>(ops, p, stream);
             if (pair_bn == 256)
                 return kw3 ? launch_pair_impl<256, 1>(ops, p, stream)
                            : (k2 ? launch_pair_impl<256, 2>(ops, p, stream) : launch_pair_impl<256, 0>(ops, p, stream));

@@ -16,6 +16,7 @@ const Entry kEntries[] = {
     {"gemm_no_pair", "LTXV_GEMM_NO_PAIR", &Options::gemm_no_pair, false},
     {"conv_no_kw3", "LTXV_CONV_NO_KW3", &Options::conv_no_kw3, false},
     {"gemm_no_raster", "LTXV_GEMM_NO_RASTER", &Options::gemm_no_raster, false},
+    {"gemm_no_epi2", "LTXV_GEMM_NO_EPI2", &Options::gemm_no_epi2, false},
     {"gemm_k2", "LTXV_GEMM_K2", &Options::gemm_k2, false},
     {"gemm_no_short_k", "LTXV_GEMM_NO_SHORT_K_RULE", &Options::gemm_no_short_k, false},
     {"attn_v1", "LTXV_ATTN_V1", &Options::attn_v1, false},

@@ -10,6 +10,7 @@ struct Options {
     int gemm_no_pair;        // LTXV_GEMM_NO_PAIR: no CTA-pair GEMM / conv kernels
     int conv_no_kw3;         // LTXV_CONV_NO_KW3: no three-taps-per-step conv mode
     int gemm_no_raster;      // LTXV_GEMM_NO_RASTER: row-fastest tile order everywhere (no L2-friendly grouping)
+    int gemm_no_epi2;        // LTXV_GEMM_NO_EPI2: no two-epilogue-warpgroup pair kernel for the short-K residual GEMMs
     int gemm_k2;             // LTXV_GEMM_K2: two k-blocks per stage (opt-in)
     int gemm_no_short_k;     // LTXV_GEMM_NO_SHORT_K_RULE: no 128x192 preference for the short-K N = K = 2048 projections
     int attn_v1;             // LTXV_ATTN_V1: general attention kernel everywhere
