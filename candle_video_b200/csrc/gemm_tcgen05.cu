@@ -1152,7 +1152,16 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int cands[4] = {256, 192, 128, 64};
-        const double rate[4] = {0.94, 0.88, 0.75, 0.50};
+        // Token-shard launches (M <= 4096: the per-rank row count of the 4/8-GPU Ulysses split): few rounds, so the
+        // narrow tiles lose nothing to the wide ones and balance better.  Re-calibrated on M = 1248 / 1672
+        // (tools/bin/gemm_test 6): at K <= 2048 128x192 and 128x128 run within 5% of 128x256 per unit area, and the
+        // 256x128 cluster tile is the fastest shape of all (1051 vs 931 TFLOP/s on the QKV shape at M = 1672).
+        const bool shard_m = !p.conv && p.M <= 4096;
+        const bool short_k = p.K <= 2048;
+        const double rate_big[4] = {0.94, 0.88, 0.75, 0.50};
+        const double rate_shard[4] = {0.94, 0.97, 0.95, 0.60};
+        const double* rate = shard_m && short_k ? rate_shard : rate_big;
+        const double pair128_rate = !shard_m ? 0.80 : (short_k ? 1.05 : 1.02);
         double best = 1e30;
         const int num_m = (p.M + kBlockM - 1) / kBlockM;
         for (int i = 0; i < 4; ++i) {
@@ -1188,8 +1197,8 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             }
             if (p.N % 128 == 0 && !(norm_pad && p.N > 128)) {  // 256x128 cluster tiles: the only way to share B when N = 128 (VAE level-3 convs)
                 const int rounds = (num_mp * (p.N / 128) + sms / 2 - 1) / (sms / 2);
-                if (rounds * 128.0 / 0.80 < best) {
-                    best = rounds * 128.0 / 0.80;
+                if (rounds * 128.0 / pair128_rate < best) {
+                    best = rounds * 128.0 / pair128_rate;
                     pair_bn = 128;
                 }
             }
@@ -1203,6 +1212,8 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             // epilogue warpgroups
             if (p.epi == EPI_RESIDUAL_F32 && p.K <= 2048 && pair_bn == 256 && !kw3 && !options().gemm_no_epi2)
                 return launch_pair_impl<256, 0, 2>(ops, p, stream);
+            if (p.epi == EPI_RESIDUAL_F32 && p.K <= 2048 && pair_bn == 128 && !kw3 && !options().gemm_no_epi2)
+                return launch_pair_impl<128, 0, 2>(ops, p, stream);
             if (pair_bn == 256)
                 return kw3 ? launch_pair_impl<256, 1>(ops, p, stream)
                            : (k2 ? launch_pair_impl<256, 2>(ops, p, stream) : launch_pair_impl<256, 0>(ops, p, stream));

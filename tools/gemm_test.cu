@@ -309,6 +309,15 @@ int main(int argc, char** argv) {
         printf("%s\n", f ? "GEMM_TEST_FAIL" : "GEMM_TEST_OK");
         return f;
     }
+    if (argc > 1 && atoi(argv[1]) == 6) {  // token-shard shapes (8-GPU Ulysses: M = 1248 at c2, 1672 at c3): every tile variant vs auto
+        for (int M : {1248, 1672}) {
+            struct Sh { int N, K, epi, act; };
+            for (const Sh& sh : {Sh{6144, 2048, EPI_STORE_BF16, 0}, Sh{2048, 2048, EPI_RESIDUAL_F32, 0}, Sh{2048, 2048, EPI_STORE_BF16, 0},
+                                 Sh{8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH}, Sh{2048, 8192, EPI_RESIDUAL_F32, 0}})
+                for (int bn : {0, 256, 192, 128, 64, -2, -3}) test_gemm(M, sh.N, sh.K, sh.epi, sh.act, bn, true);
+        }
+        return 0;
+    }
     if (argc > 1 && atoi(argv[1]) == 3) {  // every kernel variant at the [9984, 2048] x [2048, 2048] projections
         for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, bn, true);
         for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_STORE_BF16, 0, bn, true);
