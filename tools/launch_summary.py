@@ -3,6 +3,8 @@
 --csv --log-file X.csv`): launches, total / mean duration, share of the profiled region, DRAM MB per launch.
 
   python tools/launch_summary.py gpurun_out/launches.csv "header comment" > profiles/rNN_launches_summary.csv
+  python tools/launch_summary.py --traffic gpurun_out/launches.csv > profiles/rNN_gemm_traffic.json
+      (DRAM bytes per launch of the DiT GEMMs of the denoise step: every launch before the first VAE kernel)
 """
 import collections
 import csv
@@ -13,7 +15,51 @@ UNIT = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nseco
         "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
 
 
+def traffic(path):
+    import json
+    hdr, launch = None, collections.OrderedDict()
+    for r in csv.reader(open(path)):
+        if hdr is None:
+            if "Kernel Name" in r:
+                hdr = r
+                ki, mi, vi, ui, ii = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+            continue
+        if len(r) != len(hdr):
+            continue
+        d = launch.setdefault(r[ii], {"name": re.sub(r"\(.*", "", r[ki]).split("::")[-1]})
+        d[r[mi]] = float(r[vi].replace(",", "")) * UNIT.get(r[ui], 1.0)
+    step = []
+    for d in launch.values():  # the denoise step ends where the decode starts
+        if d["name"].startswith(("denorm_kernel", "vae_")):
+            break
+        step.append(d)
+    gemm = [d for d in step if d["name"].startswith(("gemm_bf16_tn_kernel", "gemm_pair_bf16_tn_kernel"))]
+    per = collections.OrderedDict()
+    for d in gemm:
+        a = per.setdefault(d["name"], [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d["gpu__time_duration.sum"]
+        a[2] += d["dram__bytes_read.sum"] * 1e6
+        a[3] += d["dram__bytes_write.sum"] * 1e6
+    step_us = sum(d["gpu__time_duration.sum"] for d in step)
+    out = {
+        "source": f"{path} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+                  "over tools/profile_step2.py: ONE batched-CFG denoise step at c2 = the forward bench.py times, M = 9984 rows "
+                  "per GEMM; ncu flushes the caches before every launch, so the bytes are cold-cache upper bounds)",
+        "dit_step_launches": len(step),
+        "dit_step_us_under_ncu": step_us,
+        "gemm_launches": len(gemm),
+        "gemm_share_of_step": sum(a[1] for a in per.values()) / step_us,
+        "bytes_per_launch_mean": sum(a[2] + a[3] for a in per.values()) / max(len(gemm), 1),
+        "per_kernel": {k: {"launches": a[0], "us_per_launch": a[1] / a[0], "dram_read_bytes_per_launch": a[2] / a[0],
+                           "dram_write_bytes_per_launch": a[3] / a[0]} for k, a in per.items()},
+    }
+    print(json.dumps(out, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(sys.argv[2])
     path = sys.argv[1]
     note = sys.argv[2] if len(sys.argv) > 2 else ""
     hdr, rows = None, []
