@@ -56,9 +56,6 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
     griddep_wait();
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPV, l = lane % LPV;
-    const int64_t nvox = static_cast<int64_t>(T) * H * W;
-    const int64_t warp0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * VPW;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * 8 * VPW;
     const int Hp = H + 2, Wp = W + 2;
 
     float sc[kMod ? CPL : 1][8], sh[kMod ? CPL : 1][8];
@@ -76,19 +73,19 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
             sh[k][4] = d.x; sh[k][5] = d.y; sh[k][6] = d.z; sh[k][7] = d.w;
         }
     }
-    // two voxel groups per iteration: both 16-byte loads are in flight before either is consumed; all index math in
-    // 32 bits (64-bit div/mod per voxel made the previous version ALU-bound: 2.2 TB/s)
-    const int nv32 = static_cast<int>(nvox);
-    const int hw = H * W;
-    auto load = [&](int vox, float (&v)[CPL][8]) {
+    // One CTA pass = one (t, h) row of the volume: the frame / halo replication flags and the destination bases are
+    // row-uniform, so all of the index arithmetic (two integer divisions, the 64-bit plane offsets, up to eleven
+    // destinations) is paid once per row.  The previous voxel-strided loop spent 60 % of its ~205 warp instructions per
+    // 256 elements there and was issue-bound at 0.43 of the copy bandwidth (profiles/r02_ncu_vae_prep.csv).
+    auto load = [&](const __nv_bfloat16* src, float (&v)[CPL][8]) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(vox) * C + (k * LPV + l) * 8));
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + k * LPV * 8));
             v[k][0] = bf16_lo(u.x); v[k][1] = bf16_hi(u.x); v[k][2] = bf16_lo(u.y); v[k][3] = bf16_hi(u.y);
             v[k][4] = bf16_lo(u.z); v[k][5] = bf16_hi(u.z); v[k][6] = bf16_lo(u.w); v[k][7] = bf16_hi(u.w);
         }
     };
-    auto finish = [&](int vox, bool valid, float (&v)[CPL][8]) {
+    auto math = [&](float (&v)[CPL][8]) {
         if (do_norm) {
             float s2 = 0.f;
 #pragma unroll
@@ -115,49 +112,70 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[k][i] = silu_fast_f32(v[k][i]);
         }
-        if (!valid) return;
-        const int t = vox / hw;
-        const int rem = vox - t * hw;
-        const int h = rem / W;
-        const int w = rem - h * W;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-            uint4 o;
-            o.x = pack_bf16x2(v[k][0], v[k][1]);
-            o.y = pack_bf16x2(v[k][2], v[k][3]);
-            o.z = pack_bf16x2(v[k][4], v[k][5]);
-            o.w = pack_bf16x2(v[k][6], v[k][7]);
-            const int c0 = (k * LPV + l) * 8;
-            auto put = [&](__nv_bfloat16* base, int hp, int hpad) {
-                const int64_t pl = static_cast<int64_t>(hpad) * Wp;
-                const int64_t row = (static_cast<int64_t>(t + tf) * hpad + hp) * Wp + (w + 1);
-                *reinterpret_cast<uint4*>(base + row * C + c0) = o;
-                if (t == 0)  // replicate frame 0
-                    for (int q = 1; q <= tf; ++q) *reinterpret_cast<uint4*>(base + (row - q * pl) * C + c0) = o;
-                if (tf == 1 && t == T - 1) *reinterpret_cast<uint4*>(base + (row + pl) * C + c0) = o;  // frame T-1
-            };
-            put(out, h + 1, Hp);
-            if (halo_up != nullptr && h == 0) put(halo_up, H_up + 1, H_up + 2);  // my first row = bottom halo of the slab above
-            if (halo_dn != nullptr && h == H - 1) put(halo_dn, 0, H_dn + 2);     // my last row  = top halo of the slab below
-        }
     };
-    const int istride = static_cast<int>(stride);
-    // U voxel groups per iteration, all loads issued before the first is consumed: with 16-byte loads the kernel needs
-    // ~8 MB in flight chip-wide to cover HBM latency (Little's law at 6.5 TB/s x 1.2 us)
-    constexpr int U = C <= 1024 ? 2 : 1;  // U = 4 measured slower at C = 128 (76 registers: one resident CTA fewer per SM)
-    for (int base = static_cast<int>(warp0); base < nv32; base += U * istride) {
-        int vox[U];
-        bool ok[U];
-        float xv[U][CPL][8];
+    constexpr int VPB = 8 * VPW;              // voxels per CTA pass
+    constexpr int U = C <= 1024 ? 2 : 1;      // passes in flight: every load is issued before the first is consumed
+    const int rows = T * H;
+    const int64_t pl_main = static_cast<int64_t>(Hp) * Wp * C;
+    const int lane_off = l * 8;
+    const int wv = (threadIdx.x >> 5) * VPW + sub;  // this thread's voxel inside a pass
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int t = row / H;
+        const int h = row - t * H;
+        const __nv_bfloat16* src = x + static_cast<int64_t>(row) * W * C + lane_off;
+        __nv_bfloat16* d_main = out + ((static_cast<int64_t>(t + tf) * Hp + h + 1) * Wp + 1) * C + lane_off;
+        const bool rep_front = t == 0;                   // replicate frame 0 into the tf planes in front of it
+        const bool rep_back = tf == 1 && t == T - 1;     // non-causal: one more copy of the last frame
+        const bool up = halo_up != nullptr && h == 0;    // my first row = bottom halo of the slab above
+        const bool dn = halo_dn != nullptr && h == H - 1;  // my last row = top halo of the slab below
+        const bool extra = rep_front || rep_back || up || dn;
+        for (int w0 = wv; w0 - wv < W; w0 += U * VPB) {  // (w0 - wv is CTA-uniform: the shuffles stay full-warp)
+            float xv[U][CPL][8];
+            int off[U];
+            bool ok[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int raw = base + u * istride + sub;
-            ok[u] = raw < nv32;  // warp-uniform only per half: the shuffles below stay full-warp
-            vox[u] = ok[u] ? raw : nv32 - 1;
-            load(vox[u], xv[u]);
+            for (int u = 0; u < U; ++u) {
+                const int w = w0 + u * VPB;
+                ok[u] = w < W;
+                off[u] = (ok[u] ? w : W - 1) * C;
+                load(src + off[u], xv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                math(xv[u]);
+                if (!ok[u]) continue;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    uint4 o;
+                    o.x = pack_bf16x2(xv[u][k][0], xv[u][k][1]);
+                    o.y = pack_bf16x2(xv[u][k][2], xv[u][k][3]);
+                    o.z = pack_bf16x2(xv[u][k][4], xv[u][k][5]);
+                    o.w = pack_bf16x2(xv[u][k][6], xv[u][k][7]);
+                    const int eo = off[u] + k * LPV * 8;
+                    *reinterpret_cast<uint4*>(d_main + eo) = o;
+                    if (extra) {
+                        auto put = [&](__nv_bfloat16* base, int64_t pl) {
+                            if (rep_front)
+                                for (int q = 1; q <= tf; ++q) *reinterpret_cast<uint4*>(base - q * pl + eo) = o;
+                            if (rep_back) *reinterpret_cast<uint4*>(base + pl + eo) = o;
+                        };
+                        put(d_main, pl_main);
+                        if (up) {
+                            const int64_t pl = static_cast<int64_t>(H_up + 2) * Wp * C;
+                            __nv_bfloat16* d = halo_up + ((static_cast<int64_t>(t + tf) * (H_up + 2) + H_up + 1) * Wp + 1) * C + lane_off;
+                            *reinterpret_cast<uint4*>(d + eo) = o;
+                            put(d, pl);
+                        }
+                        if (dn) {
+                            const int64_t pl = static_cast<int64_t>(H_dn + 2) * Wp * C;
+                            __nv_bfloat16* d = halo_dn + (static_cast<int64_t>(t + tf) * (H_dn + 2) * Wp + 1) * C + lane_off;
+                            *reinterpret_cast<uint4*>(d + eo) = o;
+                            put(d, pl);
+                        }
+                    }
+                }
+            }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) finish(vox[u], ok[u], xv[u]);
     }
 }
 
@@ -382,10 +400,10 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
     __nv_bfloat16* hu = reinterpret_cast<__nv_bfloat16*>(halo_up);
     __nv_bfloat16* hd = reinterpret_cast<__nv_bfloat16*>(halo_dn);
     const int64_t nvox = static_cast<int64_t>(T) * H * W;
-    if (nvox >= (1ll << 31) - 148 * 8 * 4) return cudaErrorInvalidValue;  // the kernel indexes voxels in 32 bits
-    const int vpb = 8 * (C == 128 ? 2 : 1);  // voxels per block pass
-    int64_t want = (nvox + vpb - 1) / vpb;
-    const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+    if (static_cast<int64_t>(T) * H >= (1ll << 31) - 148 * 8 || static_cast<int64_t>(W + 64) * C >= (1ll << 31))
+        return cudaErrorInvalidValue;  // the kernel indexes rows and the elements of a row in 32 bits
+    const int64_t rows = static_cast<int64_t>(T) * H;  // one (t, h) row per CTA pass
+    const int grid = static_cast<int>(rows < 148 * 8 ? rows : 148 * 8);
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
     ProfScope prof(PROF_VAE_PREP, 4.0 * static_cast<double>(nvox) * C, s);  // bf16 in, bf16 out
