@@ -8,7 +8,8 @@
 //   qkv    bf16 [S, 3D]   fused self-attention projections; q,k are normed + rotated in place
 //   attn   bf16 [S, D]    attention output (A operand of the out projections)
 //   ff     bf16 [S, 4D]   GELU(FFN-in) (A operand of FFN-out)
-//   ctx.kv bf16 [L][K,2D] per-layer cross-attention K (normed) | V of the text tokens (step-invariant, hoisted)
+//   ctx.kv bf16 [K, L*2D] cross-attention K (normed) | V of the text tokens for ALL layers (layer l = columns
+//                         [l*2D, (l+1)*2D)): one GEMM against the stacked attn2.to_k/to_v weights + one norm launch
 #include "dit.h"
 
 #include <math.h>
@@ -59,6 +60,10 @@ LtxVideoTransformer3DModel::LtxVideoTransformer3DModel(const ltxv_dit_config& cf
     add_slot("scale_shift_table", sst_final_, false, {2, D});
     sst_blocks_ = vec(static_cast<int64_t>(cfg.num_layers) * 6 * D);
 
+    // attn2.to_k | to_v of every layer stacked along N ([L*2D, X]) and the attn2.norm_k weights along [L*D]: the text
+    // K/V of all layers come out of ONE GEMM (M = text rows) + ONE norm launch instead of 2 x L launches of 16 + 6 us
+    kv2_all_ = make_linear(cfg.num_layers * 2 * D, X);
+    norm_k2_all_ = vec(static_cast<int64_t>(cfg.num_layers) * D);
     blocks_.resize(cfg.num_layers);
     for (int i = 0; i < cfg.num_layers; ++i) {
         DitBlockW& b = blocks_[i];
@@ -77,14 +82,17 @@ LtxVideoTransformer3DModel::LtxVideoTransformer3DModel(const ltxv_dit_config& cf
         add_slot(p + "attn1.norm_q.weight", b.norm_q1, false, {D});
         add_slot(p + "attn1.norm_k.weight", b.norm_k1, false, {D});
         linear(p + "attn2.to_q", b.q2, D, D);
-        b.kv2 = make_linear(2 * D, X);
+        b.kv2.N = 2 * D;
+        b.kv2.K = X;
+        b.kv2.w = kv2_all_.w + static_cast<int64_t>(i) * 2 * D * X;
+        b.kv2.b = kv2_all_.b + static_cast<int64_t>(i) * 2 * D;
         add_slot(p + "attn2.to_k.weight", b.kv2.w, true, {D, X});
         add_slot(p + "attn2.to_k.bias", b.kv2.b, false, {D});
         add_slot(p + "attn2.to_v.weight", b.kv2.w + static_cast<int64_t>(D) * X, true, {D, X});
         add_slot(p + "attn2.to_v.bias", b.kv2.b + D, false, {D});
         linear(p + "attn2.to_out.0", b.out2, D, D);
         b.norm_q2 = vec(D);
-        b.norm_k2 = vec(D);
+        b.norm_k2 = norm_k2_all_ + static_cast<int64_t>(i) * D;
         add_slot(p + "attn2.norm_q.weight", b.norm_q2, false, {D});
         add_slot(p + "attn2.norm_k.weight", b.norm_k2, false, {D});
         linear(p + "ff.net.0.proj", b.ff1, 4 * D, D);
@@ -309,11 +317,9 @@ void LtxVideoTransformer3DModel::prepare_context(int slot, const void* enc, int 
     c.kv.ensure(static_cast<size_t>(L) * K * 2 * D * 2);
     gemm(enc_b, K, cap1_, K, EPI_STORE_BF16, ACT_GELU_TANH, cap_mid_.p, nullptr, nullptr, s);
     gemm(cap_mid_.p, K, cap2_, K, EPI_STORE_BF16, ACT_NONE, enc_proj_.p, nullptr, nullptr, s);
-    for (int l = 0; l < L; ++l) {
-        __nv_bfloat16* kv = c.kv.as<__nv_bfloat16>() + static_cast<size_t>(l) * K * 2 * D;
-        gemm(enc_proj_.p, K, blocks_[l].kv2, K, EPI_STORE_BF16, ACT_NONE, kv, nullptr, nullptr, s);
-        LTXV_CUDA(launch_qk_norm_rope(kv, 2 * D, 0, K, D, blocks_[l].norm_k2, 1e-5f, nullptr, nullptr, s));
-    }
+    gemm(enc_proj_.p, K, kv2_all_, K, EPI_STORE_BF16, ACT_NONE, c.kv.p, nullptr, nullptr, s);  // [K, L*2D]
+    LTXV_CUDA(launch_qk_norm_rope(c.kv.p, static_cast<int64_t>(L) * 2 * D, 0, K, D, norm_k2_all_, 1e-5f, nullptr, nullptr, s,
+                                  L, 2 * D, D));
     c.has_mask = mask != nullptr;
     if (mask != nullptr) {
         // bias = (1 - mask) * -10000  (:1059-1064); computed with the affine kernel semantics
@@ -341,13 +347,10 @@ void LtxVideoTransformer3DModel::prepare_pair(int slot_a, int slot_b, cudaStream
     if (a.K != b.K) fail("the two contexts of a pair must have the same text length (%d vs %d)", a.K, b.K);
     LTXV_CUDA(cudaSetDevice(device_));
     const int D = inner_dim(), L = cfg_.num_layers, K = a.K;
-    const size_t per = static_cast<size_t>(K) * 2 * D * 2;  // bytes of one [K, 2D] bf16 block
-    pair_kv_.ensure(static_cast<size_t>(L) * 2 * per);
-    for (int l = 0; l < L; ++l) {
-        char* dst = static_cast<char*>(pair_kv_.p) + static_cast<size_t>(l) * 2 * per;
-        LTXV_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(a.kv.p) + l * per, per, cudaMemcpyDeviceToDevice, s));
-        LTXV_CUDA(cudaMemcpyAsync(dst + per, static_cast<const char*>(b.kv.p) + l * per, per, cudaMemcpyDeviceToDevice, s));
-    }
+    const size_t per = static_cast<size_t>(K) * L * 2 * D * 2;  // bytes of one context's [K, L*2D] bf16 block
+    pair_kv_.ensure(2 * per);                                   // [2][K, L*2D]: batch stride = K rows, as the attention kernel expects
+    LTXV_CUDA(cudaMemcpyAsync(pair_kv_.p, a.kv.p, per, cudaMemcpyDeviceToDevice, s));
+    LTXV_CUDA(cudaMemcpyAsync(static_cast<char*>(pair_kv_.p) + per, b.kv.p, per, cudaMemcpyDeviceToDevice, s));
     pair_has_mask_ = a.has_mask || b.has_mask;
     if (pair_has_mask_) {
         pair_bias_.ensure(static_cast<size_t>(2) * K * 4);
@@ -539,14 +542,14 @@ void LtxVideoTransformer3DModel::forward_impl(const DitContext* ctx1, int nb, co
             LTXV_CUDA(launch_qk_norm_rope(q2_.p, D, 0, M, D, b.norm_q2, 1e-5f, nullptr, nullptr, s));
         }
         {
-            const __nv_bfloat16* kv =
-                nb == 1 ? ctx1->kv.as<__nv_bfloat16>() + static_cast<size_t>(l) * ctxK * 2 * D
-                        : pair_kv_.as<__nv_bfloat16>() + static_cast<size_t>(l) * 2 * ctxK * 2 * D;  // [2][K, 2D]
+            // layer l = columns [l*2D, (l+1)*2D) of the stacked [K, L*2D] text K/V ([2][K, L*2D] for a pair)
+            const __nv_bfloat16* kv = (nb == 1 ? ctx1->kv.as<__nv_bfloat16>() : pair_kv_.as<__nv_bfloat16>()) +
+                                      static_cast<size_t>(l) * 2 * D;
             AttnParams ap{};
             ap.q = q2_.p;
             ap.k = ap.v = kv;
             ap.ldq = D;
-            ap.ldk = ap.ldv = 2 * D;
+            ap.ldk = ap.ldv = static_cast<int64_t>(cfg_.num_layers) * 2 * D;
             ap.q_col0 = 0;
             ap.k_col0 = 0;
             ap.v_col0 = D;

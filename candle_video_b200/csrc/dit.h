@@ -100,6 +100,8 @@ private:
     LinearW proj_in_, te1_, te2_, te_lin_, cap1_, cap2_, proj_out_;
     float* sst_final_ = nullptr;  // [2, D]
     float* sst_blocks_ = nullptr;  // [L, 6, D] contiguous
+    LinearW kv2_all_;                // attn2.to_k | to_v of every layer stacked along N: [L * 2D, Xd] (blocks_[l].kv2 points in)
+    float* norm_k2_all_ = nullptr;   // [L, D] attn2.norm_k weights
     std::vector<DitBlockW> blocks_;
 
     DitContext ctx_[kNumSlots + 1];

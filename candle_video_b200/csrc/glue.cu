@@ -121,13 +121,16 @@ rms_modulate_row_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int rows, int D, const float* __restrict__ w,
-                    float eps, const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+                    float eps, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int group_cols,
+                    int group_w) {
+    // blockIdx.y = column group (the stacked per-layer cross-attention keys): columns + y * group_cols, weight + y * group_w
     griddep_launch_dependents();
     griddep_wait();
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + col0);
+    w += static_cast<int64_t>(blockIdx.y) * group_w;
+    uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + col0 + static_cast<int64_t>(blockIdx.y) * group_cols);
     const int nv = D >> 3;  // 8 bf16 per 16 B
     float s2 = 0.f;
     for (int i = lane; i < nv; i += 32) {
@@ -333,14 +336,16 @@ qk_pair_norm_rope_row_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows
 // register-resident RMS norm x weight of ONE tensor, in place (the cross-attention queries: no RoPE), D = 256 * VPL
 template <int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-rms_weight_row_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int rows, const float* __restrict__ w, float eps) {
+rms_weight_row_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int col0, int rows, const float* __restrict__ w, float eps,
+                      int group_cols, int group_w) {
     constexpr int D = VPL * 256;
     griddep_launch_dependents();
     griddep_wait();
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + col0);
+    w += static_cast<int64_t>(blockIdx.y) * group_w;  // blockIdx.y = column group, see qk_norm_rope_kernel
+    uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ld + col0 + static_cast<int64_t>(blockIdx.y) * group_cols);
     uint4 q[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) q[i] = xr[lane + 32 * i];
@@ -815,19 +820,23 @@ cudaError_t launch_norm_modulate(const float* x, void* out, const float* scale, 
 }
 
 cudaError_t launch_qk_norm_rope(void* x, int64_t ld, int col0, int rows, int D, const float* w, float eps,
-                                const float* cos_t, const float* sin_t, cudaStream_t s) {
-    if (D % 8 != 0 || ld % 8 != 0 || col0 % 8 != 0) return cudaErrorInvalidValue;
-    ProfScope prof(PROF_QK_ROPE, 4.0 * rows * D + (cos_t ? 2.0 * rows * (D / 2) * 4 : 0.0), s);
+                                const float* cos_t, const float* sin_t, cudaStream_t s, int groups, int group_cols,
+                                int group_w) {
+    if (D % 8 != 0 || ld % 8 != 0 || col0 % 8 != 0 || groups < 1 || groups > 65535 || group_cols % 8 != 0 || group_w % 4 != 0 ||
+        (groups > 1 && cos_t != nullptr))
+        return cudaErrorInvalidValue;
+    ProfScope prof(PROF_QK_ROPE, groups * (4.0 * rows * D + (cos_t ? 2.0 * rows * (D / 2) * 4 : 0.0)), s);
     LTXV_TRACE_VARIANT(cos_t == nullptr && D == 2048 ? "rms_weight_row_kernel<8>" : cos_t == nullptr && D == 4096 ? "rms_weight_row_kernel<16>" : "qk_norm_rope_kernel");
+    const dim3 grid(blocks_for(rows, kWarpsPerBlock), groups);
     if (cos_t == nullptr && D == 2048)
-        launch_pdl(rms_weight_row_kernel<8>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
-                   reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, w, eps);
+        launch_pdl(rms_weight_row_kernel<8>, grid, dim3(kWarpsPerBlock * 32), 0, s, reinterpret_cast<__nv_bfloat16*>(x), ld,
+                   col0, rows, w, eps, group_cols, group_w);
     else if (cos_t == nullptr && D == 4096)
-        launch_pdl(rms_weight_row_kernel<16>, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
-                   reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, w, eps);
+        launch_pdl(rms_weight_row_kernel<16>, grid, dim3(kWarpsPerBlock * 32), 0, s, reinterpret_cast<__nv_bfloat16*>(x), ld,
+                   col0, rows, w, eps, group_cols, group_w);
     else
-        launch_pdl(qk_norm_rope_kernel, dim3(blocks_for(rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, s,
-                   reinterpret_cast<__nv_bfloat16*>(x), ld, col0, rows, D, w, eps, cos_t, sin_t);
+        launch_pdl(qk_norm_rope_kernel, grid, dim3(kWarpsPerBlock * 32), 0, s, reinterpret_cast<__nv_bfloat16*>(x), ld, col0,
+                   rows, D, w, eps, cos_t, sin_t, group_cols, group_w);
     return done();
 }
 

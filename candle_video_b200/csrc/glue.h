@@ -16,8 +16,11 @@ cudaError_t launch_norm_modulate(const float* x, void* out_bf16, const float* sc
 // In-place on a bf16 matrix [rows, ld]: for the D columns starting at col0:
 //   y = x * rsqrt(mean(x^2) + eps) * w ; if cos != null: interleaved-pair rotation with cos/sin [rows, D/2] f32
 // (RmsNorm across all heads :570-571,:671-672 + apply_rotary_emb :314-339).
+// groups > 1 (no RoPE): the same norm on `groups` column blocks of every row in ONE launch -- block g starts at column
+// col0 + g * group_cols and uses the weight w + g * group_w (the per-layer cross-attention keys of the stacked text K/V).
 cudaError_t launch_qk_norm_rope(void* x_bf16, int64_t ld, int col0, int rows, int D, const float* w, float eps,
-                                const float* cos_t, const float* sin_t, cudaStream_t s);
+                                const float* cos_t, const float* sin_t, cudaStream_t s, int groups = 1,
+                                int group_cols = 0, int group_w = 0);
 
 // cos/sin [S, D/2] f32 of the 3D video RoPE (LtxVideoRotaryPosEmbed::forward :436-524).
 // coords != null: coords [S,3] f32 (seconds, pixel-y, pixel-x), divided by base (20, 2048, 2048).

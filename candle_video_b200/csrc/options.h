@@ -17,6 +17,7 @@ struct Options {
     int attn_v4;             // LTXV_ATTN_V4: half a score row per softmax thread (flash_attn4_kernel; measured slower)
     int attn_nosplit;        // LTXV_ATTN_NOSPLIT: no key-range tail splitting
     int attn_nsplit_max;     // LTXV_ATTN_NSPLIT=n: cap on key ranges per tail unit (0 = no cap)
+    int vae_prep_u;          // LTXV_VAE_PREP_U=n: voxel passes in flight per thread in vae_prep_kernel<128> (0 = default)
     int vae_no_fused_prep;   // LTXV_VAE_NO_FUSED_PREP: no fused producer epilogue at all
     int vae_no_fuse_conv2;   // LTXV_VAE_NO_FUSE_CONV2: ... not for conv2 at C = 256
     int vae_fuse_conv2;      // LTXV_VAE_FUSE_CONV2: ... also for conv2 at C = 128 (slower)

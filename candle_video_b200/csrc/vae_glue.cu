@@ -2,6 +2,7 @@
 #include "vae_glue.h"
 #include "launch.h"
 #include "profile.h"
+#include "options.h"
 
 #include <atomic>
 
@@ -39,8 +40,8 @@ __global__ void vae_input_kernel(const TIn* __restrict__ z, __nv_bfloat16* __res
 // Channels are split into 16-byte chunks of 8; chunk j of a voxel is owned by lane (j % 32) so that every warp-wide
 // access is a contiguous 256/512-byte run.  C = 128 uses half a warp per voxel (2 voxels per warp), C >= 256 a full warp
 // with C/256 chunks per lane.  Warps stride over the voxels (persistent grid) with scale/shift held in registers.
-template <int C>
-__global__ void __launch_bounds__(256)
+template <int C, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale,
                 const float* __restrict__ shift, int do_norm, int do_silu, int T, int H, int W, int tf,
                 __nv_bfloat16* __restrict__ halo_up, __nv_bfloat16* __restrict__ halo_dn, int H_up, int H_dn) {
@@ -114,7 +115,7 @@ vae_prep_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         }
     };
     constexpr int VPB = 8 * VPW;              // voxels per CTA pass
-    constexpr int U = C <= 1024 ? 2 : 1;      // passes in flight: every load is issued before the first is consumed
+    // U passes in flight: every load is issued before the first is consumed
     const int rows = T * H;
     const int64_t pl_main = static_cast<int64_t>(Hp) * Wp * C;
     const int lane_off = l * 8;
@@ -408,12 +409,18 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
     __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
     ProfScope prof(PROF_VAE_PREP, 4.0 * static_cast<double>(nvox) * C, s);  // bf16 in, bf16 out
     LTXV_TRACE_VARIANT("vae_prep_kernel<%d>", C);
+    const int u128 = options().vae_prep_u;
     switch (C) {
-        case 128: launch_pdl(vae_prep_kernel<128>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
-        case 256: launch_pdl(vae_prep_kernel<256>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
-        case 512: launch_pdl(vae_prep_kernel<512>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
-        case 1024: launch_pdl(vae_prep_kernel<1024>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
-        case 2048: launch_pdl(vae_prep_kernel<2048>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 128:
+            if (u128 == 2) launch_pdl(vae_prep_kernel<128, 2, 4>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn);
+            else if (u128 == 3) launch_pdl(vae_prep_kernel<128, 2, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn);
+            else if (u128 == 8) launch_pdl(vae_prep_kernel<128, 8, 2>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn);
+            else launch_pdl(vae_prep_kernel<128, 4, 3>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn);
+            break;
+        case 256: launch_pdl(vae_prep_kernel<256, 2, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 512: launch_pdl(vae_prep_kernel<512, 2, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 1024: launch_pdl(vae_prep_kernel<1024, 2, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 2048: launch_pdl(vae_prep_kernel<2048, 1, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
         default: return cudaErrorInvalidValue;
     }
     return done();
