@@ -10,6 +10,7 @@
 // For D = 64 two CTAs are resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps
 // the other's MMAs.
 #include "attention.h"
+#define LTXV_PDL_CLASS 8
 #include "launch.h"
 #include "common.cuh"
 #include "tensormap.h"

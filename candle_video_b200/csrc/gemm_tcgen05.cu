@@ -10,6 +10,7 @@
 //   warps 4-7: epilogue; warp w owns TMEM lanes 32*(w%4) .. +31, one accumulator row per thread
 #include "common.cuh"
 #include "gemm.h"
+#define LTXV_PDL_CLASS 2
 #include "launch.h"
 #include "tensormap.h"
 #include "options.h"

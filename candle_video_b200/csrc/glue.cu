@@ -2,6 +2,7 @@
 // warp-shuffle reductions; nothing here is shaped into a GEMM.
 #include "common.cuh"
 #include "glue.h"
+#define LTXV_PDL_CLASS 4
 #include "launch.h"
 #include "profile.h"
 

@@ -10,8 +10,15 @@
 
 namespace ltxv {
 
-inline bool pdl_enabled() {
-    return !options().no_pdl;
+// LTXV_NO_PDL is a bit mask: 1 = no PDL anywhere, 2 = not for the GEMM / conv3d kernels, 4 = not for the DiT glue,
+// 8 = not for attention, 16 = not for the VAE glue.  A translation unit names its class with LTXV_PDL_CLASS before
+// including this header.
+#ifndef LTXV_PDL_CLASS
+#define LTXV_PDL_CLASS 0
+#endif
+static inline bool pdl_enabled() {
+    const int m = options().no_pdl;
+    return !(m & 1) && !(m & LTXV_PDL_CLASS);
 }
 
 // Function attributes (cudaFuncSetAttribute: opt-in shared memory) belong to the device that was current when they
@@ -30,7 +37,7 @@ struct PerDeviceOnce {
 };
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

@@ -27,7 +27,7 @@ const Entry kEntries[] = {
     {"vae_no_fuse_conv2", "LTXV_VAE_NO_FUSE_CONV2", &Options::vae_no_fuse_conv2, false},
     {"vae_fuse_conv2", "LTXV_VAE_FUSE_CONV2", &Options::vae_fuse_conv2, false},
     {"vae_prep_u", "LTXV_VAE_PREP_U", &Options::vae_prep_u, true},
-    {"no_pdl", "LTXV_NO_PDL", &Options::no_pdl, false},
+    {"no_pdl", "LTXV_NO_PDL", &Options::no_pdl, true},
     {"qk_unfused", "LTXV_QK_UNFUSED", &Options::qk_unfused, false},
 };
 Options from_env() {

@@ -1,5 +1,6 @@
 #include "common.cuh"
 #include "vae_glue.h"
+#define LTXV_PDL_CLASS 16
 #include "launch.h"
 #include "profile.h"
 #include "options.h"
