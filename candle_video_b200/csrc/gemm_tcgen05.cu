@@ -1162,7 +1162,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         const double rate_big[4] = {0.94, 0.88, 0.75, 0.50};
         const double rate_shard[4] = {0.94, 0.97, 0.95, 0.60};
         const double* rate = shard_m && short_k ? rate_shard : rate_big;
-        const double pair128_rate = !shard_m ? 0.80 : (short_k ? 1.05 : 1.02);
+        const double pair128_rate = !shard_m ? 0.80 : (short_k ? 1.05 : (p.M <= 2048 ? 1.02 : 0.95));  // K = 8192 at M = 3344: 256x256 pairs 1112 vs 1027 TFLOP/s
         double best = 1e30;
         const int num_m = (p.M + kBlockM - 1) / kBlockM;
         for (int i = 0; i < 4; ++i) {

@@ -310,7 +310,12 @@ int main(int argc, char** argv) {
         return f;
     }
     if (argc > 1 && atoi(argv[1]) == 6) {  // token-shard shapes (8-GPU Ulysses: M = 1248 at c2, 1672 at c3): every tile variant vs auto
-        for (int M : {1248, 1672}) {
+        std::vector<int> Ms = {1248, 1672};  // `gemm_test 6 2496 3344 ...` sweeps other shard sizes
+        if (argc > 2) {
+            Ms.clear();
+            for (int i = 2; i < argc; ++i) Ms.push_back(atoi(argv[i]));
+        }
+        for (int M : Ms) {
             struct Sh { int N, K, epi, act; };
             for (const Sh& sh : {Sh{6144, 2048, EPI_STORE_BF16, 0}, Sh{2048, 2048, EPI_RESIDUAL_F32, 0}, Sh{2048, 2048, EPI_STORE_BF16, 0},
                                  Sh{8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH}, Sh{2048, 8192, EPI_RESIDUAL_F32, 0}})
