@@ -1144,6 +1144,8 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
     if (block_n == -4) return launch_pair_impl<256, 1>(ops, p, stream);   // conv3d, three kw taps per step
     if (block_n == -5) return launch_pair_impl<128, 1>(ops, p, stream);
     if (block_n == -6) return launch_pair_impl<256, 2>(ops, p, stream);   // two k-blocks per stage
+    if (block_n == -7) return launch_pair_impl<256, 0, 2>(ops, p, stream);  // two epilogue warpgroups
+    if (block_n == -8) return launch_pair_impl<128, 0, 2>(ops, p, stream);
     if (block_n == 0) {
         // Pick the kernel / tile width that minimises (rounds over the SMs) x (per-SM tile area) / (relative rate of
         // that tile shape).  Rates from the isolated measurements at K = 8192 (profiles/r01_gemm_*): the CTA-pair
@@ -1162,7 +1164,8 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
         const double rate_big[4] = {0.94, 0.88, 0.75, 0.50};
         const double rate_shard[4] = {0.94, 0.97, 0.95, 0.60};
         const double* rate = shard_m && short_k ? rate_shard : rate_big;
-        const double pair128_rate = !shard_m ? 0.80 : (short_k ? 1.05 : (p.M <= 2048 ? 1.02 : 0.95));  // K = 8192 at M = 3344: 256x256 pairs 1112 vs 1027 TFLOP/s
+        const bool epi2 = !options().gemm_no_epi2 && (p.epi == EPI_STORE_BF16 || p.epi == EPI_QKV_ROPE);  // two epilogue warpgroups
+        const double pair128_rate = !shard_m ? 0.80 : (short_k ? (epi2 ? 1.15 : 1.05) : (p.M <= 2048 ? 1.02 : 0.95));  // K = 8192 at M = 3344: 256x256 pairs 1112 vs 1027 TFLOP/s
         double best = 1e30;
         const int num_m = (p.M + kBlockM - 1) / kBlockM;
         for (int i = 0; i < 4; ++i) {
@@ -1213,6 +1216,12 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             // epilogue warpgroups
             if (p.epi == EPI_RESIDUAL_F32 && p.K <= 2048 && pair_bn == 256 && !kw3 && !options().gemm_no_epi2)
                 return launch_pair_impl<256, 0, 2>(ops, p, stream);
+            // ... and the bf16-store epilogues behind a short main loop (FFN-in with GELU: 1293 -> 1400 TFLOP/s at
+            // M = 9984, tools/bin/gemm_test 7; K = 8192 loses 2.5 % to the missing ring stage and keeps one group)
+            if (p.epi == EPI_STORE_BF16 && !p.conv && p.K <= 2048 && pair_bn == 256 && !options().gemm_no_epi2)
+                return launch_pair_impl<256, 0, 2>(ops, p, stream);
+            if (p.epi == EPI_STORE_BF16 && !p.conv && p.K <= 2048 && pair_bn == 128 && !options().gemm_no_epi2)
+                return launch_pair_impl<128, 0, 2>(ops, p, stream);  // shard shapes: FFN-in at M = 1672 990 -> 1139 TFLOP/s
             if (p.epi == EPI_RESIDUAL_F32 && p.K <= 2048 && pair_bn == 128 && !kw3 && !options().gemm_no_epi2)
                 return launch_pair_impl<128, 0, 2>(ops, p, stream);
             if (pair_bn == 256)

@@ -418,8 +418,8 @@ cudaError_t launch_vae_prep(const void* x, void* out, const float* scale, const 
             else if (u128 == 8) launch_pdl(vae_prep_kernel<128, 8, 2>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn);
             else launch_pdl(vae_prep_kernel<128, 4, 3>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn);
             break;
-        case 256: launch_pdl(vae_prep_kernel<256, 2, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
-        case 512: launch_pdl(vae_prep_kernel<512, 2, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 256: launch_pdl(vae_prep_kernel<256, 4, 3>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
+        case 512: launch_pdl(vae_prep_kernel<512, 4, 2>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
         case 1024: launch_pdl(vae_prep_kernel<1024, 2, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
         case 2048: launch_pdl(vae_prep_kernel<2048, 1, 1>, dim3(grid), dim3(256), 0, s, xi, xo, scale, shift, do_norm, do_silu, T, H, W, tf, hu, hd, H_up, H_dn); break;
         default: return cudaErrorInvalidValue;

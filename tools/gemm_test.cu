@@ -319,7 +319,15 @@ int main(int argc, char** argv) {
             struct Sh { int N, K, epi, act; };
             for (const Sh& sh : {Sh{6144, 2048, EPI_STORE_BF16, 0}, Sh{2048, 2048, EPI_RESIDUAL_F32, 0}, Sh{2048, 2048, EPI_STORE_BF16, 0},
                                  Sh{8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH}, Sh{2048, 8192, EPI_RESIDUAL_F32, 0}})
-                for (int bn : {0, 256, 192, 128, 64, -2, -3}) test_gemm(M, sh.N, sh.K, sh.epi, sh.act, bn, true);
+                for (int bn : {0, 256, 192, 128, 64, -2, -3, -7, -8}) test_gemm(M, sh.N, sh.K, sh.epi, sh.act, bn, true);
+        }
+        return 0;
+    }
+    if (argc > 1 && atoi(argv[1]) == 7) {  // one vs two epilogue warpgroups on the short-K GEMMs with a bf16 store (FFN-in GELU, plain QKV)
+        for (int M : {9984, 13376, 4992}) {
+            for (int bn : {0, -2, -7}) test_gemm(M, 8192, 2048, EPI_STORE_BF16, ACT_GELU_TANH, bn, true);
+            for (int bn : {0, -2, -7}) test_gemm(M, 6144, 2048, EPI_STORE_BF16, 0, bn, true);
+            for (int bn : {0, -2, -7}) test_gemm(M, 2048, 8192, EPI_RESIDUAL_F32, 0, bn, true);
         }
         return 0;
     }
