@@ -329,6 +329,10 @@ int main(int argc, char** argv) {
             for (int bn : {0, -2, -7}) test_gemm(M, 6144, 2048, EPI_STORE_BF16, 0, bn, true);
             for (int bn : {0, -2, -7}) test_gemm(M, 2048, 8192, EPI_RESIDUAL_F32, 0, bn, true);
         }
+        // 13B widths (K = 4096): FFN-in, QKV, attention out-projection at the c4 batched-CFG row count
+        for (int bn : {0, -2, -7}) test_gemm(38640, 16384, 4096, EPI_STORE_BF16, ACT_GELU_TANH, bn, true);
+        for (int bn : {0, -2, -7}) test_gemm(38640, 12288, 4096, EPI_STORE_BF16, 0, bn, true);
+        for (int bn : {0, -2, -7}) test_gemm(38640, 4096, 4096, EPI_RESIDUAL_F32, 0, bn, true);
         return 0;
     }
     if (argc > 1 && atoi(argv[1]) == 3) {  // every kernel variant at the [9984, 2048] x [2048, 2048] projections
