@@ -336,8 +336,8 @@ int main(int argc, char** argv) {
         return 0;
     }
     if (argc > 1 && atoi(argv[1]) == 3) {  // every kernel variant at the [9984, 2048] x [2048, 2048] projections
-        for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, bn, true);
-        for (int bn : {192, 256, 128, -2, -3, -6}) test_gemm(9984, 2048, 2048, EPI_STORE_BF16, 0, bn, true);
+        for (int bn : {0, 192, 256, 128, -2, -3, -6, -7}) test_gemm(9984, 2048, 2048, EPI_RESIDUAL_F32, 0, bn, true);
+        for (int bn : {0, 192, 256, 128, -2, -3, -6, -7}) test_gemm(9984, 2048, 2048, EPI_STORE_BF16, 0, bn, true);
         for (int bn : {192, 256, -2, -3}) test_gemm(4992, 2048, 2048, EPI_RESIDUAL_F32, 0, bn, true);
         return 0;
     }
