@@ -66,8 +66,9 @@ int ltxv_causal_conv3d(const float* x, const float* weight, const float* bias, i
 
 /* Experiment knobs: kernel-variant switches, each initialised once per process from its LTXV_*
  * environment variable; these calls override them at run time (names: no_cfg_batch, gemm_no_pair, conv_no_kw3,
- * gemm_k2, gemm_no_short_k, attn_v1, attn_nosplit, attn_nsplit_max, vae_no_fused_prep, vae_no_fuse_conv2,
- * vae_fuse_conv2, no_pdl, qk_unfused).  Process-wide; not synchronised with in-flight calls of other threads. */
+ * gemm_no_raster, gemm_no_epi2, gemm_k2, gemm_no_short_k, attn_v1, attn_v4, attn_nosplit, attn_nsplit_max,
+ * vae_prep_u, vae_no_fused_prep, vae_no_fuse_conv2, vae_fuse_conv2, no_pdl (bit mask), qk_unfused).  Unknown names
+ * return an error.  Process-wide; not synchronised with in-flight calls of other threads. */
 int ltxv_set_option(const char* name, int value);
 int ltxv_get_option(const char* name, int* value);
 

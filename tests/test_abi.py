@@ -86,3 +86,23 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "candle_video_b200").rglob("*"):
         if p.suffix in (".py", ".cu", ".cc", ".h", ".cuh") and p.is_file():
             assert "oracle" not in p.read_text().replace("no CPU fallback", ""), p
+
+
+def test_option_knobs_round_trip_and_reject_unknown_names():
+    """ltxv_set_option / ltxv_get_option: every knob the header documents exists, holds the value it was
+    given, and an unknown name is an error instead of a silent no-op.  Host-only: no GPU involved."""
+    import candle_video_b200 as cv
+    header = (ROOT / "include" / "ltxv.h").read_text()
+    doc = header[header.index("Experiment knobs"):header.index("int ltxv_set_option")]
+    names = re.findall(r"\b((?:no|gemm|conv|attn|vae|qk)_[a-z0-9_]+)\b", doc)
+    assert len(names) >= 15 and "no_pdl" in names and "vae_prep_u" in names
+    for n in names:
+        before = cv.get_option(n)
+        cv.set_option(n, 3)
+        assert cv.get_option(n) == 3
+        cv.set_option(n, before)
+        assert cv.get_option(n) == before
+    with pytest.raises(Exception):
+        cv.set_option("no_such_knob", 1)
+    with pytest.raises(Exception):
+        cv.get_option("no_such_knob")
