@@ -803,6 +803,15 @@ flash_attn3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #ifdef LTXV_ATTN_TRACE
             const bool tr_on = (qb == 3 && head == 5 && split == 0 && lane == 0);
 #endif
+#ifdef LTXV_ATTN_STAGGER
+            // timing experiment: start the second query tile's softmax chain this many cycles late so that
+            // the two softmax warps of a sub-partition are in opposite phases (exp vs. everything else)
+            if (t == 1) {
+                const long long stagger_t0 = clock64();
+                while (clock64() - stagger_t0 < LTXV_ATTN_STAGGER) {
+                }
+            }
+#endif
             auto tile = [&](int j, auto tail_tag) {
                 constexpr bool TAIL = decltype(tail_tag)::value;
                 const int kv0 = (jt0 + j) * kTileKV;
