@@ -267,10 +267,21 @@ __device__ __forceinline__ void epilogue_load_residual(const GemmParams& p, int 
     }
 }
 
+// RoPE table rows of the 8 output rows a lane handles in epilogue_chunk_coalesced<true> (rows 4i + lane / 8 of the warp's
+// 32): the table has rope_rows rows (the batched CFG pair has M = 2 x rope_rows), 32-bit arithmetic, once per tile
+__device__ __forceinline__ void epilogue_rope_rows(const GemmParams& p, int m_warp0, int lane, int (&trow)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int mm = m_warp0 + 4 * i + (lane >> 3);
+        if (mm >= p.M) mm = p.M - 1;
+        trow[i] = static_cast<int>(static_cast<unsigned>(mm) % static_cast<unsigned>(p.rope_rows)) + p.rope_row0;
+    }
+}
+
 template <bool QK>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, int m_warp0, int col0, int lane,
                                                          float (&v)[32], float* stage, const float4 (&res)[8],
-                                                         float (&ss)[8]) {
+                                                         float (&ss)[8], const int (&trow)[8]) {
     float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiRowFloats);
 #pragma unroll
     for (int i = 0; i < 8; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -331,9 +342,9 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
         if (rot) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                int64_t m = m_warp0 + 4 * i + rsub;
-                if (m >= p.M) m = p.M - 1;
-                const int64_t tr = (static_cast<int64_t>(m % p.rope_rows) + p.rope_row0) * (p.qk_dim >> 1) + (cc >> 1);
+                // trow[i] = RoPE table row of output row 4i + rsub, computed once per tile by the caller: the
+                // 64-bit `m % rope_rows` that used to sit here ran 64 times per lane and tile (8 rows x 8 chunks)
+                const int64_t tr = static_cast<int64_t>(trow[i]) * (p.qk_dim >> 1) + (cc >> 1);
                 cs[i] = __ldg(reinterpret_cast<const float2*>(p.rope_cos + tr));
                 sn[i] = __ldg(reinterpret_cast<const float2*>(p.rope_sin + tr));
             }
@@ -708,6 +719,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float4 res_a[8], res_b[8];  // residual rows, double-buffered one chunk ahead (EPI_RESIDUAL_F32)
             const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
             const int m_warp0 = t.m0 + quad * 32;
+            int trow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if constexpr (QK) {
+                if (p.rope_cos != nullptr) epilogue_rope_rows(p, m_warp0, lane, trow);
+            }
             if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);  // before the MMAs finish
             prefetch_residual_row_l2(p, rc);
             mbar_wait_sleep(&tmem_full_bar[acc], acc_phase);
@@ -728,7 +743,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (coalesced) epilogue_chunk_coalesced<QK>(p, m_warp0, col0, lane, v, stage, res, row_ss);
+                    if (coalesced) epilogue_chunk_coalesced<QK>(p, m_warp0, col0, lane, v, stage, res, row_ss, trow);
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
@@ -977,6 +992,10 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const RowCtx rc = make_row_ctx(p, m_warp0 + lane);
             float4 res_a[8], res_b[8];
             const bool prefetch_res = coalesced && p.epi == EPI_RESIDUAL_F32;
+            int trow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if constexpr (QK) {
+                if (p.rope_cos != nullptr) epilogue_rope_rows(p, m_warp0, lane, trow);
+            }
             if (prefetch_res) epilogue_load_residual(p, m_warp0, n0, lane, res_a);
             prefetch_residual_row_l2(p, rc);
             mbar_wait_sleep(&tmem_full_bar[acc], acc_phase);
@@ -996,7 +1015,7 @@ gemm_pair_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (coalesced) epilogue_chunk_coalesced<QK>(p, m_warp0, col0, lane, v, stage_buf, res, row_ss);
+                    if (coalesced) epilogue_chunk_coalesced<QK>(p, m_warp0, col0, lane, v, stage_buf, res, row_ss, trow);
                     else epilogue_chunk(p, rc, col0, v);
                 }
             };
