@@ -892,9 +892,9 @@ def parity_block_c2(cv, dev):
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class (the DiT GEMMs), mean over
     the 231 GEMM launches of ONE batched-CFG step at the timed shape (M = 9984), from the committed ncu launch list of
-    tools/profile_step2.py (profiles/r02d_launches_step_plus_decode.csv -> profiles/r02d_gemm_traffic.json with tools/launch_summary.py --traffic; ncu cannot
+    tools/profile_step2.py (profiles/r02e_launches_step_plus_decode.csv -> profiles/r02e_gemm_traffic.json with tools/launch_summary.py --traffic; ncu cannot
     run inside the timed bench, and it flushes the caches before every launch: cold-cache upper bound)."""
-    p = ROOT / "profiles" / "r02d_gemm_traffic.json"
+    p = ROOT / "profiles" / "r02e_gemm_traffic.json"
     try:
         return json.loads(p.read_text())["bytes_per_launch_mean"]
     except Exception:
