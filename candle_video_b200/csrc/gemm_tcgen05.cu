@@ -807,7 +807,11 @@ struct PairCfg {
     static constexpr int kBStage = KW3 ? 3 * kBBytes : kKbPerStage * kBBytes;
     static constexpr int kStageBytes = kAStage + kBStage;
     static constexpr int kTxBytes = (KW3 ? kABoxBytes3 : kKbPerStage * kABytes) + kBStage;  // bytes ONE CTA credits per stage
-    static constexpr int kStages = KW3 ? (BN == 256 ? 3 : 4) : ((BN == 256 ? 6 : 8) - (TWO ? 1 : 0)) / kKbPerStage;
+#ifndef LTXV_PAIR_STAGE_EXP
+#define LTXV_PAIR_STAGE_EXP 0  // timing experiment: ring stages removed from the plain pair kernels
+#endif
+    static constexpr int kStages =
+        KW3 ? (BN == 256 ? 3 : 4) : ((BN == 256 ? 6 : 8) - (TWO ? 1 : 0) - LTXV_PAIR_STAGE_EXP) / kKbPerStage;
     static constexpr int kTmemCols = 2 * BN;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + (TWO ? 2 : 1) * kEpiStageBytes;
     static_assert(BN == 256 || BN == 128, "pair tile width");
