@@ -329,7 +329,11 @@ int main(int argc, char** argv) {
             for (int bn : {0, -2, -7}) test_gemm(M, 6144, 2048, EPI_STORE_BF16, 0, bn, true);
             for (int bn : {0, -2, -7}) test_gemm(M, 2048, 8192, EPI_RESIDUAL_F32, 0, bn, true);
         }
-        // 13B widths (K = 4096): FFN-in, QKV, attention out-projection at the c4 batched-CFG row count
+        return 0;
+    }
+    if (argc > 1 && atoi(argv[1]) == 8) {
+        // 13B widths (K = 4096): FFN-in, QKV, attention out-projection at the c4 batched-CFG row count.  SLOW: the naive
+        // reference GEMM of these shapes takes about a minute each -- give the call a generous timeout
         for (int bn : {0, -2, -7}) test_gemm(38640, 16384, 4096, EPI_STORE_BF16, ACT_GELU_TANH, bn, true);
         for (int bn : {0, -2, -7}) test_gemm(38640, 12288, 4096, EPI_STORE_BF16, 0, bn, true);
         for (int bn : {0, -2, -7}) test_gemm(38640, 4096, 4096, EPI_RESIDUAL_F32, 0, bn, true);
