@@ -28,7 +28,7 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kEpiRowFloats = 36;                              // 32 columns + 4 pad: conflict-free 128-bit smem rows
+constexpr int kEpiRowFloats = 32;                              // unpadded rows; the float4 column is XOR-swizzled with (row & 7)
 constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;     // one 32x32 f32 transpose tile per epilogue warp
 
 template <int BLOCK_N>
@@ -282,9 +282,12 @@ template <bool QK>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, int m_warp0, int col0, int lane,
                                                          float (&v)[32], float* stage, const float4 (&res)[8],
                                                          float (&ss)[8], const int (&trow)[8]) {
+    // 32x32 f32 transpose tile: row r keeps its float4 column c at slot c ^ (r & 7).  Writes (one row per lane) and reads
+    // (4 rows x 8 float4 per instruction) are both 4 wavefronts per 512 B = conflict-free without padding, which leaves
+    // room for one more ring stage in the two-epilogue-group pair kernels (18 -> 16 KB per group)
     float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiRowFloats);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) srow[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < 8; ++i) srow[i ^ (lane & 7)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     __syncwarp();
     const int cq = (lane & 7) * 4;
     const int rsub = lane >> 3;
@@ -296,7 +299,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, in
     // compiler cannot disambiguate from the next row's loads, so interleaving them would serialise 8 global round trips
     float4 x[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(stage + (4 * i + rsub) * kEpiRowFloats + cq);
+    for (int i = 0; i < 8; ++i)
+        x[i] = *reinterpret_cast<const float4*>(stage + (4 * i + rsub) * kEpiRowFloats + (((lane & 7) ^ ((4 * i + rsub) & 7)) << 2));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int64_t m = m_warp0 + 4 * i + rsub;
@@ -811,7 +815,7 @@ struct PairCfg {
 #define LTXV_PAIR_STAGE_EXP 0  // timing experiment: ring stages removed from the plain pair kernels
 #endif
     static constexpr int kStages =
-        KW3 ? (BN == 256 ? 3 : 4) : ((BN == 256 ? 6 : 8) - (TWO ? 1 : 0) - LTXV_PAIR_STAGE_EXP) / kKbPerStage;
+        KW3 ? (BN == 256 ? 3 : 4) : ((BN == 256 ? 6 : 8) - LTXV_PAIR_STAGE_EXP) / kKbPerStage;
     static constexpr int kTmemCols = 2 * BN;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + (TWO ? 2 : 1) * kEpiStageBytes;
     static_assert(BN == 256 || BN == 128, "pair tile width");
@@ -1240,7 +1244,7 @@ cudaError_t launch_gemm_bf16(const GemmOperands& ops, const GemmParams& p, int b
             if (p.epi == EPI_RESIDUAL_F32 && p.K <= 2048 && pair_bn == 256 && !kw3 && !options().gemm_no_epi2)
                 return launch_pair_impl<256, 0, 2>(ops, p, stream);
             // ... and the bf16-store epilogues behind a short main loop (FFN-in with GELU: 1293 -> 1400 TFLOP/s at
-            // M = 9984, tools/bin/gemm_test 7; K = 8192 loses 2.5 % to the missing ring stage and keeps one group)
+            // M = 9984, tools/bin/gemm_test 7; at K = 8192 the main loop hides the epilogue: one group)
             if (p.epi == EPI_STORE_BF16 && !p.conv && p.K <= 2048 && pair_bn == 256 && !options().gemm_no_epi2)
                 return launch_pair_impl<256, 0, 2>(ops, p, stream);
             if (p.epi == EPI_STORE_BF16 && !p.conv && p.K <= 2048 && pair_bn == 128 && !options().gemm_no_epi2)
