@@ -799,7 +799,7 @@ constexpr int kABoxBytes3 = kBoxRows3 * kBlockK * 2;   // bytes one KW3 A box tr
 
 // MODE 0: one 64-wide k-block per pipeline stage; MODE 1: KW3 (above); MODE 2: TWO k-blocks per stage (8 MMAs per
 // full/empty barrier round trip instead of 4 -- the plain GEMMs ran at 71 % tensor-pipe activity against 99 % for KW3).
-// TWO: two epilogue warpgroups like the conv variants, each with its own transpose tiles, one pipeline stage less.  Used
+// TWO: two epilogue warpgroups like the conv variants, each with its own (swizzled, unpadded) transpose tiles; same ring depth as the one-group kernels.  Used
 // where the epilogue outlasts a K = 2048 main loop with one group: EPI_QKV_ROPE (norm weight, RoPE table reads, sums of
 // squares) and the f32 residual read-modify-write of the attention out-projections.
 template <int BN, int MODE, bool TWO = false>  // N of the cluster tile (256 or 128); each CTA stages BN / 2 rows of B
