@@ -1,7 +1,7 @@
 //! `src/models/ltx_video/b200_ffi.rs` -- raw bindings of libltxv_b200.so (include/ltxv.h of the B200 repository).
 //!
-//! Everything the trait implementations in `b200_models.rs` call is declared here, one `extern "C"` item per C
-//! declaration, same order as the header.  Dtype codes: `LTXV_F32 = 0`, `LTXV_BF16 = 1`.
+//! Every entry point of the header is declared here, one `extern "C"` item per C declaration: first what the trait
+//! implementations in `b200_models.rs` call (same order as the header), then the rest of the ABI.  Dtype codes: `LTXV_F32 = 0`, `LTXV_BF16 = 1`.
 //! Link with `cargo:rustc-link-lib=dylib=ltxv_b200`.
 #![allow(non_camel_case_types, dead_code)]
 
@@ -204,6 +204,61 @@ extern "C" {
                                           negative_embeds: *const c_void, negative_mask: *const f32,
                                           embeds_dtype: c_int, k: c_int, stream: *mut c_void) -> c_int;
     pub fn ltxv_vae_set_comm(vae: *mut ltxv_vae, c: *mut ltxv_comm) -> c_int;
+    pub fn ltxv_pipeline_denoise_parallel_stochastic(dit: *mut ltxv_dit, c: *mut ltxv_comm,
+                                                     p: *const ltxv_pipeline_params, latents: *mut f32,
+                                                     prompt_embeds: *const c_void, prompt_mask: *const f32,
+                                                     negative_embeds: *const c_void, negative_mask: *const f32,
+                                                     embeds_dtype: c_int, k: c_int, step_noise: *const f32,
+                                                     stream: *mut c_void) -> c_int;
+
+    // ---- the rest of include/ltxv.h: not called by b200_models.rs, declared so the binding covers the whole ABI ----
+    // context slots: the text K/V of a prompt prepared once and reused by every forward of the denoise loop
+    pub fn ltxv_dit_prepare_context(m: *mut ltxv_dit, slot: c_int, enc: *const c_void, enc_dtype: c_int,
+                                    mask: *const f32, k: c_int, stream: *mut c_void) -> c_int;
+    pub fn ltxv_dit_forward_ctx(m: *mut ltxv_dit, slot: c_int, hidden: *const c_void, hidden_dtype: c_int,
+                                timestep: *const f32, s: c_int, f: c_int, h: c_int, w: c_int,
+                                rope_scale3: *const f32, video_coords: *const f32, skip_layer_mask: *const f32,
+                                out: *mut c_void, out_dtype: c_int, stream: *mut c_void) -> c_int;
+    pub fn ltxv_dit_get_config(m: *const ltxv_dit, out: *mut ltxv_dit_config) -> c_int;
+    pub fn ltxv_vae_spatial_compression_ratio(m: *const ltxv_vae) -> c_int;
+    pub fn ltxv_vae_temporal_compression_ratio(m: *const ltxv_vae) -> c_int;
+    pub fn ltxv_vae_encode_tiled(m: *mut ltxv_vae, x: *const c_void, x_dtype: c_int, b: c_int, f: c_int, h: c_int,
+                                 w: c_int, tiling: *const ltxv_vae_tiling, use_framewise_encoding: c_int,
+                                 moments: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn ltxv_scheduler_step_stochastic(latents: *mut f32, model_output: *const f32, noise: *const f32, n: i64,
+                                          sigma: f32, sigma_next: f32, stream: *mut c_void) -> c_int;
+    pub fn ltxv_decode_noise_blend(latents: *mut f32, noise: *const f32, scale: f32, n: i64,
+                                   stream: *mut c_void) -> c_int;
+    // host-buffer entry points (pageable or pinned host memory in, host memory out; they stage through the handle's
+    // pinned buffers and synchronise before returning) -- what bench.py times as `e2e`
+    pub fn ltxv_dit_forward_host(m: *mut ltxv_dit, hidden: *const c_void, hidden_dtype: c_int, enc: *const c_void,
+                                 enc_dtype: c_int, timestep: *const f32, mask: *const f32, b: c_int, s: c_int,
+                                 k: c_int, f: c_int, h: c_int, w: c_int, rope_scale3: *const f32,
+                                 video_coords: *const f32, skip_layer_mask: *const f32, out: *mut c_void,
+                                 out_dtype: c_int) -> c_int;
+    pub fn ltxv_vae_decode_host(m: *mut ltxv_vae, z: *const c_void, z_dtype: c_int, timestep: *const f32, b: c_int,
+                                f: c_int, h: c_int, w: c_int, out: *mut c_void, out_dtype: c_int,
+                                postprocess: c_int) -> c_int;
+    pub fn ltxv_vae_encode_host(m: *mut ltxv_vae, x: *const c_void, x_dtype: c_int, b: c_int, f: c_int, h: c_int,
+                                w: c_int, moments: *mut f32) -> c_int;
+    pub fn ltxv_pipeline_denoise_host(dit: *mut ltxv_dit, p: *const ltxv_pipeline_params, latents: *mut f32,
+                                      prompt_embeds: *const c_void, prompt_mask: *const f32,
+                                      negative_embeds: *const c_void, negative_mask: *const f32,
+                                      embeds_dtype: c_int, k: c_int) -> c_int;
+    pub fn ltxv_pipeline_decode_host(vae: *mut ltxv_vae, p: *const ltxv_pipeline_params, latents: *const f32,
+                                     out: *mut f32) -> c_int;
+    pub fn ltxv_pipeline_decode_host_u8(vae: *mut ltxv_vae, p: *const ltxv_pipeline_params, latents: *const f32,
+                                        out: *mut u8) -> c_int;
+    // weight-file listing, random initialisation (benchmarks), measurement and experiment hooks
+    pub fn ltxv_safetensors_list(path: *const c_char, out: *mut c_char, out_cap: u64, n_tensors: *mut i32) -> c_int;
+    pub fn ltxv_dit_init_random(m: *mut ltxv_dit, seed: u64) -> c_int;
+    pub fn ltxv_vae_init_random(m: *mut ltxv_vae, seed: u64) -> c_int;
+    pub fn ltxv_profile_begin() -> c_int;
+    pub fn ltxv_profile_end(launches8: *mut u64, ms8: *mut f64, work8: *mut f64) -> c_int;
+    pub fn ltxv_trace_begin() -> c_int;
+    pub fn ltxv_trace_end(out: *mut c_char, out_cap: u64) -> c_int;
+    pub fn ltxv_set_option(name: *const c_char, value: c_int) -> c_int;
+    pub fn ltxv_get_option(name: *const c_char, value: *mut c_int) -> c_int;
 }
 
 /// Non-zero return code -> the message `ltxv_last_error()` holds, as the error type the reference bails with

@@ -106,3 +106,24 @@ def test_option_knobs_round_trip_and_reject_unknown_names():
         cv.set_option("no_such_knob", 1)
     with pytest.raises(Exception):
         cv.get_option("no_such_knob")
+
+
+def test_rust_binding_declares_every_header_symbol():
+    """integration/b200_ffi.rs (the file a maintainer of the reference drops into src/models/ltx_video/) declares exactly
+    the entry points of include/ltxv.h -- no elisions, nothing that the library does not export."""
+    header = re.sub(r"/\*.*?\*/", " ", (ROOT / "include" / "ltxv.h").read_text(), flags=re.S)  # comments out
+    rust = re.sub(r"//[^\n]*", " ", (ROOT / "integration" / "b200_ffi.rs").read_text())
+    declared_c = set(re.findall(r"\b(ltxv_[a-z0-9_]+)\s*\(", header))
+    declared_rs = set(re.findall(r"\bfn\s+(ltxv_[a-z0-9_]+)\s*\(", rust))
+    assert declared_c == declared_rs, (sorted(declared_c - declared_rs), sorted(declared_rs - declared_c))
+    # argument counts agree too (a cheap guard against a signature drifting on one side only)
+    def arity_c(name):
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", header, re.S)
+        args = m.group(1).strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+    def arity_rs(name):
+        m = re.search(r"\bfn\s+" + name + r"\s*\(([^;]*?)\)\s*(?:->[^;]*)?;", rust, re.S)
+        args = m.group(1).strip()
+        return 0 if args == "" else args.count(",") + 1
+    bad = [(n, arity_c(n), arity_rs(n)) for n in sorted(declared_c) if arity_c(n) != arity_rs(n)]
+    assert not bad, bad
