@@ -127,3 +127,10 @@ def test_rust_binding_declares_every_header_symbol():
         return 0 if args == "" else args.count(",") + 1
     bad = [(n, arity_c(n), arity_rs(n)) for n in sorted(declared_c) if arity_c(n) != arity_rs(n)]
     assert not bad, bad
+
+
+def test_rust_model_shims_call_only_declared_entry_points():
+    """integration/b200_models.rs (the trait implementations) must not call anything b200_ffi.rs does not declare."""
+    ffi = set(re.findall(r"\bfn\s+(ltxv_[a-z0-9_]+)", (ROOT / "integration" / "b200_ffi.rs").read_text()))
+    used = set(re.findall(r"\b(ltxv_[a-z0-9_]+)\s*\(", (ROOT / "integration" / "b200_models.rs").read_text()))
+    assert len(used) >= 10 and used <= ffi, sorted(used - ffi)
