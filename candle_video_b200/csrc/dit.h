@@ -32,7 +32,7 @@ struct DitBlockW {
 struct DitContext {  // hoisted, step-invariant text path for one prompt
     bool valid = false;
     int K = 0;
-    DevBuf kv;         // [L][K, 2D] bf16: cross-attention K (normed) | V per layer
+    DevBuf kv;         // [K, L*2D] bf16: cross-attention K (normed) | V of every layer (layer l = columns [l*2D, (l+1)*2D))
     DevBuf mask_bias;  // [K] f32 additive bias, or empty when no mask
     bool has_mask = false;
 };
@@ -105,7 +105,7 @@ private:
     std::vector<DitBlockW> blocks_;
 
     DitContext ctx_[kNumSlots + 1];
-    // CFG pair: [L][2][K, 2D] cross-attention K|V and [2][K] key bias of the two contexts, batch-major
+    // CFG pair: [2][K, L*2D] cross-attention K|V and [2][K] key bias of the two contexts, batch-major
     DevBuf pair_kv_, pair_bias_;
     int pair_K_ = 0;
     bool pair_valid_ = false, pair_has_mask_ = false;
