@@ -5,9 +5,11 @@ at 512x768x97, LTX-Video 2B bf16, CFG flow-matching denoise + 3D-VAE decode; `co
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libltxv_b200.so through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
 
-A "step" is one denoise step of LtxPipeline::call (t2v_pipeline.rs:860-994): 2 DiT forwards (uncond + cond, sequential
-CFG) + CFG combine + Euler update on a [4992,128] latent; the VAE decode (97 frames) is timed in the same run and
-reported beside it.  Synthetic latents/embeddings, random-init weights of the named architecture.
+A "step" is one denoise step of LtxPipeline::call (t2v_pipeline.rs:860-994): the 2 DiT forwards of CFG (uncond + cond;
+the reference runs them one after the other, here they are ONE forward over 2 x 4992 tokens that produces the same
+bits, tests/test_gpu_pipeline.py::test_batched_cfg_pair_equals_sequential_forwards) + CFG combine + Euler update on a
+[4992,128] latent; the VAE decode (97 frames) is timed in the same run and reported beside it.  Synthetic
+latents/embeddings, random-init weights of the named architecture.
 """
 from __future__ import annotations
 
